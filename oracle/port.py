@@ -1,0 +1,230 @@
+"""ctypes binding of oracle/libsmc_oracle.so (the CPU restatement).  TEST INFRASTRUCTURE ONLY."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+dp = C.POINTER(C.c_double)
+ip = C.POINTER(C.c_int)
+
+
+class Cfg(C.Structure):
+    _fields_ = [("Maxx", C.c_int), ("Maxy", C.c_int), ("Xmin", C.c_double), ("Ymin", C.c_double),
+                ("dx", C.c_double), ("dy", C.c_double), ("width", C.c_double), ("dsq", C.c_double),
+                ("siginNN", C.c_double), ("sigma_gg", C.c_double), ("alpha", C.c_double),
+                ("shape_of_nucleons", C.c_int), ("shape_of_entropy", C.c_int), ("collision_criterion", C.c_int),
+                ("which_mc_model", C.c_int), ("sub_model", C.c_int), ("cc_fluct_model", C.c_int)]
+
+
+class Nucleus(C.Structure):
+    _fields_ = [("A", C.c_int), ("rad", C.c_double), ("dr", C.c_double), ("rmaxCut", C.c_double),
+                ("rwMax", C.c_double), ("beta2", C.c_double), ("beta4", C.c_double), ("deformed", C.c_int),
+                ("width", C.c_double), ("quark_width", C.c_double), ("quark_R", C.c_double),
+                ("quark_table", dp), ("quark_rows", C.c_int)]
+
+
+class Rand48(C.Structure):
+    _fields_ = [("x", C.c_uint64)]
+
+
+class Kln(C.Structure):
+    _fields_ = [("ecm", C.c_double), ("lambda_", C.c_double), ("siginNN200", C.c_double),
+                ("model", C.c_int), ("pt_order", C.c_int)]
+
+
+UFN = C.CFUNCTYPE(C.c_double, C.c_void_p, C.c_int, C.c_int, C.c_int)
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", HERE, "libsmc_oracle.so"])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(HERE, "libsmc_oracle.so")
+        if not os.path.exists(so):
+            build()
+        L = C.CDLL(so)
+        L.smc_o_sigma_inel.restype = C.c_double; L.smc_o_sigma_inel.argtypes = [C.c_double]
+        L.smc_o_drand48.restype = C.c_double
+        L.smc_o_six_point.restype = C.c_double; L.smc_o_six_point.argtypes = [C.c_double] * 8
+        L.smc_o_density.restype = C.c_double
+        L.smc_o_density_kln.restype = C.c_double
+        L.smc_o_kln_integrand.restype = C.c_double
+        L.smc_o_kln_dndy.restype = C.c_double
+        L.smc_o_populate.restype = C.c_long
+        L.smc_o_populate_table.restype = C.c_long
+        L.smc_o_uniform_rand48.restype = C.c_double
+        _LIB = L
+    return _LIB
+
+
+def _d(a):
+    return a.ctypes.data_as(dp)
+
+
+def sigma_inel(ecm):
+    return lib().smc_o_sigma_inel(float(ecm))
+
+
+def gauss_params(shape, siginNN, lam=4.14, user_w=0.812):
+    w, s = C.c_double(), C.c_double()
+    lib().smc_o_gauss_params(int(shape), C.c_double(siginNN), C.c_double(lam), C.c_double(user_w), C.byref(w), C.byref(s))
+    return w.value, s.value
+
+
+def make_cfg(maxx=13.0, maxy=13.0, dx=0.1, dy=0.1, ecm=2760.0, alpha=0.118, shape_of_nucleons=2,
+             shape_of_entropy=2, collision_criterion=2, which_mc_model=5, sub_model=1, cc_fluct_model=6,
+             gauss_nucl_width=0.812):
+    c = Cfg()
+    c.Xmin, c.Ymin, c.dx, c.dy = -maxx, -maxy, dx, dy
+    c.Maxx = int((2 * maxx) / dx + 0.1) + 1
+    c.Maxy = int((2 * maxy) / dy + 0.1) + 1
+    c.siginNN = sigma_inel(ecm)
+    c.width, c.sigma_gg = gauss_params(shape_of_nucleons, c.siginNN, user_w=gauss_nucl_width)
+    c.dsq = 0.1 * c.siginNN / np.pi
+    c.alpha = alpha
+    c.shape_of_nucleons, c.shape_of_entropy, c.collision_criterion = shape_of_nucleons, shape_of_entropy, collision_criterion
+    c.which_mc_model, c.sub_model, c.cc_fluct_model = which_mc_model, sub_model, cc_fluct_model
+    return c
+
+
+class Stream48:
+    """drand48 clone usable as a sequential uniform source."""
+    def __init__(self, seed=None, state=None):
+        self.s = Rand48()
+        if state is not None:
+            lib().smc_o_seed48(C.byref(self.s), C.c_ushort(int(state[0])), C.c_ushort(int(state[1])), C.c_ushort(int(state[2])))
+        else:
+            lib().smc_o_srand48(C.byref(self.s), C.c_long(int(seed)))
+
+    def next(self):
+        return lib().smc_o_drand48(C.byref(self.s))
+
+    def args(self):
+        return C.cast(lib().smc_o_uniform_rand48, C.c_void_p), C.byref(self.s)
+
+
+def philox(ctr, key):
+    c = (C.c_uint32 * 4)(*ctr); k = (C.c_uint32 * 2)(*key); o = (C.c_uint32 * 4)()
+    lib().smc_o_philox4x32_10(c, k, o)
+    return [int(v) for v in o]
+
+
+def nucleus(A, width, deformed=0, quark_width=0.3, quark_table=None):
+    n = Nucleus()
+    qt = None if quark_table is None else np.ascontiguousarray(quark_table, dtype=np.float64)
+    lib().smc_o_nucleus_init(C.byref(n), int(A), int(deformed), C.c_double(width), C.c_double(quark_width),
+                             _d(qt) if qt is not None else None, 0 if qt is None else len(qt))
+    n._keep = qt
+    return n
+
+
+def populate(n, xc, yc, stream=None, ufn=None):
+    out = np.zeros((max(n.A, 1), 7))
+    cxphi = np.zeros(2)
+    if ufn is not None:
+        cb = UFN(ufn)
+        lib().smc_o_populate(C.byref(n), C.c_double(xc), C.c_double(yc), cb, None, _d(out), _d(cxphi))
+    else:
+        f, st = stream.args()
+        lib().smc_o_populate(C.byref(n), C.c_double(xc), C.c_double(yc), f, st, _d(out), _d(cxphi))
+    return out, cxphi
+
+
+def populate_table(n, cfg3A, recentre, redraw, xc, yc, stream=None, ufn=None):
+    out = np.zeros((n.A, 7))
+    cfg3A = np.ascontiguousarray(cfg3A, dtype=np.float64)
+    if ufn is not None:
+        cb = UFN(ufn)
+        lib().smc_o_populate_table(C.byref(n), _d(cfg3A), int(recentre), int(redraw), C.c_double(xc), C.c_double(yc), cb, None, _d(out))
+    else:
+        f, st = stream.args()
+        lib().smc_o_populate_table(C.byref(n), _d(cfg3A), int(recentre), int(redraw), C.c_double(xc), C.c_double(yc), f, st, _d(out))
+    return out
+
+
+def collide(cfg, proj7, targ7, stream=None, u_in=None, want_u=False):
+    """-> dict(ncoll, ncollA, ncollB, firsthitB, pairs, u, tested)"""
+    proj7 = np.ascontiguousarray(proj7, dtype=np.float64); targ7 = np.ascontiguousarray(targ7, dtype=np.float64)
+    A, B = len(proj7), len(targ7)
+    ncA = np.zeros(A, dtype=np.int32); ncB = np.zeros(B, dtype=np.int32); fh = np.zeros(B, dtype=np.int32)
+    maxp = A * B
+    pairs = np.zeros((maxp, 2), dtype=np.int32)
+    u = np.zeros((A, B)) if want_u else None
+    tested = C.c_long()
+    if stream is not None:
+        f, st = stream.args()
+    else:
+        f, st = None, None
+    uin = None if u_in is None else np.ascontiguousarray(u_in, dtype=np.float64)
+    n = lib().smc_o_collide(C.byref(cfg), A, _d(proj7), B, _d(targ7), f, st,
+                            _d(uin) if uin is not None else None, _d(u) if u is not None else None,
+                            ncA.ctypes.data_as(ip), ncB.ctypes.data_as(ip), fh.ctypes.data_as(ip),
+                            pairs.ctypes.data_as(ip), maxp, C.byref(tested))
+    return dict(ncoll=n, ncollA=ncA, ncollB=ncB, firsthitB=fh, pairs=pairs[:n].copy(), u=u, tested=tested.value)
+
+
+def _src8(a):
+    a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1, 8)
+    return a
+
+
+def thickness(cfg, src8):
+    s = _src8(src8); g = np.zeros((cfg.Maxx, cfg.Maxy))
+    lib().smc_o_thickness(C.byref(cfg), len(s), _d(s), _d(g))
+    return g
+
+
+def unit_gauss(cfg, src8):
+    s = _src8(src8); g = np.zeros((cfg.Maxx, cfg.Maxy))
+    lib().smc_o_unit_gauss(C.byref(cfg), len(s), _d(s), _d(g))
+    return g
+
+
+def density(cfg, proj8, targ8, coll8):
+    p, t, c = _src8(proj8), _src8(targ8), _src8(coll8)
+    g = np.zeros((cfg.Maxx, cfg.Maxy))
+    dndy = lib().smc_o_density(C.byref(cfg), len(p), _d(p), len(t), _d(t), len(c), _d(c), _d(g))
+    return g, dndy
+
+
+def density_kln(cfg, TA1, TA2, table, dT):
+    table = np.ascontiguousarray(table, dtype=np.float64)
+    TA1 = np.ascontiguousarray(TA1); TA2 = np.ascontiguousarray(TA2)
+    g = np.zeros((cfg.Maxx, cfg.Maxy))
+    dndy = lib().smc_o_density_kln(C.byref(cfg), _d(TA1), _d(TA2), _d(table), table.shape[0], C.c_double(dT), _d(g))
+    return g, dndy
+
+
+def cm_angle(cfg, dens, n):
+    dens = np.ascontiguousarray(dens, dtype=np.float64); o = np.zeros(4)
+    lib().smc_o_cm_angle(C.byref(cfg), _d(dens), int(n), _d(o))
+    return o
+
+
+def eccentricities(cfg, dens, boxes4, from_order=1, to_order=9):
+    """-> dict(mom (9,5) rows [Re e_n, Im e_n, Re e'_n, Im e'_n, <r^n>] for n=1..9, rn, total, xc, yc)"""
+    dens = np.ascontiguousarray(dens, dtype=np.float64)
+    b = np.ascontiguousarray(boxes4, dtype=np.float64).reshape(-1, 4)
+    o = np.zeros(53)
+    lib().smc_o_eccentricities(C.byref(cfg), _d(dens), len(b), _d(b), int(from_order), int(to_order), _d(o))
+    mom = np.stack([o[0:10], o[10:20], o[20:30], o[30:40], o[40:50]], axis=1)
+    return dict(mom=mom[1:10], rn=o[40:50].copy(), total=o[50], xc=o[51], yc=o[52])
+
+
+def kln(ecm, lam, model=7, pt_order=1):
+    k = Kln(); k.ecm = ecm; k.lambda_ = lam; k.siginNN200 = sigma_inel(200.0); k.model = model; k.pt_order = pt_order
+    return k
+
+
+def kln_dndy(k, y, ta, tb, npt=400, nkt=200, nphi=64):
+    return lib().smc_o_kln_dndy(C.byref(k), C.c_double(y), C.c_double(ta), C.c_double(tb), npt, nkt, nphi)
+
+
+def kln_integrand(k, y, ta, tb, x3):
+    x = (C.c_double * 3)(*x3)
+    return lib().smc_o_kln_integrand(C.byref(k), C.c_double(y), C.c_double(ta), C.c_double(tb), x)
