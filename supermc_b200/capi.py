@@ -1,0 +1,223 @@
+"""ctypes binding of include/supermc_b200.h (one-to-one; no logic lives here)."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "libsupermc_b200.so")
+dp = C.POINTER(C.c_double)
+
+RUN_MOMENTS, RUN_KEEP_RHO, RUN_THICKNESS, RUN_RHO_BINARY, RUN_SPECTATORS, RUN_LISTS = 1, 2, 4, 8, 16, 32
+GRID_RHO, GRID_TA1, GRID_TA2, GRID_RHO_BINARY, GRID_SPEC_A, GRID_SPEC_B = range(6)
+
+
+class Params(C.Structure):
+    _fields_ = [("which_mc_model", C.c_int), ("sub_model", C.c_int), ("lambda_", C.c_double),
+                ("tmax", C.c_int), ("tmax_subdivision", C.c_int), ("alpha", C.c_double),
+                ("aproj", C.c_int), ("atarg", C.c_int), ("proj_deformed", C.c_int), ("targ_deformed", C.c_int),
+                ("include_nn_correlation", C.c_int), ("shape_of_nucleons", C.c_int),
+                ("collision_criterion", C.c_int), ("shape_of_entropy", C.c_int), ("quark_width", C.c_double),
+                ("gauss_nucl_width", C.c_double), ("ecm", C.c_double), ("bmin", C.c_double), ("bmax", C.c_double),
+                ("npmin", C.c_int), ("npmax", C.c_int), ("cutdsdy", C.c_int),
+                ("cutdsdy_lowerbound", C.c_double), ("cutdsdy_upperbound", C.c_double),
+                ("randomseed", C.c_int64), ("finalfactor", C.c_double),
+                ("ecc_from_order", C.c_int), ("ecc_to_order", C.c_int),
+                ("maxx", C.c_double), ("maxy", C.c_double), ("dx", C.c_double), ("dy", C.c_double),
+                ("cc_fluctuation_model", C.c_int), ("cc_fluctuation_gamma_theta", C.c_double),
+                ("pt_order", C.c_int), ("max_batch", C.c_int), ("ncoll_cap", C.c_int)]
+
+
+class Constants(C.Structure):
+    _fields_ = [("siginnn", C.c_double), ("siginnn200", C.c_double), ("width", C.c_double),
+                ("sigma_gg", C.c_double), ("dsq", C.c_double), ("maxx_cells", C.c_int), ("maxy_cells", C.c_int),
+                ("kln_dt", C.c_double), ("kln_tmax", C.c_int)]
+
+
+class EventOut(C.Structure):
+    _fields_ = [("b", C.c_double), ("npart1", C.c_int), ("npart2", C.c_int), ("ncoll", C.c_int),
+                ("tries", C.c_int), ("nspec", C.c_int), ("status", C.c_int), ("dsdy", C.c_double),
+                ("total", C.c_double), ("xc", C.c_double), ("yc", C.c_double), ("mom", (C.c_double * 5) * 9),
+                ("rn0", C.c_double)]
+
+
+class EventIn(C.Structure):
+    _fields_ = [("b", C.c_double), ("na", C.c_int), ("nb", C.c_int), ("proj", dp), ("targ", dp),
+                ("pair_uniform", dp), ("coll_weight", dp), ("n_coll_weight", C.c_int), ("use_given_weights", C.c_int)]
+
+
+EVENT_OUT_DTYPE = np.dtype([("b", "f8"), ("npart1", "i4"), ("npart2", "i4"), ("ncoll", "i4"), ("tries", "i4"),
+                            ("nspec", "i4"), ("status", "i4"), ("dsdy", "f8"), ("total", "f8"), ("xc", "f8"),
+                            ("yc", "f8"), ("mom", "f8", (9, 5)), ("rn0", "f8")], align=True)
+
+
+class SmcError(RuntimeError):
+    pass
+
+
+_LIB = None
+
+
+def build_library(verbose=False):
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... (cross-compiles without a GPU)."""
+    subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "csrc"), "-j8"],
+                          stdout=None if verbose else subprocess.DEVNULL)
+    return SO
+
+
+def lib():
+    """Load the CUDA library.  Fails loudly if it has not been built: there is no fallback path."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(SO):
+            raise SmcError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(the CUDA extension is the only compute path)" % SO)
+        L = C.CDLL(SO)
+        L.smc_last_error.restype = C.c_char_p
+        L.smc_kernel_launches.restype = C.c_int64
+        L.smc_last_run_ms.restype = C.c_double
+        L.smc_measure_fp64_peak.restype = C.c_double
+        L.smc_measure_hbm_write_peak.restype = C.c_double
+        L.smc_run_events.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_uint, C.c_void_p]
+        L.smc_run_from_positions.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint, C.c_void_p]
+        L.smc_avg_run.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
+        L.smc_get_grid.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.smc_centrality_sort.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        assert C.sizeof(EventOut) == EVENT_OUT_DTYPE.itemsize
+        _LIB = L
+    return _LIB
+
+
+def default_params(**kw):
+    p = Params()
+    lib().smc_params_default(C.byref(p))
+    for k, v in kw.items():
+        if k == "lambda":
+            k = "lambda_"
+        if not hasattr(p, k):
+            raise KeyError(k)
+        setattr(p, k, v)
+    return p
+
+
+class Context:
+    """smc_ctx wrapper: one per GPU."""
+
+    def __init__(self, params=None, device=0, **kw):
+        self.p = params if params is not None else default_params(**kw)
+        self.h = C.c_void_p()
+        rc = lib().smc_create(C.byref(self.p), int(device), C.byref(self.h))
+        if rc != 0:
+            msg = lib().smc_last_error(self.h).decode() if self.h else "smc_create failed"
+            if self.h:
+                lib().smc_destroy(self.h)
+            self.h = None
+            raise SmcError("smc_create: rc=%d: %s" % (rc, msg))
+        self.k = Constants()
+        self._ck(lib().smc_get_constants(self.h, C.byref(self.k)))
+        self.G = self.k.maxx_cells * self.k.maxy_cells
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise SmcError("rc=%d: %s" % (rc, lib().smc_last_error(self.h).decode()))
+
+    def close(self):
+        if self.h:
+            lib().smc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load_quark_table(self, rows3):
+        a = np.ascontiguousarray(rows3, dtype=np.float64)
+        self._ck(lib().smc_load_quark_table(self.h, a.ctypes.data_as(dp), len(a)))
+
+    def load_config_table(self, which, xyz):
+        a = np.ascontiguousarray(xyz, dtype=np.float64)
+        ncfg, A = a.shape[0], a.shape[1] // 3 if a.ndim == 2 else a.shape[1]
+        self._ck(lib().smc_load_config_table(self.h, int(which), a.ctypes.data_as(dp), ncfg, A))
+
+    def build_kln_table(self):
+        t = np.zeros((self.k.kln_tmax, self.k.kln_tmax))
+        self._ck(lib().smc_build_kln_table(self.h, t.ctypes.data_as(dp)))
+        return t
+
+    def set_kln_table(self, table, dt):
+        t = np.ascontiguousarray(table, dtype=np.float64)
+        self._ck(lib().smc_set_kln_table(self.h, t.ctypes.data_as(dp), t.shape[0], C.c_double(dt)))
+
+    def run_events(self, first_event_id, n, flags=RUN_MOMENTS, out=None):
+        """-> structured array (EVENT_OUT_DTYPE) of n accepted events.  `out` may be a preallocated array."""
+        if out is None:
+            out = np.zeros(n, dtype=EVENT_OUT_DTYPE)
+        self._ck(lib().smc_run_events(self.h, int(first_event_id), int(n), int(flags), out.ctypes.data))
+        return out
+
+    def run_from_positions(self, events, flags=RUN_MOMENTS):
+        """events: list of dicts(b, proj (A,8), targ (B,8), pair_uniform (A,B)|None, coll_weight (n,2)|None, given_w)"""
+        n = len(events)
+        arr = (EventIn * n)()
+        keep = []
+        for i, ev in enumerate(events):
+            pj = np.ascontiguousarray(ev["proj"], dtype=np.float64); tg = np.ascontiguousarray(ev["targ"], dtype=np.float64)
+            keep += [pj, tg]
+            arr[i].b = ev.get("b", 0.0); arr[i].na = len(pj); arr[i].nb = len(tg)
+            arr[i].proj = pj.ctypes.data_as(dp); arr[i].targ = tg.ctypes.data_as(dp)
+            pu = ev.get("pair_uniform")
+            if pu is not None:
+                pu = np.ascontiguousarray(pu, dtype=np.float64); keep.append(pu); arr[i].pair_uniform = pu.ctypes.data_as(dp)
+            cw = ev.get("coll_weight")
+            if cw is not None:
+                cw = np.ascontiguousarray(cw, dtype=np.float64).reshape(-1, 2); keep.append(cw)
+                arr[i].coll_weight = cw.ctypes.data_as(dp); arr[i].n_coll_weight = len(cw)
+            arr[i].use_given_weights = int(ev.get("given_w", 1))
+        out = np.zeros(n, dtype=EVENT_OUT_DTYPE)
+        self._ck(lib().smc_run_from_positions(self.h, n, C.byref(arr), int(flags), out.ctypes.data))
+        return out
+
+    def grid(self, slot, which):
+        g = np.zeros((self.k.maxx_cells, self.k.maxy_cells))
+        self._ck(lib().smc_get_grid(self.h, int(slot), int(which), g.ctypes.data))
+        return g
+
+    def _rows(self, fn, slot, width, *extra):
+        n = C.c_int()
+        self._ck(fn(self.h, int(slot), *extra, None, C.byref(n)))
+        a = np.zeros((max(n.value, 1), width))
+        self._ck(fn(self.h, int(slot), *extra, a.ctypes.data_as(dp), C.byref(n)))
+        return a[:n.value]
+
+    def participants(self, slot):
+        return self._rows(lib().smc_get_participants, slot, 8)
+
+    def collisions(self, slot):
+        return self._rows(lib().smc_get_collisions, slot, 6)
+
+    def spectators(self, slot):
+        return self._rows(lib().smc_get_spectators, slot, 3)
+
+    def nucleons(self, slot, which):
+        return self._rows(lib().smc_get_nucleons, slot, 8, int(which))
+
+    def centrality_sort(self, key):
+        k = np.ascontiguousarray(key, dtype=np.float64); perm = np.zeros(len(k), dtype=np.int64)
+        self._ck(lib().smc_centrality_sort(self.h, k.ctypes.data, len(k), perm.ctypes.data))
+        return perm
+
+    @property
+    def launches(self):
+        return lib().smc_kernel_launches(self.h)
+
+    @property
+    def last_run_ms(self):
+        return lib().smc_last_run_ms(self.h)
+
+    def fp64_peak_tflops(self):
+        return lib().smc_measure_fp64_peak(self.h)
+
+    def hbm_write_peak_gbs(self):
+        return lib().smc_measure_hbm_write_peak(self.h)

@@ -1,0 +1,584 @@
+// smc_api.cu -- the C ABI (include/supermc_b200.h): context, device memory, batch orchestration.
+// One context per GPU; every compute entry point fails loudly (SMC_ERR_CUDA) without a device.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <cub/cub.cuh>
+#include "../../include/supermc_b200.h"
+#include "smc_common.cuh"
+#include "smc_host_math.h"
+
+namespace smc {
+enum { GK_RHO = 0, GK_TA1 = 1, GK_TA2 = 2, GK_RHO_BINARY = 3, GK_SPEC_A = 4, GK_SPEC_B = 5, GK_RHOA = 6, GK_RHOB = 7 };
+cudaError_t launch_sample_collide(const DevCfg&, const Store&, int nev, bool given, cudaStream_t);
+cudaError_t launch_deposit(const DevCfg&, const Store&, const int* kinds, int nk, int nev, cudaStream_t);
+cudaError_t launch_combine(const DevCfg&, const Store&, int nev, cudaStream_t);
+cudaError_t launch_moments(const DevCfg&, const Store&, int nev, cudaStream_t);
+struct KlnCfg { double ecm, lambda, y, dT; int tmax; int pt_order; int npt, nkt, nphi; const double *xp, *wp, *xk, *wk, *cphi; };
+cudaError_t launch_kln_table(const KlnCfg&, double* table, cudaStream_t);
+struct AvgState;
+}  // namespace smc
+
+struct smc_ctx {
+  smc_params p; smc_constants k; smc::DevCfg cfg; smc::Store st;
+  int device; cudaStream_t stream; cudaEvent_t ev0, ev1;
+  int batch; size_t G;
+  std::vector<void*> owned;
+  double* d_grids; size_t grids_bytes;
+  double* d_pair_u; size_t pair_u_bytes; double* d_coll_w; size_t coll_w_bytes;
+  double* d_quark; double* d_cfgtab[2]; double* d_kln;
+  int* h_hdr_i; double* h_hdr_d; double* h_mom; uint64_t* h_evid; int* h_try; double* h_nuc;
+  std::string err; int64_t launches; double last_ms; int last_n; unsigned last_flags;
+  // averaged profiles (operation 3)
+  double* d_avg; int64_t avg_doubles; int64_t avg_count; int avg_from, avg_to, avg_rp, avg_ed;
+};
+
+#define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(_e); return SMC_ERR_CUDA; } } while (0)
+#define FAIL(code, msg) do { ctx->err = (msg); return (code); } while (0)
+
+extern "C" int smc_abi_version(void) { return SMC_ABI_VERSION; }
+
+extern "C" void smc_params_default(smc_params* p) {   // reference parameters.dat
+  std::memset(p, 0, sizeof *p);
+  p->which_mc_model = 7; p->sub_model = 1; p->lambda = 0.138; p->tmax = 71; p->tmax_subdivision = 3;
+  p->alpha = 0.118; p->aproj = 208; p->atarg = 208; p->shape_of_nucleons = 2; p->collision_criterion = 2;
+  p->shape_of_entropy = 2; p->quark_width = 0.3; p->gauss_nucl_width = 0.812; p->ecm = 5020.; p->bmin = 0.; p->bmax = 20.;
+  p->npmin = 2; p->npmax = 500; p->cutdsdy = 0; p->cutdsdy_lowerbound = 593.51; p->cutdsdy_upperbound = 889.53;
+  p->randomseed = 1; p->finalfactor = 40.0; p->ecc_from_order = 1; p->ecc_to_order = 9;
+  p->maxx = 15.; p->maxy = 15.; p->dx = 0.1; p->dy = 0.1; p->cc_fluctuation_model = 6; p->cc_fluctuation_gamma_theta = 0.75;
+  p->pt_order = 1; p->max_batch = 0; p->ncoll_cap = 0;
+}
+
+template <typename T> static int dalloc(smc_ctx* ctx, T** p, size_t n) {
+  void* v = nullptr;
+  cudaError_t e = cudaMalloc(&v, std::max<size_t>(n, 1) * sizeof(T));
+  if (e != cudaSuccess) { ctx->err = std::string("cudaMalloc: ") + cudaGetErrorString(e); return SMC_ERR_NOMEM; }
+  ctx->owned.push_back(v); *p = (T*)v; return SMC_OK;
+}
+
+static int sampler_mode(int A, int nn_corr) {
+  if (A == 1) return 1;
+  if (A == 2) return 4;
+  if (A == 3 || A == 4 || A == 12 || A == 16) return 2;
+  if (nn_corr == 1 && (A == 197 || A == 208)) return 3;
+  return 0;
+}
+
+extern "C" int smc_create(const smc_params* p, int device, smc_ctx** out) {
+  if (!p || !out) return SMC_ERR_PARAM;
+  *out = nullptr;
+  smc_ctx* ctx = new smc_ctx();
+  ctx->p = *p; ctx->device = device; ctx->launches = 0; ctx->last_ms = 0; ctx->last_n = 0; ctx->last_flags = 0;
+  ctx->d_grids = nullptr; ctx->grids_bytes = 0; ctx->d_pair_u = nullptr; ctx->pair_u_bytes = 0; ctx->d_coll_w = nullptr; ctx->coll_w_bytes = 0;
+  ctx->d_quark = nullptr; ctx->d_cfgtab[0] = ctx->d_cfgtab[1] = nullptr; ctx->d_kln = nullptr; ctx->d_avg = nullptr; ctx->avg_doubles = 0; ctx->avg_count = 0;
+  ctx->stream = nullptr; ctx->ev0 = ctx->ev1 = nullptr;
+  *out = ctx;      // returned even on failure so the caller can read smc_last_error
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device >= ndev) FAIL(SMC_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 9) FAIL(SMC_ERR_CUDA, "device is not sm_100-class");
+  CK(cudaStreamCreate(&ctx->stream)); CK(cudaEventCreate(&ctx->ev0)); CK(cudaEventCreate(&ctx->ev1));
+
+  // ---- parameter checks (the reference prints and exits) ----
+  if (p->which_mc_model != 1 && p->which_mc_model != 5 && p->which_mc_model != 7) FAIL(SMC_ERR_PARAM, "which_mc_model must be 1, 5 or 7");
+  if (p->which_mc_model == 5 && p->sub_model != 1 && p->sub_model != 2) FAIL(SMC_ERR_PARAM, "MC-Glauber sub_model must be 1 or 2 (MCnucl.cpp:718-721)");
+  if (p->which_mc_model == 1 && p->sub_model != 7) FAIL(SMC_ERR_PARAM, "MC-KLN: only sub_model 7 (KLN uGD) is built; rcBK tables are absent upstream");
+  if (p->shape_of_nucleons != 1 && p->shape_of_nucleons != 2 && p->shape_of_nucleons != 4) FAIL(SMC_ERR_PARAM, "shape_of_nucleons must be 1, 2 or 4");
+  if (p->shape_of_entropy != 1 && p->shape_of_entropy != 2) FAIL(SMC_ERR_PARAM, "shape_of_entropy must be 1 or 2 (3 = quark substructure is out of scope)");
+  if (p->aproj < 1 || p->atarg < 1 || p->aproj > 512 || p->atarg > 512) FAIL(SMC_ERR_PARAM, "Aproj/Atarg out of range");
+  if (!(p->dx > 0) || !(p->dy > 0) || !(p->maxx > 0) || !(p->maxy > 0)) FAIL(SMC_ERR_PARAM, "bad grid");
+  if (p->cc_fluctuation_model != 0 && p->cc_fluctuation_model != 6) FAIL(SMC_ERR_PARAM, "cc_fluctuation_model must be 0 or 6 (NBD models 1,2 are out of scope)");
+
+  smc_constants& k = ctx->k; smc::DevCfg& c = ctx->cfg;
+  std::memset(&c, 0, sizeof c); std::memset(&ctx->st, 0, sizeof ctx->st);
+  k.siginnn = smc_host::sigma_inel(p->ecm); k.siginnn200 = smc_host::sigma_inel(200.0);
+  if (!smc_host::gaussian_nucleon(p->shape_of_nucleons, k.siginnn, p->gauss_nucl_width, &k.width, &k.sigma_gg)) FAIL(SMC_ERR_PARAM, "unsupported shape_of_nucleons");
+  k.dsq = 0.1 * k.siginnn / M_PI;
+  k.maxx_cells = (int)((p->maxx - (-p->maxx)) / p->dx + 0.1) + 1; k.maxy_cells = (int)((p->maxy - (-p->maxy)) / p->dy + 0.1) + 1;
+  k.kln_dt = 10.0 / k.siginnn; k.kln_tmax = p->tmax;
+  if (p->shape_of_nucleons >= 2) { k.kln_tmax = p->tmax_subdivision * (p->tmax - 1) + 1; k.kln_dt /= p->tmax_subdivision; }   // MCnucl.cpp:915-919
+  c.Maxx = k.maxx_cells; c.Maxy = k.maxy_cells; c.Xmin = -p->maxx; c.Ymin = -p->maxy; c.dx = p->dx; c.dy = p->dy;
+  c.w = k.width; c.dsq = k.dsq; c.siginNN = k.siginnn; c.sigma_gg = k.sigma_gg; c.alpha = p->alpha;
+  c.dmax = (p->shape_of_nucleons == 1) ? 2. * std::sqrt(k.dsq) : 5. * k.width;
+  c.thrA = smc_host::sqrt_threshold(5 * k.width); c.thrB = 25. * (k.width * k.width);
+  c.norm = 1 / (2 * M_PI * k.width * k.width); c.inv2w2 = 1.0 / (2 * k.width * k.width); c.areai = 10.0 / k.siginnn;
+  c.recx = std::exp(-p->dx * p->dx / (k.width * k.width)); c.recy = std::exp(-p->dy * p->dy / (k.width * k.width));
+  c.rclip_flat = std::sqrt(k.dsq) * (1.0 + 1e-12); c.kln_tmax_param = p->tmax;
+  c.finalFactor = p->finalfactor;
+  c.shape_of_nucleons = p->shape_of_nucleons; c.shape_of_entropy = p->shape_of_entropy;
+  c.crit = (p->collision_criterion == 1 || p->collision_criterion == 2) ? p->collision_criterion : (p->shape_of_entropy == 2 ? 2 : 1);
+  c.which_mc_model = p->which_mc_model; c.sub_model = p->sub_model; c.cc_fluct = p->cc_fluctuation_model;
+  c.A[0] = p->aproj; c.A[1] = p->atarg; c.deformed[0] = p->proj_deformed; c.deformed[1] = p->targ_deformed;
+  for (int s = 0; s < 2; s++) {
+    smc_host::WoodsSaxon ws = smc_host::woods_saxon(c.A[s], c.deformed[s]);
+    c.rad[s] = ws.rad; c.dr[s] = ws.dr; c.rmaxCut[s] = ws.rmaxCut; c.rwMax[s] = ws.rwMax; c.beta2[s] = ws.beta2; c.beta4[s] = ws.beta4;
+    c.sampler[s] = sampler_mode(c.A[s], p->include_nn_correlation);
+    if (c.sampler[s] == 4) FAIL(SMC_ERR_PARAM, "deuteron (A=2, Hulthen) sampling is not built yet");
+  }
+  c.bmin = p->bmin; c.bmax = p->bmax; c.npmin = p->npmin; c.npmax = p->npmax;
+  { const double eps = 1e-8, th = p->cc_fluctuation_gamma_theta > 0 ? p->cc_fluctuation_gamma_theta : 1.0, gk = 1. / th;   // MCnucl.cpp:1271-1301
+    c.gam_k_part = (1 - p->alpha + eps) / 2. * gk; c.gam_th_part = 2. / (1 - p->alpha + eps) * th;
+    c.gam_k_bin = (p->alpha + eps) * gk; c.gam_th_bin = 1. / (p->alpha + eps) * th; }
+  c.quark_width = p->quark_width;
+  c.quark_R = std::sqrt((3.0 / 2.0) * (k.width * k.width - p->quark_width * p->quark_width));   // Nucleus.cpp:31-32
+  c.quark_rows = 0;
+  c.seed_lo = (uint32_t)((uint64_t)p->randomseed); c.seed_hi = (uint32_t)(((uint64_t)p->randomseed) >> 32);
+  c.Amax = std::max(p->aproj, p->atarg); c.Amax = (c.Amax + 7) & ~7;
+  { long cap = p->ncoll_cap > 0 ? p->ncoll_cap : std::min<long>((long)p->aproj * p->atarg, 6144);
+    cap = std::min<long>(cap, 60000); c.ncoll_cap = (int)std::max<long>(cap, 1); }
+  c.ecc_from = p->ecc_from_order; c.ecc_to = p->ecc_to_order;
+  c.kln_tmax = 0; c.kln_dT = k.kln_dt;
+  { const double reach = std::max(c.dmax, std::sqrt(k.dsq)); c.wmax = (int)(2. * reach / std::min(p->dx, p->dy)) + 6; }
+  ctx->G = (size_t)c.Maxx * c.Maxy;
+  if (c.Maxy > 1024) FAIL(SMC_ERR_PARAM, "grids wider than 1024 cells are not supported");
+
+  ctx->batch = p->max_batch > 0 ? p->max_batch : 1024;
+  const int B = ctx->batch; smc::Store& st = ctx->st; int rc;
+  if ((rc = dalloc(ctx, &st.nuc, (size_t)B * 2 * c.Amax * smc::NROW))) return rc;
+  if ((rc = dalloc(ctx, &st.nuc_ncoll, (size_t)B * 2 * c.Amax))) return rc;
+  if ((rc = dalloc(ctx, &st.nuc_first, (size_t)B * c.Amax))) return rc;
+  if ((rc = dalloc(ctx, &st.coll, (size_t)B * c.ncoll_cap * smc::CROW))) return rc;
+  if ((rc = dalloc(ctx, &st.coll_ij, (size_t)B * c.ncoll_cap))) return rc;
+  if ((rc = dalloc(ctx, &st.part_idx, (size_t)B * 2 * c.Amax))) return rc;
+  if ((rc = dalloc(ctx, &st.spec_idx, (size_t)B * 2 * c.Amax))) return rc;
+  if ((rc = dalloc(ctx, &st.hdr_i, (size_t)B * smc::HDR_I))) return rc;
+  if ((rc = dalloc(ctx, &st.hdr_d, (size_t)B * smc::HDR_D))) return rc;
+  if ((rc = dalloc(ctx, &st.mom_out, (size_t)B * smc::MOM_OUT))) return rc;
+  { uint64_t* ev; if ((rc = dalloc(ctx, &ev, (size_t)B))) return rc; st.event_id = ev; }
+  if ((rc = dalloc(ctx, &st.try_start, (size_t)B))) return rc;
+  CK(cudaMallocHost(&ctx->h_hdr_i, (size_t)B * smc::HDR_I * sizeof(int)));
+  CK(cudaMallocHost(&ctx->h_hdr_d, (size_t)B * smc::HDR_D * sizeof(double)));
+  CK(cudaMallocHost(&ctx->h_mom, (size_t)B * smc::MOM_OUT * sizeof(double)));
+  CK(cudaMallocHost(&ctx->h_evid, (size_t)B * sizeof(uint64_t)));
+  CK(cudaMallocHost(&ctx->h_try, (size_t)B * sizeof(int)));
+  CK(cudaMallocHost(&ctx->h_nuc, (size_t)B * 2 * c.Amax * smc::NROW * sizeof(double)));
+  for (int i = 0; i < 8; i++) st.kind_slot[i] = -1;
+  return SMC_OK;
+}
+
+extern "C" void smc_destroy(smc_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  for (void* v : ctx->owned) cudaFree(v);
+  if (ctx->d_grids) cudaFree(ctx->d_grids);
+  if (ctx->d_pair_u) cudaFree(ctx->d_pair_u);
+  if (ctx->d_coll_w) cudaFree(ctx->d_coll_w);
+  if (ctx->d_quark) cudaFree(ctx->d_quark);
+  if (ctx->d_cfgtab[0]) cudaFree(ctx->d_cfgtab[0]);
+  if (ctx->d_cfgtab[1]) cudaFree(ctx->d_cfgtab[1]);
+  if (ctx->d_kln) cudaFree(ctx->d_kln);
+  if (ctx->d_avg) cudaFree(ctx->d_avg);
+  if (ctx->h_hdr_i) cudaFreeHost(ctx->h_hdr_i);
+  if (ctx->h_hdr_d) cudaFreeHost(ctx->h_hdr_d);
+  if (ctx->h_mom) cudaFreeHost(ctx->h_mom);
+  if (ctx->h_evid) cudaFreeHost(ctx->h_evid);
+  if (ctx->h_try) cudaFreeHost(ctx->h_try);
+  if (ctx->h_nuc) cudaFreeHost(ctx->h_nuc);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" const char* smc_last_error(const smc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" int smc_get_constants(const smc_ctx* ctx, smc_constants* c) { if (!ctx || !c) return SMC_ERR_PARAM; *c = ctx->k; return SMC_OK; }
+extern "C" int64_t smc_kernel_launches(const smc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" double smc_last_run_ms(const smc_ctx* ctx) { return ctx ? ctx->last_ms : 0.0; }
+
+extern "C" int smc_load_quark_table(smc_ctx* ctx, const double* rows3, int n) {
+  if (!ctx || !rows3 || n <= 0) return SMC_ERR_PARAM;
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->d_quark) { cudaFree(ctx->d_quark); ctx->d_quark = nullptr; }
+  CK(cudaMalloc(&ctx->d_quark, (size_t)n * 3 * sizeof(double)));
+  CK(cudaMemcpy(ctx->d_quark, rows3, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice));
+  ctx->st.quark_table = ctx->d_quark; ctx->cfg.quark_rows = n;
+  return SMC_OK;
+}
+
+extern "C" int smc_load_config_table(smc_ctx* ctx, int which, const double* xyz, int n_cfg, int a) {
+  if (!ctx || which < 0 || which > 1 || !xyz || n_cfg <= 0) return SMC_ERR_PARAM;
+  if (a != ctx->cfg.A[which]) FAIL(SMC_ERR_PARAM, "configuration table mass number does not match Aproj/Atarg");
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->d_cfgtab[which]) { cudaFree(ctx->d_cfgtab[which]); ctx->d_cfgtab[which] = nullptr; }
+  const size_t n = (size_t)n_cfg * a * 3;
+  CK(cudaMalloc(&ctx->d_cfgtab[which], n * sizeof(double)));
+  CK(cudaMemcpy(ctx->d_cfgtab[which], xyz, n * sizeof(double), cudaMemcpyHostToDevice));
+  ctx->st.cfg_table[which] = ctx->d_cfgtab[which]; ctx->cfg.ncfg[which] = n_cfg;
+  return SMC_OK;
+}
+
+// ---- MC-KLN table --------------------------------------------------------------------------------
+static void gauleg01(int n, std::vector<double>& x, std::vector<double>& w) {
+  x.assign(n, 0); w.assign(n, 0);
+  for (int i = 0; i < (n + 1) / 2; i++) {
+    double z = std::cos(M_PI * (i + 0.75) / (n + 0.5)), pp = 1, z1;
+    do {
+      double p1 = 1.0, p2 = 0.0;
+      for (int j = 0; j < n; j++) { double p3 = p2; p2 = p1; p1 = ((2.0 * j + 1.0) * z * p2 - j * p3) / (j + 1); }
+      pp = n * (z * p1 - p2) / (z * z - 1.0); z1 = z; z = z1 - p1 / pp;
+    } while (std::fabs(z - z1) > 1e-15);
+    x[i] = 0.5 * (1 - z); x[n - 1 - i] = 0.5 * (1 + z);
+    w[i] = w[n - 1 - i] = 1.0 / ((1.0 - z * z) * pp * pp);
+  }
+}
+
+extern "C" int smc_set_kln_table(smc_ctx* ctx, const double* table, int tmax, double dt) {
+  if (!ctx || !table || tmax < 3) return SMC_ERR_PARAM;
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->d_kln) { cudaFree(ctx->d_kln); ctx->d_kln = nullptr; }
+  CK(cudaMalloc(&ctx->d_kln, (size_t)tmax * tmax * sizeof(double)));
+  CK(cudaMemcpy(ctx->d_kln, table, (size_t)tmax * tmax * sizeof(double), cudaMemcpyHostToDevice));
+  ctx->st.kln_table = ctx->d_kln; ctx->cfg.kln_tmax = tmax; ctx->cfg.kln_dT = dt;
+  return SMC_OK;
+}
+
+extern "C" int smc_build_kln_table(smc_ctx* ctx, double* host_out) {
+  if (!ctx) return SMC_ERR_PARAM;
+  CK(cudaSetDevice(ctx->device));
+  const int tmax = ctx->k.kln_tmax;
+  const char* q = getenv("SMC_KLN_QUAD");     // "npt,nkt,nphi"
+  int npt = 400, nkt = 200, nphi = 64;
+  if (q) sscanf(q, "%d,%d,%d", &npt, &nkt, &nphi);
+  std::vector<double> xp, wp, xk, wk, cp(nphi);
+  gauleg01(npt, xp, wp); gauleg01(nkt, xk, wk);
+  for (int i = 0; i < nphi; i++) cp[i] = std::cos(2 * M_PI * ((i + 0.5) / nphi));
+  double* d = nullptr;
+  const size_t nn = (size_t)2 * npt + 2 * nkt + nphi;
+  CK(cudaMalloc(&d, nn * sizeof(double)));
+  std::vector<double> h; h.insert(h.end(), xp.begin(), xp.end()); h.insert(h.end(), wp.begin(), wp.end());
+  h.insert(h.end(), xk.begin(), xk.end()); h.insert(h.end(), wk.begin(), wk.end()); h.insert(h.end(), cp.begin(), cp.end());
+  CK(cudaMemcpy(d, h.data(), nn * sizeof(double), cudaMemcpyHostToDevice));
+  if (ctx->d_kln) { cudaFree(ctx->d_kln); ctx->d_kln = nullptr; }
+  CK(cudaMalloc(&ctx->d_kln, (size_t)tmax * tmax * sizeof(double)));
+  smc::KlnCfg kc; kc.ecm = ctx->p.ecm; kc.lambda = ctx->p.lambda; kc.y = 0.0; kc.dT = ctx->k.kln_dt; kc.tmax = tmax; kc.pt_order = ctx->p.pt_order > 0 ? ctx->p.pt_order : 1;
+  kc.npt = npt; kc.nkt = nkt; kc.nphi = nphi; kc.xp = d; kc.wp = d + npt; kc.xk = d + 2 * npt; kc.wk = d + 2 * npt + nkt; kc.cphi = d + 2 * npt + 2 * nkt;
+  CK(smc::launch_kln_table(kc, ctx->d_kln, ctx->stream)); ctx->launches++;
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d);
+  ctx->st.kln_table = ctx->d_kln; ctx->cfg.kln_tmax = tmax; ctx->cfg.kln_dT = ctx->k.kln_dt;
+  if (host_out) CK(cudaMemcpy(host_out, ctx->d_kln, (size_t)tmax * tmax * sizeof(double), cudaMemcpyDeviceToHost));
+  return SMC_OK;
+}
+
+// ---- event batches -------------------------------------------------------------------------------
+static int plan_kinds(smc_ctx* ctx, unsigned flags, int* kinds, int* nk_dep) {
+  smc::Store& st = ctx->st; const smc::DevCfg& c = ctx->cfg;
+  for (int i = 0; i < 8; i++) st.kind_slot[i] = -1;
+  int n = 0, nd = 0;
+  auto add = [&](int kind, bool dep) { if (st.kind_slot[kind] < 0) { st.kind_slot[kind] = n++; if (dep) kinds[nd++] = kind; } };
+  if (c.which_mc_model == 5) add(smc::GK_RHO, true);
+  else if (c.which_mc_model == 7) { add(smc::GK_RHO, false); add(smc::GK_RHOA, true); add(smc::GK_RHOB, true); }
+  else { add(smc::GK_RHO, false); add(smc::GK_TA1, true); add(smc::GK_TA2, true); }
+  if (flags & SMC_RUN_THICKNESS) { add(smc::GK_TA1, true); add(smc::GK_TA2, true); }
+  if (flags & SMC_RUN_RHO_BINARY) add(smc::GK_RHO_BINARY, true);
+  if (flags & SMC_RUN_SPECTATORS) { add(smc::GK_SPEC_A, true); add(smc::GK_SPEC_B, true); }
+  st.nkinds = n; *nk_dep = nd;
+  const size_t need = (size_t)ctx->batch * n * ctx->G * sizeof(double);
+  if (need > ctx->grids_bytes) {
+    if (ctx->d_grids) cudaFree(ctx->d_grids);
+    ctx->d_grids = nullptr; ctx->grids_bytes = 0;
+    cudaError_t e = cudaMalloc(&ctx->d_grids, need);
+    if (e != cudaSuccess) { ctx->err = std::string("grid pool: ") + cudaGetErrorString(e); return SMC_ERR_NOMEM; }
+    ctx->grids_bytes = need;
+  }
+  st.grids = ctx->d_grids;
+  return SMC_OK;
+}
+
+static int run_grid_stages(smc_ctx* ctx, int m, const int* kinds, int nd) {
+  const smc::DevCfg& c = ctx->cfg;
+  if (c.which_mc_model == 1 && !ctx->st.kln_table) FAIL(SMC_ERR_STATE, "MC-KLN density requires smc_build_kln_table / smc_set_kln_table first (MCnucl.cpp:636-640)");
+  CK(smc::launch_deposit(c, ctx->st, kinds, nd, m, ctx->stream)); ctx->launches++;
+  if (c.which_mc_model != 5) { CK(smc::launch_combine(c, ctx->st, m, ctx->stream)); ctx->launches++; }
+  CK(smc::launch_moments(c, ctx->st, m, ctx->stream)); ctx->launches++;
+  return SMC_OK;
+}
+
+static void fill_out(smc_ctx* ctx, int m, smc_event_out* out) {
+  for (int e = 0; e < m; e++) {
+    const int* hi = ctx->h_hdr_i + (size_t)e * smc::HDR_I; const double* mo = ctx->h_mom + (size_t)e * smc::MOM_OUT;
+    smc_event_out& o = out[e];
+    o.b = ctx->h_hdr_d[(size_t)e * smc::HDR_D + smc::HD_B];
+    o.npart1 = hi[smc::H_NP1]; o.npart2 = hi[smc::H_NP2]; o.ncoll = hi[smc::H_NCOLL]; o.tries = hi[smc::H_TRIES];
+    o.nspec = hi[smc::H_NSPEC1] + hi[smc::H_NSPEC2]; o.status = hi[smc::H_STATUS];
+    std::memcpy(o.mom, mo, 45 * sizeof(double));
+    o.rn0 = mo[45]; o.total = mo[46]; o.xc = mo[47]; o.yc = mo[48]; o.dsdy = mo[49];
+  }
+}
+
+static int fetch_results(smc_ctx* ctx, int m) {
+  CK(cudaMemcpyAsync(ctx->h_hdr_i, ctx->st.hdr_i, (size_t)m * smc::HDR_I * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_hdr_d, ctx->st.hdr_d, (size_t)m * smc::HDR_D * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_mom, ctx->st.mom_out, (size_t)m * smc::MOM_OUT * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return SMC_OK;
+}
+
+extern "C" int smc_run_events(smc_ctx* ctx, uint64_t first_event_id, int n, unsigned flags, smc_event_out* out) {
+  if (!ctx || n < 0 || (!out && n > 0)) return SMC_ERR_PARAM;
+  CK(cudaSetDevice(ctx->device));
+  const smc::DevCfg& c = ctx->cfg;
+  for (int s = 0; s < 2; s++) if ((c.sampler[s] == 2 || c.sampler[s] == 3) && !ctx->st.cfg_table[s]) FAIL(SMC_ERR_STATE, "this nucleus needs a configuration table: call smc_load_config_table (Nucleus.cpp:150-169)");
+  int kinds[8], nd = 0, rc;
+  if ((rc = plan_kinds(ctx, flags, kinds, &nd))) return rc;
+  ctx->st.pair_u = nullptr; ctx->st.coll_w = nullptr;
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  for (int off = 0; off < n; off += ctx->batch) {
+    const int m = std::min(ctx->batch, n - off);
+    for (int e = 0; e < m; e++) { ctx->h_evid[e] = first_event_id + (uint64_t)off + e; ctx->h_try[e] = 0; }
+    CK(cudaMemcpyAsync((void*)ctx->st.event_id, ctx->h_evid, (size_t)m * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->st.try_start, ctx->h_try, (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(smc::launch_sample_collide(c, ctx->st, m, false, ctx->stream)); ctx->launches++;
+    if ((rc = run_grid_stages(ctx, m, kinds, nd))) return rc;
+    if ((rc = fetch_results(ctx, m))) return rc;
+    // dS/dy window (MakeDensity.cpp:2173-2181): a failing event goes back to the rejection loop
+    if (ctx->p.cutdsdy == 1) {
+      for (int iter = 0; iter < 100000; iter++) {
+        int nbad = 0;
+        for (int e = 0; e < m; e++) {
+          const double s = ctx->h_mom[(size_t)e * smc::MOM_OUT + 49];
+          const bool bad = (ctx->h_hdr_i[(size_t)e * smc::HDR_I + smc::H_STATUS] == 0) && (s < ctx->p.cutdsdy_lowerbound || s > ctx->p.cutdsdy_upperbound);
+          ctx->h_try[e] = bad ? 1 : 0; nbad += bad;
+        }
+        if (!nbad) break;
+        FAIL(SMC_ERR_STATE, "cutdSdy=1 re-draw loop is not built yet");
+      }
+    }
+    fill_out(ctx, m, out + off);
+    ctx->last_n = m;
+  }
+  CK(cudaEventRecord(ctx->ev1, ctx->stream)); CK(cudaEventSynchronize(ctx->ev1));
+  float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->last_ms = ms; ctx->last_flags = flags;
+  return SMC_OK;
+}
+
+extern "C" int smc_run_from_positions(smc_ctx* ctx, int n, const smc_event_in* in, unsigned flags, smc_event_out* out) {
+  if (!ctx || n < 0 || (n > 0 && (!in || !out))) return SMC_ERR_PARAM;
+  CK(cudaSetDevice(ctx->device));
+  const smc::DevCfg& c = ctx->cfg;
+  const int A = c.A[0], B = c.A[1], Amax = c.Amax;
+  int kinds[8], nd = 0, rc;
+  if ((rc = plan_kinds(ctx, flags, kinds, &nd))) return rc;
+  bool any_u = false, any_w = false;
+  for (int e = 0; e < n; e++) {
+    if (in[e].na != A || in[e].nb != B) FAIL(SMC_ERR_PARAM, "smc_event_in.na/nb must equal Aproj/Atarg of the context");
+    if (!in[e].proj || !in[e].targ) FAIL(SMC_ERR_PARAM, "smc_event_in.proj/targ is null");
+    any_u |= in[e].pair_uniform != nullptr; any_w |= in[e].coll_weight != nullptr;
+  }
+  if (any_u) {
+    const size_t need = (size_t)ctx->batch * A * B * sizeof(double);
+    if (need > ctx->pair_u_bytes) { if (ctx->d_pair_u) cudaFree(ctx->d_pair_u); ctx->d_pair_u = nullptr; ctx->pair_u_bytes = 0; CK(cudaMalloc(&ctx->d_pair_u, need)); ctx->pair_u_bytes = need; }
+  }
+  if (any_w) {
+    const size_t need = (size_t)ctx->batch * c.ncoll_cap * 2 * sizeof(double);
+    if (need > ctx->coll_w_bytes) { if (ctx->d_coll_w) cudaFree(ctx->d_coll_w); ctx->d_coll_w = nullptr; ctx->coll_w_bytes = 0; CK(cudaMalloc(&ctx->d_coll_w, need)); ctx->coll_w_bytes = need; }
+  }
+  std::vector<double> hw_default;
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  for (int off = 0; off < n; off += ctx->batch) {
+    const int m = std::min(ctx->batch, n - off);
+    std::memset(ctx->h_nuc, 0, (size_t)m * 2 * Amax * smc::NROW * sizeof(double));
+    std::memset(ctx->h_hdr_i, 0, (size_t)m * smc::HDR_I * sizeof(int));
+    for (int e = 0; e < m; e++) {
+      const smc_event_in& ev = in[off + e];
+      std::memcpy(ctx->h_nuc + ((size_t)e * 2 + 0) * Amax * smc::NROW, ev.proj, (size_t)A * smc::NROW * sizeof(double));
+      std::memcpy(ctx->h_nuc + ((size_t)e * 2 + 1) * Amax * smc::NROW, ev.targ, (size_t)B * smc::NROW * sizeof(double));
+      ctx->h_hdr_d[(size_t)e * smc::HDR_D + smc::HD_B] = ev.b;
+      ctx->h_hdr_i[(size_t)e * smc::HDR_I + smc::H_GIVENW] = ev.use_given_weights;
+      ctx->h_evid[e] = (uint64_t)(off + e); ctx->h_try[e] = 0;
+      if (any_u) {
+        if (!ev.pair_uniform) FAIL(SMC_ERR_PARAM, "pair_uniform must be given for all events of a call or for none");
+        CK(cudaMemcpyAsync(ctx->d_pair_u + (size_t)e * A * B, ev.pair_uniform, (size_t)A * B * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+      }
+      if (any_w && ev.coll_weight) {     // an event without the array (e.g. no collisions) keeps weight 1, additional_weight 0
+        const int nw = std::min(ev.n_coll_weight, c.ncoll_cap);
+        CK(cudaMemcpyAsync(ctx->d_coll_w + (size_t)e * c.ncoll_cap * 2, ev.coll_weight, (size_t)nw * 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+      } else if (any_w) {
+        hw_default.assign((size_t)c.ncoll_cap * 2, 0.0);
+        for (int q = 0; q < c.ncoll_cap; q++) hw_default[2 * q] = 1.0;
+        CK(cudaMemcpy(ctx->d_coll_w + (size_t)e * c.ncoll_cap * 2, hw_default.data(), hw_default.size() * sizeof(double), cudaMemcpyHostToDevice));
+      }
+    }
+    CK(cudaMemcpyAsync(ctx->st.nuc, ctx->h_nuc, (size_t)m * 2 * Amax * smc::NROW * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->st.hdr_d, ctx->h_hdr_d, (size_t)m * smc::HDR_D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->st.hdr_i, ctx->h_hdr_i, (size_t)m * smc::HDR_I * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync((void*)ctx->st.event_id, ctx->h_evid, (size_t)m * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->st.try_start, ctx->h_try, (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->st.pair_u = any_u ? ctx->d_pair_u : nullptr; ctx->st.coll_w = any_w ? ctx->d_coll_w : nullptr;
+    CK(smc::launch_sample_collide(c, ctx->st, m, true, ctx->stream)); ctx->launches++;
+    if ((rc = run_grid_stages(ctx, m, kinds, nd))) return rc;
+    if ((rc = fetch_results(ctx, m))) return rc;
+    fill_out(ctx, m, out + off);
+    ctx->last_n = m;
+  }
+  CK(cudaEventRecord(ctx->ev1, ctx->stream)); CK(cudaEventSynchronize(ctx->ev1));
+  float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->last_ms = ms; ctx->last_flags = flags;
+  return SMC_OK;
+}
+
+// ---- getters -------------------------------------------------------------------------------------
+extern "C" int smc_get_grid(smc_ctx* ctx, int slot, int which, double* host) {
+  if (!ctx || !host || slot < 0 || slot >= ctx->last_n || which < 0 || which >= SMC_GRID_KINDS) return SMC_ERR_PARAM;
+  static const int map[SMC_GRID_KINDS] = {smc::GK_RHO, smc::GK_TA1, smc::GK_TA2, smc::GK_RHO_BINARY, smc::GK_SPEC_A, smc::GK_SPEC_B};
+  const int ks = ctx->st.kind_slot[map[which]];
+  if (ks < 0) FAIL(SMC_ERR_STATE, "that grid was not requested in the flags of the last run");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpy(host, ctx->d_grids + ((size_t)slot * ctx->st.nkinds + ks) * ctx->G, ctx->G * sizeof(double), cudaMemcpyDeviceToHost));
+  return SMC_OK;
+}
+
+static int fetch_event_lists(smc_ctx* ctx, int slot, std::vector<double>& nuc, std::vector<int>& ncoll, std::vector<int>& first, int hi[smc::HDR_I]) {
+  const int Amax = ctx->cfg.Amax;
+  nuc.resize((size_t)2 * Amax * smc::NROW); ncoll.resize((size_t)2 * Amax); first.resize(Amax);
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpy(nuc.data(), ctx->st.nuc + (size_t)slot * 2 * Amax * smc::NROW, nuc.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(ncoll.data(), ctx->st.nuc_ncoll + (size_t)slot * 2 * Amax, ncoll.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(first.data(), ctx->st.nuc_first + (size_t)slot * Amax, first.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(hi, ctx->st.hdr_i + (size_t)slot * smc::HDR_I, smc::HDR_I * sizeof(int), cudaMemcpyDeviceToHost));
+  return SMC_OK;
+}
+
+extern "C" int smc_get_nucleons(smc_ctx* ctx, int slot, int which, double* host8, int* n) {
+  if (!ctx || !n || slot < 0 || slot >= ctx->last_n || which < 0 || which > 1) return SMC_ERR_PARAM;
+  *n = ctx->cfg.A[which];
+  if (!host8) return SMC_OK;
+  std::vector<double> nuc; std::vector<int> nc, fi; int hi[smc::HDR_I]; int rc;
+  if ((rc = fetch_event_lists(ctx, slot, nuc, nc, fi, hi))) return rc;
+  for (int i = 0; i < *n; i++) {
+    std::memcpy(host8 + (size_t)i * 8, nuc.data() + ((size_t)which * ctx->cfg.Amax + i) * smc::NROW, 8 * sizeof(double));
+    host8[(size_t)i * 8 + 2] = (double)nc[(size_t)which * ctx->cfg.Amax + i];     // z slot carries the collision count
+  }
+  return SMC_OK;
+}
+
+// participants in the reference's order: projectile ascending i, target by first hit (Nucleus::markWounded)
+extern "C" int smc_get_participants(smc_ctx* ctx, int slot, double* host8, int* n) {
+  if (!ctx || !n || slot < 0 || slot >= ctx->last_n) return SMC_ERR_PARAM;
+  std::vector<double> nuc; std::vector<int> nc, fi; int hi[smc::HDR_I]; int rc;
+  if ((rc = fetch_event_lists(ctx, slot, nuc, nc, fi, hi))) return rc;
+  *n = hi[smc::H_NP1] + hi[smc::H_NP2];
+  if (!host8) return SMC_OK;
+  const int Amax = ctx->cfg.Amax; int k = 0;
+  auto put = [&](int s, int i) {
+    const double* r = nuc.data() + ((size_t)s * Amax + i) * smc::NROW; double* o = host8 + (size_t)(k++) * 8;
+    o[0] = r[smc::NX]; o[1] = r[smc::NY]; o[2] = s + 1; o[3] = r[smc::NW]; o[4] = r[smc::NXL]; o[5] = r[smc::NXR]; o[6] = r[smc::NYL]; o[7] = r[smc::NYR];
+  };
+  for (int i = 0; i < ctx->cfg.A[0]; i++) if (nc[i] > 0) put(0, i);
+  std::vector<std::pair<long long, int>> ord;
+  for (int j = 0; j < ctx->cfg.A[1]; j++) if (nc[Amax + j] > 0) ord.push_back(std::make_pair((long long)fi[j] * 65536 + j, j));
+  std::sort(ord.begin(), ord.end());
+  for (auto& pr : ord) put(1, pr.second);
+  return SMC_OK;
+}
+
+extern "C" int smc_get_collisions(smc_ctx* ctx, int slot, double* host6, int* n) {
+  if (!ctx || !n || slot < 0 || slot >= ctx->last_n) return SMC_ERR_PARAM;
+  CK(cudaSetDevice(ctx->device));
+  int hi[smc::HDR_I];
+  CK(cudaMemcpy(hi, ctx->st.hdr_i + (size_t)slot * smc::HDR_I, sizeof hi, cudaMemcpyDeviceToHost));
+  const int nc = std::min(hi[smc::H_NCOLL], ctx->cfg.ncoll_cap);
+  *n = nc;
+  if (!host6 || nc == 0) return SMC_OK;
+  std::vector<double> c4((size_t)nc * smc::CROW); std::vector<int> ij(nc);
+  CK(cudaMemcpy(c4.data(), ctx->st.coll + (size_t)slot * ctx->cfg.ncoll_cap * smc::CROW, c4.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(ij.data(), ctx->st.coll_ij + (size_t)slot * ctx->cfg.ncoll_cap, ij.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  for (int k = 0; k < nc; k++) {
+    double* o = host6 + (size_t)k * 6;
+    o[0] = c4[(size_t)k * 4]; o[1] = c4[(size_t)k * 4 + 1]; o[2] = c4[(size_t)k * 4 + 2]; o[3] = c4[(size_t)k * 4 + 3]; o[4] = ij[k] >> 16; o[5] = ij[k] & 0xffff;
+  }
+  return SMC_OK;
+}
+
+// spectators: projectile nucleons first (Y>0), then target (MCnucl.cpp:1223-1249)
+extern "C" int smc_get_spectators(smc_ctx* ctx, int slot, double* host3, int* n) {
+  if (!ctx || !n || slot < 0 || slot >= ctx->last_n) return SMC_ERR_PARAM;
+  std::vector<double> nuc; std::vector<int> nc, fi; int hi[smc::HDR_I]; int rc;
+  if ((rc = fetch_event_lists(ctx, slot, nuc, nc, fi, hi))) return rc;
+  *n = hi[smc::H_NSPEC1] + hi[smc::H_NSPEC2];
+  if (!host3) return SMC_OK;
+  const double ecm = ctx->p.ecm, vz = std::sqrt(1. - 1. / ((ecm / 2.) * (ecm / 2.)));
+  const double Y = 0.5 * std::log((1. + vz) / (1. - vz + 1e-100));
+  const int Amax = ctx->cfg.Amax; int k = 0;
+  for (int s = 0; s < 2; s++) for (int i = 0; i < ctx->cfg.A[s]; i++) if (nc[(size_t)s * Amax + i] == 0) {
+    const double* r = nuc.data() + ((size_t)s * Amax + i) * smc::NROW;
+    host3[(size_t)k * 3] = r[smc::NX]; host3[(size_t)k * 3 + 1] = r[smc::NY]; host3[(size_t)k * 3 + 2] = s == 0 ? Y : -Y; k++;
+  }
+  return SMC_OK;
+}
+
+// ---- averaged profiles: filled in by smc_avg.cu ----------------------------------------------------
+// ---- centrality sort (scripts/centrality_cut_h5.py:36-110: argsort(-key)) -------------------------
+__global__ void iota_kernel(int64_t* p, int64_t n) { int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = i; }
+extern "C" int smc_centrality_sort(smc_ctx* ctx, const double* key, int64_t n, int64_t* perm) {
+  if (!ctx || !key || !perm || n <= 0 || n > 0x7fffffff) return SMC_ERR_PARAM;
+  CK(cudaSetDevice(ctx->device));
+  double *dk = nullptr, *dk2 = nullptr; int64_t *dv = nullptr, *dv2 = nullptr; void* tmp = nullptr; size_t tb = 0;
+  CK(cudaMalloc(&dk, n * sizeof(double))); CK(cudaMalloc(&dk2, n * sizeof(double)));
+  CK(cudaMalloc(&dv, n * sizeof(int64_t))); CK(cudaMalloc(&dv2, n * sizeof(int64_t)));
+  CK(cudaMemcpyAsync(dk, key, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(dv, n); ctx->launches++;
+  cub::DeviceRadixSort::SortPairsDescending(tmp, tb, dk, dk2, dv, dv2, (int)n, 0, 64, ctx->stream);
+  CK(cudaMalloc(&tmp, tb));
+  cub::DeviceRadixSort::SortPairsDescending(tmp, tb, dk, dk2, dv, dv2, (int)n, 0, 64, ctx->stream); ctx->launches++;
+  CK(cudaMemcpyAsync(perm, dv2, n * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(dk); cudaFree(dk2); cudaFree(dv); cudaFree(dv2); cudaFree(tmp);
+  return SMC_OK;
+}
+
+// ---- micro-benchmarks for the roofline denominators -----------------------------------------------
+__global__ void fp64_peak_kernel(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, b = 1e-9;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, m, b); a1 = fma(a1, m, b); a2 = fma(a2, m, b); a3 = fma(a3, m, b);
+    a4 = fma(a4, m, b); a5 = fma(a5, m, b); a6 = fma(a6, m, b); a7 = fma(a7, m, b);
+  }
+  if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 12345.678) out[0] = a0;
+}
+extern "C" double smc_measure_fp64_peak(smc_ctx* ctx) {
+  if (!ctx) return 0.0;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return 0.0;
+  cudaDeviceProp prop; cudaGetDeviceProperties(&prop, ctx->device);
+  double* d = nullptr; cudaMalloc(&d, 8);
+  const int iters = 20000, blocks = prop.multiProcessorCount * 8, threads = 256;
+  fp64_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(d, 100);
+  double best = 0;
+  for (int r = 0; r < 3; r++) {
+    cudaEventRecord(ctx->ev0, ctx->stream);
+    fp64_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(d, iters);
+    cudaEventRecord(ctx->ev1, ctx->stream); cudaEventSynchronize(ctx->ev1);
+    float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    const double tf = 2.0 * 8.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+    best = std::max(best, tf);
+  }
+  ctx->launches += 4;
+  cudaFree(d);
+  return best;
+}
+__global__ void hbm_write_kernel(double4* p, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = make_double4(1.0, 2.0, 3.0, 4.0);
+}
+extern "C" double smc_measure_hbm_write_peak(smc_ctx* ctx) {
+  if (!ctx) return 0.0;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return 0.0;
+  cudaDeviceProp prop; cudaGetDeviceProperties(&prop, ctx->device);
+  const size_t bytes = (size_t)2 << 30; double4* d = nullptr;
+  if (cudaMalloc(&d, bytes) != cudaSuccess) return 0.0;
+  double best = 0;
+  for (int r = 0; r < 4; r++) {
+    cudaEventRecord(ctx->ev0, ctx->stream);
+    hbm_write_kernel<<<prop.multiProcessorCount * 16, 512, 0, ctx->stream>>>(d, bytes / sizeof(double4));
+    cudaEventRecord(ctx->ev1, ctx->stream); cudaEventSynchronize(ctx->ev1);
+    float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    if (r) best = std::max(best, bytes / (ms * 1e-3) / 1e9);
+  }
+  ctx->launches += 4;
+  cudaFree(d);
+  return best;
+}

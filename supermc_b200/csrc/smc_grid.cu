@@ -1,0 +1,411 @@
+// smc_grid.cu -- K3 density accumulation and K4 eccentricity moments.
+//
+// K3 replaces MCnucl::setThickness, addDensity, the binary-collision loop of setDensity,
+// calculate_rho_binary and calculate_spectator_density (reference src/MCnucl.cpp:432-478, 481-531,
+// 534-614, 688-811, 822-866; Particle::getSmoothTn src/Particle.cpp:122-132).
+// K4 replaces MakeDensity::dumpEccentricities / MCnucl::getHotSpots (src/MakeDensity.cpp:2244-2430,
+// src/MCnucl.cpp:1303-1323) and GlueDensity::calcCMAngle (src/GlueDensity.cpp:87-144).
+//
+// B200 mapping of K3 (gather, no atomics): the reference scatters every source over its window with
+// one exp per (source, cell).  Here one CTA owns a band of DEP_ROWS grid rows of one event; each warp
+// owns a 32-column stripe and keeps its DEP_ROWS x 32 cells in registers.  Sources that touch the band
+// are compacted in order, then processed in chunks: a few threads expand each source's *separable*
+// factors  W*exp(-dx^2/2w^2)  (per row) and  exp(-dy^2/2w^2)  (per column) into shared memory with a
+// two-multiply Gaussian recurrence (4 exps per source instead of ~2000), together with the exactly
+// rounded dx^2, dy^2 the reference's circle masks are made of; every lane then does one DADD + compare
+// (the reference's `dc <= 25 w^2` / `r <= 5w` decision, bit for bit) and one DFMA per (source, cell).
+// Deposits are deterministic (fixed summation order) and each grid cell is written exactly once.
+#include "smc_common.cuh"
+
+namespace smc {
+
+enum { GK_RHO = 0, GK_TA1 = 1, GK_TA2 = 2, GK_RHO_BINARY = 3, GK_SPEC_A = 4, GK_SPEC_B = 5, GK_RHOA = 6, GK_RHOB = 7 };
+#define DEP_ROWS 32
+#define DEP_CH 32
+
+struct Src { double x, y, W, thr; int iL, iR, jL, jR; int flat; };
+
+__device__ __forceinline__ int src_count(const DevCfg& c, const int* hi, int kind) {
+  const int np1 = hi[H_NP1], np2 = hi[H_NP2];
+  int nc = hi[H_NCOLL]; if (nc > c.ncoll_cap) nc = c.ncoll_cap;
+  switch (kind) {
+    case GK_RHO: return ((c.sub_model == 1) ? np1 + np2 : 0) + ((c.alpha > 1e-8) ? nc : 0);
+    case GK_TA1: case GK_RHOA: return np1;
+    case GK_TA2: case GK_RHOB: return np2;
+    case GK_RHO_BINARY: return nc;
+    case GK_SPEC_A: return hi[H_NSPEC1];
+    case GK_SPEC_B: return hi[H_NSPEC2];
+  }
+  return 0;
+}
+
+// source k of `kind` for event e -> position, folded weight, window, mask threshold
+__device__ void load_src(const DevCfg& c, const Store& st, int e, const int* hi, int kind, int k, Src& s) {
+  const int Amax = c.Amax;
+  const double* nuc = st.nuc + (size_t)e * 2 * Amax * NROW;
+  const int np1 = hi[H_NP1], np2 = hi[H_NP2];
+  bool box_window = false, is_coll = false;
+  const double* row = nullptr;
+  double wgt = 1.0;
+  int shape = c.shape_of_nucleons;          // which "shape" switch the reference consults for this deposit
+  s.thr = c.thrB;
+  if (kind == GK_RHO) {
+    const int nwn = (c.sub_model == 1) ? np1 + np2 : 0;
+    shape = c.shape_of_entropy;
+    if (k < nwn) {                                                                   // addDensity, MCnucl.cpp:822-866
+      const int id = st.part_idx[(size_t)e * 2 * Amax + k];
+      row = nuc + ((size_t)(id >> 16) * Amax + (id & 0xffff)) * NROW;
+      wgt = row[NW] * ((1.0 - c.alpha) / 2.); box_window = true; s.thr = c.thrA;
+    } else {                                                                         // MCnucl.cpp:724-759
+      const double* cr = st.coll + ((size_t)e * c.ncoll_cap + (k - nwn)) * CROW;
+      row = cr; is_coll = true;
+      const double fl = (c.cc_fluct > 5) ? cr[CW] : 1.0;
+      wgt = fl * (c.alpha + (1. - c.alpha) * cr[CADDW]); s.thr = c.thrB;
+    }
+  } else if (kind == GK_RHOA || kind == GK_RHOB) {                                   // model 7, MCnucl.cpp:780-811
+    const int id = st.part_idx[(size_t)e * 2 * Amax + (kind == GK_RHOB ? np1 : 0) + k];
+    row = nuc + ((size_t)(id >> 16) * Amax + (id & 0xffff)) * NROW;
+    wgt = row[NW]; box_window = true; s.thr = c.thrA; shape = c.shape_of_entropy;
+  } else if (kind == GK_TA1 || kind == GK_TA2) {                                     // setThickness, MCnucl.cpp:432-478
+    const int id = st.part_idx[(size_t)e * 2 * Amax + (kind == GK_TA2 ? np1 : 0) + k];
+    row = nuc + ((size_t)(id >> 16) * Amax + (id & 0xffff)) * NROW;
+    s.thr = c.thrA;
+  } else if (kind == GK_RHO_BINARY) {                                                // MCnucl.cpp:481-531
+    row = st.coll + ((size_t)e * c.ncoll_cap + k) * CROW; is_coll = true;
+  } else {                                                                           // spectators, MCnucl.cpp:534-614
+    const int id = st.spec_idx[(size_t)e * 2 * Amax + (kind == GK_SPEC_B ? (c.A[0] - np1) : 0) + k];
+    row = nuc + ((size_t)(id >> 16) * Amax + (id & 0xffff)) * NROW;
+  }
+  s.x = row[0]; s.y = row[1];
+  s.flat = (shape == 1);
+  if (s.flat) { s.W = wgt * c.areai; s.thr = c.dsq; } else s.W = wgt * c.norm;
+  // +-d_max window (quirk Q7); for AABB windows (quirk Q3) the same range, widened by a cell, is only a
+  // safe clip: cells farther than the mask radius contribute nothing in the reference either
+  const double reach = (box_window && s.flat) ? c.rclip_flat : c.dmax;
+  int iL = cell_of(__dadd_rn(s.x, -reach), c.Xmin, c.dx), iR = cell_of(__dadd_rn(s.x, reach), c.Xmin, c.dx);
+  int jL = cell_of(__dadd_rn(s.y, -reach), c.Ymin, c.dy), jR = cell_of(__dadd_rn(s.y, reach), c.Ymin, c.dy);
+  if (box_window && !is_coll) {
+    const int bl = cell_of(row[NXL], c.Xmin, c.dx), br = cell_of(row[NXR], c.Xmin, c.dx);
+    const int cl = cell_of(row[NYL], c.Ymin, c.dy), cr2 = cell_of(row[NYR], c.Ymin, c.dy);
+    iL = max(bl, iL - 1); iR = min(br, iR + 2); jL = max(cl, jL - 1); jR = min(cr2, jR + 2);
+  }
+  s.iL = max(0, iL); s.iR = min(c.Maxx, iR); s.jL = max(0, jL); s.jR = min(c.Maxy, jR);
+}
+
+struct KindList { int n; int kind[8]; };
+
+#define DEP_MAXWARPS 12
+__global__ void __launch_bounds__(DEP_MAXWARPS * 32) deposit_kernel(DevCfg c, Store st, KindList kl, int nev, int nbands) {
+  extern __shared__ double smem_d[];
+  const int e = blockIdx.x, band = blockIdx.y % nbands, sgroup = blockIdx.y / nbands, kind = kl.kind[blockIdx.z];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nwarps = nthreads >> 5;
+  const int stripe = sgroup * (nthreads >> 5) + warp;
+  const int* hi = st.hdr_i + (size_t)e * HDR_I;
+  const int slot = st.kind_slot[kind];
+  double* grid = st.grids + ((size_t)e * st.nkinds + slot) * (size_t)c.Maxx * c.Maxy;
+  const int r0 = band * DEP_ROWS;
+  const int j = stripe * 32 + lane;
+  const int RS = DEP_ROWS + 2, CS = c.wmax + (c.wmax & 1);      // padded strides (doubles)
+  // shared layout
+  double* gxw = smem_d;                         // [CH][RS]
+  double* dx2 = gxw + DEP_CH * RS;              // [CH][RS]
+  double* gy = dx2 + DEP_CH * RS;               // [CH][CS]
+  double* dy2 = gy + DEP_CH * CS;               // [CH][CS]
+  double* thr = dy2 + DEP_CH * CS;              // [CH]
+  int* win = (int*)(thr + DEP_CH);              // [CH][4] rL rR jL jR
+  int* wtot = win + DEP_CH * 4;                 // [32]
+  int* nact_p = wtot + 32;                      // [1]
+  unsigned short* act = (unsigned short*)(nact_p + 4);   // [nsrc]
+
+  double acc[DEP_ROWS];
+#pragma unroll
+  for (int r = 0; r < DEP_ROWS; r++) acc[r] = 0.0;
+
+  const int status = hi[H_STATUS];
+  const int nsrc = (status == 0 || status == 4) ? src_count(c, hi, kind) : 0;
+  // ---- ordered compaction of the sources that touch this band ----
+  int nact = 0;
+  for (int base = 0; base < nsrc; base += nthreads) {
+    const int k = base + tid;
+    bool on = false;
+    if (k < nsrc) { Src s; load_src(c, st, e, hi, kind, k, s); on = (s.iL < s.iR) && (s.jL < s.jR) && (s.iL < r0 + DEP_ROWS) && (s.iR > r0); }
+    const unsigned m = __ballot_sync(0xffffffffu, on);
+    if (lane == 0) wtot[warp] = __popc(m);
+    __syncthreads();
+    int off = nact;
+    for (int w2 = 0; w2 < warp; w2++) off += wtot[w2];
+    if (on) act[off + __popc(m & ((1u << lane) - 1u))] = (unsigned short)k;
+    for (int w2 = 0; w2 < nwarps; w2++) nact += wtot[w2];
+    __syncthreads();
+  }
+  // ---- chunks of DEP_CH sources ----
+  for (int cb = 0; cb < nact; cb += DEP_CH) {
+    const int nch = min(DEP_CH, nact - cb);
+    if (tid < 3 * DEP_CH) {
+      const int t = tid % DEP_CH, part = tid / DEP_CH;
+      if (t < nch) {
+        Src s; load_src(c, st, e, hi, kind, act[cb + t], s);
+        if (part == 0) {
+          const int rL = max(s.iL - r0, 0), rR = min(s.iR - r0, DEP_ROWS);
+          win[t * 4 + 0] = rL; win[t * 4 + 1] = rR; win[t * 4 + 2] = s.jL; win[t * 4 + 3] = s.jR; thr[t] = s.thr;
+          double g = 0, q = 0;
+          for (int r = rL; r < rR; r++) {
+            const double d = __dadd_rn(s.x, -xg_of(c, r0 + r));
+            const double d2 = __dmul_rn(d, d);
+            dx2[t * RS + r] = d2;
+            if (s.flat) gxw[t * RS + r] = s.W;
+            else {
+              if (r == rL) { g = s.W * exp(-d2 * c.inv2w2); q = exp((2.0 * d * c.dx - c.dx * c.dx) * c.inv2w2); }
+              gxw[t * RS + r] = g;
+              g *= q; q *= c.recx;
+            }
+          }
+        } else {
+          const int ncol = s.jR - s.jL, half = (ncol + 1) >> 1;
+          const int c0 = (part == 1) ? 0 : half, c1 = (part == 1) ? half : ncol;
+          double g = 0, q = 0;
+          for (int cc = c0; cc < c1; cc++) {
+            const double d = __dadd_rn(s.y, -yg_of(c, s.jL + cc));
+            const double d2 = __dmul_rn(d, d);
+            dy2[t * CS + cc] = d2;
+            if (s.flat) gy[t * CS + cc] = 1.0;
+            else {
+              if (cc == c0) { g = exp(-d2 * c.inv2w2); q = exp((2.0 * d * c.dy - c.dy * c.dy) * c.inv2w2); }
+              gy[t * CS + cc] = g;
+              g *= q; q *= c.recy;
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    for (int t = 0; t < nch; t++) {
+      const int jL = win[t * 4 + 2], jR = win[t * 4 + 3];
+      if (jR <= stripe * 32 || jL >= stripe * 32 + 32) continue;      // stripe not touched (warp-uniform)
+      const int rL = win[t * 4 + 0], rR = win[t * 4 + 1];
+      const bool inw = (j >= jL) && (j < jR);
+      const double gyv = inw ? gy[t * CS + (j - jL)] : 0.0;
+      const double dy2v = inw ? dy2[t * CS + (j - jL)] : 1e300;
+      const double th = thr[t];
+      const double* gx_t = gxw + t * RS; const double* dx_t = dx2 + t * RS;
+#pragma unroll
+      for (int r = 0; r < DEP_ROWS; r++) {
+        if (r >= rL && r < rR) {
+          const double dc = __dadd_rn(dx_t[r], dy2v);                  // (x-xg)^2 + (y-yg)^2, reference rounding
+          if (dc <= th) acc[r] = fma(gx_t[r], gyv, acc[r]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (j < c.Maxy) {
+#pragma unroll
+    for (int r = 0; r < DEP_ROWS; r++) if (r0 + r < c.Maxx) grid[(size_t)(r0 + r) * c.Maxy + j] = acc[r];
+  }
+}
+
+size_t deposit_smem_bytes(const DevCfg& c, int nsrc_max) {
+  const int RS = DEP_ROWS + 2, CS = c.wmax + (c.wmax & 1);
+  size_t b = (size_t)(2 * DEP_CH * RS + 2 * DEP_CH * CS + DEP_CH) * sizeof(double);
+  b += (size_t)(DEP_CH * 4 + 32 + 4) * sizeof(int);
+  b += (size_t)(nsrc_max + 8) * sizeof(unsigned short);
+  return (b + 15) & ~(size_t)15;
+}
+
+cudaError_t launch_deposit(const DevCfg& c, const Store& st, const int* kinds, int nk, int nev, cudaStream_t s) {
+  KindList kl; kl.n = nk; for (int i = 0; i < nk; i++) kl.kind[i] = kinds[i];
+  const int nstripes = (c.Maxy + 31) / 32;
+  const int ngroups = (nstripes + DEP_MAXWARPS - 1) / DEP_MAXWARPS;
+  const int nwarps = (nstripes + ngroups - 1) / ngroups;
+  const int threads = max(nwarps, 3) * 32;
+  const size_t smem = deposit_smem_bytes(c, 2 * c.Amax + c.ncoll_cap);
+  cudaFuncSetAttribute(deposit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int nbands = (c.Maxx + DEP_ROWS - 1) / DEP_ROWS;
+  dim3 g(nev, nbands * ngroups, nk);
+  deposit_kernel<<<g, threads, smem, s>>>(c, st, kl, nev, nbands);
+  return cudaGetLastError();
+}
+
+// ---- pointwise combinations -------------------------------------------------------------------
+// which_mc_model 7: rho = sqrt(rhoA*rhoB) (MCnucl.cpp:797-803); which_mc_model 1: 6-point table lookup
+// (MCnucl.cpp:654-687, arsenal.cpp:33-54)
+__global__ void combine_kernel(DevCfg c, Store st, int nev) {
+  const int e = blockIdx.y;
+  const size_t G = (size_t)c.Maxx * c.Maxy;
+  int* hi = st.hdr_i + (size_t)e * HDR_I;
+  double* base = st.grids + (size_t)e * st.nkinds * G;
+  double* rho = base + (size_t)st.kind_slot[GK_RHO] * G;
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < G; k += (size_t)gridDim.x * blockDim.x) {
+    if (c.which_mc_model == 7) {
+      const double a = base[(size_t)st.kind_slot[GK_RHOA] * G + k], b = base[(size_t)st.kind_slot[GK_RHOB] * G + k];
+      rho[k] = sqrt(a * b);
+    } else {
+      const double ta = base[(size_t)st.kind_slot[GK_TA1] * G + k], tb = base[(size_t)st.kind_slot[GK_TA2] * G + k];
+      const double di = ta / c.kln_dT, dj = tb / c.kln_dT;
+      if (di < 0 || di >= c.kln_tmax - 2 || dj < 0 || dj >= c.kln_tmax - 2) { hi[H_STATUS] = 4; rho[k] = 0.0; continue; }
+      const int i = (int)floor(di), jj = (int)floor(dj);
+      const double x = di - i, y = dj - jj;
+      const double* T = st.kln_table; const int tm = c.kln_tmax;
+      const double v00 = T[i * tm + jj], v01 = T[i * tm + jj + 1], v02 = T[i * tm + jj + 2];
+      const double v10 = T[(i + 1) * tm + jj], v11 = T[(i + 1) * tm + jj + 1], v20 = T[(i + 2) * tm + jj];
+      const double axx = 1.0 / 2.0 * (v00 - 2 * v10 + v20), axy = v00 - v01 - v10 + v11, ayy = 1.0 / 2.0 * (v00 - 2 * v01 + v02);
+      const double bx = 1.0 / 2.0 * (-3.0 * v00 + 4 * v10 - v20), by = 1.0 / 2.0 * (-3.0 * v00 + 4 * v01 - v02);
+      rho[k] = axx * x * x + axy * x * y + ayy * y * y + bx * x + by * y + v00;
+    }
+  }
+}
+cudaError_t launch_combine(const DevCfg& c, const Store& st, int nev, cudaStream_t s) {
+  dim3 g(32, nev);
+  combine_kernel<<<g, 256, 0, s>>>(c, st, nev);
+  return cudaGetLastError();
+}
+
+// ---- K4: moments --------------------------------------------------------------------------------
+#define MOM_THREADS 256
+__device__ __forceinline__ double block_sum(double v, double* red, int tid) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((tid & 31) == 0) red[tid >> 5] = v;
+  __syncthreads();
+  double s = 0;
+  for (int w = 0; w < MOM_THREADS / 32; w++) s += red[w];
+  return s;
+}
+__device__ __forceinline__ double block_min(double v, double* red, int tid) {
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if ((tid & 31) == 0) red[tid >> 5] = v;
+  __syncthreads();
+  double s = red[0];
+  for (int w = 1; w < MOM_THREADS / 32; w++) s = fmin(s, red[w]);
+  return s;
+}
+
+__global__ void __launch_bounds__(MOM_THREADS, 1) moments_kernel(DevCfg c, Store st, int nev) {
+  extern __shared__ double smem_d[];
+  const int e = blockIdx.x, tid = threadIdx.x;
+  const int* hi = st.hdr_i + (size_t)e * HDR_I;
+  double* out = st.mom_out + (size_t)e * MOM_OUT;
+  const int status = hi[H_STATUS];
+  if (!(status == 0 || status == 4)) { if (tid < MOM_OUT) out[tid] = 0.0; return; }
+  const int Maxx = c.Maxx, Maxy = c.Maxy, MW = (Maxy + 31) / 32;
+  double* red = smem_d;                       // [64]
+  uint32_t* mask = (uint32_t*)(red + 64);     // [Maxx][MW]
+  const size_t G = (size_t)Maxx * Maxy;
+  const double* rho = st.grids + ((size_t)e * st.nkinds + st.kind_slot[GK_RHO]) * G;
+  const int Amax = c.Amax, np = hi[H_NP1] + hi[H_NP2];
+  const double* nuc = st.nuc + (size_t)e * 2 * Amax * NROW;
+  const int* pidx = st.part_idx + (size_t)e * 2 * Amax;
+  for (int k = tid; k < Maxx * MW; k += MOM_THREADS) mask[k] = 0u;
+  // hot-spot region: union of participant AABBs and the zero-size collision boxes at the origin
+  // (MCnucl.cpp:1303-1323, CollisionPair.h:15-17 -- quirk Q13)
+  double xl = 1e300, xr = -1e300, yl = 1e300, yr = -1e300;
+  for (int k = tid; k < np; k += MOM_THREADS) {
+    const int id = pidx[k]; const double* r = nuc + ((size_t)(id >> 16) * Amax + (id & 0xffff)) * NROW;
+    xl = fmin(xl, r[NXL]); xr = fmax(xr, r[NXR]); yl = fmin(yl, r[NYL]); yr = fmax(yr, r[NYR]);
+  }
+  if (hi[H_NCOLL] > 0) { xl = fmin(xl, 0.0); xr = fmax(xr, 0.0); yl = fmin(yl, 0.0); yr = fmax(yr, 0.0); }
+  const double rXL = block_min(xl, red, tid), rXR = -block_min(-xr, red, tid);
+  const double rYL = block_min(yl, red, tid), rYR = -block_min(-yr, red, tid);
+  const int nX = (int)__ddiv_rn(__dadd_rn(rXR, -rXL), c.dx), nY = (int)__ddiv_rn(__dadd_rn(rYR, -rYL), c.dy);   // MakeDensity.cpp:2343-2344
+  const int i0 = cell_of(rXL, c.Xmin, c.dx), j0 = cell_of(rYL, c.Ymin, c.dy);                                    // :2399-2400
+  __syncthreads();
+  // boolean mask (MakeDensity.cpp:2354-2358), stored in grid coordinates; one (box,row) per thread step
+  for (int k = tid; k < np; k += MOM_THREADS) {
+    const int id = pidx[k]; const double* r = nuc + ((size_t)(id >> 16) * Amax + (id & 0xffff)) * NROW;
+    int x0 = cell_of(r[NXL], rXL, c.dx), x1 = cell_of(r[NXR], rXL, c.dx);
+    int y0 = cell_of(r[NYL], rYL, c.dy), y1 = (int)__ddiv_rn(__dadd_rn(r[NYR], -rYL), c.dx);                    // sic: dx (quirk Q5)
+    x0 = max(x0, 0); x1 = min(x1, nX); y0 = max(y0, 0); y1 = min(y1, nY);
+    int ja = max(y0 + j0, 0), jb = min(y1 + j0, Maxy);
+    if (ja >= jb) continue;
+    for (int xi = x0; xi < x1; xi++) {
+      const int i = xi + i0;
+      if (i < 0 || i >= Maxx) continue;
+      for (int wd = ja >> 5; wd <= (jb - 1) >> 5; wd++) {
+        const int lo = max(ja - wd * 32, 0), hi2 = min(jb - wd * 32, 32);
+        const uint32_t bits = (hi2 - lo >= 32) ? 0xffffffffu : (((1u << (hi2 - lo)) - 1u) << lo);
+        atomicOr(&mask[i * MW + wd], bits);
+      }
+    }
+  }
+  // bounding rectangle of non-zero density = union of the source windows
+  int ilo = Maxx, ihi = 0, jlo = Maxy, jhi = 0;
+  {
+    const int kinds[3] = {GK_RHO, GK_RHOA, GK_RHOB};
+    const int nk = (c.which_mc_model == 5) ? 1 : (c.which_mc_model == 7 ? 3 : 0);
+    for (int q = (c.which_mc_model == 7 ? 1 : 0); q < nk; q++) {
+      const int ns = src_count(c, hi, kinds[q]);
+      for (int k = tid; k < ns; k += MOM_THREADS) {
+        Src s; load_src(c, st, e, hi, kinds[q], k, s);
+        if (s.iL < s.iR && s.jL < s.jR) { ilo = min(ilo, s.iL); ihi = max(ihi, s.iR); jlo = min(jlo, s.jL); jhi = max(jhi, s.jR); }
+      }
+    }
+    if (c.which_mc_model == 1) { ilo = 0; ihi = Maxx; jlo = 0; jhi = Maxy; }
+  }
+  ilo = (int)block_min((double)ilo, red, tid); ihi = -(int)block_min(-(double)ihi, red, tid);
+  jlo = (int)block_min((double)jlo, red, tid); jhi = -(int)block_min(-(double)jhi, red, tid);
+  const int nj = max(jhi - jlo, 0), ncell = max(ihi - ilo, 0) * nj;
+  // ---- pass 1: centre of mass (MakeDensity.cpp:2273-2282) ----
+  double s0 = 0, sx = 0, sy = 0;
+  for (int k = tid; k < ncell; k += MOM_THREADS) {
+    const int i = ilo + k / nj, j = jlo + k % nj;
+    const double d = rho[(size_t)i * Maxy + j] * c.finalFactor;
+    s0 += d; sx += xg_of(c, i) * d; sy += yg_of(c, j) * d;
+  }
+  const double total = block_sum(s0, red, tid);
+  const double xc = block_sum(sx, red, tid) / total, yc = block_sum(sy, red, tid) / total;
+  // ---- pass 2: <r^n>, eps_n, eps'_n (MakeDensity.cpp:2285-2298, 2389-2430) ----
+  double rn[10], mr[10], mi[10], pr[10], pi[10], npw[10], nrm = 0;
+#pragma unroll
+  for (int n = 0; n < 10; n++) { rn[n] = 0; mr[n] = 0; mi[n] = 0; pr[n] = 0; pi[n] = 0; npw[n] = 0; }
+  for (int k = tid; k < ncell; k += MOM_THREADS) {
+    const int i = ilo + k / nj, j = jlo + k % nj;
+    const double d = rho[(size_t)i * Maxy + j] * c.finalFactor;
+    if (d == 0.0) continue;
+    const double x = xg_of(c, i) - xc, y = yg_of(c, j) - yc;
+    const double r2 = x * x + y * y, r = sqrt(r2);
+    double ux = 1.0, uy = 0.0;                                   // atan2(0,0) = 0
+    if (r > 0.0) { const double ri = 1.0 / r; ux = x * ri; uy = y * ri; }
+    const bool in = (mask[i * MW + (j >> 5)] >> (j & 31)) & 1u;
+    const double d2 = d * r2, d3 = d2 * r;
+    rn[0] += d;
+    if (in) nrm += d2;
+    double an = 1.0, bn = 0.0, p = d;
+#pragma unroll
+    for (int n = 1; n < 10; n++) {
+      const double a2 = an * ux - bn * uy; bn = an * uy + bn * ux; an = a2;
+      p *= r;
+      rn[n] += p;
+      if (in) {
+        mr[n] += d2 * an; mi[n] += d2 * bn;
+        const double pm = (n == 1) ? d3 : p;
+        pr[n] += pm * an; pi[n] += pm * bn; npw[n] += pm;
+      }
+    }
+  }
+  const double eps = 1e-15;
+  const double dn = block_sum(rn[0], red, tid);
+  const double nrmS = block_sum(nrm, red, tid);
+  if (tid == 0) { out[45] = dn / dn; out[46] = total * c.dx * c.dy; out[47] = xc; out[48] = yc; out[49] = (total / c.finalFactor) * c.dx * c.dy; }
+#pragma unroll
+  for (int n = 1; n < 10; n++) {
+    const double a = block_sum(mr[n], red, tid), b = block_sum(mi[n], red, tid), cc = block_sum(pr[n], red, tid);
+    const double dd = block_sum(pi[n], red, tid), ee = block_sum(npw[n], red, tid), ff = block_sum(rn[n], red, tid);
+    if (tid == 0) {
+      const bool on = (n >= c.ecc_from && n <= c.ecc_to);        // orders outside [from,to] stay 0 (MakeDensity.cpp:2389,2475)
+      double* o = out + (n - 1) * 5;
+      o[0] = on ? -a / (nrmS + eps) : 0.0; o[1] = on ? -b / (nrmS + eps) : 0.0;
+      o[2] = on ? -cc / (ee + eps) : 0.0; o[3] = on ? -dd / (ee + eps) : 0.0;
+      o[4] = ff / dn;
+    }
+  }
+}
+
+cudaError_t launch_moments(const DevCfg& c, const Store& st, int nev, cudaStream_t s) {
+  const size_t smem = 64 * sizeof(double) + (size_t)c.Maxx * ((c.Maxy + 31) / 32) * sizeof(uint32_t);
+  cudaFuncSetAttribute(moments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  moments_kernel<<<nev, MOM_THREADS, smem, s>>>(c, st, nev);
+  return cudaGetLastError();
+}
+
+}  // namespace smc

@@ -1,0 +1,425 @@
+// smc_sample.cu -- K1 nucleus sampling + K2 binary-collision detection, one CTA (two warps) per event.
+//
+// Replaces, per event: the rejection loop of MakeDensity (reference src/MakeDensity.cpp:2147-2162),
+// Nucleus::populate / getDeformRandomWS (src/Nucleus.cpp:187-317,578-621), the Particle constructor's
+// AABB (src/Particle.cpp:16-99), MCnucl::getBinaryCollision / hit / createBinaryCollisions
+// (src/MCnucl.cpp:217-385) and the Gamma multiplicity weights (src/MCnucl.cpp:1271-1301).
+//
+// B200 mapping: warp s owns nucleus s.  The reference's strictly sequential hard-core rejection
+// ("nucleon k depends on 0..k-1") is kept *exactly* but evaluated 32 candidates at a time: each lane
+// draws one Woods-Saxon candidate from its own Philox counter, tests it against the nucleons already
+// placed (shared-memory broadcast reads), and a 32-step shuffle pass resolves conflicts inside the
+// batch in candidate order -- the accepted set equals what a sequential loop over the same candidate
+// stream produces.  Collisions are an all-pairs test, one projectile row per warp step, 32 target
+// nucleons per instruction, with the reference's AABB sweep restated as a closed-form predicate so the
+// set of pairs that consume a uniform is the reference's.
+#include "smc_common.cuh"
+
+namespace smc {
+
+struct SampleSmem {
+  double* pos;      // [2][Amax][NROW] sorted rows
+  double* tmp;      // [2][Amax][NROW] acceptance-order rows
+  double* xl;       // [2][Amax]
+  uint32_t* hit;    // [Amax][HW] hit bit masks (row = projectile)
+  int* ncB;         // [Amax]
+  int* firstB;      // [Amax]
+  int* rowoff;      // [Amax+1]
+  int* misc;        // [16]
+};
+
+__device__ __forceinline__ void rot3(double cth, double phi, double& x, double& y, double& z) {
+  // Point3D::rotate, src/MathBasics.cpp:41-50
+  double sphi, cphi; sincos(phi, &sphi, &cphi);
+  double sth = sqrt(1. - cth * cth), x0 = x, y0 = y, z0 = z;
+  x = cth * cphi * x0 - sphi * y0 + sth * cphi * z0;
+  y = cth * sphi * x0 + cphi * y0 + sth * sphi * z0;
+  z = -sth * x0 + cth * z0;
+}
+
+struct Box { double xL, xR, yL, yR, xC, yC; };
+__device__ __forceinline__ void box_center(Box& b, double x, double y) {   // Box2D::setCenter, src/Box2D.cpp:24-33
+  b.xL = __dadd_rn(b.xL, __dadd_rn(x, -b.xC)); b.xR = __dadd_rn(b.xR, __dadd_rn(x, -b.xC));
+  b.yL = __dadd_rn(b.yL, __dadd_rn(y, -b.yC)); b.yR = __dadd_rn(b.yR, __dadd_rn(y, -b.yC));
+  b.xC = x; b.yC = y;
+}
+__device__ __forceinline__ void box_square(Box& b, double size) {          // Box2D::setDimensions, src/Box2D.cpp:35-41
+  double h = size / 2;
+  b.xL = __dadd_rn(b.xC, -h); b.xR = __dadd_rn(b.xC, h); b.yL = __dadd_rn(b.yC, -h); b.yR = __dadd_rn(b.yC, h);
+}
+__device__ __forceinline__ void box_union(Box& b, const Box& o) {          // Box2D::overUnion, src/Box2D.h:49-63
+  b.xL = fmin(o.xL, b.xL); b.xR = fmax(o.xR, b.xR); b.yL = fmin(o.yL, b.yL); b.yR = fmax(o.yR, b.yR);
+  b.xC = (b.xL + b.xR) / 2.0; b.yC = (b.yL + b.yR) / 2.0;
+}
+
+// Particle::Particle -> generateQuarkPositions -> calculateBounds (src/Particle.cpp:16-99)
+__device__ void particle_box(const DevCfg& c, const Store& st, const smc_stream& sq, uint32_t cand,
+                             double x0, double y0, Box& out) {
+  Box base = {0, 0, 0, 0, 0, 0};
+  box_center(base, x0, y0); box_square(base, 8 * c.w);
+  out = base;
+  if (c.quark_rows <= 0) return;     // no table: r1 = r2 = 0, quark boxes (+-4 quark_width) lie inside the base box when quark_width <= w
+  double u0, u1, u2, u3;
+  smc_uniform2(sq, cand, 0, &u0, &u1); smc_uniform2(sq, cand, 1, &u2, &u3);
+  int index = (int)(250000 * u0);
+  double r1 = 0, r2 = 0, z12 = 0;
+  if (index < c.quark_rows) { r1 = st.quark_table[3 * index]; r2 = st.quark_table[3 * index + 1]; z12 = st.quark_table[3 * index + 2]; }
+  r1 *= c.quark_R; r2 *= c.quark_R;
+  double Theta12 = acos(z12), z1 = 2. * u1 - 1., Theta1 = acos(z1);
+  double phi1 = 2 * SMC_PI * u2, phi2 = 2 * SMC_PI * u3;
+  double s1, c1, s12, c12, sp1, cp1, s, cc;
+  sincos(Theta1, &s1, &c1); sincos(Theta1 + Theta12, &s12, &c12); sincos(phi1, &sp1, &cp1); sincos(phi2, &s, &cc);
+  double ux = s1 * cp1, uy = s1 * sp1, uz = z1, vx = s12 * cp1, vy = s12 * sp1, vz = c12;
+  double r1x = r1 * ux, r1y = r1 * uy;
+  double r2x = vx * (cc + ux * ux * (1 - cc)) + vy * (ux * uy * (1 - cc) - uz * s) + vz * (ux * uz * (1 - cc) + uy * s);
+  double r2y = vx * (ux * uy * (1 - cc) + uz * s) + vy * (cc + uy * uy * (1 - cc)) + vz * (uy * uz * (1 - cc) - ux * s);
+  r2x *= r2; r2y *= r2;
+  double qx[3] = {r1x, r2x, -r1x - r2x}, qy[3] = {r1y, r2y, -r1y - r2y};
+#pragma unroll
+  for (int q = 0; q < 3; q++) {
+    Box b = {0, 0, 0, 0, 0, 0};
+    box_center(b, qx[q], qy[q]); box_square(b, 8 * c.quark_width); box_center(b, x0 + qx[q], y0 + qy[q]);
+    box_union(out, b);
+  }
+}
+
+__device__ __forceinline__ double sph_harm2(double ct) { return (3.0 * ct * ct - 1.0) * 0.31539156525252005; }
+__device__ __forceinline__ double sph_harm4(double ct) { return (35.0 * ct * ct * ct * ct - 30.0 * ct * ct + 3.0) * 0.10578554691520431; }
+
+// One nucleus by warp `s` (side).  Leaves A sorted rows in sm.pos[s].
+__device__ void sample_nucleus(const DevCfg& c, const Store& st, const SampleSmem& sm, int s, uint64_t ev,
+                               uint32_t tr, double xCenter, double yCenter) {
+  const int lane = threadIdx.x & 31, A = c.A[s];
+  double* tmp = sm.tmp + (size_t)s * c.Amax * NROW;
+  double* pos = sm.pos + (size_t)s * c.Amax * NROW;
+  double* xl = sm.xl + (size_t)s * c.Amax;
+  const smc_stream s_or = smc_make_stream(c.seed_lo, c.seed_hi, ev, tr, SMC_K_ORIENT, s);
+  const smc_stream s_q = smc_make_stream(c.seed_lo, c.seed_hi, ev, tr, SMC_K_QUARK, s);
+  double uo0, uo1; smc_uniform2(s_or, 0, 0, &uo0, &uo1);
+  double ctr = 1.0 - 2.0 * uo0, phir = 2 * SMC_PI * uo1;       // Nucleus.cpp:193-197
+  bool recentre = true;
+  const int mode = c.sampler[s];
+  if (mode == 1) {                                              // single nucleon, Nucleus.cpp:201-202
+    if (lane == 0) { tmp[0] = xCenter; tmp[1] = yCenter; tmp[2] = 0.0; tmp[3] = 0.0; }
+    recentre = false;
+  } else if (mode == 2 || mode == 3) {                          // config tables, Nucleus.cpp:555-574,623-666
+    const smc_stream s_c = smc_make_stream(c.seed_lo, c.seed_hi, ev, tr, SMC_K_CONFIG, s);
+    double uc = smc_uniform(s_c, 0, 0);
+    int icfg = (int)(uc * c.ncfg[s]); if (icfg >= c.ncfg[s]) icfg = c.ncfg[s] - 1;
+    const double* cfg = st.cfg_table[s] + (size_t)icfg * A * 3;
+    double mx = 0, my = 0, mz = 0;
+    if (mode == 3) {
+      for (int k = lane; k < A; k += 32) { mx += cfg[3 * k]; my += cfg[3 * k + 1]; mz += cfg[3 * k + 2]; }
+      mx = warp_sum(mx) / A; my = warp_sum(my) / A; mz = warp_sum(mz) / A;
+      double u2, u3; smc_uniform2(s_or, 0, 1, &u2, &u3);
+      ctr = 1.0 - 2.0 * u2; phir = 2 * SMC_PI * u3;
+    }
+    for (int k = lane; k < A; k += 32) {
+      double x = cfg[3 * k] - mx, y = cfg[3 * k + 1] - my, z = cfg[3 * k + 2] - mz;
+      rot3(ctr, phir, x, y, z);
+      if (mode == 2) { x += xCenter; y += yCenter; }
+      tmp[k * NROW + 0] = x; tmp[k * NROW + 1] = y; tmp[k * NROW + 2] = z; tmp[k * NROW + 3] = (double)k;
+    }
+    recentre = (mode == 3);
+  } else {                                                      // Woods-Saxon + hard core, Nucleus.cpp:272-310
+    const smc_stream s_ws = smc_make_stream(c.seed_lo, c.seed_hi, ev, tr, SMC_K_WS, s);
+    const smc_stream s_an = smc_make_stream(c.seed_lo, c.seed_hi, ev, tr, SMC_K_ANGLE, s);
+    const double rad = c.rad[s], dr = c.dr[s], rmaxCut = c.rmaxCut[s], rwMax = c.rwMax[s];
+    const double rmin = 0.9 * 0.9;
+    int placed = 0; uint32_t cand_base = 0;
+    while (placed < A) {
+      const uint32_t cand = cand_base + lane;
+      double x, y, z;
+      if (c.deformed[s]) {                                      // Nucleus.cpp:585-607
+        double r, cx, rad1, rwMax1, u3; uint32_t k = 0;
+        do {
+          r = rmaxCut * cbrt(smc_uniform(s_ws, cand, 3 * k));
+          cx = 1.0 - 2.0 * smc_uniform(s_ws, cand, 3 * k + 1);
+          rad1 = rad * (1.0 + c.beta2[s] * sph_harm2(cx) + c.beta4[s] * sph_harm4(cx));
+          rwMax1 = 1.0 / (1.0 + exp(-rad1 / dr));
+          u3 = smc_uniform(s_ws, cand, 3 * k + 2); k++;
+        } while (u3 * rwMax1 > 1.0 / (1.0 + exp((r - rad1) / dr)));
+        double sx = sqrt(1.0 - cx * cx), sp, cp;
+        sincos(2 * SMC_PI * smc_uniform(s_an, cand, 1), &sp, &cp);
+        x = r * sx * cp; y = r * sx * sp; z = r * cx;
+        rot3(ctr, phir, x, y, z);
+      } else {                                                  // Nucleus.cpp:610-619
+        double r, u1, u2; uint32_t k = 0;
+        do { smc_uniform2(s_ws, cand, k, &u1, &u2); r = rmaxCut * cbrt(u1); k++; }
+        while (u2 * rwMax > 1.0 / (1.0 + exp((r - rad) / dr)));
+        double ua, ub; smc_uniform2(s_an, cand, 0, &ua, &ub);
+        double cx = 1.0 - 2.0 * ua, sx = sqrt(1.0 - cx * cx), sp, cp;
+        sincos(2 * SMC_PI * ub, &sp, &cp);
+        x = r * sx * cp; y = r * sx * sp; z = r * cx;
+      }
+      bool bad = false;
+      for (int i = 0; i < placed; i++) {                        // Nucleus.cpp:284-293
+        double ax = x - tmp[i * NROW], ay = y - tmp[i * NROW + 1], az = z - tmp[i * NROW + 2];
+        double r2 = ax * ax + ay * ay + az * az;
+        bad |= (r2 < rmin);
+      }
+      int nacc = 0;
+      unsigned okmask = __ballot_sync(0xffffffffu, !bad);
+      for (int l = 0; l < 32 && okmask; l++) {                  // in-batch conflicts, candidate order
+        if (!((okmask >> l) & 1u)) continue;
+        if (placed + nacc >= A) break;
+        double lx = __shfl_sync(0xffffffffu, x, l), ly = __shfl_sync(0xffffffffu, y, l), lz = __shfl_sync(0xffffffffu, z, l);
+        if (lane > l) { double ax = x - lx, ay = y - ly, az = z - lz; bad |= (ax * ax + ay * ay + az * az < rmin); }
+        if (lane == l) { double* t = tmp + (size_t)(placed + nacc) * NROW; t[0] = x; t[1] = y; t[2] = z; t[3] = (double)cand; }
+        nacc++;
+        okmask = __ballot_sync(0xffffffffu, !bad) & ~((2u << l) - 1u);
+      }
+      placed += nacc; cand_base += 32;
+      __syncwarp();
+    }
+  }
+  __syncwarp();
+  // centre of mass shift (Nucleus.cpp:301-309) + AABB + sort key
+  double mx = 0, my = 0, mz = 0;
+  if (recentre) {
+    for (int k = lane; k < A; k += 32) { mx += tmp[k * NROW]; my += tmp[k * NROW + 1]; mz += tmp[k * NROW + 2]; }
+    mx = warp_sum(mx); my = warp_sum(my); mz = warp_sum(mz);
+  }
+  __syncwarp();
+  for (int k = lane; k < A; k += 32) {
+    double x0 = tmp[k * NROW], y0 = tmp[k * NROW + 1], z0 = tmp[k * NROW + 2];
+    uint32_t cand = (uint32_t)tmp[k * NROW + 3];
+    Box bx; particle_box(c, st, s_q, cand, x0, y0, bx);
+    if (recentre) {
+      double x = x0 - mx / A + xCenter, y = y0 - my / A + yCenter, z = z0 - mz / A;
+      box_center(bx, x, bx.yC); box_center(bx, bx.xC, y);       // Particle::setX / setY, src/Particle.cpp:176-185
+      x0 = x; y0 = y; z0 = z;
+    }
+    double* t = tmp + (size_t)k * NROW;
+    t[NX] = x0; t[NY] = y0; t[NZ] = z0; t[NXL] = bx.xL; t[NXR] = bx.xR; t[NYL] = bx.yL; t[NYR] = bx.yR; t[NW] = 1.0;
+    xl[k] = bx.xL;
+  }
+  __syncwarp();
+  for (int k = lane; k < A; k += 32) {                          // std::sort by xL, src/Nucleus.cpp:314
+    double key = xl[k]; int rank = 0;
+    for (int j = 0; j < A; j++) { double o = xl[j]; rank += (o < key) || (o == key && j < k); }
+    const double* t = tmp + (size_t)k * NROW; double* p = pos + (size_t)rank * NROW;
+#pragma unroll
+    for (int f = 0; f < NROW; f++) p[f] = t[f];
+  }
+  __syncwarp();
+}
+
+// Marsaglia-Tsang gamma(shape a, scale th); a<1 boosted by U^(1/a).  Law-equivalent to gsl_ran_gamma
+// (reference src/MCnucl.cpp:1285,1298); the reference's stream is a separate mt19937 (quirk Q8).
+__device__ double gamma_variate(const smc_stream& s, uint32_t cand, double a, double th) {
+  double boost = 1.0, aa = a;
+  const bool small = a < 1.0;
+  if (small) aa = a + 1.0;
+  const double d = aa - 1.0 / 3.0, cc = 1.0 / sqrt(9.0 * d);
+  for (uint32_t it = 0; it < 64; it++) {
+    double u1, u2, u3, u4;
+    smc_uniform2(s, cand, 2 * it, &u1, &u2); smc_uniform2(s, cand, 2 * it + 1, &u3, &u4);
+    double x = sqrt(-2.0 * log(1.0 - u1)) * cospi(2.0 * u2);
+    double v = 1.0 + cc * x;
+    if (v <= 0.0) continue;
+    v = v * v * v;
+    if (log(1.0 - u3) < 0.5 * x * x + d - d * v + d * log(v)) {
+      if (small) boost = pow(1.0 - u4, 1.0 / a);
+      return d * v * th * boost;
+    }
+  }
+  return a * th;
+}
+
+template <bool GIVEN>
+__global__ void __launch_bounds__(64) sample_collide_kernel(DevCfg c, Store st, int nev) {
+  extern __shared__ double smem_d[];
+  const int e = blockIdx.x;
+  if (e >= nev) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int A = c.A[0], B = c.A[1], Amax = c.Amax, HW = (Amax + 31) / 32;
+  SampleSmem sm;
+  sm.pos = smem_d; sm.tmp = sm.pos + 2 * Amax * NROW; sm.xl = sm.tmp + 2 * Amax * NROW;
+  sm.hit = (uint32_t*)(sm.xl + 2 * Amax);
+  sm.ncB = (int*)(sm.hit + (size_t)Amax * HW); sm.firstB = sm.ncB + Amax; sm.rowoff = sm.firstB + Amax; sm.misc = sm.rowoff + Amax + 1;
+  const uint64_t ev = st.event_id[e];
+  double* gn = st.nuc + (size_t)e * 2 * Amax * NROW;
+  int* hi = st.hdr_i + (size_t)e * HDR_I;
+  double* hd = st.hdr_d + (size_t)e * HDR_D;
+  double b = 0.0;
+  uint32_t tr = GIVEN ? 0u : (uint32_t)st.try_start[e];
+  int ncoll = 0, np1 = 0, np2 = 0;
+  bool accepted = false;
+  for (int guard = 0; guard < 100000 && !accepted; guard++, tr++) {
+    if (GIVEN) {
+      b = hd[HD_B];
+      for (int k = tid; k < 2 * Amax * NROW; k += 64) sm.pos[k] = gn[k];
+    } else {
+      const smc_stream s_b = smc_make_stream(c.seed_lo, c.seed_hi, ev, tr, SMC_K_B, 0);
+      b = sqrt((c.bmax * c.bmax - c.bmin * c.bmin) * smc_uniform(s_b, 0, 0) + c.bmin * c.bmin);   // MakeDensity.cpp:2149
+      sample_nucleus(c, st, sm, warp, ev, tr, warp == 0 ? b / 2.0 : -b / 2.0, 0.0);                 // MCnucl.cpp:208-214
+    }
+    for (int k = tid; k < Amax; k += 64) { sm.ncB[k] = 0; sm.firstB[k] = 0x7fffffff; }
+    __syncthreads();
+    // ---- collisions: rows of the projectile, 32 target nucleons per step ----
+    const double* P = sm.pos; const double* T = sm.pos + (size_t)Amax * NROW;
+    const smc_stream s_p = smc_make_stream(c.seed_lo, c.seed_hi, ev, tr, SMC_K_PAIR, 0);
+    const double* pu = (GIVEN && st.pair_u) ? st.pair_u + (size_t)e * A * B : nullptr;
+    for (int i = warp; i < A; i += 2) {
+      const double px = P[i * NROW + NX], py = P[i * NROW + NY];
+      const double pXL = P[i * NROW + NXL], pXR = P[i * NROW + NXR], pYL = P[i * NROW + NYL], pYR = P[i * NROW + NYR];
+      int start = -1; int rowhits = 0;
+      for (int j0 = 0; j0 < B; j0 += 32) {
+        const int j = j0 + lane; const bool in = j < B;
+        const double* t = T + (size_t)(in ? j : 0) * NROW;
+        uint32_t hitbit = 0;
+        if (start < 0) {                                        // skip loop of the sweep, MCnucl.cpp:255-261
+          unsigned m = __ballot_sync(0xffffffffu, in && (t[NXR] >= pXL));
+          if (m) start = j0 + __ffs(m) - 1;
+        }
+        if (start >= 0) {
+          // the sweep tests pair j iff j >= start and projXR >= XL of the *previous* box looked at (MCnucl.cpp:266-270)
+          bool tst = in && j >= start;
+          if (tst) { int jp = j - 1 > start ? j - 1 : start; tst = pXR >= T[(size_t)jp * NROW + NXL]; }
+          const unsigned alive = __ballot_sync(0xffffffffu, tst);
+          if (tst && pYL <= t[NYR] && pYR >= t[NYL]) {
+            const double ddx = t[NX] - px, ddy = t[NY] - py;
+            const double bb = sqrt(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)));          // MCnucl.cpp:359-360
+            if (c.crit == 1) hitbit = (__dmul_rn(bb, bb) <= c.dsq);
+            else {
+              const double u = pu ? pu[(size_t)i * B + j] : smc_uniform(s_p, (uint32_t)i, (uint32_t)j);
+              const double prob = 1. - exp(-c.sigma_gg * exp(-bb * bb / (4. * c.w * c.w)) / (4. * SMC_PI * c.w * c.w));
+              hitbit = (u < prob);
+            }
+          }
+          const unsigned hm = __ballot_sync(0xffffffffu, hitbit);
+          if (lane == 0) sm.hit[(size_t)i * HW + (j0 >> 5)] = hm;
+          rowhits += __popc(hm);
+          if (hitbit) { atomicAdd(&sm.ncB[j], 1); atomicMin(&sm.firstB[j], i); }
+          if (!alive && j0 + 32 > start) {                     // x-sorted: nothing further can be tested
+            for (int jj = j0 + 32; jj < B; jj += 32) if (lane == 0) sm.hit[(size_t)i * HW + (jj >> 5)] = 0;
+            break;
+          }
+        } else if (lane == 0) sm.hit[(size_t)i * HW + (j0 >> 5)] = 0;
+      }
+      if (lane == 0) sm.rowoff[i] = rowhits;
+    }
+    __syncthreads();
+    // ---- counts ----
+    if (warp == 0) {
+      int n1 = 0, nc = 0;
+      for (int i = lane; i < A; i += 32) { int r = sm.rowoff[i]; nc += r; n1 += (r > 0); }
+      int n2 = 0;
+      for (int j = lane; j < B; j += 32) n2 += (sm.ncB[j] > 0);
+      for (int o = 16; o > 0; o >>= 1) { n1 += __shfl_xor_sync(0xffffffffu, n1, o); n2 += __shfl_xor_sync(0xffffffffu, n2, o); nc += __shfl_xor_sync(0xffffffffu, nc, o); }
+      if (lane == 0) { sm.misc[0] = n1; sm.misc[1] = n2; sm.misc[2] = nc; }
+    }
+    __syncthreads();
+    np1 = sm.misc[0]; np2 = sm.misc[1]; ncoll = sm.misc[2];
+    accepted = (ncoll > 0) && (np1 + np2 <= c.npmax) && (np1 + np2 >= c.npmin);                     // MakeDensity.cpp:2147, MCnucl.cpp:388-393
+    if (GIVEN) { tr++; break; }
+    __syncthreads();
+  }
+  // ---- emit the event record ----
+  if (tid == 0) {
+    hi[H_NP1] = np1; hi[H_NP2] = np2; hi[H_NCOLL] = ncoll; hi[H_TRIES] = (int)tr - (GIVEN ? 0 : st.try_start[e]);
+    hi[H_STATUS] = accepted ? (ncoll > c.ncoll_cap ? 4 : 0) : 100;
+    hd[HD_B] = b;
+    if (!GIVEN) st.try_start[e] = (int)tr;
+  }
+  const uint32_t trw = tr - 1;    // the accepted try
+  const double* P = sm.pos; const double* T = sm.pos + (size_t)Amax * NROW;
+  // exclusive prefix of row hit counts -> collision offsets in (i,j) order (createBinaryCollisions, MCnucl.cpp:326-352)
+  if (warp == 0) {
+    int run = 0;
+    for (int i0 = 0; i0 < A; i0 += 32) {
+      int i = i0 + lane; int v = (i < A) ? sm.rowoff[i] : 0, incl = v;
+      for (int o = 1; o < 32; o <<= 1) { int n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += n; }
+      if (i < A) sm.rowoff[i] = run + incl - v;
+      run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) sm.rowoff[A] = run;
+  }
+  __syncthreads();
+  const bool givenw = GIVEN && hi[H_GIVENW];
+  // nucleon weights (selectFluctFactors: re-drawn at every hit, last wins => one draw per wounded nucleon)
+  double* posw = sm.pos;
+  for (int k = tid; k < A + B; k += 64) {
+    const int s = k >= A, i = s ? k - A : k;
+    const int nc = s ? sm.ncB[i] : (sm.rowoff[i + 1] - sm.rowoff[i]);
+    double wv = 1.0;
+    if (givenw) wv = posw[((size_t)s * Amax + i) * NROW + NW];
+    else if (c.cc_fluct > 5 && nc > 0 && accepted) {
+      const smc_stream sg = smc_make_stream(c.seed_lo, c.seed_hi, ev, trw, SMC_K_GAMMA_PART, s);
+      wv = gamma_variate(sg, (uint32_t)i, c.gam_k_part, c.gam_th_part);
+    }
+    posw[((size_t)s * Amax + i) * NROW + NW] = wv;
+    st.nuc_ncoll[((size_t)e * 2 + s) * Amax + i] = nc;
+    if (s) st.nuc_first[(size_t)e * Amax + i] = sm.firstB[i];
+  }
+  __syncthreads();
+  for (int k = tid; k < 2 * Amax * NROW; k += 64) gn[k] = sm.pos[k];
+  // compact participant / spectator lists (ordered), warp 0 = proj, warp 1 = targ
+  {
+    const int s = warp, n = c.A[s];
+    int npart = 0, nspec = 0;
+    const int pbase = s ? np1 : 0, sbase = s ? (A - np1) : 0;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+      const int i = i0 + lane;
+      const bool in = i < n;
+      const int nc = in ? (s ? sm.ncB[i] : (sm.rowoff[i + 1] - sm.rowoff[i])) : 0;
+      const unsigned mp = __ballot_sync(0xffffffffu, in && nc > 0), ms = __ballot_sync(0xffffffffu, in && nc == 0);
+      const unsigned below = (1u << lane) - 1u;
+      if (in && nc > 0) st.part_idx[(size_t)e * 2 * Amax + pbase + npart + __popc(mp & below)] = (s << 16) | i;
+      if (in && nc == 0) st.spec_idx[(size_t)e * 2 * Amax + sbase + nspec + __popc(ms & below)] = (s << 16) | i;
+      npart += __popc(mp); nspec += __popc(ms);
+    }
+    if (lane == 0) hi[s ? H_NSPEC2 : H_NSPEC1] = nspec;
+  }
+  // collisions: midpoints + weights
+  if (accepted) {
+    const smc_stream sgc = smc_make_stream(c.seed_lo, c.seed_hi, ev, trw, SMC_K_GAMMA_COLL, 0);
+    const double* cw = (GIVEN && st.coll_w) ? st.coll_w + (size_t)e * c.ncoll_cap * 2 : nullptr;
+    for (int i = warp; i < A; i += 2) {
+      int off = sm.rowoff[i];
+      const int nci = sm.rowoff[i + 1] - off;
+      if (nci == 0) continue;
+      for (int wj = 0; wj < HW; wj++) {
+        const unsigned hm = sm.hit[(size_t)i * HW + wj];
+        if ((hm >> lane) & 1u) {
+          const int j = wj * 32 + lane, k = off + __popc(hm & ((1u << lane) - 1u));
+          if (k < c.ncoll_cap) {
+            double* cr = st.coll + ((size_t)e * c.ncoll_cap + k) * CROW;
+            cr[CX] = (P[i * NROW + NX] + T[j * NROW + NX]) / 2.0;                                    // MCnucl.cpp:339-340
+            cr[CY] = (P[i * NROW + NY] + T[j * NROW + NY]) / 2.0;
+            double wv = 1.0, addw = 0.0;
+            if (c.which_mc_model == 5 && c.sub_model == 2)                                           // integer division in the reference,
+              addw = (double)((nci == 1 ? 1 : 0) + (sm.ncB[j] == 1 ? 1 : 0));                        // MCnucl.cpp:345-348
+            if (cw) { wv = cw[2 * k]; addw = cw[2 * k + 1]; }
+            else if (c.cc_fluct > 5) wv = gamma_variate(sgc, (uint32_t)k, c.gam_k_bin, c.gam_th_bin);
+            cr[CW] = wv; cr[CADDW] = addw;
+            st.coll_ij[(size_t)e * c.ncoll_cap + k] = (i << 16) | j;
+          }
+        }
+        off += __popc(hm);
+      }
+    }
+  }
+}
+
+size_t sample_smem_bytes(int Amax) {
+  const int HW = (Amax + 31) / 32;
+  size_t d = (size_t)(2 * Amax * NROW) * 2 + 2 * Amax;
+  size_t i = (size_t)Amax * HW + 3 * Amax + 1 + 16;
+  return d * sizeof(double) + i * sizeof(int);
+}
+
+cudaError_t launch_sample_collide(const DevCfg& c, const Store& st, int nev, bool given, cudaStream_t s) {
+  const size_t smem = sample_smem_bytes(c.Amax);
+  if (given) {
+    cudaFuncSetAttribute(sample_collide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    sample_collide_kernel<true><<<nev, 64, smem, s>>>(c, st, nev);
+  } else {
+    cudaFuncSetAttribute(sample_collide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    sample_collide_kernel<false><<<nev, 64, smem, s>>>(c, st, nev);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace smc

@@ -1,0 +1,94 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref/ref_dump, built from
+/root/reference/src by oracle/ref_build/Makefile).  Run in the build container only; the fixtures are
+committed so the GPU box (where /root/reference does not exist) can check against them.
+
+    python tests/golden/make_golden.py            # all systems
+
+Per system the fixture holds, for every try of the reference's rejection loop: the sorted nucleon rows
+(x y z xL xR yL yR ncoll weight), the drand48 state before getBinaryCollision, the collision list
+(x y weight additional_weight i j), participant orders, and for accepted events the 49-column
+eccentricity row at 17 significant digits, sum(rho), the hot-spot region, and (first event only) the
+full TA1/TA2/rho/rho_binary/spectator grids.
+"""
+import os
+import subprocess
+import sys
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import refio  # noqa: E402
+
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+
+COMMON = dict(maxx=13, maxy=13, dx=0.1, dy=0.1, finalFactor=1, bmin=0, bmax=20, Npmin=2, Npmax=500,
+              shape_of_nucleons=2, collision_criterion=2, shape_of_entropy=2, cc_fluctuation_model=6)
+SYSTEMS = {
+    # name: (quark table kind, n accepted events, n events with full grids, parameters)
+    "pbpb2760_glb": ("zero", 8, 1, dict(which_mc_model=5, sub_model=1, Aproj=208, Atarg=208, ecm=2760, alpha=0.118,
+                                       cc_fluctuation_Gamma_theta=0.75, randomSeed=11)),
+    "auau200_glb_quarks": ("rand", 6, 1, dict(which_mc_model=5, sub_model=1, Aproj=197, Atarg=197, ecm=200, alpha=0.14,
+                                             cc_fluctuation_Gamma_theta=0.61, randomSeed=12)),
+    "ppb5020_glb_quarks": ("rand", 6, 1, dict(which_mc_model=5, sub_model=1, Aproj=1, Atarg=208, ecm=5020, alpha=0.118,
+                                             cc_fluctuation_Gamma_theta=0.75, randomSeed=13)),
+    "pbpb2760_sqrt_disk": ("zero", 4, 0, dict(which_mc_model=7, sub_model=1, Aproj=208, Atarg=208, ecm=2760,
+                                             collision_criterion=1, randomSeed=14)),
+    "pbpb2760_uli": ("zero", 3, 0, dict(which_mc_model=5, sub_model=2, Aproj=208, Atarg=208, ecm=2760, alpha=0.118,
+                                       randomSeed=15)),
+    "auau200_disk_nucleons": ("zero", 3, 0, dict(which_mc_model=5, sub_model=1, Aproj=197, Atarg=197, ecm=200, alpha=0.14,
+                                                 shape_of_nucleons=1, shape_of_entropy=1, collision_criterion=1,
+                                                 cc_fluctuation_model=0, randomSeed=16)),
+    "he3au200_glb": ("rand", 5, 0, dict(which_mc_model=5, sub_model=1, Aproj=3, Atarg=197, ecm=200, alpha=0.14,
+                                        cc_fluctuation_Gamma_theta=0.61, randomSeed=17)),
+    "cc200_glb": ("zero", 4, 0, dict(which_mc_model=5, sub_model=1, Aproj=12, Atarg=12, ecm=200, alpha=0.14,
+                                     cc_fluctuation_Gamma_theta=0.61, randomSeed=18)),
+    "uu193_deformed": ("zero", 3, 0, dict(which_mc_model=5, sub_model=1, Aproj=238, Atarg=238, ecm=193, alpha=0.14,
+                                          proj_deformed=1, targ_deformed=1, randomSeed=19)),
+    "pbpb2760_rotate": ("rand", 3, 1, dict(which_mc_model=5, sub_model=1, Aproj=208, Atarg=208, ecm=2760, alpha=0.118,
+                                           cc_fluctuation_Gamma_theta=0.75, randomSeed=20, bmax=12, dump_rotate=1)),
+}
+
+
+def run_system(name):
+    kind, nev, ngrid, par = SYSTEMS[name]
+    run = os.path.join(REFDIR, "run_" + kind)
+    for f in os.listdir(os.path.join(run, "data")):
+        os.remove(os.path.join(run, "data", f))
+    p = dict(COMMON); p.update(par)
+    p.update(dump_grids=1, dump_extra=1, dump_tries=1)
+    args = ["%s=%s" % kv for kv in p.items()]
+    binf = "/tmp/golden_%s.bin" % name
+    subprocess.check_call([os.path.join(REFDIR, "ref_dump"), binf, str(nev)] + args, cwd=run, stdout=subprocess.DEVNULL)
+    rec = refio.read_records(binf)
+    glob, tries = refio.group_tries(rec)
+    ncol = 53 if (p.get("proj_deformed") or p.get("targ_deformed")) else 49   # deformed rows carry 4 uninitialised extras (quirk Q9)
+    ecc = np.loadtxt(os.path.join(run, "data", "h_ecc_10.dat")).reshape(-1, ncol)[:, :49]
+    out = {"consts": glob["consts"], "params_keys": np.array(list(p.keys())), "params_vals": np.array([float(v) for v in p.values()]),
+           "quark_kind": np.array(kind), "ntries": np.array(len(tries)), "ecc_rows": ecc}
+    ia = 0
+    for it, t in enumerate(tries):
+        pre = "t%d/" % it
+        acc = int(t["hdr"][4])
+        for k in ("hdr", "proj", "targ", "proj_part", "targ_part", "coll"):
+            out[pre + k] = t[k]
+        if acc:
+            out[pre + "dndy"] = t["dndy"]; out[pre + "region"] = t["region"]; out[pre + "spectators"] = t["spectators"]
+            out[pre + "ecc_index"] = np.array(ia)
+            if ia < ngrid:
+                for k in ("TA1", "TA2", "rho", "rho_binary", "spec1", "spec2"):
+                    out[pre + k] = t[k]
+                for k in t:
+                    if k.startswith("rp") or k.startswith("rot"):
+                        if k.endswith("/TA1") or k.endswith("/TA2") or k.endswith("spec1") or k.endswith("spec2") or k.endswith("rho_binary"):
+                            continue        # keep the rotated fixtures small: rho + positions pin the sequence
+                        out[pre + k] = t[k]
+            ia += 1
+    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    np.savez_compressed(path, **out)
+    print("%-24s tries=%3d accepted=%d  %6.1f KB" % (name, len(tries), ia, os.path.getsize(path) / 1024))
+
+
+if __name__ == "__main__":
+    for n in (sys.argv[1:] or SYSTEMS):
+        run_system(n)
