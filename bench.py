@@ -1,0 +1,308 @@
+#!/usr/bin/env python3
+"""bench.py -- accepted events/sec of the superMC hot path (BASELINE.json metric).
+
+Workload (BASELINE.json configs[1], SURVEY.md 8(d) input 2): MC-Glauber Pb+Pb 2.76 TeV minimum-bias
+eccentricity scan, 261x261 grid (maxx=maxy=13, dx=dy=0.1), operation 9, orders 1..9, Gamma weights.
+A "step" is one pass of the hot path (sample -> collide -> deposit -> moments) over one batch of
+`--events-per-step` events per GPU; events are sharded across ranks by global event id (weak scaling,
+no data-path collective: only the per-event rows leave the GPU).
+
+    python bench.py --gpus 1 --steps K --warmup W            # this repo's CUDA path through the C ABI
+    python bench.py --impl reference ...                     # the reference's own CPU code on host cores
+
+value  : events / device time of the step (CUDA events on the library's stream; inputs = event ids only)
+e2e    : same metric through the public C-ABI call smc_run_events with HOST buffers, wall clock, the
+         host->device copy of the event ids and the device->host read of every result row included
+roofline: the dominant kernel against the FP64 pipe (this path is bound by the FP64
+         CUDA-core pipe, not by HBM or tensor cores), algorithmic FLOPs per event from 8(d).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(which_mc_model=5, sub_model=1, aproj=208, atarg=208, ecm=2760.0, alpha=0.118, cc_fluctuation_model=6,
+                cc_fluctuation_gamma_theta=0.75, maxx=13.0, maxy=13.0, dx=0.1, dy=0.1, bmin=0.0, bmax=20.0, npmin=2, npmax=500,
+                shape_of_nucleons=2, collision_criterion=2, shape_of_entropy=2, finalfactor=1.0, ecc_from_order=1, ecc_to_order=9)
+REF_ARGS = ["which_mc_model=5", "sub_model=1", "Aproj=208", "Atarg=208", "ecm=2760", "alpha=0.118", "cc_fluctuation_model=6",
+            "cc_fluctuation_Gamma_theta=0.75", "maxx=13", "maxy=13", "dx=0.1", "dy=0.1", "operation=9", "finalFactor=1",
+            "bmin=0", "bmax=20", "Npmin=2", "Npmax=500", "shape_of_nucleons=2", "collision_criterion=2", "shape_of_entropy=2",
+            "ecc_from_order=1", "ecc_to_order=9", "use_sd=1", "use_ed=1"]
+WORKLOAD_NAME = "MC-Glauber Pb+Pb 2.76 TeV min-bias eccentricity scan (operation 9), 261x261 grid, orders 1-9"
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True); self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_flops(ev, width, dx):
+    """F_dep = 2[Np n4^2 (rho_WN) + Nc n5^2 (rho_BC)] (operation 9 with MC-Glauber needs no
+    TA1/TA2, so that term is not claimed), F_mom = 200 per non-zero cell."""
+    import numpy as np
+    n5, n4 = 2 * 5 * width / dx, 8 * width / dx
+    npart = (ev["npart1"] + ev["npart2"]).astype(np.float64); nc = ev["ncoll"].astype(np.float64)
+    f_dep = 2.0 * (npart * n4 * n4 + nc * n5 * n5)
+    f_mom = 200.0 * ev["nonzero_cells"].astype(np.float64)
+    return float(f_dep.sum()), float(f_mom.sum())
+
+
+def ref_paths():
+    exe = os.path.join(ROOT, "oracle", "_ref", "superMC_ref.e")
+    run = os.path.join(ROOT, "oracle", "_ref", "run_zero")
+    return exe, run
+
+
+def run_reference_once(nproc, nev_each, seed0):
+    """`nproc` concurrent copies of the reference binary (its own 8-process mode,
+    CollectDataAccordingToSettings.py:110-115), separate working directories; returns wall seconds."""
+    exe, run = ref_paths()
+    dirs = []
+    for i in range(nproc):
+        d = tempfile.mkdtemp(prefix="smcref_")
+        os.makedirs(os.path.join(d, "data"))
+        for f in ("parameters.dat", "EOS", "tables"):
+            os.symlink(os.path.join(run, f), os.path.join(d, f))
+        dirs.append(d)
+    t0 = time.perf_counter()
+    procs = [subprocess.Popen([exe] + REF_ARGS + ["nev=%d" % nev_each, "randomSeed=%d" % (seed0 + i)], cwd=d,
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for i, d in enumerate(dirs)]
+    for p in procs:
+        p.wait()
+    dt = time.perf_counter() - t0
+    n_ok = 0
+    for d in dirs:
+        try:
+            with open(os.path.join(d, "data", "sn_ecc_eccp_10.dat")) as f:
+                n_ok += sum(1 for _ in f)
+        except OSError:
+            pass
+        subprocess.call(["rm", "-rf", d])
+    return dt, n_ok
+
+
+def cpu_baseline(cores, nev_each):
+    """bounded sample of the same workload on the host cores; start-up (EOS + QuarkPos load) subtracted
+    with a 1-event run as BASELINE.md section 3 prescribes."""
+    exe, _ = ref_paths()
+    if not os.path.exists(exe):
+        return None
+    t1, _ = run_reference_once(cores, 1, 77)
+    t, n = run_reference_once(cores, nev_each, 177)
+    loop = max(t - t1, 1e-3) if n > cores else t
+    return dict(value=(n - cores) / loop if n > cores else n / t, unit="events/s", cores=cores, kind="reference",
+                sample="%d concurrent process(es) x %d accepted events of the bench workload (sd+ed as in BASELINE.md), "
+                       "oracle/_ref/superMC_ref.e = unmodified reference sources, g++ -O3, GSL shim; 1-event start-up run subtracted" % (cores, nev_each),
+                wall_s=t, startup_s=t1)
+
+
+# ---------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--events-per-step", type=int, default=32768, help="events per GPU per step")
+    ap.add_argument("--batch", type=int, default=2048, help="events resident per launch wave")
+    ap.add_argument("--cpu-sample-events", type=int, default=150)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        exe, _ = ref_paths()
+        if not os.path.exists(exe):
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/superMC_ref.e is not built (needs /root/reference at build time)"}))
+            return 0
+        cores = max(1, min(os.cpu_count() or 1, 64))
+        nev_each = 24
+        t1, _ = run_reference_once(cores, 1, 5)
+        for w in range(min(a.warmup, 1)):
+            run_reference_once(cores, 2, 50 + w)
+        tot_t, tot_n = 0.0, 0
+        for s in range(a.steps):
+            t, n = run_reference_once(cores, nev_each, 1000 + 100 * s)
+            tot_t += max(t - t1, 1e-3); tot_n += max(n - cores, 0)
+        v = tot_n / tot_t
+        line = {"metric": "events/sec", "value": v, "unit": "events/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": 1e3 * tot_t / max(a.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "impl": "reference",
+                "config": {"workload": WORKLOAD_NAME, "events_per_step": cores * nev_each, "host_processes": cores},
+                "cpu_baseline": {"value": v, "unit": "events/s", "cores": cores, "kind": "reference",
+                                 "sample": "%d steps x %d processes x %d events, start-up run subtracted" % (a.steps, cores, nev_each)},
+                "e2e": {"value": v, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import numpy as np
+    import torch
+    import supermc_b200 as smc
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = smc.Context(smc.capi.default_params(max_batch=a.batch, randomseed=20261017, **WORKLOAD), device=local)
+    n = a.events_per_step
+    out = np.zeros(n, dtype=smc.capi.EVENT_OUT_DTYPE)
+
+    def barrier():
+        torch.cuda.synchronize(local)
+        if dist is not None:
+            dist.barrier()
+
+    step_id = [0]
+
+    def step():
+        first = (step_id[0] * world + rank) * n          # disjoint global event ids per (step, rank)
+        ctx.run_events(first, n, smc.RUN_MOMENTS, out=out)
+        step_id[0] += 1
+        return ctx.last_run_ms
+
+    for _ in range(a.warmup):
+        step()
+    ctx.set_profiling(True)
+    clocks = ClockSampler(local); clocks.start()
+    barrier()
+    l0 = ctx.launches
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    nz = []; f_dep = f_mom = 0.0
+    for _ in range(a.steps):
+        dev_ms += step()
+        fd, fm = algorithmic_flops(out, ctx.k.width, WORKLOAD["dx"]); f_dep += fd; f_mom += fm
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = ctx.launches - l0
+    ck = clocks.stop()
+    stage = ctx.stage_ms()
+    tm = torch.tensor([wall, dev_ms * 1e-3], dtype=torch.float64, device="cuda:%d" % local)
+    if dist is not None:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    wall_max, dev_max = float(tm[0]), float(tm[1])
+    total_events = n * a.steps * world
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    fp64_peak = ctx.fp64_peak_tflops()
+    dom = "moments" if stage["moments"] >= stage["deposit"] else "deposit"
+    dom_flops = f_mom if dom == "moments" else f_dep
+    achieved = dom_flops / (stage[dom] * 1e-3) / 1e12 if stage[dom] > 0 else 0.0
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    grid_bytes = 8.0 * ctx.G * n * a.steps      # the rho scratch grid is written once and read back per event
+    line = {
+        "metric": "events/sec", "value": total_events / dev_max, "unit": "events/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": 1e3 * dev_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD_NAME, "events_per_step_per_gpu": n, "batch": a.batch, "sharding": "event-id ranges per rank, no collective",
+                   "l2": "per-step working set (rho scratch %d MB + event records) exceeds the 126 MB L2" % int(8 * ctx.G * a.batch / 1e6)},
+        "e2e": {"value": total_events / wall_max, "unit": "events/s", "h2d_bytes_per_step": 12 * n, "d2h_bytes_per_step": int(out.itemsize) * n},
+        "gpu_launches": int(launches),
+        "clocks": ck,
+        "roofline": {"bound": "fp64", "kernel": dom + "_kernel", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                     "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
+                     "peak_source": "measured live: smc_measure_fp64_peak (8 independent DFMA chains/thread, all SMs); nominal B200 FP64 ~37-40 TFLOP/s",
+                     "algorithmic_flops_per_event": {"deposit": f_dep / (n * a.steps), "moments": f_mom / (n * a.steps)},
+                     "stage_ms_per_step": {k: v / a.steps for k, v in stage.items()},
+                     "hbm": {"achieved_gbs": 2 * grid_bytes / (dev_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak, "note": "rho scratch write+read; not the binding resource"}},
+    }
+    if not a.no_cpu_baseline:
+        cb = cpu_baseline(1, a.cpu_sample_events)
+        if cb is None:
+            # the unmodified reference binary is not on this box: time the oracle port instead
+            cb = port_baseline(a.cpu_sample_events)
+        line["cpu_baseline"] = cb
+    print(json.dumps(line))
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def port_baseline(nev):
+    """oracle port (scalar C restatement) timed on one core: sample+collide+deposit+moments per event."""
+    import numpy as np
+    from oracle import port
+    cfg = port.make_cfg(ecm=2760.0, alpha=0.118)
+    nA = port.nucleus(208, cfg.width); nB = port.nucleus(208, cfg.width)
+    st = port.Stream48(seed=5)
+    t0 = time.perf_counter(); done = 0
+    while done < nev:
+        b = np.sqrt(400.0 * st.next())
+        p, _ = port.populate(nA, b / 2, 0.0, stream=st); t, _ = port.populate(nB, -b / 2, 0.0, stream=st)
+        r = port.collide(cfg, p, t, stream=st)
+        if r["ncoll"] == 0:
+            continue
+        ia = np.nonzero(r["ncollA"])[0]; ib = np.nonzero(r["ncollB"])[0]
+        p8 = np.zeros((len(ia), 8)); p8[:, :2] = p[ia, :2]; p8[:, 2:6] = p[ia, 3:7]; p8[:, 6] = 1
+        t8 = np.zeros((len(ib), 8)); t8[:, :2] = t[ib, :2]; t8[:, 2:6] = t[ib, 3:7]; t8[:, 6] = 1
+        c8 = np.zeros((r["ncoll"], 8)); c8[:, 0] = (p[r["pairs"][:, 0], 0] + t[r["pairs"][:, 1], 0]) / 2; c8[:, 1] = (p[r["pairs"][:, 0], 1] + t[r["pairs"][:, 1], 1]) / 2; c8[:, 6] = 1
+        rho, _ = port.density(cfg, p8, t8, c8)
+        boxes = np.concatenate([p8[:, 2:6], t8[:, 2:6], np.zeros((1, 4))])
+        port.eccentricities(cfg, rho, boxes); port.eccentricities(cfg, rho, boxes)     # sd + ed
+        done += 1
+    dt = time.perf_counter() - t0
+    return dict(value=nev / dt, unit="events/s", cores=1, kind="port", sample="%d accepted events, oracle/smc_oracle.c, one core" % nev)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

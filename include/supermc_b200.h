@@ -84,6 +84,8 @@ typedef struct smc_event_out {
   double xc, yc;                 /* centre of mass of the profile    MakeDensity.cpp:2273-2282 */
   double mom[9][5];              /* n=1..9: Re eps_n, Im eps_n, Re eps'_n, Im eps'_n, <r^n>  :2389-2430 */
   double rn0;                    /* <r^0> (always 1; kept so rn[0..9] is complete) */
+  int nonzero_cells;             /* cells with rho != 0 (work measure for the roofline; not a reference output) */
+  int reserved;
 } smc_event_out;
 
 /* Parity / replay input: nuclei supplied by the caller instead of being sampled
@@ -176,7 +178,10 @@ int  smc_avg_get(smc_ctx* ctx, int order, int variant, int quantity, int branch,
 /* scripts/centrality_cut_h5.py:36-110: sort n events descending by key; perm receives the order */
 int  smc_centrality_sort(smc_ctx* ctx, const double* key, int64_t n, int64_t* perm);
 
-/* diagnostics: kernels launched by this context so far, device time of the last run [ms] */
+/* diagnostics: kernels launched by this context so far, device time of the last run [ms];
+ * with profiling on, CUDA-event time per stage {sample+collide, deposit, combine, moments} accumulates */
+int     smc_set_profiling(smc_ctx* ctx, int on);
+int     smc_get_stage_ms(const smc_ctx* ctx, double* ms4);
 int64_t smc_kernel_launches(const smc_ctx* ctx);
 double  smc_last_run_ms(const smc_ctx* ctx);
 /* FP64 FMA throughput micro-benchmark on the context's device [TFLOP/s]; the roofline denominator

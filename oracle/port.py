@@ -58,6 +58,8 @@ def lib():
         L.smc_o_populate.restype = C.c_long
         L.smc_o_populate_table.restype = C.c_long
         L.smc_o_uniform_rand48.restype = C.c_double
+        L.smc_o_uniform_philox.restype = C.c_double
+        L.smc_o_uniform_philox.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         _LIB = L
     return _LIB
 
@@ -106,6 +108,22 @@ class Stream48:
 
     def args(self):
         return C.cast(lib().smc_o_uniform_rand48, C.c_void_p), C.byref(self.s)
+
+
+class PhiloxStream(C.Structure):
+    _fields_ = [("seed_lo", C.c_uint32), ("seed_hi", C.c_uint32), ("event", C.c_uint64), ("tr", C.c_uint32), ("nuc", C.c_int)]
+
+
+class StreamPhilox:
+    """the CUDA path's counter-based event stream, restated in the oracle (uniform source for the port)"""
+    def __init__(self, seed, event, tr, nuc):
+        self.s = PhiloxStream(seed & 0xffffffff, (seed >> 32) & 0xffffffff, event, tr, nuc)
+
+    def u(self, kind, cand, slot):
+        return lib().smc_o_uniform_philox(C.byref(self.s), kind, cand, slot)
+
+    def args(self):
+        return C.cast(lib().smc_o_uniform_philox, C.c_void_p), C.byref(self.s)
 
 
 def philox(ctr, key):

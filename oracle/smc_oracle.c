@@ -97,6 +97,17 @@ void smc_o_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t 
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+double smc_o_uniform_philox(void* st, int kind, int cand, int slot) {
+  const smc_o_philox_stream* s = (const smc_o_philox_stream*)st;
+  uint32_t ctr[4] = {(uint32_t)s->event, (uint32_t)(s->event >> 32),
+                     (s->tr << 8) | ((uint32_t)kind << 1) | (uint32_t)s->nuc, ((uint32_t)cand << 12) | ((uint32_t)slot >> 1)};
+  uint32_t key[2] = {s->seed_lo, s->seed_hi}, o[4];
+  smc_o_philox4x32_10(ctr, key, o);
+  uint32_t a = o[2 * (slot & 1)], b = o[2 * (slot & 1) + 1];
+  uint64_t m = ((uint64_t)a << 21) | ((uint64_t)b >> 11);
+  return (double)m * (1.0 / 9007199254740992.0);
+}
+
 /* ======================================================================================
  * Box2D semantics (Box2D.cpp:14-41, Box2D.h:49-63) on a 6-double box {xL,xR,yL,yR,xC,yC}
  * ====================================================================================== */

@@ -49,6 +49,11 @@ double smc_o_drand48(smc_o_rand48* s);
 /* Philox4x32-10 (Salmon et al., SC'11) -- the counter-based stream of the CUDA path */
 void smc_o_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 
+/* The event streams of the CUDA path, restated independently from the layout documented in
+ * supermc_b200/csrc/smc_philox.h: key=(seed_lo,seed_hi), ctr=(event lo, event hi,
+ * try<<8|kind<<1|nucleus, cand<<12|slot>>1), component slot&1, 53-bit mantissa */
+typedef struct { uint32_t seed_lo, seed_hi; uint64_t event; uint32_t tr; int nuc; } smc_o_philox_stream;
+double smc_o_uniform_philox(void* st, int kind, int cand, int slot);
 /* A uniform source: kind/cand/slot address a counter-based stream; a sequential stream ignores them */
 typedef double (*smc_o_uniform_fn)(void* st, int kind, int cand, int slot);
 double smc_o_uniform_rand48(void* st, int kind, int cand, int slot);

@@ -38,7 +38,7 @@ class EventOut(C.Structure):
     _fields_ = [("b", C.c_double), ("npart1", C.c_int), ("npart2", C.c_int), ("ncoll", C.c_int),
                 ("tries", C.c_int), ("nspec", C.c_int), ("status", C.c_int), ("dsdy", C.c_double),
                 ("total", C.c_double), ("xc", C.c_double), ("yc", C.c_double), ("mom", (C.c_double * 5) * 9),
-                ("rn0", C.c_double)]
+                ("rn0", C.c_double), ("nonzero_cells", C.c_int), ("reserved", C.c_int)]
 
 
 class EventIn(C.Structure):
@@ -48,7 +48,7 @@ class EventIn(C.Structure):
 
 EVENT_OUT_DTYPE = np.dtype([("b", "f8"), ("npart1", "i4"), ("npart2", "i4"), ("ncoll", "i4"), ("tries", "i4"),
                             ("nspec", "i4"), ("status", "i4"), ("dsdy", "f8"), ("total", "f8"), ("xc", "f8"),
-                            ("yc", "f8"), ("mom", "f8", (9, 5)), ("rn0", "f8")], align=True)
+                            ("yc", "f8"), ("mom", "f8", (9, 5)), ("rn0", "f8"), ("nonzero_cells", "i4"), ("reserved", "i4")], align=True)
 
 
 class SmcError(RuntimeError):
@@ -207,6 +207,14 @@ class Context:
         k = np.ascontiguousarray(key, dtype=np.float64); perm = np.zeros(len(k), dtype=np.int64)
         self._ck(lib().smc_centrality_sort(self.h, k.ctypes.data, len(k), perm.ctypes.data))
         return perm
+
+    def set_profiling(self, on=True):
+        self._ck(lib().smc_set_profiling(self.h, int(bool(on))))
+
+    def stage_ms(self):
+        a = (C.c_double * 4)()
+        self._ck(lib().smc_get_stage_ms(self.h, a))
+        return dict(sample_collide=a[0], deposit=a[1], combine=a[2], moments=a[3])
 
     @property
     def launches(self):

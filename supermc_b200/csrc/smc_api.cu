@@ -34,6 +34,7 @@ struct smc_ctx {
   int* h_hdr_i; double* h_hdr_d; double* h_mom; uint64_t* h_evid; int* h_try; double* h_nuc;
   std::string err; int64_t launches; double last_ms; int last_n; unsigned last_flags;
   // averaged profiles (operation 3)
+  int profile; double stage_ms[8]; cudaEvent_t pev[8];
   double* d_avg; int64_t avg_doubles; int64_t avg_count; int avg_from, avg_to, avg_rp, avg_ed;
 };
 
@@ -75,7 +76,8 @@ extern "C" int smc_create(const smc_params* p, int device, smc_ctx** out) {
   ctx->p = *p; ctx->device = device; ctx->launches = 0; ctx->last_ms = 0; ctx->last_n = 0; ctx->last_flags = 0;
   ctx->d_grids = nullptr; ctx->grids_bytes = 0; ctx->d_pair_u = nullptr; ctx->pair_u_bytes = 0; ctx->d_coll_w = nullptr; ctx->coll_w_bytes = 0;
   ctx->d_quark = nullptr; ctx->d_cfgtab[0] = ctx->d_cfgtab[1] = nullptr; ctx->d_kln = nullptr; ctx->d_avg = nullptr; ctx->avg_doubles = 0; ctx->avg_count = 0;
-  ctx->stream = nullptr; ctx->ev0 = ctx->ev1 = nullptr;
+  ctx->stream = nullptr; ctx->ev0 = ctx->ev1 = nullptr; ctx->profile = 0;
+  for (int i = 0; i < 8; i++) { ctx->stage_ms[i] = 0; ctx->pev[i] = nullptr; }
   *out = ctx;      // returned even on failure so the caller can read smc_last_error
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device >= ndev) FAIL(SMC_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
@@ -83,6 +85,7 @@ extern "C" int smc_create(const smc_params* p, int device, smc_ctx** out) {
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
   if (prop.major < 9) FAIL(SMC_ERR_CUDA, "device is not sm_100-class");
   CK(cudaStreamCreate(&ctx->stream)); CK(cudaEventCreate(&ctx->ev0)); CK(cudaEventCreate(&ctx->ev1));
+  for (int i = 0; i < 8; i++) CK(cudaEventCreate(&ctx->pev[i]));
 
   // ---- parameter checks (the reference prints and exits) ----
   if (p->which_mc_model != 1 && p->which_mc_model != 5 && p->which_mc_model != 7) FAIL(SMC_ERR_PARAM, "which_mc_model must be 1, 5 or 7");
@@ -179,6 +182,7 @@ extern "C" void smc_destroy(smc_ctx* ctx) {
   if (ctx->h_evid) cudaFreeHost(ctx->h_evid);
   if (ctx->h_try) cudaFreeHost(ctx->h_try);
   if (ctx->h_nuc) cudaFreeHost(ctx->h_nuc);
+  for (int i = 0; i < 8; i++) if (ctx->pev[i]) cudaEventDestroy(ctx->pev[i]);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -187,6 +191,8 @@ extern "C" void smc_destroy(smc_ctx* ctx) {
 
 extern "C" const char* smc_last_error(const smc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 extern "C" int smc_get_constants(const smc_ctx* ctx, smc_constants* c) { if (!ctx || !c) return SMC_ERR_PARAM; *c = ctx->k; return SMC_OK; }
+extern "C" int smc_set_profiling(smc_ctx* ctx, int on) { if (!ctx) return SMC_ERR_PARAM; ctx->profile = on; for (int i = 0; i < 8; i++) ctx->stage_ms[i] = 0; return SMC_OK; }
+extern "C" int smc_get_stage_ms(const smc_ctx* ctx, double* ms4) { if (!ctx || !ms4) return SMC_ERR_PARAM; for (int i = 0; i < 4; i++) ms4[i] = ctx->stage_ms[i]; return SMC_OK; }
 extern "C" int64_t smc_kernel_launches(const smc_ctx* ctx) { return ctx ? ctx->launches : 0; }
 extern "C" double smc_last_run_ms(const smc_ctx* ctx) { return ctx ? ctx->last_ms : 0.0; }
 
@@ -293,10 +299,20 @@ static int plan_kinds(smc_ctx* ctx, unsigned flags, int* kinds, int* nk_dep) {
 static int run_grid_stages(smc_ctx* ctx, int m, const int* kinds, int nd) {
   const smc::DevCfg& c = ctx->cfg;
   if (c.which_mc_model == 1 && !ctx->st.kln_table) FAIL(SMC_ERR_STATE, "MC-KLN density requires smc_build_kln_table / smc_set_kln_table first (MCnucl.cpp:636-640)");
+  if (ctx->profile) CK(cudaEventRecord(ctx->pev[1], ctx->stream));
   CK(smc::launch_deposit(c, ctx->st, kinds, nd, m, ctx->stream)); ctx->launches++;
+  if (ctx->profile) CK(cudaEventRecord(ctx->pev[2], ctx->stream));
   if (c.which_mc_model != 5) { CK(smc::launch_combine(c, ctx->st, m, ctx->stream)); ctx->launches++; }
+  if (ctx->profile) CK(cudaEventRecord(ctx->pev[3], ctx->stream));
   CK(smc::launch_moments(c, ctx->st, m, ctx->stream)); ctx->launches++;
+  if (ctx->profile) CK(cudaEventRecord(ctx->pev[4], ctx->stream));
   return SMC_OK;
+}
+
+// per-stage device time of the batch that was just synchronised (profiling mode only)
+static void collect_stage_ms(smc_ctx* ctx) {
+  if (!ctx->profile) return;
+  for (int i = 0; i < 4; i++) { float ms = 0; if (cudaEventElapsedTime(&ms, ctx->pev[i], ctx->pev[i + 1]) == cudaSuccess) ctx->stage_ms[i] += ms; }
 }
 
 static void fill_out(smc_ctx* ctx, int m, smc_event_out* out) {
@@ -307,7 +323,7 @@ static void fill_out(smc_ctx* ctx, int m, smc_event_out* out) {
     o.npart1 = hi[smc::H_NP1]; o.npart2 = hi[smc::H_NP2]; o.ncoll = hi[smc::H_NCOLL]; o.tries = hi[smc::H_TRIES];
     o.nspec = hi[smc::H_NSPEC1] + hi[smc::H_NSPEC2]; o.status = hi[smc::H_STATUS];
     std::memcpy(o.mom, mo, 45 * sizeof(double));
-    o.rn0 = mo[45]; o.total = mo[46]; o.xc = mo[47]; o.yc = mo[48]; o.dsdy = mo[49];
+    o.rn0 = mo[45]; o.total = mo[46]; o.xc = mo[47]; o.yc = mo[48]; o.dsdy = mo[49]; o.nonzero_cells = (int)mo[50];
   }
 }
 
@@ -333,9 +349,11 @@ extern "C" int smc_run_events(smc_ctx* ctx, uint64_t first_event_id, int n, unsi
     for (int e = 0; e < m; e++) { ctx->h_evid[e] = first_event_id + (uint64_t)off + e; ctx->h_try[e] = 0; }
     CK(cudaMemcpyAsync((void*)ctx->st.event_id, ctx->h_evid, (size_t)m * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->st.try_start, ctx->h_try, (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->profile) CK(cudaEventRecord(ctx->pev[0], ctx->stream));
     CK(smc::launch_sample_collide(c, ctx->st, m, false, ctx->stream)); ctx->launches++;
     if ((rc = run_grid_stages(ctx, m, kinds, nd))) return rc;
     if ((rc = fetch_results(ctx, m))) return rc;
+    collect_stage_ms(ctx);
     // dS/dy window (MakeDensity.cpp:2173-2181): a failing event goes back to the rejection loop
     if (ctx->p.cutdsdy == 1) {
       for (int iter = 0; iter < 100000; iter++) {
@@ -410,9 +428,11 @@ extern "C" int smc_run_from_positions(smc_ctx* ctx, int n, const smc_event_in* i
     CK(cudaMemcpyAsync((void*)ctx->st.event_id, ctx->h_evid, (size_t)m * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->st.try_start, ctx->h_try, (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     ctx->st.pair_u = any_u ? ctx->d_pair_u : nullptr; ctx->st.coll_w = any_w ? ctx->d_coll_w : nullptr;
+    if (ctx->profile) CK(cudaEventRecord(ctx->pev[0], ctx->stream));
     CK(smc::launch_sample_collide(c, ctx->st, m, true, ctx->stream)); ctx->launches++;
     if ((rc = run_grid_stages(ctx, m, kinds, nd))) return rc;
     if ((rc = fetch_results(ctx, m))) return rc;
+    collect_stage_ms(ctx);
     fill_out(ctx, m, out + off);
     ctx->last_n = m;
   }

@@ -20,8 +20,6 @@
 namespace smc {
 
 enum { GK_RHO = 0, GK_TA1 = 1, GK_TA2 = 2, GK_RHO_BINARY = 3, GK_SPEC_A = 4, GK_SPEC_B = 5, GK_RHOA = 6, GK_RHOB = 7 };
-#define DEP_ROWS 32
-#define DEP_CH 32
 
 struct Src { double x, y, W, thr; int iL, iR, jL, jR; int flat; };
 
@@ -94,32 +92,44 @@ __device__ void load_src(const DevCfg& c, const Store& st, int e, const int* hi,
 
 struct KindList { int n; int kind[8]; };
 
-#define DEP_MAXWARPS 12
-__global__ void __launch_bounds__(DEP_MAXWARPS * 32) deposit_kernel(DevCfg c, Store st, KindList kl, int nev, int nbands) {
-  extern __shared__ double smem_d[];
+// Deposit geometry: a CTA owns a band of DEP_BAND rows; warp (wr, stripe) keeps DEP_WROWS rows x 32
+// columns of it in registers.  Sources are processed in chunks of DEP_CH whose factor tables live in
+// shared memory:  xtab[r][t] = (W*exp(-dx^2/2w^2), dx^2)  and  ytab[t][c] = (exp(-dy^2/2w^2), dy^2).
+#define DEP_BAND 32
+#define DEP_WROWS 16
+#define DEP_CH 64
+#define DEP_PART 8
+#define DEP_MAXSTRIPES 10
+
+struct DepSmem {
+  double2* xtab;      // [DEP_BAND][DEP_CH]
+  double2* ytab;      // [DEP_CH][CS]
+  double* sx; double* sy; double* sW; double* sthr;   // [DEP_CH] chunk descriptors
+  int* siL; int* siR; int* sjL; int* sjR; int* sflat;  // [DEP_CH]
+  int* wtot;          // [32]
+  unsigned short* act;
+};
+
+__global__ void __launch_bounds__(2 * DEP_MAXSTRIPES * 32, 1) deposit_kernel(DevCfg c, Store st, KindList kl, int nev, int nbands, int CS) {
+  extern __shared__ double2 smem_d2[];
   const int e = blockIdx.x, band = blockIdx.y % nbands, sgroup = blockIdx.y / nbands, kind = kl.kind[blockIdx.z];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nwarps = nthreads >> 5;
-  const int stripe = sgroup * (nthreads >> 5) + warp;
+  const int nstr = nwarps >> 1;                       // stripes handled by this CTA
+  const int wr = warp / nstr, stripe = sgroup * nstr + (warp % nstr);
   const int* hi = st.hdr_i + (size_t)e * HDR_I;
   const int slot = st.kind_slot[kind];
   double* grid = st.grids + ((size_t)e * st.nkinds + slot) * (size_t)c.Maxx * c.Maxy;
-  const int r0 = band * DEP_ROWS;
+  const int r0 = band * DEP_BAND, rw0 = r0 + wr * DEP_WROWS;
   const int j = stripe * 32 + lane;
-  const int RS = DEP_ROWS + 2, CS = c.wmax + (c.wmax & 1);      // padded strides (doubles)
-  // shared layout
-  double* gxw = smem_d;                         // [CH][RS]
-  double* dx2 = gxw + DEP_CH * RS;              // [CH][RS]
-  double* gy = dx2 + DEP_CH * RS;               // [CH][CS]
-  double* dy2 = gy + DEP_CH * CS;               // [CH][CS]
-  double* thr = dy2 + DEP_CH * CS;              // [CH]
-  int* win = (int*)(thr + DEP_CH);              // [CH][4] rL rR jL jR
-  int* wtot = win + DEP_CH * 4;                 // [32]
-  int* nact_p = wtot + 32;                      // [1]
-  unsigned short* act = (unsigned short*)(nact_p + 4);   // [nsrc]
+  DepSmem sm;
+  sm.xtab = smem_d2; sm.ytab = sm.xtab + DEP_BAND * DEP_CH;
+  sm.sx = (double*)(sm.ytab + (size_t)DEP_CH * CS); sm.sy = sm.sx + DEP_CH; sm.sW = sm.sy + DEP_CH; sm.sthr = sm.sW + DEP_CH;
+  sm.siL = (int*)(sm.sthr + DEP_CH); sm.siR = sm.siL + DEP_CH; sm.sjL = sm.siR + DEP_CH; sm.sjR = sm.sjL + DEP_CH; sm.sflat = sm.sjR + DEP_CH;
+  sm.wtot = sm.sflat + DEP_CH; sm.act = (unsigned short*)(sm.wtot + 32);
 
-  double acc[DEP_ROWS];
+  double acc[DEP_WROWS];
 #pragma unroll
-  for (int r = 0; r < DEP_ROWS; r++) acc[r] = 0.0;
+  for (int r = 0; r < DEP_WROWS; r++) acc[r] = 0.0;
 
   const int status = hi[H_STATUS];
   const int nsrc = (status == 0 || status == 4) ? src_count(c, hi, kind) : 0;
@@ -128,71 +138,92 @@ __global__ void __launch_bounds__(DEP_MAXWARPS * 32) deposit_kernel(DevCfg c, St
   for (int base = 0; base < nsrc; base += nthreads) {
     const int k = base + tid;
     bool on = false;
-    if (k < nsrc) { Src s; load_src(c, st, e, hi, kind, k, s); on = (s.iL < s.iR) && (s.jL < s.jR) && (s.iL < r0 + DEP_ROWS) && (s.iR > r0); }
+    if (k < nsrc) { Src s; load_src(c, st, e, hi, kind, k, s); on = (s.iL < s.iR) && (s.jL < s.jR) && (s.iL < r0 + DEP_BAND) && (s.iR > r0); }
     const unsigned m = __ballot_sync(0xffffffffu, on);
-    if (lane == 0) wtot[warp] = __popc(m);
+    if (lane == 0) sm.wtot[warp] = __popc(m);
     __syncthreads();
     int off = nact;
-    for (int w2 = 0; w2 < warp; w2++) off += wtot[w2];
-    if (on) act[off + __popc(m & ((1u << lane) - 1u))] = (unsigned short)k;
-    for (int w2 = 0; w2 < nwarps; w2++) nact += wtot[w2];
+    for (int w2 = 0; w2 < warp; w2++) off += sm.wtot[w2];
+    if (on) sm.act[off + __popc(m & ((1u << lane) - 1u))] = (unsigned short)k;
+    for (int w2 = 0; w2 < nwarps; w2++) nact += sm.wtot[w2];
     __syncthreads();
   }
-  // ---- chunks of DEP_CH sources ----
+  const int nxp = DEP_BAND / DEP_PART, nyp = (CS + DEP_PART - 1) / DEP_PART;
   for (int cb = 0; cb < nact; cb += DEP_CH) {
     const int nch = min(DEP_CH, nact - cb);
-    if (tid < 3 * DEP_CH) {
-      const int t = tid % DEP_CH, part = tid / DEP_CH;
-      if (t < nch) {
-        Src s; load_src(c, st, e, hi, kind, act[cb + t], s);
-        if (part == 0) {
-          const int rL = max(s.iL - r0, 0), rR = min(s.iR - r0, DEP_ROWS);
-          win[t * 4 + 0] = rL; win[t * 4 + 1] = rR; win[t * 4 + 2] = s.jL; win[t * 4 + 3] = s.jR; thr[t] = s.thr;
-          double g = 0, q = 0;
-          for (int r = rL; r < rR; r++) {
-            const double d = __dadd_rn(s.x, -xg_of(c, r0 + r));
+    // ---- chunk descriptors ----
+    if (tid < nch) {
+      Src s; load_src(c, st, e, hi, kind, sm.act[cb + tid], s);
+      sm.sx[tid] = s.x; sm.sy[tid] = s.y; sm.sW[tid] = s.W; sm.sthr[tid] = s.thr;
+      sm.siL[tid] = s.iL; sm.siR[tid] = s.iR; sm.sjL[tid] = s.jL; sm.sjR[tid] = s.jR; sm.sflat[tid] = s.flat;
+    }
+    __syncthreads();
+    // ---- factor tables: one (source, 8-entry part) per thread step; 2 exps start a two-multiply recurrence ----
+    for (int wk = tid; wk < (nxp + nyp) * DEP_CH; wk += nthreads) {
+      const int t = wk % DEP_CH, part = wk / DEP_CH;
+      if (t >= nch) continue;
+      const int flat = sm.sflat[t];
+      if (part < nxp) {
+        const double x = sm.sx[t], W = sm.sW[t];
+        const int iL = sm.siL[t], iR = sm.siR[t];
+        double g = 0, q = 0; bool started = false;
+#pragma unroll
+        for (int k = 0; k < DEP_PART; k++) {
+          const int r = part * DEP_PART + k, i = r0 + r;
+          double2 v = make_double2(0.0, 1e300);
+          if (i >= iL && i < iR) {
+            const double d = __dadd_rn(x, -xg_of(c, i));
             const double d2 = __dmul_rn(d, d);
-            dx2[t * RS + r] = d2;
-            if (s.flat) gxw[t * RS + r] = s.W;
+            if (flat) v.x = W;
             else {
-              if (r == rL) { g = s.W * exp(-d2 * c.inv2w2); q = exp((2.0 * d * c.dx - c.dx * c.dx) * c.inv2w2); }
-              gxw[t * RS + r] = g;
-              g *= q; q *= c.recx;
+              if (!started) { g = W * exp(-d2 * c.inv2w2); q = exp((2.0 * d * c.dx - c.dx * c.dx) * c.inv2w2); started = true; }
+              v.x = g; g *= q; q *= c.recx;
             }
+            v.y = d2;
           }
-        } else {
-          const int ncol = s.jR - s.jL, half = (ncol + 1) >> 1;
-          const int c0 = (part == 1) ? 0 : half, c1 = (part == 1) ? half : ncol;
-          double g = 0, q = 0;
-          for (int cc = c0; cc < c1; cc++) {
-            const double d = __dadd_rn(s.y, -yg_of(c, s.jL + cc));
+          sm.xtab[r * DEP_CH + t] = v;
+        }
+      } else {
+        const int p = part - nxp;
+        const double y = sm.sy[t];
+        const int jL = sm.sjL[t], ncol = sm.sjR[t] - jL;
+        double g = 0, q = 0;
+#pragma unroll
+        for (int k = 0; k < DEP_PART; k++) {
+          const int cc = p * DEP_PART + k;
+          if (cc < ncol && cc < CS) {
+            const double d = __dadd_rn(y, -yg_of(c, jL + cc));
             const double d2 = __dmul_rn(d, d);
-            dy2[t * CS + cc] = d2;
-            if (s.flat) gy[t * CS + cc] = 1.0;
-            else {
-              if (cc == c0) { g = exp(-d2 * c.inv2w2); q = exp((2.0 * d * c.dy - c.dy * c.dy) * c.inv2w2); }
-              gy[t * CS + cc] = g;
-              g *= q; q *= c.recy;
+            double2 v = make_double2(1.0, d2);
+            if (!flat) {
+              if (k == 0) { g = exp(-d2 * c.inv2w2); q = exp((2.0 * d * c.dy - c.dy * c.dy) * c.inv2w2); }
+              v.x = g; g *= q; q *= c.recy;
             }
+            sm.ytab[(size_t)t * CS + cc] = v;
           }
         }
       }
     }
     __syncthreads();
-    for (int t = 0; t < nch; t++) {
-      const int jL = win[t * 4 + 2], jR = win[t * 4 + 3];
-      if (jR <= stripe * 32 || jL >= stripe * 32 + 32) continue;      // stripe not touched (warp-uniform)
-      const int rL = win[t * 4 + 0], rR = win[t * 4 + 1];
-      const bool inw = (j >= jL) && (j < jR);
-      const double gyv = inw ? gy[t * CS + (j - jL)] : 0.0;
-      const double dy2v = inw ? dy2[t * CS + (j - jL)] : 1e300;
-      const double th = thr[t];
-      const double* gx_t = gxw + t * RS; const double* dx_t = dx2 + t * RS;
+    // ---- accumulate: every warp walks the chunk, 32 sources per ballot ----
+    for (int tb = 0; tb < nch; tb += 32) {
+      const int tt = tb + lane;
+      bool hit = false;
+      if (tt < nch) hit = (sm.sjR[tt] > stripe * 32) && (sm.sjL[tt] < stripe * 32 + 32) && (sm.siR[tt] > rw0) && (sm.siL[tt] < rw0 + DEP_WROWS);
+      unsigned m = __ballot_sync(0xffffffffu, hit);
+      while (m) {
+        const int t = tb + __ffs(m) - 1; m &= m - 1;
+        const int jL = sm.sjL[t], jR = sm.sjR[t];
+        const bool inw = (j >= jL) && (j < jR);
+        double2 yv = make_double2(0.0, 1e300);
+        if (inw) yv = sm.ytab[(size_t)t * CS + (j - jL)];
+        const double th = sm.sthr[t];
+        const double2* xt = sm.xtab + (wr * DEP_WROWS) * DEP_CH + t;
 #pragma unroll
-      for (int r = 0; r < DEP_ROWS; r++) {
-        if (r >= rL && r < rR) {
-          const double dc = __dadd_rn(dx_t[r], dy2v);                  // (x-xg)^2 + (y-yg)^2, reference rounding
-          if (dc <= th) acc[r] = fma(gx_t[r], gyv, acc[r]);
+        for (int r = 0; r < DEP_WROWS; r++) {
+          const double2 xv = xt[r * DEP_CH];
+          const double dc = __dadd_rn(xv.y, yv.y);                      // (x-xg)^2 + (y-yg)^2, reference rounding
+          if (dc <= th) acc[r] = fma(xv.x, yv.x, acc[r]);
         }
       }
     }
@@ -200,14 +231,16 @@ __global__ void __launch_bounds__(DEP_MAXWARPS * 32) deposit_kernel(DevCfg c, St
   }
   if (j < c.Maxy) {
 #pragma unroll
-    for (int r = 0; r < DEP_ROWS; r++) if (r0 + r < c.Maxx) grid[(size_t)(r0 + r) * c.Maxy + j] = acc[r];
+    for (int r = 0; r < DEP_WROWS; r++) if (rw0 + r < c.Maxx) grid[(size_t)(rw0 + r) * c.Maxy + j] = acc[r];
   }
 }
 
+static int dep_cs(const DevCfg& c) { int cs = c.wmax; while ((cs & 7) != 1) cs++; return cs; }
+
 size_t deposit_smem_bytes(const DevCfg& c, int nsrc_max) {
-  const int RS = DEP_ROWS + 2, CS = c.wmax + (c.wmax & 1);
-  size_t b = (size_t)(2 * DEP_CH * RS + 2 * DEP_CH * CS + DEP_CH) * sizeof(double);
-  b += (size_t)(DEP_CH * 4 + 32 + 4) * sizeof(int);
+  const int CS = dep_cs(c);
+  size_t b = (size_t)(DEP_BAND * DEP_CH + (size_t)DEP_CH * CS) * sizeof(double2);
+  b += (size_t)4 * DEP_CH * sizeof(double) + (size_t)(5 * DEP_CH + 32) * sizeof(int);
   b += (size_t)(nsrc_max + 8) * sizeof(unsigned short);
   return (b + 15) & ~(size_t)15;
 }
@@ -215,14 +248,14 @@ size_t deposit_smem_bytes(const DevCfg& c, int nsrc_max) {
 cudaError_t launch_deposit(const DevCfg& c, const Store& st, const int* kinds, int nk, int nev, cudaStream_t s) {
   KindList kl; kl.n = nk; for (int i = 0; i < nk; i++) kl.kind[i] = kinds[i];
   const int nstripes = (c.Maxy + 31) / 32;
-  const int ngroups = (nstripes + DEP_MAXWARPS - 1) / DEP_MAXWARPS;
-  const int nwarps = (nstripes + ngroups - 1) / ngroups;
-  const int threads = max(nwarps, 3) * 32;
+  const int ngroups = (nstripes + DEP_MAXSTRIPES - 1) / DEP_MAXSTRIPES;
+  const int nstr = (nstripes + ngroups - 1) / ngroups;
+  const int threads = 2 * max(nstr, 2) * 32;
   const size_t smem = deposit_smem_bytes(c, 2 * c.Amax + c.ncoll_cap);
   cudaFuncSetAttribute(deposit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  const int nbands = (c.Maxx + DEP_ROWS - 1) / DEP_ROWS;
+  const int nbands = (c.Maxx + DEP_BAND - 1) / DEP_BAND;
   dim3 g(nev, nbands * ngroups, nk);
-  deposit_kernel<<<g, threads, smem, s>>>(c, st, kl, nev, nbands);
+  deposit_kernel<<<g, threads, smem, s>>>(c, st, kl, nev, nbands, dep_cs(c));
   return cudaGetLastError();
 }
 
@@ -355,13 +388,14 @@ __global__ void __launch_bounds__(MOM_THREADS, 1) moments_kernel(DevCfg c, Store
   const double total = block_sum(s0, red, tid);
   const double xc = block_sum(sx, red, tid) / total, yc = block_sum(sy, red, tid) / total;
   // ---- pass 2: <r^n>, eps_n, eps'_n (MakeDensity.cpp:2285-2298, 2389-2430) ----
-  double rn[10], mr[10], mi[10], pr[10], pi[10], npw[10], nrm = 0;
+  double rn[10], mr[10], mi[10], pr[10], pi[10], npw[10], nrm = 0, nnz = 0;
 #pragma unroll
   for (int n = 0; n < 10; n++) { rn[n] = 0; mr[n] = 0; mi[n] = 0; pr[n] = 0; pi[n] = 0; npw[n] = 0; }
   for (int k = tid; k < ncell; k += MOM_THREADS) {
     const int i = ilo + k / nj, j = jlo + k % nj;
     const double d = rho[(size_t)i * Maxy + j] * c.finalFactor;
     if (d == 0.0) continue;
+    nnz += 1.0;
     const double x = xg_of(c, i) - xc, y = yg_of(c, j) - yc;
     const double r2 = x * x + y * y, r = sqrt(r2);
     double ux = 1.0, uy = 0.0;                                   // atan2(0,0) = 0
@@ -386,7 +420,8 @@ __global__ void __launch_bounds__(MOM_THREADS, 1) moments_kernel(DevCfg c, Store
   const double eps = 1e-15;
   const double dn = block_sum(rn[0], red, tid);
   const double nrmS = block_sum(nrm, red, tid);
-  if (tid == 0) { out[45] = dn / dn; out[46] = total * c.dx * c.dy; out[47] = xc; out[48] = yc; out[49] = (total / c.finalFactor) * c.dx * c.dy; }
+  const double nnzS = block_sum(nnz, red, tid);
+  if (tid == 0) { out[45] = dn / dn; out[46] = total * c.dx * c.dy; out[47] = xc; out[48] = yc; out[49] = (total / c.finalFactor) * c.dx * c.dy; out[50] = nnzS; }
 #pragma unroll
   for (int n = 1; n < 10; n++) {
     const double a = block_sum(mr[n], red, tid), b = block_sum(mi[n], red, tid), cc = block_sum(pr[n], red, tid);
