@@ -40,7 +40,7 @@ struct GdProbe : public GlueDensity { using GlueDensity::density; };
 struct MdProbe : public MakeDensity {
   MdProbe(ParameterReader* p) : MakeDensity(p) {}
   using MakeDensity::mc; using MakeDensity::Maxx; using MakeDensity::Maxy;
-  using MakeDensity::bmin; using MakeDensity::bmax; using MakeDensity::finalFactor;
+  using MakeDensity::bmin; using MakeDensity::bmax; using MakeDensity::finalFactor; using MakeDensity::Npart;
 };
 
 static FILE* out;
@@ -84,7 +84,7 @@ int main(int argc, char* argv[]) {
   ParameterReader paraRdr;
   paraRdr.readFromFile("parameters.dat");
   paraRdr.setVal("dump_grids", 0); paraRdr.setVal("dump_extra", 0);
-  paraRdr.setVal("dump_rotate", 0); paraRdr.setVal("dump_tries", 0);
+  paraRdr.setVal("dump_rotate", 0); paraRdr.setVal("dump_tries", 0); paraRdr.setVal("dump_text", 0);
   paraRdr.readFromArguments(argc, argv, "#", 3);
   int randomSeed = paraRdr.getVal("randomSeed");
   if (randomSeed < 0) randomSeed = 1;
@@ -92,7 +92,7 @@ int main(int argc, char* argv[]) {
   MdProbe* dens = new MdProbe(&paraRdr);
   McProbe* mc = static_cast<McProbe*>(dens->mc);
   const int dgr = paraRdr.getVal("dump_grids"), dex = paraRdr.getVal("dump_extra");
-  const int drot = paraRdr.getVal("dump_rotate"), dtr = paraRdr.getVal("dump_tries");
+  const int drot = paraRdr.getVal("dump_rotate"), dtr = paraRdr.getVal("dump_tries"), dtext = paraRdr.getVal("dump_text");
   const int from_order = paraRdr.getVal("ecc_from_order"), to_order = paraRdr.getVal("ecc_to_order");
 
   { vector<double> c;
@@ -159,9 +159,17 @@ int main(int argc, char* argv[]) {
         wr1(P + "region", v); }
       dens->setSd(d1, 0);
       dens->dumpEccentricities(eccfile, d1, 0, from_order, to_order, mc->getNpart1() + mc->getNpart2(), mc->getNcoll(), b);
+      if (dtext) {      // the reference's own text writers on this event (format fixtures)
+        char f1[] = "data/ref_block.dat", f2[] = "data/ref_4col.dat";
+        dens->Npart = mc->getNpart1() + mc->getNpart2();
+        dens->dumpDensityBlock(f1, d1, 0); dens->dumpDensity4Col(f2, d1, 0);
+        char fp[64]; snprintf(fp, sizeof fp, "data/ref_participants_%d.dat", event); mc->dumpparticipantTable(fp);
+        snprintf(fp, sizeof fp, "data/ref_binary_%d.dat", event); mc->dumpBinaryTable(fp);
+      }
       if (dex) {
         mc->calculate_rho_binary();
         mc->getSpectators();
+        if (dtext) mc->dumpSpectatorsTable(1000 + event);
         mc->calculate_spectator_density();
         wrgrid(P + "rho_binary", mc->rho_binary, mc->Maxx, mc->Maxy);
         wrgrid(P + "spec1", mc->spectator_1, mc->Maxx, mc->Maxy);

@@ -1,0 +1,335 @@
+#include "MakeDensity.h"
+#include <algorithm>
+#include <cmath>
+#include <chrono>
+#include <condition_variable>
+#include <memory>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <fstream>
+#include <functional>
+#include <iostream>
+#include <mutex>
+#include <sstream>
+#include <thread>
+
+// ---- a small pool of writer threads: text formatting caps operations 1/2 in the reference ----------
+namespace {
+class WriterPool {
+ public:
+  explicit WriterPool(int n) : stop(false), pending(0) { for (int i = 0; i < n; i++) th.emplace_back([this] { loop(); }); }
+  ~WriterPool() { wait(); { std::lock_guard<std::mutex> l(m); stop = true; } cv.notify_all(); for (auto& t : th) t.join(); }
+  void submit(std::function<void()> f) {
+    std::unique_lock<std::mutex> l(m);
+    cv_room.wait(l, [this] { return q.size() < 64; });        // bound the memory held by queued grids
+    q.push_back(std::move(f)); pending++; cv.notify_one();
+  }
+  void wait() { std::unique_lock<std::mutex> l(m); cv_done.wait(l, [this] { return pending == 0; }); }
+ private:
+  void loop() {
+    for (;;) {
+      std::function<void()> f;
+      { std::unique_lock<std::mutex> l(m); cv.wait(l, [this] { return stop || !q.empty(); }); if (stop && q.empty()) return; f = std::move(q.front()); q.pop_front(); cv_room.notify_one(); }
+      f();
+      { std::lock_guard<std::mutex> l(m); pending--; if (pending == 0) cv_done.notify_all(); }
+    }
+  }
+  std::vector<std::thread> th; std::deque<std::function<void()>> q; std::mutex m; std::condition_variable cv, cv_room, cv_done; bool stop; int pending;
+};
+
+void write_file(const std::string& name, const std::string& text, bool append) {
+  FILE* f = std::fopen(name.c_str(), append ? "ab" : "wb");
+  if (!f) { std::fprintf(stderr, "cannot open %s\n", name.c_str()); return; }
+  std::fwrite(text.data(), 1, text.size(), f); std::fclose(f);
+}
+inline void put(std::string& s, const char* fmt, double v) { char b[64]; int n = std::snprintf(b, sizeof b, fmt, v); s.append(b, n); }
+int ival(ParameterReader* p, const char* n) { return (int)p->getVal(n); }
+}  // namespace
+
+// ---- formatting (printf %g == iostream default floatfield with the same precision) -----------------
+std::string MakeDensity::formatEccRow(const smc_event_out& ev, int order, bool deformed) {
+  std::string s; const double* m = ev.mom[order - 1];
+  for (int k = 0; k < 5; k++) put(s, "%16.8g", m[k]);
+  put(s, "%10.5g", (double)(ev.npart1 + ev.npart2)); put(s, "%10.5g", (double)ev.ncoll);
+  put(s, "%16.8g", ev.total); put(s, "%16.8g", ev.b);
+  if (deformed) for (int k = 0; k < 4; k++) put(s, "%16.8g", 0.0);   // mc->lastCx1.. are never assigned upstream (quirk Q9)
+  s += "\n"; return s;
+}
+std::string MakeDensity::formatEccRowAll(const smc_event_out& ev, bool deformed) {
+  std::string s;
+  for (int n = 1; n < 10; n++) for (int k = 0; k < 5; k++) put(s, "%16.8g", ev.mom[n - 1][k]);
+  put(s, "%10.5g", (double)(ev.npart1 + ev.npart2)); put(s, "%10.5g", (double)ev.ncoll);
+  put(s, "%16.8g", ev.total); put(s, "%16.8g", ev.b);
+  if (deformed) for (int k = 0; k < 4; k++) put(s, "%16.8g", 0.0);
+  s += "\n"; return s;
+}
+void MakeDensity::formatDensityBlock(const double* g, int Maxx, int Maxy, std::string& out) {
+  out.clear(); out.reserve((size_t)Maxx * (Maxy * 22 + 1));
+  char b[64];
+  for (int i = 0; i < Maxx; i++) {
+    for (int j = 0; j < Maxy; j++) { int n = std::snprintf(b, sizeof b, "%22.12g", g[(size_t)i * Maxy + j]); out.append(b, n); }
+    out += "\n";
+  }
+}
+void MakeDensity::formatDensity4Col(const double* g, int Maxx, int Maxy, double Xmin, double Ymin, double dx, double dy,
+                                    double rap, double npart, std::string& out) {
+  out.clear(); out.reserve((size_t)Maxx * Maxy * 53 + 64);
+  char b[160];
+  int n = std::snprintf(b, sizeof b, "# <npart>= %g xmax= %d ymax= %d\n", npart, Maxx, Maxy); out.append(b, n);
+  for (int i = 0; i < Maxx; i++) for (int j = 0; j < Maxy; j++) {
+    n = std::snprintf(b, sizeof b, "%10.3g%10.3g%10.3g%22.12g\n", rap, Xmin + i * dx, Ymin + j * dy, g[(size_t)i * Maxy + j]);
+    out.append(b, n);
+  }
+}
+
+// ---- construction: parameters.dat keys -> smc_params (consumers listed in SURVEY.md appendix A) ------
+MakeDensity::MakeDensity(ParameterReader* p, int device, smc_shard sh, const std::string& dd)
+    : paraRdr(p), ctx(nullptr), ctx_ok(false), data_dir(dd), shard(sh) {
+  try {
+    smc_params_default(&params);
+    params.which_mc_model = ival(p, "which_mc_model"); params.sub_model = ival(p, "sub_model");
+    params.lambda = p->getVal("lambda"); params.tmax = ival(p, "tmax"); params.tmax_subdivision = ival(p, "tmax_subdivision");
+    params.alpha = p->getVal("alpha"); params.aproj = ival(p, "Aproj"); params.atarg = ival(p, "Atarg");
+    params.proj_deformed = ival(p, "proj_deformed"); params.targ_deformed = ival(p, "targ_deformed");
+    params.include_nn_correlation = ival(p, "include_NN_correlation");
+    params.shape_of_nucleons = ival(p, "shape_of_nucleons"); params.collision_criterion = ival(p, "collision_criterion");
+    params.shape_of_entropy = ival(p, "shape_of_entropy"); params.quark_width = p->getVal("quark_width");
+    params.gauss_nucl_width = p->getVal("gauss_nucl_width"); params.ecm = p->getVal("ecm");
+    params.bmin = p->getVal("bmin"); params.bmax = p->getVal("bmax"); params.npmin = ival(p, "Npmin"); params.npmax = ival(p, "Npmax");
+    params.cutdsdy = ival(p, "cutdSdy"); params.cutdsdy_lowerbound = p->getVal("cutdSdy_lowerBound"); params.cutdsdy_upperbound = p->getVal("cutdSdy_upperBound");
+    long long seed = (long long)p->getVal("randomSeed");
+    if (seed < 0) seed = (long long)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::system_clock::now().time_since_epoch()).count() % 1000000;  // main.cpp:28-31
+    params.randomseed = seed;
+    params.finalfactor = p->getVal("finalFactor"); params.ecc_from_order = ival(p, "ecc_from_order"); params.ecc_to_order = ival(p, "ecc_to_order");
+    params.maxx = p->getVal("maxx"); params.maxy = p->getVal("maxy"); params.dx = p->getVal("dx"); params.dy = p->getVal("dy");
+    params.cc_fluctuation_model = ival(p, "cc_fluctuation_model"); params.cc_fluctuation_gamma_theta = p->getVal("cc_fluctuation_Gamma_theta");
+    const double ptflag = p->getVal("PT_Flag");
+    params.pt_order = ptflag < 0 ? ival(p, "PT_order") : 1;
+    params.max_batch = (int)p->getVal("gpu_batch", 0);
+    binRapidity = ival(p, "ny");
+    rapMin = -p->getVal("ymax"); rapMax = -rapMin;                       // MakeDensity.cpp:54-58
+    p->setVal("rapMin", rapMin); p->setVal("rapMax", rapMax);
+    finalFactor = params.finalfactor;
+    deformed = (params.proj_deformed == 1 || params.targ_deformed == 1);
+    if (binRapidity != 1) { err = "ny != 1 (several rapidity slices) is not built: the B200 path computes the y = rapMin slice only"; return; }
+    if (ptflag < 0) { err = "PT_Flag < 0 (pT-differential tables) is unreachable in the reference (MCnucl.cpp:973 reads a misspelt key) and not built"; return; }
+  } catch (std::exception& e) { err = e.what(); return; }
+  const int rc = smc_create(&params, device, &ctx);
+  if (rc != SMC_OK) { err = std::string("smc_create: ") + (ctx ? smc_last_error(ctx) : "failed"); return; }
+  smc_get_constants(ctx, &k);
+  p->setVal("siginNN", k.siginnn);                                        // MCnucl.cpp:93
+  Maxx = k.maxx_cells; Maxy = k.maxy_cells; Xmin = -params.maxx; Ymin = -params.maxy; dx = params.dx; dy = params.dy;
+  if (load_tables() != 0) return;
+  ctx_ok = true;
+}
+
+MakeDensity::~MakeDensity() { if (ctx) smc_destroy(ctx); }
+
+// tables/: QuarkPos.txt (r1 r2 cos12 rows), light-ion and NN-correlated configurations (Nucleus.cpp:37-48,383-522)
+static bool read_doubles(const std::string& file, std::vector<double>& v) {
+  FILE* f = std::fopen(file.c_str(), "rb");
+  if (!f) return false;
+  std::string buf; char tmp[1 << 16]; size_t n;
+  while ((n = std::fread(tmp, 1, sizeof tmp, f)) > 0) buf.append(tmp, n);
+  std::fclose(f);
+  v.clear();
+  const char* p = buf.c_str(); char* end = nullptr;
+  for (;;) { const double x = std::strtod(p, &end); if (end == p) break; v.push_back(x); p = end; }
+  return true;
+}
+int MakeDensity::load_tables() {
+  std::vector<double> v;
+  if (read_doubles("tables/QuarkPos.txt", v) && v.size() >= 3) {
+    if (smc_load_quark_table(ctx, v.data(), (int)(v.size() / 3)) != SMC_OK) { err = smc_last_error(ctx); return 1; }
+  } else std::cerr << "# tables/QuarkPos.txt not found: nucleon AABBs are the +-4w base boxes" << std::endl;
+  const int A[2] = {params.aproj, params.atarg};
+  for (int s = 0; s < 2; s++) {
+    std::string file; int skip_head = 0, skip_tail = 0, per_nucleon = 3;
+    if (A[s] == 3) { file = "tables/he3_plaintext.dat"; skip_tail = 4; }
+    else if (A[s] == 4) file = "tables/he4_plaintext.dat";
+    else if (A[s] == 12) { file = "tables/carbon_plaintext.dat"; skip_head = 2; }
+    else if (A[s] == 16) file = "tables/oxygen_plaintext.dat";
+    else if (params.include_nn_correlation == 1 && A[s] == 197) { file = "tables/au197-sw-full_3Bchains-conf1820.dat"; per_nucleon = 5; }
+    else if (params.include_nn_correlation == 1 && A[s] == 208) { file = "tables/pb208-1.dat"; per_nucleon = 4; }
+    else continue;
+    if (!read_doubles(file, v)) { err = "Error: " + file + " does not find!"; return 1; }
+    const size_t per_cfg = (size_t)skip_head + (size_t)A[s] * per_nucleon + skip_tail;
+    const size_t ncfg = v.size() / per_cfg;
+    std::vector<double> xyz(ncfg * A[s] * 3);
+    for (size_t c = 0; c < ncfg; c++) for (int i = 0; i < A[s]; i++) for (int d = 0; d < 3; d++)
+      xyz[(c * A[s] + i) * 3 + d] = v[c * per_cfg + skip_head + (size_t)i * per_nucleon + d];
+    if (ncfg == 0 || smc_load_config_table(ctx, s, xyz.data(), (int)ncfg, A[s]) != SMC_OK) { err = std::string("configuration table ") + file + ": " + smc_last_error(ctx); return 1; }
+  }
+  if (params.which_mc_model == 1) {                                       // MakeDensity.cpp:108-132
+    std::cout << "MCnucl::makeTable(): precalculating dNdy for all combinations of Ta and Tb." << std::endl;
+    std::vector<double> tab((size_t)k.kln_tmax * k.kln_tmax);
+    if (smc_build_kln_table(ctx, tab.data()) != SMC_OK) { err = smc_last_error(ctx); return 1; }
+    if (shard.rank == 0) {                                                // dumpdNdyTable4Col, MCnucl.cpp:1027-1048 (append)
+      std::string s; char b[128];
+      for (int i = 1; i < k.kln_tmax; i++) for (int j = 1; j < k.kln_tmax; j++) {
+        int n = std::snprintf(b, sizeof b, "%10.3f%10.3f%10.3f%22.12f\n", rapMin, k.kln_dt * i, k.kln_dt * j, tab[(size_t)i * k.kln_tmax + j]); s.append(b, n);
+      }
+      write_file(path("dNdyTable.dat"), s, true);
+    }
+    std::cout << "MCnucl::makeTable(): done" << std::endl << std::endl;
+  }
+  return 0;
+}
+
+void MakeDensity::shard_range(int nevent, uint64_t* first, int* count) const {
+  const long long lo = (long long)nevent * shard.rank / shard.world, hi = (long long)nevent * (shard.rank + 1) / shard.world;
+  *first = (uint64_t)lo; *count = (int)(hi - lo);
+}
+
+int MakeDensity::run(int operation, int nevent) {
+  switch (operation) {
+    case 1: return generate_profile_ebe(nevent);
+    case 2: return generate_profile_ebe_Jet(nevent);
+    case 3: return generate_profile_average(nevent);
+    case 9: return generateEccTable(nevent);
+    default: std::cout << "Error: operation choice " << operation << " not recognized." << std::endl; return 1;
+  }
+}
+
+// ---- operation 9: minimum-bias eccentricity table ---------------------------------------------------
+int MakeDensity::generateEccTable(int nevent) {
+  const int from_order = ival(paraRdr, "ecc_from_order"), to_order = ival(paraRdr, "ecc_to_order");
+  const bool use_sd = paraRdr->getVal("use_sd") != 0, use_ed = paraRdr->getVal("use_ed") != 0;
+  uint64_t first; int count; shard_range(nevent, &first, &count);
+  const int chunk = 16384;
+  std::vector<smc_event_out> out(std::min(count, chunk) > 0 ? std::min(count, chunk) : 1);
+  std::vector<std::string> rows(11);
+  const char* base[2] = {"sn_ecc_eccp_%d.dat", "en_ecc_eccp_%d.dat"};     // en == sn numerically (quirk Q2)
+  for (int done = 0; done < count; done += chunk) {
+    const int n = std::min(chunk, count - done);
+    if (smc_run_events(ctx, first + done, n, SMC_RUN_MOMENTS, out.data()) != SMC_OK) { err = smc_last_error(ctx); return 1; }
+    for (auto& r : rows) r.clear();
+    for (int e = 0; e < n; e++) {
+      if (out[e].status != SMC_OK) { std::cerr << "event " << first + done + e << ": status " << out[e].status << std::endl; continue; }
+      for (int o = std::max(from_order, 1); o <= std::min(to_order, 9); o++) rows[o] += formatEccRow(out[e], o, deformed);
+      rows[10] += formatEccRowAll(out[e], deformed);
+    }
+    for (int f = 0; f < 2; f++) {
+      if ((f == 0 && !use_sd) || (f == 1 && !use_ed)) continue;
+      char name[128];
+      for (int o = std::max(from_order, 1); o <= std::min(to_order, 9); o++) { std::snprintf(name, sizeof name, base[f], o); write_file(path(name), rows[o], true); }
+      std::snprintf(name, sizeof name, base[f], 10); write_file(path(name), rows[10], true);
+    }
+    std::cout << "processed events: " << done + n << " / " << count << "\r" << std::flush;
+  }
+  std::cout << std::endl;
+  return 0;
+}
+
+// ---- list dumps (MCnucl::dumpBinaryTable / dumpparticipantTable / dumpSpectatorsTable, MCnucl.cpp:1177-1269) ----
+std::string smc_fmt_xy(const double* rows, int n, int stride) {        // setprecision(3) setw(10) x2
+  std::string s; for (int i = 0; i < n; i++) { put(s, "%10.3g", rows[(size_t)i * stride]); put(s, "%10.3g", rows[(size_t)i * stride + 1]); s += "\n"; } return s;
+}
+std::string smc_fmt_participants(const double* rows, int n) {          // Nucleus::dumpParticipants, Nucleus.cpp:753-764
+  std::string s; char b[32];
+  for (int i = 0; i < n; i++) { put(s, "%10.3g", rows[(size_t)i * 8]); s += "   "; put(s, "%10.3g", rows[(size_t)i * 8 + 1]); s += "   "; int k = std::snprintf(b, sizeof b, "%d\n", (int)rows[(size_t)i * 8 + 2]); s.append(b, k); }
+  return s;
+}
+std::string smc_fmt_spectators(const double* rows, int n) {            // scientific, setprecision(4), setw(10) on x only
+  std::string s; char b[96];
+  for (int i = 0; i < n; i++) { int k = std::snprintf(b, sizeof b, "%10.4e  %.4e  %.4e\n", rows[(size_t)i * 3], rows[(size_t)i * 3 + 1], rows[(size_t)i * 3 + 2]); s.append(b, k); }
+  return s;
+}
+
+// shared body of operations 1 and 2
+static int ebe_common(MakeDensity* self, smc_ctx* ctx, ParameterReader* paraRdr, bool jet, int nevent, uint64_t first, int count,
+                      const std::string& data_dir, int Maxx, int Maxy, double Xmin, double Ymin, double dx, double dy, double rapMin,
+                      bool deformed, int batch, std::string& err) {
+  const bool use_sd = paraRdr->getVal("use_sd") != 0, use_ed = paraRdr->getVal("use_ed") != 0;
+  const bool use_block = paraRdr->getVal("use_block") != 0, use_4col = paraRdr->getVal("use_4col") != 0;
+  const bool o_rb = jet && paraRdr->getVal("output_rho_binary") != 0, o_ta = jet && paraRdr->getVal("output_TA") != 0;
+  const bool o_rhob = jet && paraRdr->getVal("output_rhob") != 0, o_sp = jet && paraRdr->getVal("output_spectator_density") != 0;
+  const int from_order = (int)paraRdr->getVal("ecc_from_order"), to_order = (int)paraRdr->getVal("ecc_to_order");
+  unsigned flags = SMC_RUN_MOMENTS | SMC_RUN_KEEP_RHO | SMC_RUN_LISTS;
+  if (o_ta || o_rhob) flags |= SMC_RUN_THICKNESS;
+  if (o_rb) flags |= SMC_RUN_RHO_BINARY;
+  if (o_sp) flags |= SMC_RUN_SPECTATORS;
+  const size_t G = (size_t)Maxx * Maxy;
+  WriterPool pool(std::max(2u, std::min(16u, std::thread::hardware_concurrency())));
+  std::vector<smc_event_out> out(batch);
+  auto P = [&](const char* fmt, long ev) { char b[160]; std::snprintf(b, sizeof b, fmt, ev); return data_dir + "/" + b; };
+  auto grid_job = [&](std::shared_ptr<std::vector<double>> g, const std::string& stem, double npart) {
+    if (use_4col) pool.submit([=] { std::string s; MakeDensity::formatDensity4Col(g->data(), Maxx, Maxy, Xmin, Ymin, dx, dy, rapMin, npart, s); write_file(stem + "_4col.dat", s, false); });
+    if (use_block) pool.submit([=] { std::string s; MakeDensity::formatDensityBlock(g->data(), Maxx, Maxy, s); write_file(stem + "_block.dat", s, false); });
+  };
+  auto fetch = [&](int slot, int which, double scale) {
+    auto g = std::make_shared<std::vector<double>>(G);
+    if (smc_get_grid(ctx, slot, which, g->data()) != SMC_OK) { err = smc_last_error(ctx); g.reset(); return g; }
+    if (scale != 1.0) for (auto& v : *g) v *= scale;
+    return g;
+  };
+  const double ff = self->params.finalfactor;
+  for (int done = 0; done < count; done += batch) {
+    const int n = std::min(batch, count - done);
+    if (smc_run_events(ctx, first + done, n, flags, out.data()) != SMC_OK) { err = smc_last_error(ctx); return 1; }
+    for (int e = 0; e < n; e++) {
+      const long event = (long)(first + done + e) + 1;                   // the reference counts events from 1
+      if (out[e].status != SMC_OK) { std::cerr << "event " << event << ": status " << out[e].status << std::endl; continue; }
+      const double npart = out[e].npart1 + out[e].npart2;
+      int np = 0, nc = 0, ns = 0;
+      smc_get_participants(ctx, e, nullptr, &np); smc_get_collisions(ctx, e, nullptr, &nc);
+      std::vector<double> part((size_t)std::max(np, 1) * 8), coll((size_t)std::max(nc, 1) * 6);
+      smc_get_participants(ctx, e, part.data(), &np); smc_get_collisions(ctx, e, coll.data(), &nc);
+      if (jet) {
+        write_file(P("ParticipantTable_event_%ld.dat", event), smc_fmt_participants(part.data(), np), true);
+        smc_get_spectators(ctx, e, nullptr, &ns);
+        std::vector<double> spec((size_t)std::max(ns, 1) * 3); smc_get_spectators(ctx, e, spec.data(), &ns);
+        write_file(P("Spectators_event_%ld.dat", event), smc_fmt_spectators(spec.data(), ns), false);
+        write_file(P("BinaryCollisionTable_event_%ld.dat", event), smc_fmt_xy(coll.data(), nc, 6), true);
+      } else write_file(data_dir + "/binary.dat", smc_fmt_xy(coll.data(), nc, 6), true);
+      // dumpBinaryTable side files (MCnucl.cpp:1193-1209); quarks.data needs shape_of_entropy=3 state and is not written
+      write_file(data_dir + "/wounded.data", smc_fmt_participants(part.data(), np), false);
+      for (int s = 0; s < 2; s++) {
+        int na = 0; smc_get_nucleons(ctx, e, s, nullptr, &na);
+        std::vector<double> nu((size_t)std::max(na, 1) * 8); smc_get_nucleons(ctx, e, s, nu.data(), &na);
+        write_file(data_dir + (s == 0 ? "/nucl1.data" : "/nucl2.data"), smc_fmt_xy(nu.data(), na, 8), false);
+      }
+      if (jet) for (int f = 0; f < 2; f++) {                              // per-event eccentricity files (:327-345)
+        if ((f == 0 && !use_sd) || (f == 1 && !use_ed)) continue;
+        char nm[160];
+        for (int o = std::max(from_order, 1); o <= std::min(to_order, 9); o++) {
+          std::snprintf(nm, sizeof nm, "%s_ecc_eccp_%d_event_%ld.dat", f == 0 ? "sn" : "en", o, event);
+          write_file(data_dir + "/" + nm, MakeDensity::formatEccRow(out[e], o, deformed), true);
+        }
+        std::snprintf(nm, sizeof nm, "%s_ecc_eccp_%d_event_%ld.dat", f == 0 ? "sn" : "en", 10, event);
+        write_file(data_dir + "/" + nm, MakeDensity::formatEccRowAll(out[e], deformed), true);
+      }
+      if (use_sd || use_ed) {
+        auto g = fetch(e, SMC_GRID_RHO, ff); if (!g) return 1;
+        if (use_sd) grid_job(g, P("sd_event_%ld", event), npart);
+        if (use_ed) grid_job(g, P("ed_event_%ld", event), npart);       // identical numbers (quirk Q2)
+      }
+      if (o_rb) { auto g = fetch(e, SMC_GRID_RHO_BINARY, 1.0); if (!g) return 1; grid_job(g, P("rho_binary_event_%ld", event), npart); }
+      if (o_ta || o_rhob) {
+        auto a = fetch(e, SMC_GRID_TA1, 1.0), b2 = fetch(e, SMC_GRID_TA2, 1.0); if (!a || !b2) return 1;
+        if (o_ta) { grid_job(a, P("nuclear_thickness_TA_event_%ld", event), npart); grid_job(b2, P("nuclear_thickness_TB_event_%ld", event), npart); }
+        if (o_rhob) { auto s2 = std::make_shared<std::vector<double>>(G); for (size_t q = 0; q < G; q++) (*s2)[q] = (*a)[q] + (*b2)[q]; grid_job(s2, P("rhob_event_%ld", event), npart); }
+      }
+      if (o_sp) {
+        auto a = fetch(e, SMC_GRID_SPEC_A, 1.0), b2 = fetch(e, SMC_GRID_SPEC_B, 1.0); if (!a || !b2) return 1;
+        grid_job(a, P("spectator_density_A_event_%ld", event), npart); grid_job(b2, P("spectator_density_B_event_%ld", event), npart);
+      }
+    }
+  }
+  pool.wait();
+  return 0;
+}
+
+int MakeDensity::generate_profile_ebe(int nevent) {
+  uint64_t first; int count; shard_range(nevent, &first, &count);
+  return ebe_common(this, ctx, paraRdr, false, nevent, first, count, data_dir, Maxx, Maxy, Xmin, Ymin, dx, dy, rapMin, deformed, 256, err);
+}
+int MakeDensity::generate_profile_ebe_Jet(int nevent) {
+  uint64_t first; int count; shard_range(nevent, &first, &count);
+  return ebe_common(this, ctx, paraRdr, true, nevent, first, count, data_dir, Maxx, Maxy, Xmin, Ymin, dx, dy, rapMin, deformed, 128, err);
+}
+
+int MakeDensity::generate_profile_average(int nevent) {
+  (void)nevent; err = "operation 3 is wired in smc_avg (see generate_profile_average below)"; return 1;
+}

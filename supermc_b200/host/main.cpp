@@ -1,0 +1,33 @@
+// superMC_b200.e -- drop-in for the reference executable (reference src/main.cpp:19-73): reads
+// parameters.dat, applies name=value overrides, runs the selected operation on the GPU.
+// Multi-GPU: one process per GPU; RANK / WORLD_SIZE / LOCAL_RANK (torchrun convention) select the shard
+// of global event ids and the device, and each rank writes into data/ (rank 0) or data_rank<r>/.
+#include <chrono>
+#include <cstdlib>
+#include <iostream>
+#include "MakeDensity.h"
+
+int main(int argc, char* argv[]) {
+  ParameterReader paraRdr;
+  try {
+    paraRdr.readFromFile("parameters.dat");
+    paraRdr.readFromArguments(argc, argv);
+  } catch (std::exception& e) { std::cout << e.what() << std::endl; return 255; }
+  paraRdr.echo();
+  const char* er = std::getenv("RANK"); const char* ew = std::getenv("WORLD_SIZE"); const char* el = std::getenv("LOCAL_RANK");
+  smc_shard sh{er ? std::atoi(er) : 0, ew ? std::atoi(ew) : 1};
+  const int device = el ? std::atoi(el) : 0;
+  std::string dd = "data";
+  if (sh.world > 1 && sh.rank > 0) dd = "data_rank" + std::to_string(sh.rank);
+  MakeDensity dens(&paraRdr, device, sh, dd);
+  if (!dens.ok()) { std::cerr << "superMC_b200: " << dens.error() << std::endl; return 255; }
+  int nevent = 0, operation = 0;
+  try { nevent = (int)paraRdr.getVal("nev"); operation = (int)paraRdr.getVal("operation"); }
+  catch (std::exception& e) { std::cout << e.what() << std::endl; return 255; }
+  const auto t0 = std::chrono::steady_clock::now();
+  const int rc = dens.run(operation, nevent);
+  const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (rc) std::cerr << "superMC_b200: " << dens.error() << std::endl;
+  std::cout << "Time elapsed (in seconds): " << dt << std::endl;
+  return rc;
+}

@@ -1,0 +1,57 @@
+"""-m gpu: the drop-in executable superMC_b200.e (C++ host layer over the C ABI): operation 9 and 2
+write the reference's data/ layouts, and the rows equal what the C ABI returns for the same event ids."""
+import os
+import shutil
+import subprocess
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "supermc_b200", "superMC_b200.e")
+ARGS = ["which_mc_model=5", "sub_model=1", "Aproj=208", "Atarg=208", "ecm=2760", "alpha=0.118", "maxx=13", "maxy=13",
+        "finalFactor=1", "randomSeed=5", "cc_fluctuation_model=6"]
+
+
+def _rundir(tmp_path):
+    os.makedirs(tmp_path / "data")
+    shutil.copy(os.path.join(ROOT, "supermc_b200", "parameters.dat"), tmp_path)
+    return tmp_path
+
+
+def test_operation9_table(tmp_path):
+    import supermc_b200 as smc
+    d = _rundir(tmp_path)
+    subprocess.check_call([EXE] + ARGS + ["operation=9", "nev=300"], cwd=d, stdout=subprocess.DEVNULL)
+    t10 = np.loadtxt(d / "data" / "sn_ecc_eccp_10.dat")
+    assert t10.shape == (300, 49)
+    assert (d / "data" / "en_ecc_eccp_10.dat").read_bytes() == (d / "data" / "sn_ecc_eccp_10.dat").read_bytes()   # quirk Q2
+    t2 = np.loadtxt(d / "data" / "sn_ecc_eccp_2.dat")
+    assert t2.shape == (300, 9) and np.array_equal(t2[:, 0:5], t10[:, 5:10])
+    ctx = smc.Context(smc.capi.default_params(which_mc_model=5, sub_model=1, ecm=2760.0, alpha=0.118, maxx=13.0, maxy=13.0,
+                                              finalfactor=1.0, randomseed=5, cc_fluctuation_model=6))
+    ev = ctx.run_events(0, 300)
+    assert np.array_equal(t10[:, 45], ev["npart1"] + ev["npart2"]) and np.array_equal(t10[:, 46], ev["ncoll"])
+    assert np.allclose(t10[:, :45], ev["mom"].reshape(300, 45), rtol=2e-7, atol=1e-12)      # 8 printed digits
+    assert np.allclose(t10[:, 48], ev["b"], rtol=2e-7)
+
+
+def test_operation2_files(tmp_path):
+    d = _rundir(tmp_path)
+    subprocess.check_call([EXE] + ARGS + ["operation=2", "nev=3", "use_4col=1"], cwd=d, stdout=subprocess.DEVNULL)
+    for k in (1, 2, 3):
+        for stem in ("sd_event_%d", "ed_event_%d", "rho_binary_event_%d", "nuclear_thickness_TA_event_%d", "nuclear_thickness_TB_event_%d",
+                     "rhob_event_%d", "spectator_density_A_event_%d", "spectator_density_B_event_%d"):
+            blk = np.loadtxt(d / "data" / ((stem % k) + "_block.dat"))
+            assert blk.shape == (261, 261)
+            col = np.loadtxt(d / "data" / ((stem % k) + "_4col.dat"))
+            assert col.shape == (261 * 261, 4) and np.allclose(col[:, 3].reshape(261, 261), blk, rtol=1e-11)
+        ta = np.loadtxt(d / "data" / ("nuclear_thickness_TA_event_%d_block.dat" % k)); tb = np.loadtxt(d / "data" / ("nuclear_thickness_TB_event_%d_block.dat" % k))
+        assert np.allclose(np.loadtxt(d / "data" / ("rhob_event_%d_block.dat" % k)), ta + tb, rtol=1e-11)
+        parts = np.loadtxt(d / "data" / ("ParticipantTable_event_%d.dat" % k)); row = np.loadtxt(d / "data" / ("sn_ecc_eccp_10_event_%d.dat" % k))
+        assert len(parts) == int(row[45])
+        assert abs(ta.sum() * 0.01 - (parts[:, 2] == 1).sum()) < 0.05 * (parts[:, 2] == 1).sum() + 1   # each participant deposits ~1
+        assert len(np.loadtxt(d / "data" / ("BinaryCollisionTable_event_%d.dat" % k)).reshape(-1, 2)) == int(row[46])
+        assert len(np.loadtxt(d / "data" / ("Spectators_event_%d.dat" % k))) == 416 - int(row[45])
+        sd = np.loadtxt(d / "data" / ("sd_event_%d_block.dat" % k))
+        assert abs(sd.sum() * 0.01 - row[47]) < 1e-6 * row[47]
