@@ -101,6 +101,10 @@ typedef struct smc_event_in {
                                     (fluctfactor, additional_weight); NULL = draw / derive on device */
   int n_coll_weight;
   int use_given_weights;         /* 1: nucleon weights come from proj/targ column 7 (reference: last draw wins) */
+  /* averaged profiles only (smc_avg_run_from_positions): rows of 16 per nucleon -- stale base box xL xR yL yR
+   * (Particle::baseBox, quirk Q4), three valence-quark offsets (x y z each), AABB centre x y, one spare; NULL = derive */
+  const double* proj_extra;
+  const double* targ_extra;
 } smc_event_in;
 
 /* what a run materialises besides the smc_event_out rows */
@@ -164,7 +168,8 @@ int  smc_get_nucleons(smc_ctx* ctx, int slot, int which, double* host8, int* n);
  * (see SMC_AVG_*), a Maxx*Maxy sum on the device; smc_avg_run adds `n` accepted events. */
 enum { SMC_AVG_SD = 0, SMC_AVG_TATB = 1, SMC_AVG_RHO_BINARY = 2, SMC_AVG_TA = 3, SMC_AVG_TB = 4,
        SMC_AVG_SPEC_A = 5, SMC_AVG_SPEC_B = 6, SMC_AVG_QUANTITIES = 7 };
-int  smc_avg_begin(smc_ctx* ctx, int from_order, int to_order, int with_rp, int branch_ed);
+/* branches: bit 0 = entropy (use_sd), bit 1 = energy (use_ed) accumulators */
+int  smc_avg_begin(smc_ctx* ctx, int from_order, int to_order, int with_rp, int branches);
 int  smc_avg_run(smc_ctx* ctx, uint64_t first_event_id, int n, smc_event_out* out);
 int  smc_avg_run_from_positions(smc_ctx* ctx, int n, const smc_event_in* in, smc_event_out* out);
 /* device address + element count of the accumulator block and of the accepted-event counter, so the

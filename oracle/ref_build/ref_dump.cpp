@@ -43,6 +43,7 @@ struct MdProbe : public MakeDensity {
   using MakeDensity::bmin; using MakeDensity::bmax; using MakeDensity::finalFactor; using MakeDensity::Npart;
 };
 
+struct PartProbe : public Particle { using Particle::baseBox; };
 static FILE* out;
 static void wr(const string& name, const vector<long>& dims, const double* d) {
   long nl = name.size(); fwrite(&nl, 8, 1, out); fwrite(name.data(), 1, nl, out);
@@ -68,6 +69,16 @@ static void dump_nucleus(const string& name, Nucleus* nuc) {
     v.push_back((double)n[i]->getNumberOfCollision()); v.push_back(n[i]->getFluctfactor());
   }
   wr2(name, (long)n.size(), 9, v);
+  // state the averaged-profile path depends on (quirk Q4): stale base box, quark offsets, AABB centre
+  vector<double> x;
+  for (size_t i = 0; i < n.size(); i++) {
+    Box2D bb = static_cast<PartProbe*>(n[i])->baseBox, cb = n[i]->getBoundingBox();
+    x.push_back(bb.getXL()); x.push_back(bb.getXR()); x.push_back(bb.getYL()); x.push_back(bb.getYR());
+    vector<Quark>& q = n[i]->getQuarks();
+    for (int k = 0; k < 3; k++) { x.push_back(q[k].getLocalX()); x.push_back(q[k].getLocalY()); x.push_back(q[k].getLocalZ()); }
+    x.push_back(cb.getX()); x.push_back(cb.getY()); x.push_back(0.0);
+  }
+  wr2(name + "_x", (long)n.size(), 16, x);
 }
 
 static void dump_grids(const string& pfx, McProbe* mc) {

@@ -43,7 +43,8 @@ class EventOut(C.Structure):
 
 class EventIn(C.Structure):
     _fields_ = [("b", C.c_double), ("na", C.c_int), ("nb", C.c_int), ("proj", dp), ("targ", dp),
-                ("pair_uniform", dp), ("coll_weight", dp), ("n_coll_weight", C.c_int), ("use_given_weights", C.c_int)]
+                ("pair_uniform", dp), ("coll_weight", dp), ("n_coll_weight", C.c_int), ("use_given_weights", C.c_int),
+                ("proj_extra", dp), ("targ_extra", dp)]
 
 
 EVENT_OUT_DTYPE = np.dtype([("b", "f8"), ("npart1", "i4"), ("npart2", "i4"), ("ncoll", "i4"), ("tries", "i4"),
@@ -81,6 +82,8 @@ def lib():
         L.smc_run_events.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_uint, C.c_void_p]
         L.smc_run_from_positions.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint, C.c_void_p]
         L.smc_avg_run.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
+        L.smc_avg_run_from_positions.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.smc_avg_get.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.smc_get_grid.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.smc_centrality_sort.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         assert C.sizeof(EventOut) == EVENT_OUT_DTYPE.itemsize
@@ -157,7 +160,7 @@ class Context:
         self._ck(lib().smc_run_events(self.h, int(first_event_id), int(n), int(flags), out.ctypes.data))
         return out
 
-    def run_from_positions(self, events, flags=RUN_MOMENTS):
+    def _event_in_array(self, events):
         """events: list of dicts(b, proj (A,8), targ (B,8), pair_uniform (A,B)|None, coll_weight (n,2)|None, given_w)"""
         n = len(events)
         arr = (EventIn * n)()
@@ -175,9 +178,52 @@ class Context:
                 cw = np.ascontiguousarray(cw, dtype=np.float64).reshape(-1, 2); keep.append(cw)
                 arr[i].coll_weight = cw.ctypes.data_as(dp); arr[i].n_coll_weight = len(cw)
             arr[i].use_given_weights = int(ev.get("given_w", 1))
-        out = np.zeros(n, dtype=EVENT_OUT_DTYPE)
-        self._ck(lib().smc_run_from_positions(self.h, n, C.byref(arr), int(flags), out.ctypes.data))
+            for key in ("proj_extra", "targ_extra"):
+                x = ev.get(key)
+                if x is not None:
+                    x = np.ascontiguousarray(x, dtype=np.float64); keep.append(x); setattr(arr[i], key, x.ctypes.data_as(dp))
+        return arr, keep
+
+    def run_from_positions(self, events, flags=RUN_MOMENTS):
+        """events: list of dicts(b, proj (A,8), targ (B,8), pair_uniform (A,B)|None, coll_weight (n,2)|None, given_w)"""
+        arr, keep = self._event_in_array(events)
+        out = np.zeros(len(events), dtype=EVENT_OUT_DTYPE)
+        self._ck(lib().smc_run_from_positions(self.h, len(events), C.byref(arr), int(flags), out.ctypes.data))
         return out
+
+    # ---- averaged profiles (operation 3) ----
+    def avg_begin(self, from_order, to_order, with_rp=True, branches=3):
+        self._ck(lib().smc_avg_begin(self.h, int(from_order), int(to_order), int(bool(with_rp)), int(branches)))
+
+    def avg_run(self, first_event_id, n):
+        out = np.zeros(n, dtype=EVENT_OUT_DTYPE)
+        self._ck(lib().smc_avg_run(self.h, int(first_event_id), int(n), out.ctypes.data))
+        return out
+
+    def avg_run_from_positions(self, events):
+        arr, keep = self._event_in_array(events)
+        out = np.zeros(len(events), dtype=EVENT_OUT_DTYPE)
+        self._ck(lib().smc_avg_run_from_positions(self.h, len(events), C.byref(arr), out.ctypes.data))
+        return out
+
+    def avg_get(self, order, variant, quantity, branch=0):
+        g = np.zeros((self.k.maxx_cells, self.k.maxy_cells))
+        self._ck(lib().smc_avg_get(self.h, int(order), int(variant), int(quantity), int(branch), g.ctypes.data))
+        return g
+
+    def avg_count(self):
+        n = C.c_int64()
+        self._ck(lib().smc_avg_count(self.h, C.byref(n)))
+        return n.value
+
+    def avg_set_count(self, n):
+        self._ck(lib().smc_avg_set_count(self.h, C.c_int64(int(n))))
+
+    def avg_device_buffer(self):
+        """(device pointer, n_doubles) of the accumulator sums, for an all-reduce across GPUs"""
+        p = C.c_void_p(); n = C.c_int64()
+        self._ck(lib().smc_avg_device_buffer(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
 
     def grid(self, slot, which):
         g = np.zeros((self.k.maxx_cells, self.k.maxy_cells))

@@ -12,34 +12,7 @@
 #include "smc_common.cuh"
 #include "smc_host_math.h"
 
-namespace smc {
-enum { GK_RHO = 0, GK_TA1 = 1, GK_TA2 = 2, GK_RHO_BINARY = 3, GK_SPEC_A = 4, GK_SPEC_B = 5, GK_RHOA = 6, GK_RHOB = 7 };
-cudaError_t launch_sample_collide(const DevCfg&, const Store&, int nev, bool given, cudaStream_t);
-cudaError_t launch_deposit(const DevCfg&, const Store&, const int* kinds, int nk, int nev, cudaStream_t);
-cudaError_t launch_combine(const DevCfg&, const Store&, int nev, cudaStream_t);
-cudaError_t launch_moments(const DevCfg&, const Store&, int nev, cudaStream_t);
-struct KlnCfg { double ecm, lambda, y, dT; int tmax; int pt_order; int npt, nkt, nphi; const double *xp, *wp, *xk, *wk, *cphi; };
-cudaError_t launch_kln_table(const KlnCfg&, double* table, cudaStream_t);
-struct AvgState;
-}  // namespace smc
-
-struct smc_ctx {
-  smc_params p; smc_constants k; smc::DevCfg cfg; smc::Store st;
-  int device; cudaStream_t stream; cudaEvent_t ev0, ev1;
-  int batch; size_t G;
-  std::vector<void*> owned;
-  double* d_grids; size_t grids_bytes;
-  double* d_pair_u; size_t pair_u_bytes; double* d_coll_w; size_t coll_w_bytes;
-  double* d_quark; double* d_cfgtab[2]; double* d_kln;
-  int* h_hdr_i; double* h_hdr_d; double* h_mom; uint64_t* h_evid; int* h_try; double* h_nuc;
-  std::string err; int64_t launches; double last_ms; int last_n; unsigned last_flags;
-  // averaged profiles (operation 3)
-  int profile; double stage_ms[8]; cudaEvent_t pev[8];
-  double* d_avg; int64_t avg_doubles; int64_t avg_count; int avg_from, avg_to, avg_rp, avg_ed;
-};
-
-#define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(_e); return SMC_ERR_CUDA; } } while (0)
-#define FAIL(code, msg) do { ctx->err = (msg); return (code); } while (0)
+#include "smc_ctx.h"
 
 extern "C" int smc_abi_version(void) { return SMC_ABI_VERSION; }
 
@@ -154,6 +127,8 @@ extern "C" int smc_create(const smc_params* p, int device, smc_ctx** out) {
   if ((rc = dalloc(ctx, &st.mom_out, (size_t)B * smc::MOM_OUT))) return rc;
   { uint64_t* ev; if ((rc = dalloc(ctx, &ev, (size_t)B))) return rc; st.event_id = ev; }
   if ((rc = dalloc(ctx, &st.try_start, (size_t)B))) return rc;
+  if ((rc = dalloc(ctx, &ctx->d_redo, (size_t)B))) return rc;
+  if ((rc = dalloc(ctx, &st.cm, (size_t)B * 4))) return rc;
   CK(cudaMallocHost(&ctx->h_hdr_i, (size_t)B * smc::HDR_I * sizeof(int)));
   CK(cudaMallocHost(&ctx->h_hdr_d, (size_t)B * smc::HDR_D * sizeof(double)));
   CK(cudaMallocHost(&ctx->h_mom, (size_t)B * smc::MOM_OUT * sizeof(double)));
@@ -272,7 +247,7 @@ extern "C" int smc_build_kln_table(smc_ctx* ctx, double* host_out) {
 }
 
 // ---- event batches -------------------------------------------------------------------------------
-static int plan_kinds(smc_ctx* ctx, unsigned flags, int* kinds, int* nk_dep) {
+int smc_plan_kinds(smc_ctx* ctx, unsigned flags, int* kinds, int* nk_dep) {
   smc::Store& st = ctx->st; const smc::DevCfg& c = ctx->cfg;
   for (int i = 0; i < 8; i++) st.kind_slot[i] = -1;
   int n = 0, nd = 0;
@@ -296,7 +271,9 @@ static int plan_kinds(smc_ctx* ctx, unsigned flags, int* kinds, int* nk_dep) {
   return SMC_OK;
 }
 
-static int run_grid_stages(smc_ctx* ctx, int m, const int* kinds, int nd) {
+int smc_run_grid_stages(smc_ctx* ctx, int m, const int* kinds, int nd);
+static int run_grid_stages(smc_ctx* ctx, int m, const int* kinds, int nd) { return smc_run_grid_stages(ctx, m, kinds, nd); }
+int smc_run_grid_stages(smc_ctx* ctx, int m, const int* kinds, int nd) {
   const smc::DevCfg& c = ctx->cfg;
   if (c.which_mc_model == 1 && !ctx->st.kln_table) FAIL(SMC_ERR_STATE, "MC-KLN density requires smc_build_kln_table / smc_set_kln_table first (MCnucl.cpp:636-640)");
   if (ctx->profile) CK(cudaEventRecord(ctx->pev[1], ctx->stream));
@@ -315,7 +292,7 @@ static void collect_stage_ms(smc_ctx* ctx) {
   for (int i = 0; i < 4; i++) { float ms = 0; if (cudaEventElapsedTime(&ms, ctx->pev[i], ctx->pev[i + 1]) == cudaSuccess) ctx->stage_ms[i] += ms; }
 }
 
-static void fill_out(smc_ctx* ctx, int m, smc_event_out* out) {
+void smc_fill_out(smc_ctx* ctx, int m, smc_event_out* out) {
   for (int e = 0; e < m; e++) {
     const int* hi = ctx->h_hdr_i + (size_t)e * smc::HDR_I; const double* mo = ctx->h_mom + (size_t)e * smc::MOM_OUT;
     smc_event_out& o = out[e];
@@ -327,12 +304,55 @@ static void fill_out(smc_ctx* ctx, int m, smc_event_out* out) {
   }
 }
 
-static int fetch_results(smc_ctx* ctx, int m) {
+int smc_fetch_results(smc_ctx* ctx, int m) {
   CK(cudaMemcpyAsync(ctx->h_hdr_i, ctx->st.hdr_i, (size_t)m * smc::HDR_I * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(ctx->h_hdr_d, ctx->st.hdr_d, (size_t)m * smc::HDR_D * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(ctx->h_mom, ctx->st.mom_out, (size_t)m * smc::MOM_OUT * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return SMC_OK;
+}
+
+// one batch of sampled events: ids -> device, K1+K2
+int smc_sample_batch(smc_ctx* ctx, uint64_t first_event_id, int m) {
+  for (int e = 0; e < m; e++) { ctx->h_evid[e] = first_event_id + (uint64_t)e; ctx->h_try[e] = 0; }
+  CK(cudaMemcpyAsync((void*)ctx->st.event_id, ctx->h_evid, (size_t)m * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->st.try_start, ctx->h_try, (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->st.pair_u = nullptr; ctx->st.coll_w = nullptr; ctx->st.redo = nullptr;
+  if (ctx->profile) CK(cudaEventRecord(ctx->pev[0], ctx->stream));
+  CK(smc::launch_sample_collide(ctx->cfg, ctx->st, m, false, ctx->stream)); ctx->launches++;
+  return SMC_OK;
+}
+
+// dS/dy window (MakeDensity.cpp:2173-2181): an event whose sum(rho) dx dy falls outside goes back to the
+// rejection loop; its Philox stream simply continues at the next try index.
+static int dsdy_cut_loop(smc_ctx* ctx, int m, const int* kinds, int nd) {
+  if (ctx->p.cutdsdy != 1) return SMC_OK;
+  int rc;
+  for (int iter = 0; iter < 100000; iter++) {
+    int nbad = 0;
+    for (int e = 0; e < m; e++) {
+      const double s = ctx->h_mom[(size_t)e * smc::MOM_OUT + 49];
+      const bool bad = (ctx->h_hdr_i[(size_t)e * smc::HDR_I + smc::H_STATUS] == 0) && (s < ctx->p.cutdsdy_lowerbound || s > ctx->p.cutdsdy_upperbound);
+      ctx->h_try[e] = bad ? 1 : 0; nbad += bad;
+    }
+    if (!nbad) break;
+    CK(cudaMemcpyAsync(ctx->d_redo, ctx->h_try, (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->st.redo = ctx->d_redo;
+    CK(smc::launch_sample_collide(ctx->cfg, ctx->st, m, false, ctx->stream)); ctx->launches++;
+    if ((rc = run_grid_stages(ctx, m, kinds, nd))) { ctx->st.redo = nullptr; return rc; }
+    ctx->st.redo = nullptr;
+    if ((rc = smc_fetch_results(ctx, m))) return rc;
+  }
+  return SMC_OK;
+}
+
+// density + moments + results to the host + dS/dy window, for a batch whose records are on the device
+int smc_events_first_pass(smc_ctx* ctx, int m, const int* kinds, int nd) {
+  int rc;
+  if ((rc = run_grid_stages(ctx, m, kinds, nd))) return rc;
+  if ((rc = smc_fetch_results(ctx, m))) return rc;
+  collect_stage_ms(ctx);
+  return dsdy_cut_loop(ctx, m, kinds, nd);
 }
 
 extern "C" int smc_run_events(smc_ctx* ctx, uint64_t first_event_id, int n, unsigned flags, smc_event_out* out) {
@@ -341,33 +361,16 @@ extern "C" int smc_run_events(smc_ctx* ctx, uint64_t first_event_id, int n, unsi
   const smc::DevCfg& c = ctx->cfg;
   for (int s = 0; s < 2; s++) if ((c.sampler[s] == 2 || c.sampler[s] == 3) && !ctx->st.cfg_table[s]) FAIL(SMC_ERR_STATE, "this nucleus needs a configuration table: call smc_load_config_table (Nucleus.cpp:150-169)");
   int kinds[8], nd = 0, rc;
-  if ((rc = plan_kinds(ctx, flags, kinds, &nd))) return rc;
-  ctx->st.pair_u = nullptr; ctx->st.coll_w = nullptr;
+  if ((rc = smc_plan_kinds(ctx, flags, kinds, &nd))) return rc;
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   for (int off = 0; off < n; off += ctx->batch) {
     const int m = std::min(ctx->batch, n - off);
-    for (int e = 0; e < m; e++) { ctx->h_evid[e] = first_event_id + (uint64_t)off + e; ctx->h_try[e] = 0; }
-    CK(cudaMemcpyAsync((void*)ctx->st.event_id, ctx->h_evid, (size_t)m * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->st.try_start, ctx->h_try, (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    if (ctx->profile) CK(cudaEventRecord(ctx->pev[0], ctx->stream));
-    CK(smc::launch_sample_collide(c, ctx->st, m, false, ctx->stream)); ctx->launches++;
+    if ((rc = smc_sample_batch(ctx, first_event_id + (uint64_t)off, m))) return rc;
     if ((rc = run_grid_stages(ctx, m, kinds, nd))) return rc;
-    if ((rc = fetch_results(ctx, m))) return rc;
+    if ((rc = smc_fetch_results(ctx, m))) return rc;
     collect_stage_ms(ctx);
-    // dS/dy window (MakeDensity.cpp:2173-2181): a failing event goes back to the rejection loop
-    if (ctx->p.cutdsdy == 1) {
-      for (int iter = 0; iter < 100000; iter++) {
-        int nbad = 0;
-        for (int e = 0; e < m; e++) {
-          const double s = ctx->h_mom[(size_t)e * smc::MOM_OUT + 49];
-          const bool bad = (ctx->h_hdr_i[(size_t)e * smc::HDR_I + smc::H_STATUS] == 0) && (s < ctx->p.cutdsdy_lowerbound || s > ctx->p.cutdsdy_upperbound);
-          ctx->h_try[e] = bad ? 1 : 0; nbad += bad;
-        }
-        if (!nbad) break;
-        FAIL(SMC_ERR_STATE, "cutdSdy=1 re-draw loop is not built yet");
-      }
-    }
-    fill_out(ctx, m, out + off);
+    if ((rc = dsdy_cut_loop(ctx, m, kinds, nd))) return rc;
+    smc_fill_out(ctx, m, out + off);
     ctx->last_n = m;
   }
   CK(cudaEventRecord(ctx->ev1, ctx->stream)); CK(cudaEventSynchronize(ctx->ev1));
@@ -375,65 +378,92 @@ extern "C" int smc_run_events(smc_ctx* ctx, uint64_t first_event_id, int n, unsi
   return SMC_OK;
 }
 
-extern "C" int smc_run_from_positions(smc_ctx* ctx, int n, const smc_event_in* in, unsigned flags, smc_event_out* out) {
-  if (!ctx || n < 0 || (n > 0 && (!in || !out))) return SMC_ERR_PARAM;
-  CK(cudaSetDevice(ctx->device));
+// host nuclei -> device for events [off, off+m), then K2 only
+int smc_stage_positions(smc_ctx* ctx, int off, int m, const smc_event_in* in, bool any_u, bool any_w) {
   const smc::DevCfg& c = ctx->cfg;
   const int A = c.A[0], B = c.A[1], Amax = c.Amax;
-  int kinds[8], nd = 0, rc;
-  if ((rc = plan_kinds(ctx, flags, kinds, &nd))) return rc;
-  bool any_u = false, any_w = false;
+  std::vector<double> hw_default;
+  std::memset(ctx->h_nuc, 0, (size_t)m * 2 * Amax * smc::NROW * sizeof(double));
+  std::memset(ctx->h_hdr_i, 0, (size_t)m * smc::HDR_I * sizeof(int));
+  for (int e = 0; e < m; e++) {
+    const smc_event_in& ev = in[off + e];
+    std::memcpy(ctx->h_nuc + ((size_t)e * 2 + 0) * Amax * smc::NROW, ev.proj, (size_t)A * smc::NROW * sizeof(double));
+    std::memcpy(ctx->h_nuc + ((size_t)e * 2 + 1) * Amax * smc::NROW, ev.targ, (size_t)B * smc::NROW * sizeof(double));
+    ctx->h_hdr_d[(size_t)e * smc::HDR_D + smc::HD_B] = ev.b;
+    ctx->h_hdr_i[(size_t)e * smc::HDR_I + smc::H_GIVENW] = ev.use_given_weights;
+    ctx->h_evid[e] = (uint64_t)(off + e); ctx->h_try[e] = 0;
+    if (any_u) {
+      if (!ev.pair_uniform) FAIL(SMC_ERR_PARAM, "pair_uniform must be given for all events of a call or for none");
+      CK(cudaMemcpyAsync(ctx->d_pair_u + (size_t)e * A * B, ev.pair_uniform, (size_t)A * B * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (any_w && ev.coll_weight) {     // an event without the array (e.g. no collisions) keeps weight 1, additional_weight 0
+      const int nw = std::min(ev.n_coll_weight, c.ncoll_cap);
+      CK(cudaMemcpyAsync(ctx->d_coll_w + (size_t)e * c.ncoll_cap * 2, ev.coll_weight, (size_t)nw * 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    } else if (any_w) {
+      hw_default.assign((size_t)c.ncoll_cap * 2, 0.0);
+      for (int q = 0; q < c.ncoll_cap; q++) hw_default[2 * q] = 1.0;
+      CK(cudaMemcpy(ctx->d_coll_w + (size_t)e * c.ncoll_cap * 2, hw_default.data(), hw_default.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    if (ctx->st.nuc_extra) {           // operation-3 state (stale base boxes, quark offsets), else derived from the rows
+      std::vector<double> ex((size_t)2 * Amax * smc::NEXTRA, 0.0);
+      for (int s = 0; s < 2; s++) {
+        const double* rows = s ? ev.targ : ev.proj; const double* given = s ? ev.targ_extra : ev.proj_extra; const int n = s ? B : A;
+        for (int i = 0; i < n; i++) {
+          double* x = ex.data() + ((size_t)s * Amax + i) * smc::NEXTRA;
+          if (given) std::memcpy(x, given + (size_t)i * smc::NEXTRA, smc::NEXTRA * sizeof(double));
+          else { x[smc::XBXL] = rows[i * 8 + 3]; x[smc::XBXR] = rows[i * 8 + 4]; x[smc::XBYL] = rows[i * 8 + 5]; x[smc::XBYR] = rows[i * 8 + 6];
+                 x[smc::XCX] = 0.5 * (rows[i * 8 + 3] + rows[i * 8 + 4]); x[smc::XCY] = 0.5 * (rows[i * 8 + 5] + rows[i * 8 + 6]); }
+        }
+      }
+      CK(cudaMemcpy(ctx->st.nuc_extra + (size_t)e * 2 * Amax * smc::NEXTRA, ex.data(), ex.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+  }
+  CK(cudaMemcpyAsync(ctx->st.nuc, ctx->h_nuc, (size_t)m * 2 * Amax * smc::NROW * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->st.hdr_d, ctx->h_hdr_d, (size_t)m * smc::HDR_D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->st.hdr_i, ctx->h_hdr_i, (size_t)m * smc::HDR_I * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync((void*)ctx->st.event_id, ctx->h_evid, (size_t)m * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->st.try_start, ctx->h_try, (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->st.pair_u = any_u ? ctx->d_pair_u : nullptr; ctx->st.coll_w = any_w ? ctx->d_coll_w : nullptr; ctx->st.redo = nullptr;
+  if (ctx->profile) CK(cudaEventRecord(ctx->pev[0], ctx->stream));
+  CK(smc::launch_sample_collide(c, ctx->st, m, true, ctx->stream)); ctx->launches++;
+  return SMC_OK;
+}
+
+int smc_check_positions(smc_ctx* ctx, int n, const smc_event_in* in, bool* any_u, bool* any_w) {
+  const smc::DevCfg& c = ctx->cfg;
+  const int A = c.A[0], B = c.A[1];
+  *any_u = false; *any_w = false;
   for (int e = 0; e < n; e++) {
     if (in[e].na != A || in[e].nb != B) FAIL(SMC_ERR_PARAM, "smc_event_in.na/nb must equal Aproj/Atarg of the context");
     if (!in[e].proj || !in[e].targ) FAIL(SMC_ERR_PARAM, "smc_event_in.proj/targ is null");
-    any_u |= in[e].pair_uniform != nullptr; any_w |= in[e].coll_weight != nullptr;
+    *any_u |= in[e].pair_uniform != nullptr; *any_w |= in[e].coll_weight != nullptr;
   }
-  if (any_u) {
+  if (*any_u) {
     const size_t need = (size_t)ctx->batch * A * B * sizeof(double);
     if (need > ctx->pair_u_bytes) { if (ctx->d_pair_u) cudaFree(ctx->d_pair_u); ctx->d_pair_u = nullptr; ctx->pair_u_bytes = 0; CK(cudaMalloc(&ctx->d_pair_u, need)); ctx->pair_u_bytes = need; }
   }
-  if (any_w) {
+  if (*any_w) {
     const size_t need = (size_t)ctx->batch * c.ncoll_cap * 2 * sizeof(double);
     if (need > ctx->coll_w_bytes) { if (ctx->d_coll_w) cudaFree(ctx->d_coll_w); ctx->d_coll_w = nullptr; ctx->coll_w_bytes = 0; CK(cudaMalloc(&ctx->d_coll_w, need)); ctx->coll_w_bytes = need; }
   }
-  std::vector<double> hw_default;
+  return SMC_OK;
+}
+
+extern "C" int smc_run_from_positions(smc_ctx* ctx, int n, const smc_event_in* in, unsigned flags, smc_event_out* out) {
+  if (!ctx || n < 0 || (n > 0 && (!in || !out))) return SMC_ERR_PARAM;
+  CK(cudaSetDevice(ctx->device));
+  int kinds[8], nd = 0, rc;
+  if ((rc = smc_plan_kinds(ctx, flags, kinds, &nd))) return rc;
+  bool any_u, any_w;
+  if ((rc = smc_check_positions(ctx, n, in, &any_u, &any_w))) return rc;
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   for (int off = 0; off < n; off += ctx->batch) {
     const int m = std::min(ctx->batch, n - off);
-    std::memset(ctx->h_nuc, 0, (size_t)m * 2 * Amax * smc::NROW * sizeof(double));
-    std::memset(ctx->h_hdr_i, 0, (size_t)m * smc::HDR_I * sizeof(int));
-    for (int e = 0; e < m; e++) {
-      const smc_event_in& ev = in[off + e];
-      std::memcpy(ctx->h_nuc + ((size_t)e * 2 + 0) * Amax * smc::NROW, ev.proj, (size_t)A * smc::NROW * sizeof(double));
-      std::memcpy(ctx->h_nuc + ((size_t)e * 2 + 1) * Amax * smc::NROW, ev.targ, (size_t)B * smc::NROW * sizeof(double));
-      ctx->h_hdr_d[(size_t)e * smc::HDR_D + smc::HD_B] = ev.b;
-      ctx->h_hdr_i[(size_t)e * smc::HDR_I + smc::H_GIVENW] = ev.use_given_weights;
-      ctx->h_evid[e] = (uint64_t)(off + e); ctx->h_try[e] = 0;
-      if (any_u) {
-        if (!ev.pair_uniform) FAIL(SMC_ERR_PARAM, "pair_uniform must be given for all events of a call or for none");
-        CK(cudaMemcpyAsync(ctx->d_pair_u + (size_t)e * A * B, ev.pair_uniform, (size_t)A * B * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-      }
-      if (any_w && ev.coll_weight) {     // an event without the array (e.g. no collisions) keeps weight 1, additional_weight 0
-        const int nw = std::min(ev.n_coll_weight, c.ncoll_cap);
-        CK(cudaMemcpyAsync(ctx->d_coll_w + (size_t)e * c.ncoll_cap * 2, ev.coll_weight, (size_t)nw * 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-      } else if (any_w) {
-        hw_default.assign((size_t)c.ncoll_cap * 2, 0.0);
-        for (int q = 0; q < c.ncoll_cap; q++) hw_default[2 * q] = 1.0;
-        CK(cudaMemcpy(ctx->d_coll_w + (size_t)e * c.ncoll_cap * 2, hw_default.data(), hw_default.size() * sizeof(double), cudaMemcpyHostToDevice));
-      }
-    }
-    CK(cudaMemcpyAsync(ctx->st.nuc, ctx->h_nuc, (size_t)m * 2 * Amax * smc::NROW * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->st.hdr_d, ctx->h_hdr_d, (size_t)m * smc::HDR_D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->st.hdr_i, ctx->h_hdr_i, (size_t)m * smc::HDR_I * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync((void*)ctx->st.event_id, ctx->h_evid, (size_t)m * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->st.try_start, ctx->h_try, (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    ctx->st.pair_u = any_u ? ctx->d_pair_u : nullptr; ctx->st.coll_w = any_w ? ctx->d_coll_w : nullptr;
-    if (ctx->profile) CK(cudaEventRecord(ctx->pev[0], ctx->stream));
-    CK(smc::launch_sample_collide(c, ctx->st, m, true, ctx->stream)); ctx->launches++;
+    if ((rc = smc_stage_positions(ctx, off, m, in, any_u, any_w))) return rc;
     if ((rc = run_grid_stages(ctx, m, kinds, nd))) return rc;
-    if ((rc = fetch_results(ctx, m))) return rc;
+    if ((rc = smc_fetch_results(ctx, m))) return rc;
     collect_stage_ms(ctx);
-    fill_out(ctx, m, out + off);
+    smc_fill_out(ctx, m, out + off);
     ctx->last_n = m;
   }
   CK(cudaEventRecord(ctx->ev1, ctx->stream)); CK(cudaEventSynchronize(ctx->ev1));

@@ -1,9 +1,251 @@
-// smc_avg.cu -- averaged profiles (operation 3): entry points of include/supermc_b200.h.
-#include "../../include/supermc_b200.h"
-extern "C" int smc_avg_begin(smc_ctx*, int, int, int, int) { return SMC_ERR_STATE; }
-extern "C" int smc_avg_run(smc_ctx*, uint64_t, int, smc_event_out*) { return SMC_ERR_STATE; }
-extern "C" int smc_avg_run_from_positions(smc_ctx*, int, const smc_event_in*, smc_event_out*) { return SMC_ERR_STATE; }
-extern "C" int smc_avg_device_buffer(smc_ctx*, void**, int64_t*) { return SMC_ERR_STATE; }
-extern "C" int smc_avg_count(smc_ctx*, int64_t*) { return SMC_ERR_STATE; }
-extern "C" int smc_avg_set_count(smc_ctx*, int64_t) { return SMC_ERR_STATE; }
-extern "C" int smc_avg_get(smc_ctx*, int, int, int, int, double*) { return SMC_ERR_STATE; }
+// smc_avg.cu -- K6: averaged smooth profiles (operation 3).
+//
+// Replaces the body of MakeDensity::generate_profile_average (reference src/MakeDensity.cpp:1240-1577):
+// per accepted event and per order n, [recentre -> redeposit -> accumulate] for the reaction-plane
+// average, then [recentre + rotate by the participant-plane angle Psi_n -> redeposit -> accumulate],
+// for the entropy branch and again for the energy branch, mutating the event's positions cumulatively
+// exactly as the reference does.  GlueDensity::calcCMAngle (src/GlueDensity.cpp:87-144),
+// MCnucl::recenterGrid / rotateGrid (src/MCnucl.cpp:1119-1174), Particle::rotate / calculateBounds
+// (src/Particle.cpp:94-99,191-200; the stale-baseBox behaviour is SURVEY.md quirk Q4).
+//
+// The reference keeps a sequential running mean (old*(k-1)+new)/k; here every GPU keeps plain sums in
+// device memory plus an event counter, so that the only cross-GPU step is one sum-allreduce of the
+// accumulator block (smc_avg_device_buffer) -- the mean differs from the sequential form at 1e-16.
+#include <algorithm>
+#include <cstring>
+#include "smc_ctx.h"
+
+namespace smc {
+
+#define AVG_THREADS 256
+__device__ __forceinline__ double bsum(double v, double* red, int tid) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((tid & 31) == 0) red[tid >> 5] = v;
+  __syncthreads();
+  double s = 0;
+  for (int w = 0; w < AVG_THREADS / 32; w++) s += red[w];
+  return s;
+}
+
+// GlueDensity::calcCMAngle: centre of mass and n-th order participant-plane angle of rho*scale
+__global__ void __launch_bounds__(AVG_THREADS) cm_angle_kernel(DevCfg c, Store st, int order, double scale) {
+  __shared__ double red[AVG_THREADS / 32];
+  const int e = blockIdx.x, tid = threadIdx.x;
+  const int* hi = st.hdr_i + (size_t)e * HDR_I;
+  if (hi[H_STATUS] != 0) return;
+  const size_t G = (size_t)c.Maxx * c.Maxy;
+  const double* rho = st.grids + ((size_t)e * st.nkinds + st.kind_slot[GK_RHO]) * G;
+  double w = 0, sx = 0, sy = 0;
+  for (size_t k = tid; k < G; k += AVG_THREADS) {
+    const int i = (int)(k / c.Maxy), j = (int)(k % c.Maxy);
+    const double wei = rho[k] * scale * c.dx * c.dy;
+    w += wei; sx += xg_of(c, i) * wei; sy += yg_of(c, j) * wei;
+  }
+  const double weight = bsum(w, red, tid);
+  const double xc = bsum(sx, red, tid) / weight, yc = bsum(sy, red, tid) / weight;
+  double nr = 0, ni = 0;
+  for (size_t k = tid; k < G; k += AVG_THREADS) {
+    const double d = rho[k] * scale;
+    if (d == 0.0) continue;
+    const int i = (int)(k / c.Maxy), j = (int)(k % c.Maxy);
+    const double x = xg_of(c, i) - xc, y = yg_of(c, j) - yc;
+    double a = 1.0, b = 0.0;                 // (x + i y)^n = r^n e^{i n theta}
+    for (int q = 0; q < order; q++) { const double a2 = a * x - b * y; b = a * y + b * x; a = a2; }
+    nr += a * d; ni += b * d;
+  }
+  const double Nr = bsum(nr, red, tid), Ni = bsum(ni, red, tid);
+  if (tid == 0) { double* o = st.cm + (size_t)e * 4; o[0] = xc; o[1] = yc; o[2] = -atan2(-Ni, -Nr) / order; o[3] = weight; }
+}
+
+// recenterGrid (rotate=0) or rotateGrid (rotate=1) applied to participants, collisions and spectators
+__global__ void transform_kernel(DevCfg c, Store st, int rotate) {
+  const int e = blockIdx.x;
+  const int* hi = st.hdr_i + (size_t)e * HDR_I;
+  if (hi[H_STATUS] != 0) return;
+  const double xc = st.cm[(size_t)e * 4], yc = st.cm[(size_t)e * 4 + 1], ang = st.cm[(size_t)e * 4 + 2];
+  double sn, cs; sincos(ang, &sn, &cs);
+  const int Amax = c.Amax;
+  for (int k = threadIdx.x; k < c.A[0] + c.A[1]; k += blockDim.x) {
+    const int s = k >= c.A[0], i = s ? k - c.A[0] : k;
+    double* r = st.nuc + (((size_t)e * 2 + s) * Amax + i) * NROW;
+    double* x = st.nuc_extra + (((size_t)e * 2 + s) * Amax + i) * NEXTRA;
+    const bool part = st.nuc_ncoll[((size_t)e * 2 + s) * Amax + i] > 0;
+    double px = r[NX] - xc, py = r[NY] - yc;               // setX(getX()-x), setY(getY()-y)   MCnucl.cpp:1125-1137
+    if (part) {                                             // Box2D::setCenter keeps the extent, moves the centre
+      const double ddx = __dadd_rn(px, -x[XCX]), ddy = __dadd_rn(py, -x[XCY]);
+      r[NXL] = __dadd_rn(r[NXL], ddx); r[NXR] = __dadd_rn(r[NXR], ddx); r[NYL] = __dadd_rn(r[NYL], ddy); r[NYR] = __dadd_rn(r[NYR], ddy);
+      x[XCX] = px; x[XCY] = py;
+    }
+    if (rotate) {                                           // Point3D::rotate(cos 0, angle)   MathBasics.cpp:41-50
+      const double x0 = px, y0 = py;
+      px = cs * x0 - sn * y0; py = sn * x0 + cs * y0;
+      if (part) {
+        // Particle::rotate turns the quark offsets too; calculateBounds() then rebuilds the AABB from the
+        // STALE constructor-time base box and the quark boxes at the current position (quirk Q4)
+        double xl = x[XBXL], xr = x[XBXR], yl = x[XBYL], yr = x[XBYR];
+        const double hq = 8 * c.quark_width / 2;
+        for (int q = 0; q < 3; q++) {
+          const double qx = x[XQ + 3 * q], qy = x[XQ + 3 * q + 1];
+          const double rx = cs * qx - sn * qy, ry = sn * qx + cs * qy;
+          x[XQ + 3 * q] = rx; x[XQ + 3 * q + 1] = ry;
+          xl = fmin(xl, px + rx - hq); xr = fmax(xr, px + rx + hq); yl = fmin(yl, py + ry - hq); yr = fmax(yr, py + ry + hq);
+        }
+        r[NXL] = xl; r[NXR] = xr; r[NYL] = yl; r[NYR] = yr;
+        x[XCX] = (xl + xr) / 2.0; x[XCY] = (yl + yr) / 2.0;
+      }
+    }
+    r[NX] = px; r[NY] = py;
+  }
+  int nc = hi[H_NCOLL]; if (nc > c.ncoll_cap) nc = c.ncoll_cap;
+  for (int k = threadIdx.x; k < nc; k += blockDim.x) {
+    double* cr = st.coll + ((size_t)e * c.ncoll_cap + k) * CROW;
+    double px = cr[CX] - xc, py = cr[CY] - yc;
+    if (rotate) { const double x0 = px, y0 = py; px = cs * x0 - sn * y0; py = sn * x0 + cs * y0; }
+    cr[CX] = px; cr[CY] = py;
+  }
+}
+
+struct AccList { int n; int dst[8]; int srcA[8]; int srcB[8]; double scale[8]; };
+// acc[dst] += sum over the batch of grid[srcA] (* grid[srcB]) * scale, event order fixed => deterministic
+__global__ void accumulate_kernel(DevCfg c, Store st, AccList al, double* acc, int nev) {
+  const size_t G = (size_t)c.Maxx * c.Maxy;
+  const int q = blockIdx.y;
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < G; k += (size_t)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int e = 0; e < nev; e++) {
+      if (st.hdr_i[(size_t)e * HDR_I + H_STATUS] != 0) continue;
+      const double* base = st.grids + (size_t)e * st.nkinds * G;
+      double v = base[(size_t)st.kind_slot[al.srcA[q]] * G + k];
+      if (al.srcB[q] >= 0) v *= base[(size_t)st.kind_slot[al.srcB[q]] * G + k];
+      s += v * al.scale[q];
+    }
+    acc[(size_t)al.dst[q] * G + k] += s;
+  }
+}
+}  // namespace smc
+
+// accumulator slot of (order index, variant 0 rotated / 1 reaction plane, branch 0 sd / 1 ed, quantity)
+static inline int avg_slot(int io, int variant, int branch, int quantity) { return ((io * 2 + variant) * 2 + branch) * SMC_AVG_QUANTITIES + quantity; }
+
+extern "C" int smc_avg_begin(smc_ctx* ctx, int from_order, int to_order, int with_rp, int branches) {
+  if (!ctx || from_order < 1 || to_order < from_order || to_order > 9 || !(branches & 3)) return SMC_ERR_PARAM;
+  CK(cudaSetDevice(ctx->device));
+  ctx->avg_from = from_order; ctx->avg_to = to_order; ctx->avg_rp = with_rp ? 1 : 0; ctx->avg_ed = branches; ctx->avg_count = 0;
+  const int norders = to_order - from_order + 1;
+  ctx->avg_doubles = (int64_t)norders * 4 * SMC_AVG_QUANTITIES * (int64_t)ctx->G;
+  if (ctx->d_avg) { cudaFree(ctx->d_avg); ctx->d_avg = nullptr; }
+  CK(cudaMalloc(&ctx->d_avg, (size_t)ctx->avg_doubles * sizeof(double)));
+  CK(cudaMemset(ctx->d_avg, 0, (size_t)ctx->avg_doubles * sizeof(double)));
+  const size_t nx = (size_t)ctx->batch * 2 * ctx->cfg.Amax * smc::NEXTRA;
+  if (!ctx->st.nuc_extra) {
+    CK(cudaMalloc(&ctx->st.nuc_extra, nx * sizeof(double))); ctx->owned.push_back(ctx->st.nuc_extra);
+    CK(cudaMalloc(&ctx->st.nuc_extra_tmp, nx * sizeof(double))); ctx->owned.push_back(ctx->st.nuc_extra_tmp);
+  }
+  return SMC_OK;
+}
+
+// the per-order sequence on a batch whose event records are on the device
+static int avg_sequence(smc_ctx* ctx, int m) {
+  const smc::DevCfg& c = ctx->cfg; smc::Store& st = ctx->st;
+  int kinds[8], nd = 0, rc;
+  if ((rc = smc_plan_kinds(ctx, SMC_RUN_THICKNESS | SMC_RUN_RHO_BINARY | SMC_RUN_SPECTATORS, kinds, &nd))) return rc;
+  if (c.which_mc_model == 1 && !st.kln_table) FAIL(SMC_ERR_STATE, "MC-KLN needs its table first");
+  auto density = [&]() -> int {          // calculateThickness + setDensity + calculate_rho_binary + calculate_spectator_density
+    CK(smc::launch_deposit(c, st, kinds, nd, m, ctx->stream)); ctx->launches++;
+    if (c.which_mc_model != 5) { CK(smc::launch_combine(c, st, m, ctx->stream)); ctx->launches++; }
+    return SMC_OK;
+  };
+  auto cm = [&](int order, double scale) -> int { smc::cm_angle_kernel<<<m, AVG_THREADS, 0, ctx->stream>>>(c, st, order, scale); ctx->launches++; CK(cudaGetLastError()); return SMC_OK; };
+  auto tf = [&](int rot) -> int { smc::transform_kernel<<<m, 128, 0, ctx->stream>>>(c, st, rot); ctx->launches++; CK(cudaGetLastError()); return SMC_OK; };
+  auto acc = [&](int io, int variant, int branch) -> int {
+    smc::AccList al; int n = 0;
+    auto add = [&](int quantity, int a, int b, double scale) { al.dst[n] = avg_slot(io, variant, branch, quantity); al.srcA[n] = a; al.srcB[n] = b; al.scale[n] = scale; n++; };
+    add(SMC_AVG_SD, smc::GK_RHO, -1, c.finalFactor);                                  // setSd/setEd: rho * finalFactor
+    add(SMC_AVG_TATB, smc::GK_TA1, smc::GK_TA2, 1.0); add(SMC_AVG_RHO_BINARY, smc::GK_RHO_BINARY, -1, 1.0);
+    add(SMC_AVG_TA, smc::GK_TA1, -1, 1.0); add(SMC_AVG_TB, smc::GK_TA2, -1, 1.0);
+    if (variant == 0) { add(SMC_AVG_SPEC_A, smc::GK_SPEC_A, -1, 1.0); add(SMC_AVG_SPEC_B, smc::GK_SPEC_B, -1, 1.0); }
+    al.n = n;
+    dim3 g(64, n);
+    smc::accumulate_kernel<<<g, 256, 0, ctx->stream>>>(c, st, al, ctx->d_avg, m); ctx->launches++; CK(cudaGetLastError());
+    return SMC_OK;
+  };
+  for (int order = ctx->avg_from; order <= ctx->avg_to; order++) {
+    const int io = order - ctx->avg_from;
+    if ((rc = density())) return rc;                                                   // MakeDensity.cpp:1275
+    for (int branch = 0; branch < 2; branch++) {
+      if (!(ctx->avg_ed & (1 << branch))) continue;
+      double scale = branch == 1 ? c.finalFactor : 1.0;                                // ed branch: setRho(rho*finalFactor) first (:1391-1396)
+      if (ctx->avg_rp) {                                                               // :1289-1330 / :1397-1438
+        if ((rc = cm(order, scale)) || (rc = tf(0)) || (rc = density()) || (rc = acc(io, 1, branch))) return rc;
+        scale = 1.0;
+      }
+      if ((rc = cm(order, scale)) || (rc = tf(1)) || (rc = density()) || (rc = acc(io, 0, branch))) return rc;   // :1331-1386 / :1439-1493
+    }
+  }
+  return SMC_OK;
+}
+
+static int64_t count_ok(smc_ctx* ctx, int m) { int64_t n = 0; for (int e = 0; e < m; e++) n += ctx->h_hdr_i[(size_t)e * smc::HDR_I + smc::H_STATUS] == 0; return n; }
+
+extern "C" int smc_avg_run(smc_ctx* ctx, uint64_t first_event_id, int n, smc_event_out* out) {
+  if (!ctx || n < 0) return SMC_ERR_PARAM;
+  if (!ctx->d_avg) FAIL(SMC_ERR_STATE, "smc_avg_begin first");
+  CK(cudaSetDevice(ctx->device));
+  int kinds[8], nd = 0, rc;
+  std::vector<smc_event_out> tmp;
+  for (int off = 0; off < n; off += ctx->batch) {
+    const int m = std::min(ctx->batch, n - off);
+    if ((rc = smc_plan_kinds(ctx, SMC_RUN_THICKNESS | SMC_RUN_RHO_BINARY | SMC_RUN_SPECTATORS, kinds, &nd))) return rc;
+    if ((rc = smc_sample_batch(ctx, first_event_id + (uint64_t)off, m))) return rc;
+    // the un-rotated event: moments for the caller, sum(rho) for the dS/dy window
+    if ((rc = smc_events_first_pass(ctx, m, kinds, nd))) return rc;
+    if (out) smc_fill_out(ctx, m, out + off);
+    if ((rc = avg_sequence(ctx, m))) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->avg_count += count_ok(ctx, m);
+    ctx->last_n = m;
+  }
+  return SMC_OK;
+}
+
+extern "C" int smc_avg_run_from_positions(smc_ctx* ctx, int n, const smc_event_in* in, smc_event_out* out) {
+  if (!ctx || n < 0 || (n > 0 && !in)) return SMC_ERR_PARAM;
+  if (!ctx->d_avg) FAIL(SMC_ERR_STATE, "smc_avg_begin first");
+  CK(cudaSetDevice(ctx->device));
+  int kinds[8], nd = 0, rc; bool any_u, any_w;
+  if ((rc = smc_check_positions(ctx, n, in, &any_u, &any_w))) return rc;
+  for (int off = 0; off < n; off += ctx->batch) {
+    const int m = std::min(ctx->batch, n - off);
+    if ((rc = smc_plan_kinds(ctx, SMC_RUN_THICKNESS | SMC_RUN_RHO_BINARY | SMC_RUN_SPECTATORS, kinds, &nd))) return rc;
+    if ((rc = smc_stage_positions(ctx, off, m, in, any_u, any_w))) return rc;
+    if ((rc = smc_run_grid_stages(ctx, m, kinds, nd))) return rc;
+    if ((rc = smc_fetch_results(ctx, m))) return rc;
+    if (out) smc_fill_out(ctx, m, out + off);
+    if ((rc = avg_sequence(ctx, m))) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->avg_count += count_ok(ctx, m);
+    ctx->last_n = m;
+  }
+  return SMC_OK;
+}
+
+extern "C" int smc_avg_device_buffer(smc_ctx* ctx, void** dev_ptr, int64_t* n_doubles) {
+  if (!ctx || !dev_ptr || !n_doubles) return SMC_ERR_PARAM;
+  if (!ctx->d_avg) FAIL(SMC_ERR_STATE, "smc_avg_begin first");
+  *dev_ptr = ctx->d_avg; *n_doubles = ctx->avg_doubles; return SMC_OK;
+}
+extern "C" int smc_avg_count(smc_ctx* ctx, int64_t* count) { if (!ctx || !count) return SMC_ERR_PARAM; *count = ctx->avg_count; return SMC_OK; }
+extern "C" int smc_avg_set_count(smc_ctx* ctx, int64_t count) { if (!ctx) return SMC_ERR_PARAM; ctx->avg_count = count; return SMC_OK; }
+
+extern "C" int smc_avg_get(smc_ctx* ctx, int order, int variant, int quantity, int branch, double* host) {
+  if (!ctx || !host || variant < 0 || variant > 1 || branch < 0 || branch > 1 || quantity < 0 || quantity >= SMC_AVG_QUANTITIES) return SMC_ERR_PARAM;
+  if (!ctx->d_avg) FAIL(SMC_ERR_STATE, "smc_avg_begin first");
+  if (order < ctx->avg_from || order > ctx->avg_to) FAIL(SMC_ERR_PARAM, "order outside [average_from_order, average_to_order]");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpy(host, ctx->d_avg + (size_t)avg_slot(order - ctx->avg_from, variant, branch, quantity) * ctx->G, ctx->G * sizeof(double), cudaMemcpyDeviceToHost));
+  const double inv = ctx->avg_count > 0 ? 1.0 / (double)ctx->avg_count : 0.0;
+  for (size_t k = 0; k < ctx->G; k++) host[k] *= inv;
+  return SMC_OK;
+}

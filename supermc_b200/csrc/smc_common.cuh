@@ -10,6 +10,8 @@ namespace smc {
 
 // nucleon row layout (also the C-ABI layout of smc_event_in.proj/targ)
 enum { NX = 0, NY = 1, NZ = 2, NXL = 3, NXR = 4, NYL = 5, NYR = 6, NW = 7, NROW = 8 };
+// extra nucleon state for operation 3: stale base box (Particle::baseBox), valence-quark offsets, AABB centre
+enum { XBXL = 0, XBXR = 1, XBYL = 2, XBYR = 3, XQ = 4 /* 9 doubles */, XCX = 13, XCY = 14, NEXTRA = 16 };
 // collision row layout
 enum { CX = 0, CY = 1, CW = 2, CADDW = 3, CROW = 4 };
 
@@ -69,6 +71,10 @@ struct Store {
   const double* coll_w;        // [batch][ncoll_cap][2] or null
   const uint64_t* event_id;    // [batch]
   int* try_start;              // [batch] first try index to use (dS/dy-cut re-runs)
+  const int* redo;             // [batch] or null: only events with redo[e] != 0 are (re)processed
+  double* nuc_extra;           // [batch][2][Amax][NEXTRA] or null: state the averaged-profile path needs (quirk Q4)
+  double* nuc_extra_tmp;       // same, acceptance order (scratch of the sampler)
+  double* cm;                  // [batch][4] xcm, ycm, angle, weight  (GlueDensity::calcCMAngle)
   double* grids;      // [batch][nkinds][G]
   int kind_slot[8];   // grid kind -> slot in grids (or -1)
   int nkinds;

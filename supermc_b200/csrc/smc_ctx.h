@@ -1,0 +1,45 @@
+// smc_ctx.h -- the context object behind the C ABI (shared by smc_api.cu and smc_avg.cu)
+#pragma once
+#include <string>
+#include <vector>
+#include "../../include/supermc_b200.h"
+#include "smc_common.cuh"
+
+namespace smc {
+enum { GK_RHO = 0, GK_TA1 = 1, GK_TA2 = 2, GK_RHO_BINARY = 3, GK_SPEC_A = 4, GK_SPEC_B = 5, GK_RHOA = 6, GK_RHOB = 7 };
+cudaError_t launch_sample_collide(const DevCfg&, const Store&, int nev, bool given, cudaStream_t);
+cudaError_t launch_deposit(const DevCfg&, const Store&, const int* kinds, int nk, int nev, cudaStream_t);
+cudaError_t launch_combine(const DevCfg&, const Store&, int nev, cudaStream_t);
+cudaError_t launch_moments(const DevCfg&, const Store&, int nev, cudaStream_t);
+struct KlnCfg { double ecm, lambda, y, dT; int tmax; int pt_order; int npt, nkt, nphi; const double *xp, *wp, *xk, *wk, *cphi; };
+cudaError_t launch_kln_table(const KlnCfg&, double* table, cudaStream_t);
+}  // namespace smc
+
+struct smc_ctx {
+  smc_params p; smc_constants k; smc::DevCfg cfg; smc::Store st;
+  int device; cudaStream_t stream; cudaEvent_t ev0, ev1;
+  int batch; size_t G;
+  std::vector<void*> owned;
+  double* d_grids; size_t grids_bytes;
+  double* d_pair_u; size_t pair_u_bytes; double* d_coll_w; size_t coll_w_bytes;
+  double* d_quark; double* d_cfgtab[2]; double* d_kln; int* d_redo;
+  int* h_hdr_i; double* h_hdr_d; double* h_mom; uint64_t* h_evid; int* h_try; double* h_nuc;
+  std::string err; int64_t launches; double last_ms; int last_n; unsigned last_flags;
+  // averaged profiles (operation 3)
+  int profile; double stage_ms[8]; cudaEvent_t pev[8];
+  double* d_avg; int64_t avg_doubles; int64_t avg_count; int avg_from, avg_to, avg_rp, avg_ed;
+};
+
+#define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(_e); return SMC_ERR_CUDA; } } while (0)
+#define FAIL(code, msg) do { ctx->err = (msg); return (code); } while (0)
+
+
+// helpers of smc_api.cu used by the averaged-profile driver
+int smc_plan_kinds(smc_ctx* ctx, unsigned flags, int* kinds, int* nk_dep);
+int smc_fetch_results(smc_ctx* ctx, int m);
+void smc_fill_out(smc_ctx* ctx, int m, smc_event_out* out);
+int smc_stage_positions(smc_ctx* ctx, int off, int m, const smc_event_in* in, bool any_u, bool any_w);
+int smc_sample_batch(smc_ctx* ctx, uint64_t first_event_id, int m);
+int smc_check_positions(smc_ctx* ctx, int n, const smc_event_in* in, bool* any_u, bool* any_w);
+int smc_run_grid_stages(smc_ctx* ctx, int m, const int* kinds, int nd);
+int smc_events_first_pass(smc_ctx* ctx, int m, const int* kinds, int nd);

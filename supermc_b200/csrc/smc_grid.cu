@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(2 * DEP_MAXSTRIPES * 32, 1) deposit_kernel(Dev
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nwarps = nthreads >> 5;
   const int nstr = nwarps >> 1;                       // stripes handled by this CTA
   const int wr = warp / nstr, stripe = sgroup * nstr + (warp % nstr);
+  if (st.redo && !st.redo[e]) return;
   const int* hi = st.hdr_i + (size_t)e * HDR_I;
   const int slot = st.kind_slot[kind];
   double* grid = st.grids + ((size_t)e * st.nkinds + slot) * (size_t)c.Maxx * c.Maxy;
@@ -264,6 +265,7 @@ cudaError_t launch_deposit(const DevCfg& c, const Store& st, const int* kinds, i
 // (MCnucl.cpp:654-687, arsenal.cpp:33-54)
 __global__ void combine_kernel(DevCfg c, Store st, int nev) {
   const int e = blockIdx.y;
+  if (st.redo && !st.redo[e]) return;
   const size_t G = (size_t)c.Maxx * c.Maxy;
   int* hi = st.hdr_i + (size_t)e * HDR_I;
   double* base = st.grids + (size_t)e * st.nkinds * G;
@@ -317,6 +319,7 @@ __device__ __forceinline__ double block_min(double v, double* red, int tid) {
 __global__ void __launch_bounds__(MOM_THREADS, 1) moments_kernel(DevCfg c, Store st, int nev) {
   extern __shared__ double smem_d[];
   const int e = blockIdx.x, tid = threadIdx.x;
+  if (st.redo && !st.redo[e]) return;
   const int* hi = st.hdr_i + (size_t)e * HDR_I;
   double* out = st.mom_out + (size_t)e * MOM_OUT;
   const int status = hi[H_STATUS];

@@ -54,11 +54,17 @@ __device__ __forceinline__ void box_union(Box& b, const Box& o) {          // Bo
 
 // Particle::Particle -> generateQuarkPositions -> calculateBounds (src/Particle.cpp:16-99)
 __device__ void particle_box(const DevCfg& c, const Store& st, const smc_stream& sq, uint32_t cand,
-                             double x0, double y0, Box& out) {
+                             double x0, double y0, Box& out, double* extra) {
   Box base = {0, 0, 0, 0, 0, 0};
   box_center(base, x0, y0); box_square(base, 8 * c.w);
   out = base;
-  if (c.quark_rows <= 0) return;     // no table: r1 = r2 = 0, quark boxes (+-4 quark_width) lie inside the base box when quark_width <= w
+  if (extra) { extra[XBXL] = base.xL; extra[XBXR] = base.xR; extra[XBYL] = base.yL; extra[XBYR] = base.yR; for (int q = 0; q < 9; q++) extra[XQ + q] = 0.0; }
+  if (c.quark_rows <= 0) {           // no table: r1 = r2 = 0, the three quark boxes sit on the nucleon
+    Box b = {0, 0, 0, 0, 0, 0};
+    box_center(b, 0.0, 0.0); box_square(b, 8 * c.quark_width); box_center(b, x0, y0);
+    box_union(out, b); box_union(out, b); box_union(out, b);
+    return;
+  }
   double u0, u1, u2, u3;
   smc_uniform2(sq, cand, 0, &u0, &u1); smc_uniform2(sq, cand, 1, &u2, &u3);
   int index = (int)(250000 * u0);
@@ -70,11 +76,13 @@ __device__ void particle_box(const DevCfg& c, const Store& st, const smc_stream&
   double s1, c1, s12, c12, sp1, cp1, s, cc;
   sincos(Theta1, &s1, &c1); sincos(Theta1 + Theta12, &s12, &c12); sincos(phi1, &sp1, &cp1); sincos(phi2, &s, &cc);
   double ux = s1 * cp1, uy = s1 * sp1, uz = z1, vx = s12 * cp1, vy = s12 * sp1, vz = c12;
-  double r1x = r1 * ux, r1y = r1 * uy;
+  double r1x = r1 * ux, r1y = r1 * uy, r1z = r1 * uz;
+  double r2z = (vx * (uz * ux * (1 - cc) - uy * s) + vy * (uz * uy * (1 - cc) + ux * s) + vz * (cc + uz * uz * (1 - cc))) * r2;
   double r2x = vx * (cc + ux * ux * (1 - cc)) + vy * (ux * uy * (1 - cc) - uz * s) + vz * (ux * uz * (1 - cc) + uy * s);
   double r2y = vx * (ux * uy * (1 - cc) + uz * s) + vy * (cc + uy * uy * (1 - cc)) + vz * (uy * uz * (1 - cc) - ux * s);
   r2x *= r2; r2y *= r2;
   double qx[3] = {r1x, r2x, -r1x - r2x}, qy[3] = {r1y, r2y, -r1y - r2y};
+  if (extra) { const double qz[3] = {r1z, r2z, -r1z - r2z}; for (int q = 0; q < 3; q++) { extra[XQ + 3 * q] = qx[q]; extra[XQ + 3 * q + 1] = qy[q]; extra[XQ + 3 * q + 2] = qz[q]; } }
 #pragma unroll
   for (int q = 0; q < 3; q++) {
     Box b = {0, 0, 0, 0, 0, 0};
@@ -87,7 +95,7 @@ __device__ __forceinline__ double sph_harm2(double ct) { return (3.0 * ct * ct -
 __device__ __forceinline__ double sph_harm4(double ct) { return (35.0 * ct * ct * ct * ct - 30.0 * ct * ct + 3.0) * 0.10578554691520431; }
 
 // One nucleus by warp `s` (side).  Leaves A sorted rows in sm.pos[s].
-__device__ void sample_nucleus(const DevCfg& c, const Store& st, const SampleSmem& sm, int s, uint64_t ev,
+__device__ void sample_nucleus(const DevCfg& c, const Store& st, const SampleSmem& sm, int e, int s, uint64_t ev,
                                uint32_t tr, double xCenter, double yCenter) {
   const int lane = threadIdx.x & 31, A = c.A[s];
   double* tmp = sm.tmp + (size_t)s * c.Amax * NROW;
@@ -184,13 +192,15 @@ __device__ void sample_nucleus(const DevCfg& c, const Store& st, const SampleSme
   for (int k = lane; k < A; k += 32) {
     double x0 = tmp[k * NROW], y0 = tmp[k * NROW + 1], z0 = tmp[k * NROW + 2];
     uint32_t cand = (uint32_t)tmp[k * NROW + 3];
-    Box bx; particle_box(c, st, s_q, cand, x0, y0, bx);
+    double* ex = st.nuc_extra_tmp ? st.nuc_extra_tmp + (((size_t)e * 2 + s) * c.Amax + k) * NEXTRA : nullptr;
+    Box bx; particle_box(c, st, s_q, cand, x0, y0, bx, ex);
     if (recentre) {
       double x = x0 - mx / A + xCenter, y = y0 - my / A + yCenter, z = z0 - mz / A;
       box_center(bx, x, bx.yC); box_center(bx, bx.xC, y);       // Particle::setX / setY, src/Particle.cpp:176-185
       x0 = x; y0 = y; z0 = z;
     }
     double* t = tmp + (size_t)k * NROW;
+    if (ex) { ex[XCX] = bx.xC; ex[XCY] = bx.yC; }
     t[NX] = x0; t[NY] = y0; t[NZ] = z0; t[NXL] = bx.xL; t[NXR] = bx.xR; t[NYL] = bx.yL; t[NYR] = bx.yR; t[NW] = 1.0;
     xl[k] = bx.xL;
   }
@@ -201,6 +211,10 @@ __device__ void sample_nucleus(const DevCfg& c, const Store& st, const SampleSme
     const double* t = tmp + (size_t)k * NROW; double* p = pos + (size_t)rank * NROW;
 #pragma unroll
     for (int f = 0; f < NROW; f++) p[f] = t[f];
+    if (st.nuc_extra_tmp) {
+      const double* a = st.nuc_extra_tmp + (((size_t)e * 2 + s) * c.Amax + k) * NEXTRA; double* b2 = st.nuc_extra + (((size_t)e * 2 + s) * c.Amax + rank) * NEXTRA;
+      for (int f = 0; f < NEXTRA; f++) b2[f] = a[f];
+    }
   }
   __syncwarp();
 }
@@ -232,6 +246,7 @@ __global__ void __launch_bounds__(64) sample_collide_kernel(DevCfg c, Store st, 
   extern __shared__ double smem_d[];
   const int e = blockIdx.x;
   if (e >= nev) return;
+  if (st.redo && !st.redo[e]) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int A = c.A[0], B = c.A[1], Amax = c.Amax, HW = (Amax + 31) / 32;
   SampleSmem sm;
@@ -253,7 +268,7 @@ __global__ void __launch_bounds__(64) sample_collide_kernel(DevCfg c, Store st, 
     } else {
       const smc_stream s_b = smc_make_stream(c.seed_lo, c.seed_hi, ev, tr, SMC_K_B, 0);
       b = sqrt((c.bmax * c.bmax - c.bmin * c.bmin) * smc_uniform(s_b, 0, 0) + c.bmin * c.bmin);   // MakeDensity.cpp:2149
-      sample_nucleus(c, st, sm, warp, ev, tr, warp == 0 ? b / 2.0 : -b / 2.0, 0.0);                 // MCnucl.cpp:208-214
+      sample_nucleus(c, st, sm, e, warp, ev, tr, warp == 0 ? b / 2.0 : -b / 2.0, 0.0);                 // MCnucl.cpp:208-214
     }
     for (int k = tid; k < Amax; k += 64) { sm.ncB[k] = 0; sm.firstB[k] = 0x7fffffff; }
     __syncthreads();
@@ -318,7 +333,7 @@ __global__ void __launch_bounds__(64) sample_collide_kernel(DevCfg c, Store st, 
   }
   // ---- emit the event record ----
   if (tid == 0) {
-    hi[H_NP1] = np1; hi[H_NP2] = np2; hi[H_NCOLL] = ncoll; hi[H_TRIES] = (int)tr - (GIVEN ? 0 : st.try_start[e]);
+    hi[H_NP1] = np1; hi[H_NP2] = np2; hi[H_NCOLL] = ncoll; hi[H_TRIES] = (st.redo ? hi[H_TRIES] : 0) + (int)tr - (GIVEN ? 0 : st.try_start[e]);
     hi[H_STATUS] = accepted ? (ncoll > c.ncoll_cap ? 4 : 0) : 100;
     hd[HD_B] = b;
     if (!GIVEN) st.try_start[e] = (int)tr;

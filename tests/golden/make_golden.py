@@ -72,6 +72,8 @@ def run_system(name):
         acc = int(t["hdr"][4])
         for k in ("hdr", "proj", "targ", "proj_part", "targ_part", "coll"):
             out[pre + k] = t[k]
+        if par.get("dump_rotate"):
+            out[pre + "proj_x"] = t["proj_x"]; out[pre + "targ_x"] = t["targ_x"]
         if acc:
             out[pre + "dndy"] = t["dndy"]; out[pre + "region"] = t["region"]; out[pre + "spectators"] = t["spectators"]
             out[pre + "ecc_index"] = np.array(ia)
@@ -80,7 +82,7 @@ def run_system(name):
                     out[pre + k] = t[k]
                 for k in t:
                     if k.startswith("rp") or k.startswith("rot"):
-                        if k.endswith("/TA1") or k.endswith("/TA2") or k.endswith("spec1") or k.endswith("spec2") or k.endswith("rho_binary"):
+                        if k.endswith("/TA1") or k.endswith("/TA2") or k.endswith("spec1") or k.endswith("spec2") or k.endswith("rho_binary") or k.endswith("_x"):
                             continue        # keep the rotated fixtures small: rho + positions pin the sequence
                         out[pre + k] = t[k]
             ia += 1
