@@ -330,6 +330,77 @@ int MakeDensity::generate_profile_ebe_Jet(int nevent) {
   return ebe_common(this, ctx, paraRdr, true, nevent, first, count, data_dir, Maxx, Maxy, Xmin, Ymin, dx, dy, rapMin, deformed, 128, err);
 }
 
+// ---- operation 3: averaged profiles (src/MakeDensity.cpp:736-2103) ----------------------------------
+int MakeDensity::average_accumulate(int nevent) {
+  const int from = ival(paraRdr, "average_from_order"), to = ival(paraRdr, "average_to_order");
+  const int branches = (paraRdr->getVal("use_sd") != 0 ? 1 : 0) | (paraRdr->getVal("use_ed") != 0 ? 2 : 0);
+  if (!branches) { err = "operation 3 needs use_sd or use_ed"; return 1; }
+  if (smc_avg_begin(ctx, from, to, ival(paraRdr, "generate_reaction_plane_avg_profile") == 1, branches) != SMC_OK) { err = smc_last_error(ctx); return 1; }
+  uint64_t first; int count; shard_range(nevent, &first, &count);
+  const int chunk = 1024;
+  std::vector<smc_event_out> out(chunk);
+  for (int done = 0; done < count; done += chunk) {
+    const int n = std::min(chunk, count - done);
+    if (smc_avg_run(ctx, first + done, n, out.data()) != SMC_OK) { err = smc_last_error(ctx); return 1; }
+    last_npart = out[n - 1].npart1 + out[n - 1].npart2;
+    std::cout << "processing event: " << done + n << std::endl;          // :1574
+  }
+  return 0;
+}
+
+int MakeDensity::average_write() {
+  const int from = ival(paraRdr, "average_from_order"), to = ival(paraRdr, "average_to_order");
+  const bool use_sd = paraRdr->getVal("use_sd") != 0, use_ed = paraRdr->getVal("use_ed") != 0;
+  const bool use_block = paraRdr->getVal("use_block") != 0, use_4col = paraRdr->getVal("use_4col") != 0;
+  const bool rp = ival(paraRdr, "generate_reaction_plane_avg_profile") == 1;
+  const bool o_tatb = ival(paraRdr, "output_TATB") == 1, o_rb = ival(paraRdr, "output_rho_binary") == 1;
+  const bool o_ta = ival(paraRdr, "output_TA") == 1, o_sp = ival(paraRdr, "output_spectator_density") == 1;
+  const size_t G = (size_t)Maxx * Maxy;
+  WriterPool pool(std::max(2u, std::min(16u, std::thread::hardware_concurrency())));
+  auto emit = [&](int order, int variant, int quantity, int branch, const char* fmt) -> int {
+    auto g = std::make_shared<std::vector<double>>(G);
+    if (smc_avg_get(ctx, order, variant, quantity, branch, g->data()) != SMC_OK) { err = smc_last_error(ctx); return 1; }
+    char stem[200]; std::snprintf(stem, sizeof stem, fmt, order);
+    const std::string st = path(stem); const double npart = last_npart;
+    const int mx = Maxx, my = Maxy; const double x0 = Xmin, y0 = Ymin, ddx = dx, ddy = dy, rap = rapMin;
+    if (use_4col) pool.submit([=] { std::string s; MakeDensity::formatDensity4Col(g->data(), mx, my, x0, y0, ddx, ddy, rap, npart, s); write_file(st + "_4col.dat", s, false); });
+    if (use_block) pool.submit([=] { std::string s; MakeDensity::formatDensityBlock(g->data(), mx, my, s); write_file(st + "_block.dat", s, false); });
+    return 0;
+  };
+  for (int order = from; order <= to; order++) {
+    for (int branch = 0; branch < 2; branch++) {
+      if ((branch == 0 && !use_sd) || (branch == 1 && !use_ed)) continue;
+      const bool sd = branch == 0;
+      if (emit(order, 0, SMC_AVG_SD, branch, sd ? "sdAvg_order_%d" : "edAvg_order_%d")) return 1;
+      if (rp && emit(order, 1, SMC_AVG_SD, branch, sd ? "sdAvg_RP_order_%d" : "edAvg_RP_order_%d")) return 1;
+      if (o_tatb) {
+        if (emit(order, 0, SMC_AVG_TATB, branch, sd ? "TATB_fromSd_order_%d" : "TATB_fromEd_order_%d")) return 1;
+        if (rp && emit(order, 1, SMC_AVG_TATB, branch, sd ? "TATB_fromSd_RP_order_%d" : "TATB_fromEd_RP_order_%d")) return 1;
+      }
+      if (o_rb) {
+        if (emit(order, 0, SMC_AVG_RHO_BINARY, branch, sd ? "rho_binary_fromSd_order_%d" : "rho_binary_fromEd_order_%d")) return 1;
+        if (rp && emit(order, 1, SMC_AVG_RHO_BINARY, branch, sd ? "rho_binary_fromSd_RP_order_%d" : "rho_binary_fromEd_RP_order_%d")) return 1;
+      }
+      if (o_ta) {
+        if (emit(order, 0, SMC_AVG_TA, branch, sd ? "nuclear_thickness_TA_fromSd_order_%d" : "nuclear_thickness_TA_fromEd_order_%d")) return 1;
+        if (emit(order, 0, SMC_AVG_TB, branch, sd ? "nuclear_thickness_TB_fromSd_order_%d" : "nuclear_thickness_TB_fromEd_order_%d")) return 1;
+        if (rp) {
+          if (emit(order, 1, SMC_AVG_TA, branch, sd ? "nuclear_thickness_TA_fromSd_RP_order_%d" : "nuclear_thickness_TA_fromEd_RP_order_%d")) return 1;
+          if (emit(order, 1, SMC_AVG_TB, branch, sd ? "nuclear_thickness_TB_fromSd_RP_order_%d" : "nuclear_thickness_TB_fromEd_RP_order_%d")) return 1;
+        }
+      }
+      if (o_sp) {
+        if (emit(order, 0, SMC_AVG_SPEC_A, branch, sd ? "spectator_density_A_fromSd_order_%d" : "spectator_density_A_fromEd_order_%d")) return 1;
+        if (emit(order, 0, SMC_AVG_SPEC_B, branch, sd ? "spectator_density_B_fromSd_order_%d" : "spectator_density_B_fromEd_order_%d")) return 1;
+      }
+    }
+  }
+  pool.wait();
+  return 0;
+}
+
 int MakeDensity::generate_profile_average(int nevent) {
-  (void)nevent; err = "operation 3 is wired in smc_avg (see generate_profile_average below)"; return 1;
+  if (average_accumulate(nevent)) return 1;
+  if (shard.world > 1) { err = "operation 3 on several GPUs: run through `python -m supermc_b200.launch` so the accumulators are all-reduced"; return 1; }
+  return average_write();
 }

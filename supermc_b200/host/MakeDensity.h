@@ -28,6 +28,8 @@ class MakeDensity {
   int generate_profile_ebe_Jet(int nevent);    // operation 2, src/MakeDensity.cpp:148-498
   int generate_profile_average(int nevent);    // operation 3, src/MakeDensity.cpp:736-2103
   int generateEccTable(int nevent);            // operation 9, src/MakeDensity.cpp:2108-2240
+  int average_accumulate(int nevent);          // operation 3, event loop only (sums stay on the GPU)
+  int average_write();                         // operation 3, the files of src/MakeDensity.cpp:1579-1900
   int run(int operation, int nevent);
 
   // text writers, byte-compatible with the reference's iostream formatting
@@ -53,4 +55,5 @@ class MakeDensity {
   double Xmin, Ymin, dx, dy, rapMin, rapMax, finalFactor;
   int binRapidity;
   bool deformed;
+  double last_npart = 0;
 };

@@ -5,6 +5,26 @@
 #include "MakeDensity.h"
 
 extern "C" {
+// ---- driver handle for the multi-GPU launcher (supermc_b200/launch.py): one per rank ----
+struct smc_host { ParameterReader rdr; MakeDensity* md; std::string err; };
+smc_host* smc_host_create(const char* parameter_file, int argc, char** argv, int device, int rank, int world, const char* data_dir) {
+  smc_host* h = new smc_host(); h->md = nullptr;
+  try { h->rdr.readFromFile(parameter_file); h->rdr.readFromArguments(argc, argv, "#", 0); }
+  catch (std::exception& e) { h->err = e.what(); return h; }
+  h->md = new MakeDensity(&h->rdr, device, smc_shard{rank, world}, data_dir);
+  if (!h->md->ok()) { h->err = h->md->error(); delete h->md; h->md = nullptr; }
+  return h;
+}
+const char* smc_host_error(smc_host* h) { return h ? (h->md && !h->md->error().empty() ? h->md->error().c_str() : h->err.c_str()) : "null"; }
+void smc_host_destroy(smc_host* h) { if (h) { delete h->md; delete h; } }
+smc_ctx* smc_host_context(smc_host* h) { return (h && h->md) ? h->md->context() : nullptr; }
+int smc_host_run(smc_host* h) {            // operations 1, 2, 9 (and 3 on one GPU)
+  if (!h || !h->md) return 1;
+  try { return h->md->run((int)h->rdr.getVal("operation"), (int)h->rdr.getVal("nev")); } catch (std::exception& e) { h->err = e.what(); return 1; }
+}
+int smc_host_average_accumulate(smc_host* h) { if (!h || !h->md) return 1; try { return h->md->average_accumulate((int)h->rdr.getVal("nev")); } catch (std::exception& e) { h->err = e.what(); return 1; } }
+int smc_host_average_write(smc_host* h) { if (!h || !h->md) return 1; try { return h->md->average_write(); } catch (std::exception& e) { h->err = e.what(); return 1; } }
+int smc_host_get(smc_host* h, const char* name, double* v) { if (!h) return 1; try { *v = h->rdr.getVal(name); return 0; } catch (std::exception&) { return 1; } }
 // parse `text` (a parameters.dat body) then `overrides` (space-separated name=value); returns the value of `name`
 int smc_host_param(const char* text, const char* overrides, const char* name, double* value) {
   try {
