@@ -45,6 +45,8 @@ SYSTEMS = {
                                      cc_fluctuation_Gamma_theta=0.61, randomSeed=18)),
     "uu193_deformed": ("zero", 3, 0, dict(which_mc_model=5, sub_model=1, Aproj=238, Atarg=238, ecm=193, alpha=0.14,
                                           proj_deformed=1, targ_deformed=1, randomSeed=19)),
+    "auau200_kln": ("zero", 4, 1, dict(which_mc_model=1, sub_model=7, Aproj=197, Atarg=197, ecm=200, tmax=14, tmax_subdivision=3,
+                                       cc_fluctuation_model=0, randomSeed=21, bmin=8)),
     "pbpb2760_rotate": ("rand", 3, 1, dict(which_mc_model=5, sub_model=1, Aproj=208, Atarg=208, ecm=2760, alpha=0.118,
                                            cc_fluctuation_Gamma_theta=0.75, randomSeed=20, bmax=12, dump_rotate=1)),
 }
@@ -57,6 +59,8 @@ def run_system(name):
         os.remove(os.path.join(run, "data", f))
     p = dict(COMMON); p.update(par)
     p.update(dump_grids=1, dump_extra=1, dump_tries=1)
+    if "lambda" not in p and p.get("which_mc_model") == 1:
+        p["lambda"] = 0.218
     args = ["%s=%s" % kv for kv in p.items()]
     binf = "/tmp/golden_%s.bin" % name
     subprocess.check_call([os.path.join(REFDIR, "ref_dump"), binf, str(nev)] + args, cwd=run, stdout=subprocess.DEVNULL)
@@ -64,8 +68,9 @@ def run_system(name):
     glob, tries = refio.group_tries(rec)
     ncol = 53 if (p.get("proj_deformed") or p.get("targ_deformed")) else 49   # deformed rows carry 4 uninitialised extras (quirk Q9)
     ecc = np.loadtxt(os.path.join(run, "data", "h_ecc_10.dat")).reshape(-1, ncol)[:, :49]
-    out = {"consts": glob["consts"], "params_keys": np.array(list(p.keys())), "params_vals": np.array([float(v) for v in p.values()]),
-           "quark_kind": np.array(kind), "ntries": np.array(len(tries)), "ecc_rows": ecc}
+    out = {k: glob[k] for k in ("kln_table", "kln_consts") if k in glob}
+    out.update({"consts": glob["consts"], "params_keys": np.array(list(p.keys())), "params_vals": np.array([float(v) for v in p.values()]),
+           "quark_kind": np.array(kind), "ntries": np.array(len(tries)), "ecc_rows": ecc})
     ia = 0
     for it, t in enumerate(tries):
         pre = "t%d/" % it

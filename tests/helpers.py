@@ -5,6 +5,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
+KLN_SYSTEM = "auau200_kln"
 SYSTEMS = ["pbpb2760_glb", "auau200_glb_quarks", "ppb5020_glb_quarks", "pbpb2760_sqrt_disk", "pbpb2760_uli",
            "auau200_disk_nucleons", "he3au200_glb", "cc200_glb", "uu193_deformed", "pbpb2760_rotate"]
 
@@ -43,6 +44,8 @@ class Golden:
                   finalfactor=p["finalfactor"], maxx=p["maxx"], maxy=p["maxy"], dx=p["dx"], dy=p["dy"],
                   cc_fluctuation_model=int(p["cc_fluctuation_model"]),
                   cc_fluctuation_gamma_theta=p.get("cc_fluctuation_gamma_theta", 0.75), randomseed=int(p["randomseed"]))
+        if "lambda" in p:
+            kw.update({"lambda": p["lambda"], "tmax": int(p["tmax"]), "tmax_subdivision": int(p["tmax_subdivision"])})
         kw.update(over)
         return capi.default_params(**kw)
 

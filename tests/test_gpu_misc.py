@@ -1,0 +1,65 @@
+"""-m gpu: centrality sort, dS/dy window re-draw loop, table-driven nuclei on the sampled path."""
+import os
+import numpy as np
+import pytest
+
+from helpers import Golden, ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def test_centrality_sort_is_argsort_descending():
+    import supermc_b200 as smc
+    g = Golden("pbpb2760_glb")
+    ctx = smc.Context(g.smc_params(smc.capi, max_batch=512))
+    ev = ctx.run_events(0, 5000)
+    key = ev["total"]
+    perm = ctx.centrality_sort(key)
+    assert np.array_equal(np.sort(perm), np.arange(len(key)))
+    assert np.all(np.diff(key[perm]) <= 0)
+    # scripts/centrality_cut_h5.py:78-90: the 0-5 % bin
+    nsample = int(len(key) * 5 / 100) - 1
+    top = ev[perm[:nsample]]
+    assert top["npart1"].min() + top["npart2"].min() > 150 and top["b"].max() < 6.5
+    ctx.close()
+
+
+def test_dsdy_window_redraws_until_inside():
+    import supermc_b200 as smc
+    g = Golden("pbpb2760_glb")
+    lo, hi = 60.0, 120.0
+    ctx = smc.Context(g.smc_params(smc.capi, max_batch=128, cutdsdy=1, cutdsdy_lowerbound=lo, cutdsdy_upperbound=hi, randomseed=3))
+    ev = ctx.run_events(0, 300)
+    assert ((ev["dsdy"] >= lo) & (ev["dsdy"] <= hi)).all() and (ev["status"] == 0).all()
+    free = smc.Context(g.smc_params(smc.capi, max_batch=128, randomseed=3)).run_events(0, 300)
+    inside = (free["dsdy"] >= lo) & (free["dsdy"] <= hi)
+    # events that were inside the window at their first accepted try are untouched; the others consumed more tries
+    assert np.array_equal(ev["b"][inside], free["b"][inside]) and (ev["tries"][~inside] > free["tries"][~inside]).all()
+    ctx.close()
+
+
+def test_he3_table_sampling_equals_oracle(oracle_lib):
+    import supermc_b200 as smc
+    port = oracle_lib
+    g = Golden("he3au200_glb"); cfg = g.oracle_cfg(port)
+    raw = np.loadtxt(os.path.join(ROOT, "tests", "golden", "he3_configs_small.txt"))
+    seed = 11
+    ctx = smc.Context(g.smc_params(smc.capi, max_batch=16, randomseed=seed))
+    ctx.load_config_table(0, raw)
+    nA = port.nucleus(3, cfg.width); nB = port.nucleus(197, cfg.width)
+    out = ctx.run_events(50, 4)
+    for e in range(4):
+        ev = 50 + e
+        for tr in range(200):
+            b = np.sqrt(400.0 * port.StreamPhilox(seed, ev, tr, 0).u(0, 0, 0))
+            icfg = int(port.StreamPhilox(seed, ev, tr, 0).u(8, 0, 0) * len(raw))
+            p = port.populate_table(nA, raw[icfg], 0, 0, b / 2, 0.0, stream=port.StreamPhilox(seed, ev, tr, 0))
+            t, _ = port.populate(nB, -b / 2, 0.0, stream=port.StreamPhilox(seed, ev, tr, 1))
+            r = port.collide(cfg, p, t, stream=port.StreamPhilox(seed, ev, tr, 0))
+            npart = int((r["ncollA"] > 0).sum() + (r["ncollB"] > 0).sum())
+            if r["ncoll"] > 0 and npart >= 2:
+                break
+        assert out[e]["tries"] == tr + 1 and out[e]["ncoll"] == r["ncoll"]
+        got = ctx.nucleons(e, 0)
+        assert np.abs(got[:, [0, 1, 3, 4, 5, 6]] - p[:, [0, 1, 3, 4, 5, 6]]).max() < 1e-11
+    ctx.close()

@@ -1,0 +1,84 @@
+"""MC-KLN.
+
+CPU: the oracle's deterministic quadrature of the restated integrand against the reference's own BASES
+Monte-Carlo table (tests/golden/auau200_kln.npz, 40x40 entries built by the unmodified reference): the
+reference's stated MC accuracy is 0.1 %, observed differences are -0.02 .. -0.2 %, gate 0.5 %.
+GPU: (1) the device table against the oracle quadrature on the same nodes (1e-10), (2) the 6-point table
+look-up + moments on the reference's golden KLN events, with the reference's own table installed."""
+import numpy as np
+import pytest
+
+from helpers import Golden, KLN_SYSTEM, event_in_from, src8_from, rel_err
+
+ENTRIES = [(1, 1), (2, 17), (5, 9), (11, 3), (20, 20), (3, 30), (33, 12), (38, 38), (39, 1)]
+
+
+def test_oracle_quadrature_vs_reference_bases_table(oracle_lib):
+    port = oracle_lib
+    g = Golden(KLN_SYSTEM)
+    T = g.z["kln_table"]; dT, tmax = g.z["kln_consts"]
+    assert T.shape == (40, 40) and (T[0] == 0).all() and (T[:, 0] == 0).all()         # MCnucl.cpp:937-944
+    k = port.kln(g.par["ecm"], g.par["lambda"])
+    for i, j in ENTRIES:
+        v = port.kln_dndy(k, 0.0, dT * i, dT * j, 400, 200, 64)
+        assert abs(v / T[i, j] - 1) < 5e-3, (i, j, v, T[i, j])
+    # y = 0: dN/dy(TA,TB) = dN/dy(TB,TA)
+    assert abs(port.kln_dndy(k, 0.0, dT * 4, dT * 9, 200, 100, 32) / port.kln_dndy(k, 0.0, dT * 9, dT * 4, 200, 100, 32) - 1) < 1e-12
+
+
+def test_oracle_kln_density_on_reference_events(oracle_lib):
+    """six-point look-up (MCnucl.cpp:654-687) with the reference's table on the reference's TA1/TA2: bit-exact rho"""
+    port = oracle_lib
+    g = Golden(KLN_SYSTEM); cfg = g.oracle_cfg(port)
+    T = g.z["kln_table"]; dT, tmax = g.z["kln_consts"]
+    done = 0
+    for t in g.tries():
+        if "rho" not in t:
+            continue
+        rho, dndy = port.density_kln(cfg, t["TA1"], t["TA2"], T, float(dT))
+        assert np.array_equal(rho, t["rho"]) and dndy == t["dndy"][0]
+        done += 1
+    assert done >= 1
+
+
+@pytest.mark.gpu
+def test_gpu_table_equals_oracle_quadrature(oracle_lib, monkeypatch):
+    import supermc_b200 as smc
+    port = oracle_lib
+    g = Golden(KLN_SYSTEM)
+    monkeypatch.setenv("SMC_KLN_QUAD", "200,100,32")
+    ctx = smc.Context(g.smc_params(smc.capi, max_batch=8))
+    T = ctx.build_kln_table()
+    dT = ctx.k.kln_dt
+    assert T.shape == (40, 40) and abs(dT - float(g.z["kln_consts"][0])) < 1e-15
+    k = port.kln(g.par["ecm"], g.par["lambda"])
+    for i, j in ENTRIES:
+        v = port.kln_dndy(k, 0.0, dT * i, dT * j, 200, 100, 32)
+        assert abs(T[i, j] / v - 1) < 1e-10, (i, j, T[i, j], v)
+    assert np.abs(T - T.T).max() <= 1e-12 * T.max() and (T[0] == 0).all()
+    ref = g.z["kln_table"]
+    assert np.abs(T[1:, 1:] / ref[1:, 1:] - 1).max() < 5e-3          # the reference's BASES table, to its MC error
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_kln_events_match_reference(oracle_lib):
+    import supermc_b200 as smc
+    port = oracle_lib
+    g = Golden(KLN_SYSTEM); cfg = g.oracle_cfg(port)
+    ctx = smc.Context(g.smc_params(smc.capi, max_batch=8))
+    ctx.set_kln_table(g.z["kln_table"], float(g.z["kln_consts"][0]))
+    tries = g.tries()
+    out = ctx.run_from_positions([event_in_from(t, port, cfg) for t in tries], smc.RUN_MOMENTS | smc.RUN_THICKNESS)
+    for it, t in enumerate(tries):
+        hdr = t["hdr"]
+        assert (out[it]["ncoll"], out[it]["npart1"], out[it]["npart2"]) == (int(hdr[1]), int(hdr[2]), int(hdr[3]))
+        if not int(hdr[4]):
+            continue
+        row = g.ecc_rows[int(t["ecc_index"])]
+        assert np.abs(out[it]["mom"][:, :4] - row[:45].reshape(9, 5)[:, :4]).max() < 1e-9
+        assert abs(out[it]["total"] / row[47] - 1) < 1e-10
+        if "rho" in t:
+            assert rel_err(ctx.grid(it, smc.GRID_RHO), t["rho"]).max() < 1e-9
+            assert rel_err(ctx.grid(it, smc.GRID_TA1), t["TA1"]).max() < 1e-9
+    ctx.close()
