@@ -5,7 +5,7 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO = os.path.join(HERE, "libsupermc_b200.so")
+SO = os.environ.get("SMC_LIB") or os.path.join(HERE, "libsupermc_b200.so")
 dp = C.POINTER(C.c_double)
 
 RUN_MOMENTS, RUN_KEEP_RHO, RUN_THICKNESS, RUN_RHO_BINARY, RUN_SPECTATORS, RUN_LISTS = 1, 2, 4, 8, 16, 32

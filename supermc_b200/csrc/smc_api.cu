@@ -259,6 +259,7 @@ int smc_plan_kinds(smc_ctx* ctx, unsigned flags, int* kinds, int* nk_dep) {
   if (flags & SMC_RUN_RHO_BINARY) add(smc::GK_RHO_BINARY, true);
   if (flags & SMC_RUN_SPECTATORS) { add(smc::GK_SPEC_A, true); add(smc::GK_SPEC_B, true); }
   st.nkinds = n; *nk_dep = nd;
+  ctx->need_zero = !(c.which_mc_model == 5 && (flags & ~(unsigned)SMC_RUN_MOMENTS) == 0);
   const size_t need = (size_t)ctx->batch * n * ctx->G * sizeof(double);
   if (need > ctx->grids_bytes) {
     if (ctx->d_grids) cudaFree(ctx->d_grids);
@@ -277,7 +278,9 @@ int smc_run_grid_stages(smc_ctx* ctx, int m, const int* kinds, int nd) {
   const smc::DevCfg& c = ctx->cfg;
   if (c.which_mc_model == 1 && !ctx->st.kln_table) FAIL(SMC_ERR_STATE, "MC-KLN density requires smc_build_kln_table / smc_set_kln_table first (MCnucl.cpp:636-640)");
   if (ctx->profile) CK(cudaEventRecord(ctx->pev[1], ctx->stream));
-  CK(smc::launch_deposit(c, ctx->st, kinds, nd, m, ctx->stream)); ctx->launches++;
+  // deposit CTAs only cover each event's bounding rectangle: whoever reads whole grids needs zeros elsewhere
+  if (ctx->need_zero) CK(cudaMemsetAsync(ctx->d_grids, 0, (size_t)m * ctx->st.nkinds * ctx->G * sizeof(double), ctx->stream));
+  CK(smc::launch_deposit(c, ctx->st, kinds, nd, m, ctx->stream)); ctx->launches += 2;
   if (ctx->profile) CK(cudaEventRecord(ctx->pev[2], ctx->stream));
   if (c.which_mc_model != 5) { CK(smc::launch_combine(c, ctx->st, m, ctx->stream)); ctx->launches++; }
   if (ctx->profile) CK(cudaEventRecord(ctx->pev[3], ctx->stream));

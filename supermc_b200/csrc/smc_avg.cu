@@ -152,7 +152,8 @@ static int avg_sequence(smc_ctx* ctx, int m) {
   if ((rc = smc_plan_kinds(ctx, SMC_RUN_THICKNESS | SMC_RUN_RHO_BINARY | SMC_RUN_SPECTATORS, kinds, &nd))) return rc;
   if (c.which_mc_model == 1 && !st.kln_table) FAIL(SMC_ERR_STATE, "MC-KLN needs its table first");
   auto density = [&]() -> int {          // calculateThickness + setDensity + calculate_rho_binary + calculate_spectator_density
-    CK(smc::launch_deposit(c, st, kinds, nd, m, ctx->stream)); ctx->launches++;
+    CK(cudaMemsetAsync(ctx->d_grids, 0, (size_t)m * st.nkinds * ctx->G * sizeof(double), ctx->stream));
+    CK(smc::launch_deposit(c, st, kinds, nd, m, ctx->stream)); ctx->launches += 2;
     if (c.which_mc_model != 5) { CK(smc::launch_combine(c, st, m, ctx->stream)); ctx->launches++; }
     return SMC_OK;
   };

@@ -20,7 +20,7 @@ struct smc_ctx {
   int device; cudaStream_t stream; cudaEvent_t ev0, ev1;
   int batch; size_t G;
   std::vector<void*> owned;
-  double* d_grids; size_t grids_bytes;
+  double* d_grids; size_t grids_bytes; bool need_zero;
   double* d_pair_u; size_t pair_u_bytes; double* d_coll_w; size_t coll_w_bytes;
   double* d_quark; double* d_cfgtab[2]; double* d_kln; int* d_redo;
   int* h_hdr_i; double* h_hdr_d; double* h_mom; uint64_t* h_evid; int* h_try; double* h_nuc;

@@ -95,11 +95,51 @@ struct KindList { int n; int kind[8]; };
 // Deposit geometry: a CTA owns a band of DEP_BAND rows; warp (wr, stripe) keeps DEP_WROWS rows x 32
 // columns of it in registers.  Sources are processed in chunks of DEP_CH whose factor tables live in
 // shared memory:  xtab[r][t] = (W*exp(-dx^2/2w^2), dx^2)  and  ytab[t][c] = (exp(-dy^2/2w^2), dy^2).
+#ifndef DEP_BAND
 #define DEP_BAND 32
+#endif
 #define DEP_WROWS 16
+#define DEP_NWR (DEP_BAND / DEP_WROWS)
+#ifndef DEP_CH
 #define DEP_CH 64
+#endif
+#ifndef DEP_MINCTA
+#define DEP_MINCTA 2
+#endif
 #define DEP_PART 8
-#define DEP_MAXSTRIPES 10
+#define DEP_MAXSTRIPES 4
+
+// bounding rectangle (cells) of every source window of the participant/collision deposits of one event
+__global__ void bbox_kernel(DevCfg c, Store st, KindList kl, int nev) {
+  __shared__ int red[4][4];
+  const int e = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (st.redo && !st.redo[e]) return;
+  int* hi = st.hdr_i + (size_t)e * HDR_I;
+  int ilo = c.Maxx, ihi = 0, jlo = c.Maxy, jhi = 0;
+  const int status = hi[H_STATUS];
+  if (status == 0 || status == 4) {
+    for (int q = 0; q < kl.n; q++) {
+      const int kind = kl.kind[q];
+      if (kind == GK_SPEC_A || kind == GK_SPEC_B) continue;
+      const int ns = src_count(c, hi, kind);
+      for (int k = tid; k < ns; k += blockDim.x) {
+        Src s; load_src(c, st, e, hi, kind, k, s);
+        if (s.iL < s.iR && s.jL < s.jR) { ilo = min(ilo, s.iL); ihi = max(ihi, s.iR); jlo = min(jlo, s.jL); jhi = max(jhi, s.jR); }
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    ilo = min(ilo, __shfl_xor_sync(0xffffffffu, ilo, o)); ihi = max(ihi, __shfl_xor_sync(0xffffffffu, ihi, o));
+    jlo = min(jlo, __shfl_xor_sync(0xffffffffu, jlo, o)); jhi = max(jhi, __shfl_xor_sync(0xffffffffu, jhi, o));
+  }
+  if (lane == 0) { red[warp][0] = ilo; red[warp][1] = ihi; red[warp][2] = jlo; red[warp][3] = jhi; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++) { ilo = min(ilo, red[w][0]); ihi = max(ihi, red[w][1]); jlo = min(jlo, red[w][2]); jhi = max(jhi, red[w][3]); }
+    if (ihi <= ilo || jhi <= jlo) { ilo = ihi = jlo = jhi = 0; }
+    hi[H_RLO] = ilo; hi[H_RHI] = ihi; hi[H_CLO] = jlo; hi[H_CHI] = jhi;
+  }
+}
 
 struct DepSmem {
   double2* xtab;      // [DEP_BAND][DEP_CH]
@@ -110,18 +150,26 @@ struct DepSmem {
   unsigned short* act;
 };
 
-__global__ void __launch_bounds__(2 * DEP_MAXSTRIPES * 32, 1) deposit_kernel(DevCfg c, Store st, KindList kl, int nev, int nbands, int CS) {
+__global__ void __launch_bounds__(DEP_NWR * DEP_MAXSTRIPES * 32, DEP_MINCTA) deposit_kernel(DevCfg c, Store st, KindList kl, int nev, int nbands, int CS) {
   extern __shared__ double2 smem_d2[];
   const int e = blockIdx.x, band = blockIdx.y % nbands, sgroup = blockIdx.y / nbands, kind = kl.kind[blockIdx.z];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nwarps = nthreads >> 5;
-  const int nstr = nwarps >> 1;                       // stripes handled by this CTA
-  const int wr = warp / nstr, stripe = sgroup * nstr + (warp % nstr);
+  const int nstr = nwarps / DEP_NWR;                  // stripes handled by this CTA
+  const int wr = warp / nstr;
   if (st.redo && !st.redo[e]) return;
   const int* hi = st.hdr_i + (size_t)e * HDR_I;
   const int slot = st.kind_slot[kind];
   double* grid = st.grids + ((size_t)e * st.nkinds + slot) * (size_t)c.Maxx * c.Maxy;
-  const int r0 = band * DEP_BAND, rw0 = r0 + wr * DEP_WROWS;
-  const int j = stripe * 32 + lane;
+  // bands and column groups are laid out from the corner of the event's own bounding rectangle (bbox_kernel),
+  // so a CTA is either inside the populated region or exits at once; spectator grids span the whole lattice
+  const bool whole = (kind == GK_SPEC_A || kind == GK_SPEC_B);
+  const int r_org = whole ? 0 : hi[H_RLO], r_end = whole ? c.Maxx : hi[H_RHI];
+  const int c_org = whole ? 0 : hi[H_CLO], c_end = whole ? c.Maxy : hi[H_CHI];
+  const int r0 = r_org + band * DEP_BAND, rw0 = r0 + wr * DEP_WROWS;
+  const int c0 = c_org + sgroup * nstr * 32;
+  if (r0 >= r_end || c0 >= c_end) return;
+  const int sc0 = c0 + (warp % nstr) * 32;            // first column of this warp's stripe
+  const int j = sc0 + lane;
   DepSmem sm;
   sm.xtab = smem_d2; sm.ytab = sm.xtab + DEP_BAND * DEP_CH;
   sm.sx = (double*)(sm.ytab + (size_t)DEP_CH * CS); sm.sy = sm.sx + DEP_CH; sm.sW = sm.sy + DEP_CH; sm.sthr = sm.sW + DEP_CH;
@@ -139,7 +187,7 @@ __global__ void __launch_bounds__(2 * DEP_MAXSTRIPES * 32, 1) deposit_kernel(Dev
   for (int base = 0; base < nsrc; base += nthreads) {
     const int k = base + tid;
     bool on = false;
-    if (k < nsrc) { Src s; load_src(c, st, e, hi, kind, k, s); on = (s.iL < s.iR) && (s.jL < s.jR) && (s.iL < r0 + DEP_BAND) && (s.iR > r0); }
+    if (k < nsrc) { Src s; load_src(c, st, e, hi, kind, k, s); on = (s.iL < s.iR) && (s.jL < s.jR) && (s.iL < r0 + DEP_BAND) && (s.iR > r0) && (s.jL < c0 + nstr * 32) && (s.jR > c0); }
     const unsigned m = __ballot_sync(0xffffffffu, on);
     if (lane == 0) sm.wtot[warp] = __popc(m);
     __syncthreads();
@@ -210,7 +258,7 @@ __global__ void __launch_bounds__(2 * DEP_MAXSTRIPES * 32, 1) deposit_kernel(Dev
     for (int tb = 0; tb < nch; tb += 32) {
       const int tt = tb + lane;
       bool hit = false;
-      if (tt < nch) hit = (sm.sjR[tt] > stripe * 32) && (sm.sjL[tt] < stripe * 32 + 32) && (sm.siR[tt] > rw0) && (sm.siL[tt] < rw0 + DEP_WROWS);
+      if (tt < nch) hit = (sm.sjR[tt] > sc0) && (sm.sjL[tt] < sc0 + 32) && (sm.siR[tt] > rw0) && (sm.siL[tt] < rw0 + DEP_WROWS);
       unsigned m = __ballot_sync(0xffffffffu, hit);
       while (m) {
         const int t = tb + __ffs(m) - 1; m &= m - 1;
@@ -246,15 +294,16 @@ size_t deposit_smem_bytes(const DevCfg& c, int nsrc_max) {
   return (b + 15) & ~(size_t)15;
 }
 
+#define DEP_GS 4      // stripes (of 32 columns) per CTA
 cudaError_t launch_deposit(const DevCfg& c, const Store& st, const int* kinds, int nk, int nev, cudaStream_t s) {
   KindList kl; kl.n = nk; for (int i = 0; i < nk; i++) kl.kind[i] = kinds[i];
-  const int nstripes = (c.Maxy + 31) / 32;
-  const int ngroups = (nstripes + DEP_MAXSTRIPES - 1) / DEP_MAXSTRIPES;
-  const int nstr = (nstripes + ngroups - 1) / ngroups;
-  const int threads = 2 * max(nstr, 2) * 32;
+  bbox_kernel<<<nev, 128, 0, s>>>(c, st, kl, nev);
+  const int nstr = DEP_GS;
+  const int ngroups = (c.Maxy + nstr * 32 - 1) / (nstr * 32) + 1;      // +1: groups start at the event's own first column
+  const int nbands = (c.Maxx + DEP_BAND - 1) / DEP_BAND + 1;
+  const int threads = DEP_NWR * nstr * 32;
   const size_t smem = deposit_smem_bytes(c, 2 * c.Amax + c.ncoll_cap);
   cudaFuncSetAttribute(deposit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  const int nbands = (c.Maxx + DEP_BAND - 1) / DEP_BAND;
   dim3 g(nev, nbands * ngroups, nk);
   deposit_kernel<<<g, threads, smem, s>>>(c, st, kl, nev, nbands, dep_cs(c));
   return cudaGetLastError();
@@ -364,22 +413,9 @@ __global__ void __launch_bounds__(MOM_THREADS, 1) moments_kernel(DevCfg c, Store
       }
     }
   }
-  // bounding rectangle of non-zero density = union of the source windows
-  int ilo = Maxx, ihi = 0, jlo = Maxy, jhi = 0;
-  {
-    const int kinds[3] = {GK_RHO, GK_RHOA, GK_RHOB};
-    const int nk = (c.which_mc_model == 5) ? 1 : (c.which_mc_model == 7 ? 3 : 0);
-    for (int q = (c.which_mc_model == 7 ? 1 : 0); q < nk; q++) {
-      const int ns = src_count(c, hi, kinds[q]);
-      for (int k = tid; k < ns; k += MOM_THREADS) {
-        Src s; load_src(c, st, e, hi, kinds[q], k, s);
-        if (s.iL < s.iR && s.jL < s.jR) { ilo = min(ilo, s.iL); ihi = max(ihi, s.iR); jlo = min(jlo, s.jL); jhi = max(jhi, s.jR); }
-      }
-    }
-    if (c.which_mc_model == 1) { ilo = 0; ihi = Maxx; jlo = 0; jhi = Maxy; }
-  }
-  ilo = (int)block_min((double)ilo, red, tid); ihi = -(int)block_min(-(double)ihi, red, tid);
-  jlo = (int)block_min((double)jlo, red, tid); jhi = -(int)block_min(-(double)jhi, red, tid);
+  // bounding rectangle of non-zero density = union of the source windows (bbox_kernel); MC-KLN: whole lattice
+  int ilo = hi[H_RLO], ihi = hi[H_RHI], jlo = hi[H_CLO], jhi = hi[H_CHI];
+  if (c.which_mc_model == 1) { ilo = 0; ihi = Maxx; jlo = 0; jhi = Maxy; }
   const int nj = max(jhi - jlo, 0), ncell = max(ihi - ilo, 0) * nj;
   // ---- pass 1: centre of mass (MakeDensity.cpp:2273-2282) ----
   double s0 = 0, sx = 0, sy = 0;

@@ -18,9 +18,9 @@
 namespace smc {
 
 struct SampleSmem {
-  double* pos;      // [2][Amax][NROW] sorted rows
-  double* tmp;      // [2][Amax][NROW] acceptance-order rows
-  double* xl;       // [2][Amax]
+  double* soa;      // [2][NROW][Amax]: structure of arrays (lane-consecutive => conflict-free), first in
+                    // acceptance order (x y z, candidate id in the weight slot), then sorted in place by xL
+  int Amax;
   uint32_t* hit;    // [Amax][HW] hit bit masks (row = projectile)
   int* ncB;         // [Amax]
   int* firstB;      // [Amax]
@@ -36,6 +36,9 @@ __device__ __forceinline__ void rot3(double cth, double phi, double& x, double& 
   y = cth * sphi * x0 + cphi * y0 + sth * sphi * z0;
   z = -sth * x0 + cth * z0;
 }
+
+#define S_(sm, side, f, i) (sm).soa[((size_t)(side) * NROW + (f)) * (sm).Amax + (i)]
+#define SMC_MAXK 16      // ceil(512 / 32): nucleons per lane
 
 struct Box { double xL, xR, yL, yR, xC, yC; };
 __device__ __forceinline__ void box_center(Box& b, double x, double y) {   // Box2D::setCenter, src/Box2D.cpp:24-33
@@ -98,9 +101,6 @@ __device__ __forceinline__ double sph_harm4(double ct) { return (35.0 * ct * ct 
 __device__ void sample_nucleus(const DevCfg& c, const Store& st, const SampleSmem& sm, int e, int s, uint64_t ev,
                                uint32_t tr, double xCenter, double yCenter) {
   const int lane = threadIdx.x & 31, A = c.A[s];
-  double* tmp = sm.tmp + (size_t)s * c.Amax * NROW;
-  double* pos = sm.pos + (size_t)s * c.Amax * NROW;
-  double* xl = sm.xl + (size_t)s * c.Amax;
   const smc_stream s_or = smc_make_stream(c.seed_lo, c.seed_hi, ev, tr, SMC_K_ORIENT, s);
   const smc_stream s_q = smc_make_stream(c.seed_lo, c.seed_hi, ev, tr, SMC_K_QUARK, s);
   double uo0, uo1; smc_uniform2(s_or, 0, 0, &uo0, &uo1);
@@ -108,7 +108,7 @@ __device__ void sample_nucleus(const DevCfg& c, const Store& st, const SampleSme
   bool recentre = true;
   const int mode = c.sampler[s];
   if (mode == 1) {                                              // single nucleon, Nucleus.cpp:201-202
-    if (lane == 0) { tmp[0] = xCenter; tmp[1] = yCenter; tmp[2] = 0.0; tmp[3] = 0.0; }
+    if (lane == 0) { S_(sm, s, NX, 0) = xCenter; S_(sm, s, NY, 0) = yCenter; S_(sm, s, NZ, 0) = 0.0; S_(sm, s, NW, 0) = 0.0; }
     recentre = false;
   } else if (mode == 2 || mode == 3) {                          // config tables, Nucleus.cpp:555-574,623-666
     const smc_stream s_c = smc_make_stream(c.seed_lo, c.seed_hi, ev, tr, SMC_K_CONFIG, s);
@@ -126,7 +126,7 @@ __device__ void sample_nucleus(const DevCfg& c, const Store& st, const SampleSme
       double x = cfg[3 * k] - mx, y = cfg[3 * k + 1] - my, z = cfg[3 * k + 2] - mz;
       rot3(ctr, phir, x, y, z);
       if (mode == 2) { x += xCenter; y += yCenter; }
-      tmp[k * NROW + 0] = x; tmp[k * NROW + 1] = y; tmp[k * NROW + 2] = z; tmp[k * NROW + 3] = (double)k;
+      S_(sm, s, NX, k) = x; S_(sm, s, NY, k) = y; S_(sm, s, NZ, k) = z; S_(sm, s, NW, k) = (double)k;
     }
     recentre = (mode == 3);
   } else {                                                      // Woods-Saxon + hard core, Nucleus.cpp:272-310
@@ -162,7 +162,7 @@ __device__ void sample_nucleus(const DevCfg& c, const Store& st, const SampleSme
       }
       bool bad = false;
       for (int i = 0; i < placed; i++) {                        // Nucleus.cpp:284-293
-        double ax = x - tmp[i * NROW], ay = y - tmp[i * NROW + 1], az = z - tmp[i * NROW + 2];
+        double ax = x - S_(sm, s, NX, i), ay = y - S_(sm, s, NY, i), az = z - S_(sm, s, NZ, i);
         double r2 = ax * ax + ay * ay + az * az;
         bad |= (r2 < rmin);
       }
@@ -173,7 +173,7 @@ __device__ void sample_nucleus(const DevCfg& c, const Store& st, const SampleSme
         if (placed + nacc >= A) break;
         double lx = __shfl_sync(0xffffffffu, x, l), ly = __shfl_sync(0xffffffffu, y, l), lz = __shfl_sync(0xffffffffu, z, l);
         if (lane > l) { double ax = x - lx, ay = y - ly, az = z - lz; bad |= (ax * ax + ay * ay + az * az < rmin); }
-        if (lane == l) { double* t = tmp + (size_t)(placed + nacc) * NROW; t[0] = x; t[1] = y; t[2] = z; t[3] = (double)cand; }
+        if (lane == l) { const int q = placed + nacc; S_(sm, s, NX, q) = x; S_(sm, s, NY, q) = y; S_(sm, s, NZ, q) = z; S_(sm, s, NW, q) = (double)cand; }
         nacc++;
         okmask = __ballot_sync(0xffffffffu, !bad) & ~((2u << l) - 1u);
       }
@@ -185,13 +185,13 @@ __device__ void sample_nucleus(const DevCfg& c, const Store& st, const SampleSme
   // centre of mass shift (Nucleus.cpp:301-309) + AABB + sort key
   double mx = 0, my = 0, mz = 0;
   if (recentre) {
-    for (int k = lane; k < A; k += 32) { mx += tmp[k * NROW]; my += tmp[k * NROW + 1]; mz += tmp[k * NROW + 2]; }
+    for (int k = lane; k < A; k += 32) { mx += S_(sm, s, NX, k); my += S_(sm, s, NY, k); mz += S_(sm, s, NZ, k); }
     mx = warp_sum(mx); my = warp_sum(my); mz = warp_sum(mz);
   }
   __syncwarp();
   for (int k = lane; k < A; k += 32) {
-    double x0 = tmp[k * NROW], y0 = tmp[k * NROW + 1], z0 = tmp[k * NROW + 2];
-    uint32_t cand = (uint32_t)tmp[k * NROW + 3];
+    double x0 = S_(sm, s, NX, k), y0 = S_(sm, s, NY, k), z0 = S_(sm, s, NZ, k);
+    uint32_t cand = (uint32_t)S_(sm, s, NW, k);
     double* ex = st.nuc_extra_tmp ? st.nuc_extra_tmp + (((size_t)e * 2 + s) * c.Amax + k) * NEXTRA : nullptr;
     Box bx; particle_box(c, st, s_q, cand, x0, y0, bx, ex);
     if (recentre) {
@@ -199,21 +199,41 @@ __device__ void sample_nucleus(const DevCfg& c, const Store& st, const SampleSme
       box_center(bx, x, bx.yC); box_center(bx, bx.xC, y);       // Particle::setX / setY, src/Particle.cpp:176-185
       x0 = x; y0 = y; z0 = z;
     }
-    double* t = tmp + (size_t)k * NROW;
     if (ex) { ex[XCX] = bx.xC; ex[XCY] = bx.yC; }
-    t[NX] = x0; t[NY] = y0; t[NZ] = z0; t[NXL] = bx.xL; t[NXR] = bx.xR; t[NYL] = bx.yL; t[NYR] = bx.yR; t[NW] = 1.0;
-    xl[k] = bx.xL;
+    S_(sm, s, NX, k) = x0; S_(sm, s, NY, k) = y0; S_(sm, s, NZ, k) = z0; S_(sm, s, NXL, k) = bx.xL; S_(sm, s, NXR, k) = bx.xR;
+    S_(sm, s, NYL, k) = bx.yL; S_(sm, s, NYR, k) = bx.yR; S_(sm, s, NW, k) = 1.0;
   }
   __syncwarp();
-  for (int k = lane; k < A; k += 32) {                          // std::sort by xL, src/Nucleus.cpp:314
-    double key = xl[k]; int rank = 0;
-    for (int j = 0; j < A; j++) { double o = xl[j]; rank += (o < key) || (o == key && j < k); }
-    const double* t = tmp + (size_t)k * NROW; double* p = pos + (size_t)rank * NROW;
+  // std::sort by xL (src/Nucleus.cpp:314): rank by counting, then an in-place permutation field by field
+  int rk[SMC_MAXK];
 #pragma unroll
-    for (int f = 0; f < NROW; f++) p[f] = t[f];
-    if (st.nuc_extra_tmp) {
-      const double* a = st.nuc_extra_tmp + (((size_t)e * 2 + s) * c.Amax + k) * NEXTRA; double* b2 = st.nuc_extra + (((size_t)e * 2 + s) * c.Amax + rank) * NEXTRA;
-      for (int f = 0; f < NEXTRA; f++) b2[f] = a[f];
+  for (int m = 0; m < SMC_MAXK; m++) {
+    const int k = lane + 32 * m; rk[m] = 0;
+    if (k < A) {
+      const double key = S_(sm, s, NXL, k); int rank = 0;
+      for (int j = 0; j < A; j++) { const double o = S_(sm, s, NXL, j); rank += (o < key) || (o == key && j < k); }
+      rk[m] = rank;
+    }
+  }
+  __syncwarp();
+#pragma unroll 1
+  for (int f = 0; f < NROW; f++) {
+    double v[SMC_MAXK];
+#pragma unroll
+    for (int m = 0; m < SMC_MAXK; m++) { const int k = lane + 32 * m; if (k < A) v[m] = S_(sm, s, f, k); }
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < SMC_MAXK; m++) { const int k = lane + 32 * m; if (k < A) S_(sm, s, f, rk[m]) = v[m]; }
+    __syncwarp();
+  }
+  if (st.nuc_extra_tmp) {
+#pragma unroll
+    for (int m = 0; m < SMC_MAXK; m++) {
+      const int k = lane + 32 * m;
+      if (k < A) {
+        const double* a = st.nuc_extra_tmp + (((size_t)e * 2 + s) * c.Amax + k) * NEXTRA; double* b2 = st.nuc_extra + (((size_t)e * 2 + s) * c.Amax + rk[m]) * NEXTRA;
+        for (int f = 0; f < NEXTRA; f++) b2[f] = a[f];
+      }
     }
   }
   __syncwarp();
@@ -250,8 +270,8 @@ __global__ void __launch_bounds__(64) sample_collide_kernel(DevCfg c, Store st, 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int A = c.A[0], B = c.A[1], Amax = c.Amax, HW = (Amax + 31) / 32;
   SampleSmem sm;
-  sm.pos = smem_d; sm.tmp = sm.pos + 2 * Amax * NROW; sm.xl = sm.tmp + 2 * Amax * NROW;
-  sm.hit = (uint32_t*)(sm.xl + 2 * Amax);
+  sm.soa = smem_d; sm.Amax = Amax;
+  sm.hit = (uint32_t*)(sm.soa + 2 * Amax * NROW);
   sm.ncB = (int*)(sm.hit + (size_t)Amax * HW); sm.firstB = sm.ncB + Amax; sm.rowoff = sm.firstB + Amax; sm.misc = sm.rowoff + Amax + 1;
   const uint64_t ev = st.event_id[e];
   double* gn = st.nuc + (size_t)e * 2 * Amax * NROW;
@@ -264,7 +284,7 @@ __global__ void __launch_bounds__(64) sample_collide_kernel(DevCfg c, Store st, 
   for (int guard = 0; guard < 100000 && !accepted; guard++, tr++) {
     if (GIVEN) {
       b = hd[HD_B];
-      for (int k = tid; k < 2 * Amax * NROW; k += 64) sm.pos[k] = gn[k];
+      for (int k = tid; k < 2 * Amax * NROW; k += 64) { const int sd = k / (Amax * NROW), i = (k / NROW) % Amax, f = k % NROW; S_(sm, sd, f, i) = gn[k]; }
     } else {
       const smc_stream s_b = smc_make_stream(c.seed_lo, c.seed_hi, ev, tr, SMC_K_B, 0);
       b = sqrt((c.bmax * c.bmax - c.bmin * c.bmin) * smc_uniform(s_b, 0, 0) + c.bmin * c.bmin);   // MakeDensity.cpp:2149
@@ -273,34 +293,39 @@ __global__ void __launch_bounds__(64) sample_collide_kernel(DevCfg c, Store st, 
     for (int k = tid; k < Amax; k += 64) { sm.ncB[k] = 0; sm.firstB[k] = 0x7fffffff; }
     __syncthreads();
     // ---- collisions: rows of the projectile, 32 target nucleons per step ----
-    const double* P = sm.pos; const double* T = sm.pos + (size_t)Amax * NROW;
     const smc_stream s_p = smc_make_stream(c.seed_lo, c.seed_hi, ev, tr, SMC_K_PAIR, 0);
+    const float hit_c1f = (float)(c.sigma_gg / (4. * SMC_PI * c.w * c.w)), hit_c2f = (float)(1.0 / (4. * c.w * c.w));
     const double* pu = (GIVEN && st.pair_u) ? st.pair_u + (size_t)e * A * B : nullptr;
     for (int i = warp; i < A; i += 2) {
-      const double px = P[i * NROW + NX], py = P[i * NROW + NY];
-      const double pXL = P[i * NROW + NXL], pXR = P[i * NROW + NXR], pYL = P[i * NROW + NYL], pYR = P[i * NROW + NYR];
+      const double px = S_(sm, 0, NX, i), py = S_(sm, 0, NY, i);
+      const double pXL = S_(sm, 0, NXL, i), pXR = S_(sm, 0, NXR, i), pYL = S_(sm, 0, NYL, i), pYR = S_(sm, 0, NYR, i);
       int start = -1; int rowhits = 0;
       for (int j0 = 0; j0 < B; j0 += 32) {
         const int j = j0 + lane; const bool in = j < B;
-        const double* t = T + (size_t)(in ? j : 0) * NROW;
+        const int jj = in ? j : 0;
         uint32_t hitbit = 0;
         if (start < 0) {                                        // skip loop of the sweep, MCnucl.cpp:255-261
-          unsigned m = __ballot_sync(0xffffffffu, in && (t[NXR] >= pXL));
+          unsigned m = __ballot_sync(0xffffffffu, in && (S_(sm, 1, NXR, jj) >= pXL));
           if (m) start = j0 + __ffs(m) - 1;
         }
         if (start >= 0) {
           // the sweep tests pair j iff j >= start and projXR >= XL of the *previous* box looked at (MCnucl.cpp:266-270)
           bool tst = in && j >= start;
-          if (tst) { int jp = j - 1 > start ? j - 1 : start; tst = pXR >= T[(size_t)jp * NROW + NXL]; }
+          if (tst) { int jp = j - 1 > start ? j - 1 : start; tst = pXR >= S_(sm, 1, NXL, jp); }
           const unsigned alive = __ballot_sync(0xffffffffu, tst);
-          if (tst && pYL <= t[NYR] && pYR >= t[NYL]) {
-            const double ddx = t[NX] - px, ddy = t[NY] - py;
+          if (tst && pYL <= S_(sm, 1, NYR, jj) && pYR >= S_(sm, 1, NYL, jj)) {
+            const double ddx = S_(sm, 1, NX, jj) - px, ddy = S_(sm, 1, NY, jj) - py;
             const double bb = sqrt(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)));          // MCnucl.cpp:359-360
             if (c.crit == 1) hitbit = (__dmul_rn(bb, bb) <= c.dsq);
             else {
               const double u = pu ? pu[(size_t)i * B + j] : smc_uniform(s_p, (uint32_t)i, (uint32_t)j);
-              const double prob = 1. - exp(-c.sigma_gg * exp(-bb * bb / (4. * c.w * c.w)) / (4. * SMC_PI * c.w * c.w));
-              hitbit = (u < prob);
+              // P = 1 - exp(-t) <= t: a single-precision over-estimate of t settles almost every pair;
+              // only u below it pays for the double-precision evaluation the reference does
+              const float tub = hit_c1f * __expf(-(float)(bb * bb) * hit_c2f) * 1.01f;
+              if (u <= (double)tub) {
+                const double prob = 1. - exp(-c.sigma_gg * exp(-bb * bb / (4. * c.w * c.w)) / (4. * SMC_PI * c.w * c.w));
+                hitbit = (u < prob);
+              }
             }
           }
           const unsigned hm = __ballot_sync(0xffffffffu, hitbit);
@@ -339,7 +364,6 @@ __global__ void __launch_bounds__(64) sample_collide_kernel(DevCfg c, Store st, 
     if (!GIVEN) st.try_start[e] = (int)tr;
   }
   const uint32_t trw = tr - 1;    // the accepted try
-  const double* P = sm.pos; const double* T = sm.pos + (size_t)Amax * NROW;
   // exclusive prefix of row hit counts -> collision offsets in (i,j) order (createBinaryCollisions, MCnucl.cpp:326-352)
   if (warp == 0) {
     int run = 0;
@@ -354,22 +378,21 @@ __global__ void __launch_bounds__(64) sample_collide_kernel(DevCfg c, Store st, 
   __syncthreads();
   const bool givenw = GIVEN && hi[H_GIVENW];
   // nucleon weights (selectFluctFactors: re-drawn at every hit, last wins => one draw per wounded nucleon)
-  double* posw = sm.pos;
   for (int k = tid; k < A + B; k += 64) {
     const int s = k >= A, i = s ? k - A : k;
     const int nc = s ? sm.ncB[i] : (sm.rowoff[i + 1] - sm.rowoff[i]);
     double wv = 1.0;
-    if (givenw) wv = posw[((size_t)s * Amax + i) * NROW + NW];
+    if (givenw) wv = S_(sm, s, NW, i);
     else if (c.cc_fluct > 5 && nc > 0 && accepted) {
       const smc_stream sg = smc_make_stream(c.seed_lo, c.seed_hi, ev, trw, SMC_K_GAMMA_PART, s);
       wv = gamma_variate(sg, (uint32_t)i, c.gam_k_part, c.gam_th_part);
     }
-    posw[((size_t)s * Amax + i) * NROW + NW] = wv;
+    S_(sm, s, NW, i) = wv;
     st.nuc_ncoll[((size_t)e * 2 + s) * Amax + i] = nc;
     if (s) st.nuc_first[(size_t)e * Amax + i] = sm.firstB[i];
   }
   __syncthreads();
-  for (int k = tid; k < 2 * Amax * NROW; k += 64) gn[k] = sm.pos[k];
+  for (int k = tid; k < 2 * Amax * NROW; k += 64) { const int sd = k / (Amax * NROW), i = (k / NROW) % Amax, f = k % NROW; gn[k] = S_(sm, sd, f, i); }
   // compact participant / spectator lists (ordered), warp 0 = proj, warp 1 = targ
   {
     const int s = warp, n = c.A[s];
@@ -401,8 +424,8 @@ __global__ void __launch_bounds__(64) sample_collide_kernel(DevCfg c, Store st, 
           const int j = wj * 32 + lane, k = off + __popc(hm & ((1u << lane) - 1u));
           if (k < c.ncoll_cap) {
             double* cr = st.coll + ((size_t)e * c.ncoll_cap + k) * CROW;
-            cr[CX] = (P[i * NROW + NX] + T[j * NROW + NX]) / 2.0;                                    // MCnucl.cpp:339-340
-            cr[CY] = (P[i * NROW + NY] + T[j * NROW + NY]) / 2.0;
+            cr[CX] = (S_(sm, 0, NX, i) + S_(sm, 1, NX, j)) / 2.0;                                           // MCnucl.cpp:339-340
+            cr[CY] = (S_(sm, 0, NY, i) + S_(sm, 1, NY, j)) / 2.0;
             double wv = 1.0, addw = 0.0;
             if (c.which_mc_model == 5 && c.sub_model == 2)                                           // integer division in the reference,
               addw = (double)((nci == 1 ? 1 : 0) + (sm.ncB[j] == 1 ? 1 : 0));                        // MCnucl.cpp:345-348
@@ -420,7 +443,7 @@ __global__ void __launch_bounds__(64) sample_collide_kernel(DevCfg c, Store st, 
 
 size_t sample_smem_bytes(int Amax) {
   const int HW = (Amax + 31) / 32;
-  size_t d = (size_t)(2 * Amax * NROW) * 2 + 2 * Amax;
+  size_t d = (size_t)(2 * Amax * NROW);
   size_t i = (size_t)Amax * HW + 3 * Amax + 1 + 16;
   return d * sizeof(double) + i * sizeof(int);
 }
