@@ -205,15 +205,13 @@ __device__ void sample_nucleus(const DevCfg& c, const Store& st, const SampleSme
   }
   __syncwarp();
   // std::sort by xL (src/Nucleus.cpp:314): rank by counting, then an in-place permutation field by field
-  int rk[SMC_MAXK];
+  int rk[SMC_MAXK]; double key[SMC_MAXK];
 #pragma unroll
-  for (int m = 0; m < SMC_MAXK; m++) {
-    const int k = lane + 32 * m; rk[m] = 0;
-    if (k < A) {
-      const double key = S_(sm, s, NXL, k); int rank = 0;
-      for (int j = 0; j < A; j++) { const double o = S_(sm, s, NXL, j); rank += (o < key) || (o == key && j < k); }
-      rk[m] = rank;
-    }
+  for (int m = 0; m < SMC_MAXK; m++) { const int k = lane + 32 * m; rk[m] = 0; key[m] = (k < A) ? S_(sm, s, NXL, k) : 0.0; }
+  for (int j = 0; j < A; j++) {
+    const double o = S_(sm, s, NXL, j);
+#pragma unroll
+    for (int m = 0; m < SMC_MAXK; m++) rk[m] += (o < key[m]) || (o == key[m] && j < lane + 32 * m);
   }
   __syncwarp();
 #pragma unroll 1
@@ -249,11 +247,14 @@ __device__ double gamma_variate(const smc_stream& s, uint32_t cand, double a, do
   for (uint32_t it = 0; it < 64; it++) {
     double u1, u2, u3, u4;
     smc_uniform2(s, cand, 2 * it, &u1, &u2); smc_uniform2(s, cand, 2 * it + 1, &u3, &u4);
-    double x = sqrt(-2.0 * log(1.0 - u1)) * cospi(2.0 * u2);
+    // the normal deviate and the acceptance test run in single precision (the weight itself stays double)
+    const float xf = sqrtf(-2.0f * __logf(fmaxf(1.0f - (float)u1, 1e-37f))) * cospif(2.0f * (float)u2);
+    const double x = (double)xf;
     double v = 1.0 + cc * x;
     if (v <= 0.0) continue;
     v = v * v * v;
-    if (log(1.0 - u3) < 0.5 * x * x + d - d * v + d * log(v)) {
+    const float df = (float)d, vf = (float)v;
+    if (__logf(fmaxf(1.0f - (float)u3, 1e-37f)) < 0.5f * xf * xf + df - df * vf + df * __logf(vf)) {
       if (small) boost = pow(1.0 - u4, 1.0 / a);
       return d * v * th * boost;
     }
@@ -262,7 +263,7 @@ __device__ double gamma_variate(const smc_stream& s, uint32_t cand, double a, do
 }
 
 template <bool GIVEN>
-__global__ void __launch_bounds__(64) sample_collide_kernel(DevCfg c, Store st, int nev) {
+__global__ void __launch_bounds__(64, 6) sample_collide_kernel(DevCfg c, Store st, int nev) {
   extern __shared__ double smem_d[];
   const int e = blockIdx.x;
   if (e >= nev) return;
@@ -296,17 +297,20 @@ __global__ void __launch_bounds__(64) sample_collide_kernel(DevCfg c, Store st, 
     const smc_stream s_p = smc_make_stream(c.seed_lo, c.seed_hi, ev, tr, SMC_K_PAIR, 0);
     const float hit_c1f = (float)(c.sigma_gg / (4. * SMC_PI * c.w * c.w)), hit_c2f = (float)(1.0 / (4. * c.w * c.w));
     const double* pu = (GIVEN && st.pair_u) ? st.pair_u + (size_t)e * A * B : nullptr;
+    int start_carry = 0;                                        // start(i) is non-decreasing in i (x-sorted sweep)
     for (int i = warp; i < A; i += 2) {
       const double px = S_(sm, 0, NX, i), py = S_(sm, 0, NY, i);
       const double pXL = S_(sm, 0, NXL, i), pXR = S_(sm, 0, NXR, i), pYL = S_(sm, 0, NYL, i), pYR = S_(sm, 0, NYR, i);
       int start = -1; int rowhits = 0;
-      for (int j0 = 0; j0 < B; j0 += 32) {
+      const int jbeg = start_carry & ~31;
+      for (int jz = 0; jz < jbeg; jz += 32) if (lane == 0) sm.hit[(size_t)i * HW + (jz >> 5)] = 0;
+      for (int j0 = jbeg; j0 < B; j0 += 32) {
         const int j = j0 + lane; const bool in = j < B;
         const int jj = in ? j : 0;
         uint32_t hitbit = 0;
         if (start < 0) {                                        // skip loop of the sweep, MCnucl.cpp:255-261
-          unsigned m = __ballot_sync(0xffffffffu, in && (S_(sm, 1, NXR, jj) >= pXL));
-          if (m) start = j0 + __ffs(m) - 1;
+          unsigned m = __ballot_sync(0xffffffffu, in && j >= start_carry && (S_(sm, 1, NXR, jj) >= pXL));
+          if (m) { start = j0 + __ffs(m) - 1; start_carry = start; }
         }
         if (start >= 0) {
           // the sweep tests pair j iff j >= start and projXR >= XL of the *previous* box looked at (MCnucl.cpp:266-270)
@@ -452,9 +456,11 @@ cudaError_t launch_sample_collide(const DevCfg& c, const Store& st, int nev, boo
   const size_t smem = sample_smem_bytes(c.Amax);
   if (given) {
     cudaFuncSetAttribute(sample_collide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(sample_collide_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     sample_collide_kernel<true><<<nev, 64, smem, s>>>(c, st, nev);
   } else {
     cudaFuncSetAttribute(sample_collide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(sample_collide_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     sample_collide_kernel<false><<<nev, 64, smem, s>>>(c, st, nev);
   }
   return cudaGetLastError();
