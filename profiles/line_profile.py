@@ -7,10 +7,10 @@ top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 # offset -> (file, line) from nvdisasm
 off2line = {}; cur = None; inside = False
 for ln in open(dis, errors="ignore"):
-    if ln.startswith(mangled + ":"):
+    if ln.startswith(mangled + ":") or ln.startswith(".text." + mangled + ":"):
         inside = True; continue
-    if inside and ln.startswith(".L_x_") is False and re.match(r"^[_A-Za-z.].*:\s*$", ln) and not ln.startswith(".L_"):
-        if not ln.startswith(mangled): inside = False
+    if inside and ln.startswith("//--------------------- .text.") and mangled not in ln:
+        inside = False
     if not inside: continue
     m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
     if m: cur = (m.group(1).split("/")[-1], int(m.group(2))); continue

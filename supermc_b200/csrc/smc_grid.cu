@@ -101,12 +101,14 @@ struct KindList { int n; int kind[8]; };
 #define DEP_WROWS 16
 #define DEP_NWR (DEP_BAND / DEP_WROWS)
 #ifndef DEP_CH
-#define DEP_CH 64
+#define DEP_CH 32
 #endif
 #ifndef DEP_MINCTA
 #define DEP_MINCTA 2
 #endif
-#define DEP_PART 8
+#ifndef DEP_PART
+#define DEP_PART 16
+#endif
 #define DEP_MAXSTRIPES 4
 
 // bounding rectangle (cells) of every source window of the participant/collision deposits of one event
@@ -142,10 +144,10 @@ __global__ void bbox_kernel(DevCfg c, Store st, KindList kl, int nev) {
 }
 
 struct DepSmem {
-  double2* xtab;      // [DEP_BAND][DEP_CH]
-  double2* ytab;      // [DEP_CH][CS]
-  double* sx; double* sy; double* sW; double* sthr;   // [DEP_CH] chunk descriptors
-  int* siL; int* siR; int* sjL; int* sjR; int* sflat;  // [DEP_CH]
+  double2* xtab;      // [2][DEP_BAND][DEP_CH]   (double-buffered)
+  double2* ytab;      // [2][DEP_CH][CS]
+  double* sthr;       // [2][DEP_CH] chunk descriptors
+  int* siL; int* siR; int* sjL; int* sjR;   // [2][DEP_CH]
   int* wtot;          // [32]
   unsigned short* act;
 };
@@ -171,10 +173,10 @@ __global__ void __launch_bounds__(DEP_NWR * DEP_MAXSTRIPES * 32, DEP_MINCTA) dep
   const int sc0 = c0 + (warp % nstr) * 32;            // first column of this warp's stripe
   const int j = sc0 + lane;
   DepSmem sm;
-  sm.xtab = smem_d2; sm.ytab = sm.xtab + DEP_BAND * DEP_CH;
-  sm.sx = (double*)(sm.ytab + (size_t)DEP_CH * CS); sm.sy = sm.sx + DEP_CH; sm.sW = sm.sy + DEP_CH; sm.sthr = sm.sW + DEP_CH;
-  sm.siL = (int*)(sm.sthr + DEP_CH); sm.siR = sm.siL + DEP_CH; sm.sjL = sm.siR + DEP_CH; sm.sjR = sm.sjL + DEP_CH; sm.sflat = sm.sjR + DEP_CH;
-  sm.wtot = sm.sflat + DEP_CH; sm.act = (unsigned short*)(sm.wtot + 32);
+  sm.xtab = smem_d2; sm.ytab = sm.xtab + 2 * DEP_BAND * DEP_CH;
+  sm.sthr = (double*)(sm.ytab + (size_t)2 * DEP_CH * CS);
+  sm.siL = (int*)(sm.sthr + 2 * DEP_CH); sm.siR = sm.siL + 2 * DEP_CH; sm.sjL = sm.siR + 2 * DEP_CH; sm.sjR = sm.sjL + 2 * DEP_CH;
+  sm.wtot = sm.sjR + 2 * DEP_CH; sm.act = (unsigned short*)(sm.wtot + 32);
 
   double acc[DEP_WROWS];
 #pragma unroll
@@ -197,77 +199,81 @@ __global__ void __launch_bounds__(DEP_NWR * DEP_MAXSTRIPES * 32, DEP_MINCTA) dep
     for (int w2 = 0; w2 < nwarps; w2++) nact += sm.wtot[w2];
     __syncthreads();
   }
-  const int nxp = DEP_BAND / DEP_PART, nyp = (CS + DEP_PART - 1) / DEP_PART;
-  for (int cb = 0; cb < nact; cb += DEP_CH) {
-    const int nch = min(DEP_CH, nact - cb);
-    // ---- chunk descriptors ----
-    if (tid < nch) {
-      Src s; load_src(c, st, e, hi, kind, sm.act[cb + tid], s);
-      sm.sx[tid] = s.x; sm.sy[tid] = s.y; sm.sW[tid] = s.W; sm.sthr[tid] = s.thr;
-      sm.siL[tid] = s.iL; sm.siR[tid] = s.iR; sm.sjL[tid] = s.jL; sm.sjR[tid] = s.jR; sm.sflat[tid] = s.flat;
-    }
-    __syncthreads();
-    // ---- factor tables: one (source, 8-entry part) per thread step; 2 exps start a two-multiply recurrence ----
-    for (int wk = tid; wk < (nxp + nyp) * DEP_CH; wk += nthreads) {
+  const int nxp = DEP_BAND / DEP_PART, nyp = (CS + DEP_PART - 1) / DEP_PART, nitems = (nxp + nyp) * DEP_CH;
+  const int nchunks = (nact + DEP_CH - 1) / DEP_CH;
+  // One table item = (source t of the chunk, part): DEP_PART consecutive rows or columns of its separable
+  // factors, started by 2 exps and continued by the two-multiply Gaussian recurrence.  Items of chunk n+1 are
+  // handed out dynamically (shared counter) into the *other* table buffer while chunk n is being consumed, so
+  // warps whose stripe holds few sources spend their slack building tables: one barrier per chunk.
+  auto build_items = [&](int chunk, int first, int stride_all) {
+    const int buf = chunk & 1, cb = chunk * DEP_CH, nch = min(DEP_CH, nact - cb);
+    double2* xtab = sm.xtab + (size_t)buf * DEP_BAND * DEP_CH; double2* ytab = sm.ytab + (size_t)buf * DEP_CH * CS;
+    for (int wk = first; wk < nitems; wk += stride_all) {
       const int t = wk % DEP_CH, part = wk / DEP_CH;
       if (t >= nch) continue;
-      const int flat = sm.sflat[t];
+      Src s; load_src(c, st, e, hi, kind, sm.act[cb + t], s);
+      if (part == 0) {
+        const int o = buf * DEP_CH + t;
+        sm.sthr[o] = s.thr; sm.siL[o] = s.iL; sm.siR[o] = s.iR; sm.sjL[o] = s.jL; sm.sjR[o] = s.jR;
+      }
       if (part < nxp) {
-        const double x = sm.sx[t], W = sm.sW[t];
-        const int iL = sm.siL[t], iR = sm.siR[t];
         double g = 0, q = 0; bool started = false;
-#pragma unroll
+#pragma unroll 4
         for (int k = 0; k < DEP_PART; k++) {
           const int r = part * DEP_PART + k, i = r0 + r;
           double2 v = make_double2(0.0, 1e300);
-          if (i >= iL && i < iR) {
-            const double d = __dadd_rn(x, -xg_of(c, i));
+          if (i >= s.iL && i < s.iR) {
+            const double d = __dadd_rn(s.x, -xg_of(c, i));
             const double d2 = __dmul_rn(d, d);
-            if (flat) v.x = W;
+            if (s.flat) v.x = s.W;
             else {
-              if (!started) { g = W * exp(-d2 * c.inv2w2); q = exp((2.0 * d * c.dx - c.dx * c.dx) * c.inv2w2); started = true; }
+              if (!started) { g = s.W * exp(-d2 * c.inv2w2); q = exp((2.0 * d * c.dx - c.dx * c.dx) * c.inv2w2); started = true; }
               v.x = g; g *= q; q *= c.recx;
             }
             v.y = d2;
           }
-          sm.xtab[r * DEP_CH + t] = v;
+          xtab[r * DEP_CH + t] = v;
         }
       } else {
-        const int p = part - nxp;
-        const double y = sm.sy[t];
-        const int jL = sm.sjL[t], ncol = sm.sjR[t] - jL;
+        const int p = part - nxp, ncol = s.jR - s.jL;
         double g = 0, q = 0;
-#pragma unroll
+#pragma unroll 4
         for (int k = 0; k < DEP_PART; k++) {
           const int cc = p * DEP_PART + k;
           if (cc < ncol && cc < CS) {
-            const double d = __dadd_rn(y, -yg_of(c, jL + cc));
+            const double d = __dadd_rn(s.y, -yg_of(c, s.jL + cc));
             const double d2 = __dmul_rn(d, d);
             double2 v = make_double2(1.0, d2);
-            if (!flat) {
+            if (!s.flat) {
               if (k == 0) { g = exp(-d2 * c.inv2w2); q = exp((2.0 * d * c.dy - c.dy * c.dy) * c.inv2w2); }
               v.x = g; g *= q; q *= c.recy;
             }
-            sm.ytab[(size_t)t * CS + cc] = v;
+            ytab[(size_t)t * CS + cc] = v;
           }
         }
       }
     }
-    __syncthreads();
+  };
+  if (tid < 2) sm.wtot[tid] = 0;                      // wtot[0..1] double as the item counters from here on
+  if (nchunks > 0) build_items(0, tid, nthreads);
+  __syncthreads();
+  for (int n = 0; n < nchunks; n++) {
+    const int buf = n & 1, nch = min(DEP_CH, nact - n * DEP_CH);
+    const double2* xtab = sm.xtab + (size_t)buf * DEP_BAND * DEP_CH; const double2* ytab = sm.ytab + (size_t)buf * DEP_CH * CS;
     // ---- accumulate: every warp walks the chunk, 32 sources per ballot ----
     for (int tb = 0; tb < nch; tb += 32) {
-      const int tt = tb + lane;
+      const int tt = tb + lane, o = buf * DEP_CH + tt;
       bool hit = false;
-      if (tt < nch) hit = (sm.sjR[tt] > sc0) && (sm.sjL[tt] < sc0 + 32) && (sm.siR[tt] > rw0) && (sm.siL[tt] < rw0 + DEP_WROWS);
+      if (tt < nch) hit = (sm.sjR[o] > sc0) && (sm.sjL[o] < sc0 + 32) && (sm.siR[o] > rw0) && (sm.siL[o] < rw0 + DEP_WROWS);
       unsigned m = __ballot_sync(0xffffffffu, hit);
       while (m) {
         const int t = tb + __ffs(m) - 1; m &= m - 1;
-        const int jL = sm.sjL[t], jR = sm.sjR[t];
+        const int jL = sm.sjL[buf * DEP_CH + t], jR = sm.sjR[buf * DEP_CH + t];
         const bool inw = (j >= jL) && (j < jR);
         double2 yv = make_double2(0.0, 1e300);
-        if (inw) yv = sm.ytab[(size_t)t * CS + (j - jL)];
-        const double th = sm.sthr[t];
-        const double2* xt = sm.xtab + (wr * DEP_WROWS) * DEP_CH + t;
+        if (inw) yv = ytab[(size_t)t * CS + (j - jL)];
+        const double th = sm.sthr[buf * DEP_CH + t];
+        const double2* xt = xtab + (wr * DEP_WROWS) * DEP_CH + t;
 #pragma unroll
         for (int r = 0; r < DEP_WROWS; r++) {
           const double2 xv = xt[r * DEP_CH];
@@ -276,6 +282,18 @@ __global__ void __launch_bounds__(DEP_NWR * DEP_MAXSTRIPES * 32, DEP_MINCTA) dep
         }
       }
     }
+    // ---- then help building the tables of the next chunk ----
+    if (n + 1 < nchunks) {
+      int* counter = &sm.wtot[(n + 1) & 1];
+      for (;;) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(counter, 32);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= nitems) break;
+        build_items(n + 1, base + lane, nitems);         // one item per lane
+      }
+    }
+    if (tid == 0) sm.wtot[n & 1] = 0;                      // counter of chunk n+2
     __syncthreads();
   }
   if (j < c.Maxy) {
@@ -288,8 +306,8 @@ static int dep_cs(const DevCfg& c) { int cs = c.wmax; while ((cs & 7) != 1) cs++
 
 size_t deposit_smem_bytes(const DevCfg& c, int nsrc_max) {
   const int CS = dep_cs(c);
-  size_t b = (size_t)(DEP_BAND * DEP_CH + (size_t)DEP_CH * CS) * sizeof(double2);
-  b += (size_t)4 * DEP_CH * sizeof(double) + (size_t)(5 * DEP_CH + 32) * sizeof(int);
+  size_t b = (size_t)2 * (DEP_BAND * DEP_CH + (size_t)DEP_CH * CS) * sizeof(double2);
+  b += (size_t)2 * DEP_CH * sizeof(double) + (size_t)(8 * DEP_CH + 32) * sizeof(int);
   b += (size_t)(nsrc_max + 8) * sizeof(unsigned short);
   return (b + 15) & ~(size_t)15;
 }
