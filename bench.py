@@ -92,7 +92,9 @@ def algorithmic_flops(ev, width, dx):
     npart = (ev["npart1"] + ev["npart2"]).astype(np.float64); nc = ev["ncoll"].astype(np.float64)
     f_dep = 2.0 * (npart * n4 * n4 + nc * n5 * n5)
     f_mom = 200.0 * ev["nonzero_cells"].astype(np.float64)
-    return float(f_dep.sum()), float(f_mom.sum())
+    # collisions 6AB FLOP per try, hard-core scan 3A^2 per nucleus per try (A = B = 208)
+    f_smp = ev["tries"].astype(np.float64) * (6.0 * 208 * 208 + 2 * 3.0 * 208 * 208)
+    return float(f_dep.sum()), float(f_mom.sum()), float(f_smp.sum())
 
 
 def ref_paths():
@@ -219,10 +221,10 @@ def main():
     l0 = ctx.launches
     t0 = time.perf_counter()
     dev_ms = 0.0
-    nz = []; f_dep = f_mom = 0.0
+    f_dep = f_mom = f_smp = 0.0
     for _ in range(a.steps):
         dev_ms += step()
-        fd, fm = algorithmic_flops(out, ctx.k.width, WORKLOAD["dx"]); f_dep += fd; f_mom += fm
+        fd, fm, fs = algorithmic_flops(out, ctx.k.width, WORKLOAD["dx"]); f_dep += fd; f_mom += fm; f_smp += fs
     barrier()
     wall = time.perf_counter() - t0
     launches = ctx.launches - l0
@@ -244,8 +246,15 @@ def main():
     except Exception:
         pass
     fp64_peak = ctx.fp64_peak_tflops()
-    dom = "moments" if stage["moments"] >= stage["deposit"] else "deposit"
-    dom_flops = f_mom if dom == "moments" else f_dep
+    flops = {"deposit": f_dep, "moments": f_mom, "sample_collide": f_smp}
+    dom = max(("deposit", "moments", "sample_collide"), key=lambda k: stage[k])
+    dom_flops = flops[dom]
+    traffic = None
+    try:      # DRAM bytes per event of each kernel from the committed `ncu --set full` capture of this command
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json")))
+        traffic = tj[dom + "_kernel"]["dram_bytes_per_event"] * a.batch      # per launch (one launch = one batch)
+    except Exception:
+        pass
     achieved = dom_flops / (stage[dom] * 1e-3) / 1e12 if stage[dom] > 0 else 0.0
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     grid_bytes = 8.0 * ctx.G * n * a.steps      # the rho scratch grid is written once and read back per event
@@ -259,9 +268,10 @@ def main():
         "gpu_launches": int(launches),
         "clocks": ck,
         "roofline": {"bound": "fp64", "kernel": dom + "_kernel", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                     "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
+                     "frac": achieved / fp64_peak if fp64_peak else None, "traffic": traffic,
                      "peak_source": "measured live: smc_measure_fp64_peak (8 independent DFMA chains/thread, all SMs); nominal B200 FP64 ~37-40 TFLOP/s",
-                     "algorithmic_flops_per_event": {"deposit": f_dep / (n * a.steps), "moments": f_mom / (n * a.steps)},
+                     "algorithmic_flops_per_event": {"deposit": f_dep / (n * a.steps), "moments": f_mom / (n * a.steps), "sample_collide": f_smp / (n * a.steps)},
+                     "all_kernels_tflops": {k: (flops[k] / (stage[k] * 1e-3) / 1e12 if stage[k] > 0 else None) for k in flops},
                      "stage_ms_per_step": {k: v / a.steps for k, v in stage.items()},
                      "hbm": {"achieved_gbs": 2 * grid_bytes / (dev_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak, "note": "rho scratch write+read; not the binding resource"}},
     }

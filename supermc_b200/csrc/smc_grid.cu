@@ -448,9 +448,11 @@ __global__ void __launch_bounds__(MOM_THREADS, 1) moments_kernel(DevCfg c, Store
   double rn[10], mr[10], mi[10], pr[10], pi[10], npw[10], nrm = 0, nnz = 0;
 #pragma unroll
   for (int n = 0; n < 10; n++) { rn[n] = 0; mr[n] = 0; mi[n] = 0; pr[n] = 0; pi[n] = 0; npw[n] = 0; }
+  double dnext = (tid < ncell) ? rho[(size_t)(ilo + tid / nj) * Maxy + (jlo + tid % nj)] : 0.0;
   for (int k = tid; k < ncell; k += MOM_THREADS) {
     const int i = ilo + k / nj, j = jlo + k % nj;
-    const double d = rho[(size_t)i * Maxy + j] * c.finalFactor;
+    const double d = dnext * c.finalFactor;
+    { const int k2 = k + MOM_THREADS; if (k2 < ncell) dnext = rho[(size_t)(ilo + k2 / nj) * Maxy + (jlo + k2 % nj)]; }   // prefetch
     if (d == 0.0) continue;
     nnz += 1.0;
     const double x = xg_of(c, i) - xc, y = yg_of(c, j) - yc;
