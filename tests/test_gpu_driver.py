@@ -55,3 +55,35 @@ def test_operation2_files(tmp_path):
         assert len(np.loadtxt(d / "data" / ("Spectators_event_%d.dat" % k))) == 416 - int(row[45])
         sd = np.loadtxt(d / "data" / ("sd_event_%d_block.dat" % k))
         assert abs(sd.sum() * 0.01 - row[47]) < 1e-6 * row[47]
+
+
+def test_operation1_and_3_files(tmp_path):
+    d = _rundir(tmp_path)
+    subprocess.check_call([EXE] + ARGS + ["operation=1", "nev=2", "use_ed=0"], cwd=d, stdout=subprocess.DEVNULL)
+    for k in (1, 2):
+        assert np.loadtxt(d / "data" / ("sd_event_%d_block.dat" % k)).shape == (261, 261)
+    assert len(np.loadtxt(d / "data" / "nucl1.data")) == 208 and (d / "data" / "binary.dat").stat().st_size > 0
+    d3 = _rundir(tmp_path / "op3")
+    subprocess.check_call([EXE] + ARGS + ["operation=3", "nev=40", "bmin=6", "bmax=8", "average_from_order=2", "average_to_order=3"], cwd=d3, stdout=subprocess.DEVNULL)
+    names = sorted(os.listdir(d3 / "data"))
+    assert len(names) == 48, names            # the reference writes 48 files for 2 orders with its default switches
+    sd = np.loadtxt(d3 / "data" / "sdAvg_order_2_block.dat"); ed = np.loadtxt(d3 / "data" / "edAvg_order_2_block.dat")
+    assert sd.shape == (261, 261) and sd.sum() > 0 and abs(ed.sum() / sd.sum() - 1) < 0.05
+
+
+def test_light_ion_tables_through_the_executable(tmp_path):
+    d = _rundir(tmp_path)
+    os.makedirs(d / "tables")
+    raw = np.loadtxt(os.path.join(ROOT, "tests", "golden", "carbon_configs_small.txt"))
+    np.savetxt(d / "tables" / "carbon_plaintext.dat", raw, fmt="%.6f")
+    rng = np.random.default_rng(3)
+    np.savetxt(d / "tables" / "oxygen_plaintext.dat", rng.normal(0, 1.6, (50, 48)), fmt="%.6f")      # synthetic: the O table is a missing blob upstream
+    subprocess.check_call([EXE, "which_mc_model=5", "sub_model=1", "Aproj=12", "Atarg=12", "ecm=200", "maxx=13", "maxy=13", "operation=9", "nev=100",
+                           "randomSeed=2", "finalFactor=1", "bmax=8"], cwd=d, stdout=subprocess.DEVNULL)
+    t = np.loadtxt(d / "data" / "sn_ecc_eccp_10.dat")
+    assert t.shape == (100, 49) and t[:, 45].max() <= 24 and t[:, 45].min() >= 2
+    for f in os.listdir(d / "data"):
+        os.remove(d / "data" / f)
+    subprocess.check_call([EXE, "which_mc_model=5", "sub_model=1", "Aproj=16", "Atarg=16", "ecm=200", "maxx=13", "maxy=13", "operation=9", "nev=50",
+                           "randomSeed=2", "finalFactor=1", "bmax=8"], cwd=d, stdout=subprocess.DEVNULL)
+    assert np.loadtxt(d / "data" / "sn_ecc_eccp_10.dat").shape == (50, 49)
