@@ -57,6 +57,9 @@ def lib():
         L.smc_o_kln_dndy.restype = C.c_double
         L.smc_o_populate.restype = C.c_long
         L.smc_o_populate_table.restype = C.c_long
+        L.smc_o_populate_deuteron.restype = C.c_long
+        L.smc_o_hulthen_inv_cdf.restype = C.c_double
+        L.smc_o_hulthen_inv_cdf.argtypes = [C.c_double]
         L.smc_o_uniform_rand48.restype = C.c_double
         L.smc_o_uniform_philox.restype = C.c_double
         L.smc_o_uniform_philox.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
@@ -162,6 +165,13 @@ def populate_table(n, cfg3A, recentre, redraw, xc, yc, stream=None, ufn=None):
     else:
         f, st = stream.args()
         lib().smc_o_populate_table(C.byref(n), _d(cfg3A), int(recentre), int(redraw), C.c_double(xc), C.c_double(yc), f, st, _d(out))
+    return out
+
+
+def populate_deuteron(n, xc, yc, stream):
+    out = np.zeros((2, 7))
+    f, st = stream.args()
+    lib().smc_o_populate_deuteron(C.byref(n), C.c_double(xc), C.c_double(yc), f, st, _d(out))
     return out
 
 

@@ -323,6 +323,43 @@ long smc_o_populate_table(const smc_o_nucleus* n, const double* cfg, int recentr
   return nu;
 }
 
+/* deuteron: Hulthen wave function, inverse CDF by the reference's Newton iteration with a numeric
+ * derivative (HulthenFunc.cpp:27-41, arsenal.cpp invertFunc :318-380, RandomVariable.cpp:70-76,140-145;
+ * Nucleus.cpp:203-209,342-359) */
+static double hulthen_cdf(double r) {
+  const double alpha = .228, beta = 1.18;
+  if (r <= 0) return 0;
+  const double c = (alpha * beta * (alpha + beta)) / ((alpha - beta) * (alpha - beta));
+  return 2 * c * (2 * (exp(-r * (alpha + beta)) / (alpha + beta)) - .5 * exp(-2 * alpha * r) / alpha - .5 * exp(-2 * beta * r) / beta + .5 / alpha + .5 / beta - 2 / (alpha + beta));
+}
+double smc_o_hulthen_inv_cdf(double y) {
+  const double xL = 0, xR = 100.0, dx = 0.001, accuracy = dx * 0.001;
+  double XX2 = 1.0, XX1 = XX2 - 10 * accuracy; int impatience = 0;
+  while (fabs(XX2 - XX1) > accuracy) {
+    XX1 = XX2;
+    double F0 = hulthen_cdf(XX1) - y;
+    double X1 = (XX1 > xL + dx) ? XX1 - dx : xL, X2 = (XX1 < xR - dx) ? XX1 + dx : xR;
+    double F3 = (hulthen_cdf(X1) - hulthen_cdf(X2)) / (X1 - X2);
+    XX2 = XX1 - F0 / F3;
+    if (++impatience > 60) break;
+  }
+  return XX2;
+}
+long smc_o_populate_deuteron(const smc_o_nucleus* n, double xCenter, double yCenter, smc_o_uniform_fn U, void* st, double* out7) {
+  double ctr = 1.0 - 2.0 * U(st, 1, 0, 0), phir = 2 * M_PI * U(st, 1, 0, 1);
+  double u = U(st, 9, 0, 0);
+  double d = smc_o_hulthen_inv_cdf(0.0 + 1e-30 + (1.0 - 2 * 1e-30) * u);
+  double x1 = d / 2.0, y1 = 0, z1 = 0;
+  rot3(ctr, phir, &x1, &y1, &z1);
+  part_t P[2];
+  P[0].x = x1 + xCenter; P[0].y = y1 + yCenter; P[0].z = z1; P[0].idx = 0;
+  P[1].x = -x1 + xCenter; P[1].y = -y1 + yCenter; P[1].z = -z1; P[1].idx = 1;
+  particle_box(n, P[0].x, P[0].y, U, st, 0, &P[0].box);
+  particle_box(n, P[1].x, P[1].y, U, st, 1, &P[1].box);
+  emit_sorted(P, 2, out7);
+  return 11;
+}
+
 /* ======================================================================================
  * collisions: AABB sweep + hit test (MCnucl.cpp:242-295,357-385; GaussianNucleonsCal.cpp:59-67)
  * ====================================================================================== */

@@ -75,6 +75,10 @@ long smc_o_populate(const smc_o_nucleus* n, double xCenter, double yCenter,
 long smc_o_populate_table(const smc_o_nucleus* n, const double* cfg, int recentre, int redraw_rotation,
                           double xCenter, double yCenter, smc_o_uniform_fn U, void* st, double* out7);
 
+/* deuteron (Nucleus.cpp:203-209,342-359; HulthenFunc.cpp:27-41) */
+double smc_o_hulthen_inv_cdf(double y);
+long smc_o_populate_deuteron(const smc_o_nucleus* n, double xCenter, double yCenter, smc_o_uniform_fn U, void* st, double* out7);
+
 /* ---- collisions (MCnucl.cpp:217-308,357-385; GaussianNucleonsCal.cpp:59-67) ---- */
 /* proj7/targ7: rows (x,y,z,xL,xR,yL,yR) sorted by xL.  u_dense (A*B, may be NULL): receives the
  * uniform consumed by pair (i,j) in sweep order, -1 where the sweep never tested the pair.

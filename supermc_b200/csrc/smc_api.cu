@@ -94,7 +94,6 @@ extern "C" int smc_create(const smc_params* p, int device, smc_ctx** out) {
     smc_host::WoodsSaxon ws = smc_host::woods_saxon(c.A[s], c.deformed[s]);
     c.rad[s] = ws.rad; c.dr[s] = ws.dr; c.rmaxCut[s] = ws.rmaxCut; c.rwMax[s] = ws.rwMax; c.beta2[s] = ws.beta2; c.beta4[s] = ws.beta4;
     c.sampler[s] = sampler_mode(c.A[s], p->include_nn_correlation);
-    if (c.sampler[s] == 4) FAIL(SMC_ERR_PARAM, "deuteron (A=2, Hulthen) sampling is not built yet");
   }
   c.bmin = p->bmin; c.bmax = p->bmax; c.npmin = p->npmin; c.npmax = p->npmax;
   { const double eps = 1e-8, th = p->cc_fluctuation_gamma_theta > 0 ? p->cc_fluctuation_gamma_theta : 1.0, gk = 1. / th;   // MCnucl.cpp:1271-1301

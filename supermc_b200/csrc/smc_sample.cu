@@ -97,6 +97,26 @@ __device__ void particle_box(const DevCfg& c, const Store& st, const smc_stream&
 __device__ __forceinline__ double sph_harm2(double ct) { return (3.0 * ct * ct - 1.0) * 0.31539156525252005; }
 __device__ __forceinline__ double sph_harm4(double ct) { return (35.0 * ct * ct * ct * ct - 30.0 * ct * ct + 3.0) * 0.10578554691520431; }
 
+// deuteron: inverse CDF of the Hulthen distribution by the reference's own Newton iteration with a numeric
+// derivative (src/HulthenFunc.cpp:27-41, src/arsenal.cpp invertFunc: x0 = 1, dx = 1e-3, accuracy 1e-6)
+__device__ double hulthen_cdf(double r) {
+  const double alpha = .228, beta = 1.18;
+  if (r <= 0) return 0;
+  const double cc = (alpha * beta * (alpha + beta)) / ((alpha - beta) * (alpha - beta));
+  return 2 * cc * (2 * (exp(-r * (alpha + beta)) / (alpha + beta)) - .5 * exp(-2 * alpha * r) / alpha - .5 * exp(-2 * beta * r) / beta + .5 / alpha + .5 / beta - 2 / (alpha + beta));
+}
+__device__ double hulthen_inv_cdf(double y) {
+  const double xL = 0, xR = 100.0, dx = 0.001, accuracy = dx * 0.001;
+  double XX2 = 1.0, XX1 = XX2 - 10 * accuracy;
+  for (int it = 0; it <= 60 && fabs(XX2 - XX1) > accuracy; it++) {
+    XX1 = XX2;
+    const double F0 = hulthen_cdf(XX1) - y;
+    const double X1 = (XX1 > xL + dx) ? XX1 - dx : xL, X2 = (XX1 < xR - dx) ? XX1 + dx : xR;
+    XX2 = XX1 - F0 / ((hulthen_cdf(X1) - hulthen_cdf(X2)) / (X1 - X2));
+  }
+  return XX2;
+}
+
 // One nucleus by warp `s` (side).  Leaves A sorted rows in sm.pos[s].
 __device__ void sample_nucleus(const DevCfg& c, const Store& st, const SampleSmem& sm, int e, int s, uint64_t ev,
                                uint32_t tr, double xCenter, double yCenter) {
@@ -109,6 +129,16 @@ __device__ void sample_nucleus(const DevCfg& c, const Store& st, const SampleSme
   const int mode = c.sampler[s];
   if (mode == 1) {                                              // single nucleon, Nucleus.cpp:201-202
     if (lane == 0) { S_(sm, s, NX, 0) = xCenter; S_(sm, s, NY, 0) = yCenter; S_(sm, s, NZ, 0) = 0.0; S_(sm, s, NW, 0) = 0.0; }
+    recentre = false;
+  } else if (mode == 4) {                                       // deuteron, Nucleus.cpp:203-209,342-359
+    if (lane == 0) {
+      const smc_stream s_d = smc_make_stream(c.seed_lo, c.seed_hi, ev, tr, SMC_K_DEUT, s);
+      const double d = hulthen_inv_cdf(1e-30 + (1.0 - 2e-30) * smc_uniform(s_d, 0, 0));
+      double x1 = d / 2.0, y1 = 0.0, z1 = 0.0;
+      rot3(ctr, phir, x1, y1, z1);
+      S_(sm, s, NX, 0) = x1 + xCenter; S_(sm, s, NY, 0) = y1 + yCenter; S_(sm, s, NZ, 0) = z1; S_(sm, s, NW, 0) = 0.0;
+      S_(sm, s, NX, 1) = -x1 + xCenter; S_(sm, s, NY, 1) = -y1 + yCenter; S_(sm, s, NZ, 1) = -z1; S_(sm, s, NW, 1) = 1.0;
+    }
     recentre = false;
   } else if (mode == 2 || mode == 3) {                          // config tables, Nucleus.cpp:555-574,623-666
     const smc_stream s_c = smc_make_stream(c.seed_lo, c.seed_hi, ev, tr, SMC_K_CONFIG, s);

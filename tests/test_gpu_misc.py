@@ -63,3 +63,27 @@ def test_he3_table_sampling_equals_oracle(oracle_lib):
         got = ctx.nucleons(e, 0)
         assert np.abs(got[:, [0, 1, 3, 4, 5, 6]] - p[:, [0, 1, 3, 4, 5, 6]]).max() < 1e-11
     ctx.close()
+
+
+def test_deuteron_sampling_equals_oracle(oracle_lib):
+    """d+Au: Hulthen inverse-CDF sampler (oracle restatement is bit-equal to the reference with drand48)"""
+    import supermc_b200 as smc
+    port = oracle_lib
+    g = Golden("auau200_glb_quarks"); cfg = g.oracle_cfg(port)
+    seed = 5
+    ctx = smc.Context(g.smc_params(smc.capi, max_batch=16, randomseed=seed, aproj=2))
+    nA = port.nucleus(2, cfg.width); nB = port.nucleus(197, cfg.width)
+    out = ctx.run_events(10, 6)
+    for e in range(6):
+        ev = 10 + e
+        for tr in range(300):
+            b = np.sqrt(400.0 * port.StreamPhilox(seed, ev, tr, 0).u(0, 0, 0))
+            p = port.populate_deuteron(nA, b / 2, 0.0, port.StreamPhilox(seed, ev, tr, 0))
+            t, _ = port.populate(nB, -b / 2, 0.0, stream=port.StreamPhilox(seed, ev, tr, 1))
+            r = port.collide(cfg, p, t, stream=port.StreamPhilox(seed, ev, tr, 0))
+            npart = int((r["ncollA"] > 0).sum() + (r["ncollB"] > 0).sum())
+            if r["ncoll"] > 0 and npart >= 2:
+                break
+        assert out[e]["tries"] == tr + 1 and out[e]["ncoll"] == r["ncoll"]
+        assert np.abs(ctx.nucleons(e, 0)[:, [0, 1, 3, 4, 5, 6]] - p[:, [0, 1, 3, 4, 5, 6]]).max() < 1e-10
+    ctx.close()

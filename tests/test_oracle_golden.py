@@ -90,3 +90,13 @@ def test_six_point_and_kln_integrand(oracle_lib):
     k = port.kln(200.0, 0.218)
     a = port.kln_integrand(k, 0.0, 1.2, 0.7, [0.2, 0.5, 0.25]); b = port.kln_integrand(k, 0.0, 0.7, 1.2, [0.2, 0.5, 0.75])
     assert a > 0 and abs(a - b) < 1e-12 * a      # TA<->TB symmetry at y=0 under phi -> phi + pi
+
+
+def test_hulthen_inverse_cdf(oracle_lib):
+    """deuteron separation: CDF(invCDF(u)) == u to the reference's own accuracy (1e-6 in r)"""
+    L = oracle_lib.lib()
+    for u in (0.01, 0.2, 0.5, 0.9, 0.999):
+        r = L.smc_o_hulthen_inv_cdf(u)
+        a, b = .228, 1.18; c = a * b * (a + b) / (a - b) ** 2
+        cdf = 2 * c * (2 * np.exp(-r * (a + b)) / (a + b) - .5 * np.exp(-2 * a * r) / a - .5 * np.exp(-2 * b * r) / b + .5 / a + .5 / b - 2 / (a + b))
+        assert abs(cdf - u) < 1e-6 and r > 0
