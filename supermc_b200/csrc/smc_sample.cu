@@ -97,6 +97,43 @@ __device__ void particle_box(const DevCfg& c, const Store& st, const smc_stream&
 __device__ __forceinline__ double sph_harm2(double ct) { return (3.0 * ct * ct - 1.0) * 0.31539156525252005; }
 __device__ __forceinline__ double sph_harm4(double ct) { return (35.0 * ct * ct * ct * ct - 30.0 * ct * ct + 3.0) * 0.10578554691520431; }
 
+// std::sort by xL (src/Nucleus.cpp:314): rank by counting (one pass over the keys updates all of this lane's
+// nucleons), then an in-place permutation field by field.  MK = nucleons per lane (compile-time so that the
+// rank/key/value arrays stay in registers).
+template <int MK>
+__device__ __forceinline__ void sort_by_xl(const DevCfg& c, const Store& st, const SampleSmem& sm, int e, int s, int A, int lane) {
+  int rk[MK]; double key[MK];
+#pragma unroll
+  for (int m = 0; m < MK; m++) { const int k = lane + 32 * m; rk[m] = 0; key[m] = (k < A) ? S_(sm, s, NXL, k) : 0.0; }
+  for (int j = 0; j < A; j++) {
+    const double o = S_(sm, s, NXL, j);
+#pragma unroll
+    for (int m = 0; m < MK; m++) rk[m] += (o < key[m]) || (o == key[m] && j < lane + 32 * m);
+  }
+  __syncwarp();
+#pragma unroll 1
+  for (int f = 0; f < NROW; f++) {
+    double v[MK];
+#pragma unroll
+    for (int m = 0; m < MK; m++) { const int k = lane + 32 * m; if (k < A) v[m] = S_(sm, s, f, k); }
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < MK; m++) { const int k = lane + 32 * m; if (k < A) S_(sm, s, f, rk[m]) = v[m]; }
+    __syncwarp();
+  }
+  if (st.nuc_extra_tmp) {
+#pragma unroll
+    for (int m = 0; m < MK; m++) {
+      const int k = lane + 32 * m;
+      if (k < A) {
+        const double* a = st.nuc_extra_tmp + (((size_t)e * 2 + s) * c.Amax + k) * NEXTRA; double* b2 = st.nuc_extra + (((size_t)e * 2 + s) * c.Amax + rk[m]) * NEXTRA;
+        for (int f = 0; f < NEXTRA; f++) b2[f] = a[f];
+      }
+    }
+  }
+  __syncwarp();
+}
+
 // deuteron: inverse CDF of the Hulthen distribution by the reference's own Newton iteration with a numeric
 // derivative (src/HulthenFunc.cpp:27-41, src/arsenal.cpp invertFunc: x0 = 1, dx = 1e-3, accuracy 1e-6)
 __device__ double hulthen_cdf(double r) {
@@ -234,37 +271,9 @@ __device__ void sample_nucleus(const DevCfg& c, const Store& st, const SampleSme
     S_(sm, s, NYL, k) = bx.yL; S_(sm, s, NYR, k) = bx.yR; S_(sm, s, NW, k) = 1.0;
   }
   __syncwarp();
-  // std::sort by xL (src/Nucleus.cpp:314): rank by counting, then an in-place permutation field by field
-  int rk[SMC_MAXK]; double key[SMC_MAXK];
-#pragma unroll
-  for (int m = 0; m < SMC_MAXK; m++) { const int k = lane + 32 * m; rk[m] = 0; key[m] = (k < A) ? S_(sm, s, NXL, k) : 0.0; }
-  for (int j = 0; j < A; j++) {
-    const double o = S_(sm, s, NXL, j);
-#pragma unroll
-    for (int m = 0; m < SMC_MAXK; m++) rk[m] += (o < key[m]) || (o == key[m] && j < lane + 32 * m);
-  }
-  __syncwarp();
-#pragma unroll 1
-  for (int f = 0; f < NROW; f++) {
-    double v[SMC_MAXK];
-#pragma unroll
-    for (int m = 0; m < SMC_MAXK; m++) { const int k = lane + 32 * m; if (k < A) v[m] = S_(sm, s, f, k); }
-    __syncwarp();
-#pragma unroll
-    for (int m = 0; m < SMC_MAXK; m++) { const int k = lane + 32 * m; if (k < A) S_(sm, s, f, rk[m]) = v[m]; }
-    __syncwarp();
-  }
-  if (st.nuc_extra_tmp) {
-#pragma unroll
-    for (int m = 0; m < SMC_MAXK; m++) {
-      const int k = lane + 32 * m;
-      if (k < A) {
-        const double* a = st.nuc_extra_tmp + (((size_t)e * 2 + s) * c.Amax + k) * NEXTRA; double* b2 = st.nuc_extra + (((size_t)e * 2 + s) * c.Amax + rk[m]) * NEXTRA;
-        for (int f = 0; f < NEXTRA; f++) b2[f] = a[f];
-      }
-    }
-  }
-  __syncwarp();
+  if (A <= 32) sort_by_xl<1>(c, st, sm, e, s, A, lane);
+  else if (A <= 256) sort_by_xl<8>(c, st, sm, e, s, A, lane);
+  else sort_by_xl<SMC_MAXK>(c, st, sm, e, s, A, lane);
 }
 
 // Marsaglia-Tsang gamma(shape a, scale th); a<1 boosted by U^(1/a).  Law-equivalent to gsl_ran_gamma
@@ -333,7 +342,7 @@ __global__ void __launch_bounds__(64, 6) sample_collide_kernel(DevCfg c, Store s
       const double pXL = S_(sm, 0, NXL, i), pXR = S_(sm, 0, NXR, i), pYL = S_(sm, 0, NYL, i), pYR = S_(sm, 0, NYR, i);
       int start = -1; int rowhits = 0;
       const int jbeg = start_carry & ~31;
-      for (int jz = 0; jz < jbeg; jz += 32) if (lane == 0) sm.hit[(size_t)i * HW + (jz >> 5)] = 0;
+      if (lane < (jbeg >> 5)) sm.hit[(size_t)i * HW + lane] = 0;
       for (int j0 = jbeg; j0 < B; j0 += 32) {
         const int j = j0 + lane; const bool in = j < B;
         const int jj = in ? j : 0;
@@ -367,7 +376,7 @@ __global__ void __launch_bounds__(64, 6) sample_collide_kernel(DevCfg c, Store s
           rowhits += __popc(hm);
           if (hitbit) { atomicAdd(&sm.ncB[j], 1); atomicMin(&sm.firstB[j], i); }
           if (!alive && j0 + 32 > start) {                     // x-sorted: nothing further can be tested
-            for (int jj = j0 + 32; jj < B; jj += 32) if (lane == 0) sm.hit[(size_t)i * HW + (jj >> 5)] = 0;
+            { const int w0 = (j0 >> 5) + 1 + lane; if (w0 < HW && w0 * 32 < B) sm.hit[(size_t)i * HW + w0] = 0; }
             break;
           }
         } else if (lane == 0) sm.hit[(size_t)i * HW + (j0 >> 5)] = 0;
