@@ -1,6 +1,7 @@
 // smc_api.cu -- the C ABI (include/supermc_b200.h): context, device memory, batch orchestration.
 // One context per GPU; every compute entry point fails loudly (SMC_ERR_CUDA) without a device.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -13,6 +14,8 @@
 #include "smc_host_math.h"
 
 #include "smc_ctx.h"
+
+static void slot_store(smc_ctx* ctx, smc_slot& sl);
 
 extern "C" int smc_abi_version(void) { return SMC_ABI_VERSION; }
 
@@ -49,7 +52,8 @@ extern "C" int smc_create(const smc_params* p, int device, smc_ctx** out) {
   ctx->p = *p; ctx->device = device; ctx->launches = 0; ctx->last_ms = 0; ctx->last_n = 0; ctx->last_flags = 0;
   ctx->d_grids = nullptr; ctx->grids_bytes = 0; ctx->d_pair_u = nullptr; ctx->pair_u_bytes = 0; ctx->d_coll_w = nullptr; ctx->coll_w_bytes = 0;
   ctx->d_quark = nullptr; ctx->d_cfgtab[0] = ctx->d_cfgtab[1] = nullptr; ctx->d_kln = nullptr; ctx->d_avg = nullptr; ctx->avg_doubles = 0; ctx->avg_count = 0;
-  ctx->stream = nullptr; ctx->ev0 = ctx->ev1 = nullptr; ctx->profile = 0;
+  ctx->stream = nullptr; ctx->ev0 = ctx->ev1 = nullptr; ctx->profile = 0; ctx->cur_slot = 0;
+  std::memset(ctx->slots, 0, sizeof ctx->slots);
   for (int i = 0; i < 8; i++) { ctx->stage_ms[i] = 0; ctx->pev[i] = nullptr; }
   *out = ctx;      // returned even on failure so the caller can read smc_last_error
   int ndev = 0;
@@ -150,6 +154,17 @@ extern "C" void smc_destroy(smc_ctx* ctx) {
   if (ctx->d_cfgtab[1]) cudaFree(ctx->d_cfgtab[1]);
   if (ctx->d_kln) cudaFree(ctx->d_kln);
   if (ctx->d_avg) cudaFree(ctx->d_avg);
+  if (ctx->slots[0].ready || ctx->slots[1].ready) {     // return the active view to its slot, then release the other one
+    slot_store(ctx, ctx->slots[ctx->cur_slot]);
+    smc_slot& o = ctx->slots[ctx->cur_slot ^ 1];
+    if (o.ready && o.stream) {
+      if (o.d_grids) cudaFree(o.d_grids);
+      cudaFreeHost(o.h_hdr_i); cudaFreeHost(o.h_hdr_d); cudaFreeHost(o.h_mom); cudaFreeHost(o.h_evid); cudaFreeHost(o.h_try);
+      for (int i = 0; i < 8; i++) if (o.pev[i]) cudaEventDestroy(o.pev[i]);
+      cudaStreamDestroy(o.stream);
+    }
+    for (int q = 0; q < 2; q++) if (ctx->slots[q].ready && ctx->slots[q].done) cudaEventDestroy(ctx->slots[q].done);
+  }
   if (ctx->h_hdr_i) cudaFreeHost(ctx->h_hdr_i);
   if (ctx->h_hdr_d) cudaFreeHost(ctx->h_hdr_d);
   if (ctx->h_mom) cudaFreeHost(ctx->h_mom);
@@ -314,6 +329,63 @@ int smc_fetch_results(smc_ctx* ctx, int m) {
   return SMC_OK;
 }
 
+// ---- pipeline slots ------------------------------------------------------------------------------
+static void slot_store(smc_ctx* ctx, smc_slot& sl) {          // ctx (active view) -> slot
+  smc::Store& st = ctx->st;
+  sl.nuc = st.nuc; sl.nuc_ncoll = st.nuc_ncoll; sl.nuc_first = st.nuc_first; sl.coll = st.coll; sl.coll_ij = st.coll_ij;
+  sl.part_idx = st.part_idx; sl.spec_idx = st.spec_idx; sl.hdr_i = st.hdr_i; sl.hdr_d = st.hdr_d; sl.mom_out = st.mom_out;
+  sl.event_id = (uint64_t*)st.event_id; sl.try_start = st.try_start; sl.cm = st.cm; sl.d_redo = ctx->d_redo;
+  sl.d_grids = ctx->d_grids; sl.grids_bytes = ctx->grids_bytes; sl.stream = ctx->stream;
+  for (int i = 0; i < 8; i++) sl.pev[i] = ctx->pev[i];
+  sl.h_hdr_i = ctx->h_hdr_i; sl.h_hdr_d = ctx->h_hdr_d; sl.h_mom = ctx->h_mom; sl.h_evid = ctx->h_evid; sl.h_try = ctx->h_try;
+}
+static void slot_load(smc_ctx* ctx, const smc_slot& sl) {     // slot -> ctx (active view)
+  smc::Store& st = ctx->st;
+  st.nuc = sl.nuc; st.nuc_ncoll = sl.nuc_ncoll; st.nuc_first = sl.nuc_first; st.coll = sl.coll; st.coll_ij = sl.coll_ij;
+  st.part_idx = sl.part_idx; st.spec_idx = sl.spec_idx; st.hdr_i = sl.hdr_i; st.hdr_d = sl.hdr_d; st.mom_out = sl.mom_out;
+  st.event_id = sl.event_id; st.try_start = sl.try_start; st.cm = sl.cm; ctx->d_redo = sl.d_redo;
+  ctx->d_grids = sl.d_grids; ctx->grids_bytes = sl.grids_bytes; st.grids = sl.d_grids; ctx->stream = sl.stream;
+  for (int i = 0; i < 8; i++) ctx->pev[i] = sl.pev[i];
+  ctx->h_hdr_i = sl.h_hdr_i; ctx->h_hdr_d = sl.h_hdr_d; ctx->h_mom = sl.h_mom; ctx->h_evid = sl.h_evid; ctx->h_try = sl.h_try;
+}
+static int slot_alloc(smc_ctx* ctx, smc_slot& sl) {            // the second slot: same sizes as the first
+  const smc::DevCfg& c = ctx->cfg; const int B = ctx->batch; int rc;
+  if ((rc = dalloc(ctx, &sl.nuc, (size_t)B * 2 * c.Amax * smc::NROW))) return rc;
+  if ((rc = dalloc(ctx, &sl.nuc_ncoll, (size_t)B * 2 * c.Amax))) return rc;
+  if ((rc = dalloc(ctx, &sl.nuc_first, (size_t)B * c.Amax))) return rc;
+  if ((rc = dalloc(ctx, &sl.coll, (size_t)B * c.ncoll_cap * smc::CROW))) return rc;
+  if ((rc = dalloc(ctx, &sl.coll_ij, (size_t)B * c.ncoll_cap))) return rc;
+  if ((rc = dalloc(ctx, &sl.part_idx, (size_t)B * 2 * c.Amax))) return rc;
+  if ((rc = dalloc(ctx, &sl.spec_idx, (size_t)B * 2 * c.Amax))) return rc;
+  if ((rc = dalloc(ctx, &sl.hdr_i, (size_t)B * smc::HDR_I))) return rc;
+  if ((rc = dalloc(ctx, &sl.hdr_d, (size_t)B * smc::HDR_D))) return rc;
+  if ((rc = dalloc(ctx, &sl.mom_out, (size_t)B * smc::MOM_OUT))) return rc;
+  if ((rc = dalloc(ctx, &sl.event_id, (size_t)B))) return rc;
+  if ((rc = dalloc(ctx, &sl.try_start, (size_t)B))) return rc;
+  if ((rc = dalloc(ctx, &sl.cm, (size_t)B * 4))) return rc;
+  if ((rc = dalloc(ctx, &sl.d_redo, (size_t)B))) return rc;
+  sl.d_grids = nullptr; sl.grids_bytes = 0;
+  CK(cudaStreamCreate(&sl.stream));
+  for (int i = 0; i < 8; i++) CK(cudaEventCreate(&sl.pev[i]));
+  CK(cudaMallocHost(&sl.h_hdr_i, (size_t)B * smc::HDR_I * sizeof(int)));
+  CK(cudaMallocHost(&sl.h_hdr_d, (size_t)B * smc::HDR_D * sizeof(double)));
+  CK(cudaMallocHost(&sl.h_mom, (size_t)B * smc::MOM_OUT * sizeof(double)));
+  CK(cudaMallocHost(&sl.h_evid, (size_t)B * sizeof(uint64_t)));
+  CK(cudaMallocHost(&sl.h_try, (size_t)B * sizeof(int)));
+  return SMC_OK;
+}
+int smc_activate_slot(smc_ctx* ctx, int s) {
+  if (s == ctx->cur_slot && ctx->slots[s].ready) return SMC_OK;
+  if (!ctx->slots[ctx->cur_slot].ready) { CK(cudaEventCreateWithFlags(&ctx->slots[ctx->cur_slot].done, cudaEventDisableTiming)); ctx->slots[ctx->cur_slot].ready = true; }
+  slot_store(ctx, ctx->slots[ctx->cur_slot]);
+  if (!ctx->slots[s].ready) {
+    int rc = slot_alloc(ctx, ctx->slots[s]); if (rc) return rc;
+    CK(cudaEventCreateWithFlags(&ctx->slots[s].done, cudaEventDisableTiming)); ctx->slots[s].ready = true;
+  }
+  slot_load(ctx, ctx->slots[s]); ctx->cur_slot = s;
+  return SMC_OK;
+}
+
 // one batch of sampled events: ids -> device, K1+K2
 int smc_sample_batch(smc_ctx* ctx, uint64_t first_event_id, int m) {
   for (int e = 0; e < m; e++) { ctx->h_evid[e] = first_event_id + (uint64_t)e; ctx->h_try[e] = 0; }
@@ -364,6 +436,38 @@ extern "C" int smc_run_events(smc_ctx* ctx, uint64_t first_event_id, int n, unsi
   for (int s = 0; s < 2; s++) if ((c.sampler[s] == 2 || c.sampler[s] == 3) && !ctx->st.cfg_table[s]) FAIL(SMC_ERR_STATE, "this nucleus needs a configuration table: call smc_load_config_table (Nucleus.cpp:150-169)");
   int kinds[8], nd = 0, rc;
   if ((rc = smc_plan_kinds(ctx, flags, kinds, &nd))) return rc;
+  const int nb = (n + ctx->batch - 1) / ctx->batch;
+  if (nb >= 2 && ctx->p.cutdsdy != 1 && !ctx->profile && !getenv("SMC_NO_PIPELINE")) {
+    // two-slot software pipeline: batch i runs on stream (i & 1); its rows are read back when the slot comes
+    // round again, so K1/K2 of one batch overlap K3/K4 and the copies of the other
+    for (int sidx = 0; sidx < 2; sidx++) { if ((rc = smc_activate_slot(ctx, sidx))) return rc; if ((rc = smc_plan_kinds(ctx, flags, kinds, &nd))) return rc; }
+    CK(cudaEventRecord(ctx->ev0, ctx->slots[0].stream));
+    for (int i = 0; i < nb + 2; i++) {
+      if ((rc = smc_activate_slot(ctx, i & 1))) return rc;
+      if (i >= 2) {                                     // retire batch i-2 of this slot
+        CK(cudaEventSynchronize(ctx->slots[i & 1].done));
+        const int off = (i - 2) * ctx->batch, m = std::min(ctx->batch, n - off);
+        smc_fill_out(ctx, m, out + off); ctx->last_n = m;
+      }
+      if (i < nb) {
+        const int off = i * ctx->batch, m = std::min(ctx->batch, n - off);
+        if ((rc = smc_sample_batch(ctx, first_event_id + (uint64_t)off, m))) return rc;
+        if ((rc = run_grid_stages(ctx, m, kinds, nd))) return rc;
+        CK(cudaMemcpyAsync(ctx->h_hdr_i, ctx->st.hdr_i, (size_t)m * smc::HDR_I * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_hdr_d, ctx->st.hdr_d, (size_t)m * smc::HDR_D * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_mom, ctx->st.mom_out, (size_t)m * smc::MOM_OUT * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaEventRecord(ctx->slots[i & 1].done, ctx->stream));
+      }
+    }
+    if ((rc = smc_activate_slot(ctx, (nb - 1) & 1))) return rc;      // getters address the last batch
+    ctx->last_n = std::min(ctx->batch, n - (nb - 1) * ctx->batch);
+    // device time of the whole call: from the first operation of slot 0 to the end of both streams
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->slots[(nb - 2) & 1].done, 0));
+    CK(cudaEventRecord(ctx->ev1, ctx->stream)); CK(cudaEventSynchronize(ctx->ev1));
+    { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->last_ms = ms; }
+    ctx->last_flags = flags;
+    return SMC_OK;
+  }
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   for (int off = 0; off < n; off += ctx->batch) {
     const int m = std::min(ctx->batch, n - off);

@@ -15,6 +15,17 @@ struct KlnCfg { double ecm, lambda, y, dT; int tmax; int pt_order; int npt, nkt,
 cudaError_t launch_kln_table(const KlnCfg&, double* table, cudaStream_t);
 }  // namespace smc
 
+// Per-batch device/host buffers of one pipeline slot.  Two slots let sample+collide of batch n+1 run on a
+// second stream while deposit/moments of batch n are still in flight (smc_run_events).
+struct smc_slot {
+  bool ready;
+  double* nuc; int* nuc_ncoll; int* nuc_first; double* coll; int* coll_ij; int* part_idx; int* spec_idx;
+  int* hdr_i; double* hdr_d; double* mom_out; uint64_t* event_id; int* try_start; double* cm; int* d_redo;
+  double* d_grids; size_t grids_bytes;
+  cudaStream_t stream; cudaEvent_t done; cudaEvent_t pev[8];
+  int* h_hdr_i; double* h_hdr_d; double* h_mom; uint64_t* h_evid; int* h_try;
+};
+
 struct smc_ctx {
   smc_params p; smc_constants k; smc::DevCfg cfg; smc::Store st;
   int device; cudaStream_t stream; cudaEvent_t ev0, ev1;
@@ -27,6 +38,7 @@ struct smc_ctx {
   std::string err; int64_t launches; double last_ms; int last_n; unsigned last_flags;
   // averaged profiles (operation 3)
   int profile; double stage_ms[8]; cudaEvent_t pev[8];
+  smc_slot slots[2]; int cur_slot;
   double* d_avg; int64_t avg_doubles; int64_t avg_count; int avg_from, avg_to, avg_rp, avg_ed;
 };
 
@@ -42,4 +54,5 @@ int smc_stage_positions(smc_ctx* ctx, int off, int m, const smc_event_in* in, bo
 int smc_sample_batch(smc_ctx* ctx, uint64_t first_event_id, int m);
 int smc_check_positions(smc_ctx* ctx, int n, const smc_event_in* in, bool* any_u, bool* any_w);
 int smc_run_grid_stages(smc_ctx* ctx, int m, const int* kinds, int nd);
+int smc_activate_slot(smc_ctx* ctx, int s);
 int smc_events_first_pass(smc_ctx* ctx, int m, const int* kinds, int nd);
