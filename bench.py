@@ -283,7 +283,7 @@ def main():
                      "stage_note": "kernel durations from a second, serial pass over the same steps (CUDA events around every launch); the timed region overlaps consecutive batches on two streams",
                      "hbm": {"achieved_gbs": 2 * grid_bytes / (dev_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak, "note": "rho scratch write+read; not the binding resource"}},
     }
-    if not a.no_cpu_baseline:
+    if not a.no_cpu_baseline and world == 1:       # reported at N=1 only
         cb = cpu_baseline(1, a.cpu_sample_events)
         if cb is None:
             # the unmodified reference binary is not on this box: time the oracle port instead

@@ -363,7 +363,12 @@ cudaError_t launch_combine(const DevCfg& c, const Store& st, int nev, cudaStream
 }
 
 // ---- K4: moments --------------------------------------------------------------------------------
+#ifndef MOM_THREADS
 #define MOM_THREADS 256
+#endif
+#ifndef MOM_MINCTA
+#define MOM_MINCTA 2
+#endif
 __device__ __forceinline__ double block_sum(double v, double* red, int tid) {
   v = warp_sum(v);
   __syncthreads();
@@ -383,7 +388,7 @@ __device__ __forceinline__ double block_min(double v, double* red, int tid) {
   return s;
 }
 
-__global__ void __launch_bounds__(MOM_THREADS, 1) moments_kernel(DevCfg c, Store st, int nev) {
+__global__ void __launch_bounds__(MOM_THREADS, MOM_MINCTA) moments_kernel(DevCfg c, Store st, int nev) {
   extern __shared__ double smem_d[];
   const int e = blockIdx.x, tid = threadIdx.x;
   if (st.redo && !st.redo[e]) return;
