@@ -33,7 +33,7 @@ enum {
  * (src/ParameterReader.cpp:61-69).  Integers are the reference's doubles truncated at use. */
 typedef struct smc_params {
   int which_mc_model;            /* 1 MC-KLN, 5 MC-Glauber, 7 sqrt(TA TB)      MCnucl.cpp:86 */
-  int sub_model;                 /* Glb: 1 classic, 2 "Uli"; KLN: 7            MCnucl.cpp:87 */
+  int sub_model;                 /* Glb: 1 classic, 2 "Uli"; KLN: 7, rcBK 100/101  MCnucl.cpp:87, ParamDefs.h */
   double lambda;                 /* KLN saturation-scale exponent              MakeDensity.cpp:97 */
   int tmax, tmax_subdivision;    /* KLN table size                             MCnucl.cpp:30,917-918 */
   double alpha;                  /* WN/BC mixing                               MCnucl.cpp:27 */
@@ -141,6 +141,9 @@ int  smc_load_config_table(smc_ctx* ctx, int which, const double* xyz, int n_cfg
 /* MCnucl::makeTable (src/MCnucl.cpp:911-960): builds the tmax^2 dN/dy(TA,TB) table on the device with
  * a deterministic quadrature of KLNModel::func (src/KLNModel.cpp:219-277); host_out (tmax*tmax) optional */
 int  smc_build_kln_table(smc_ctx* ctx, double* host_out);
+/* rcBKfunc::rcBKfunc (src/rcBKfunc.cpp:15-210), sub_model 100 (59 files) / 101 (30 files): kt and N_A columns of the
+ * javier/ft_rcbk_mv_qs02_*.dat files as [maxq0][maxy][maxkt]; needed before smc_build_kln_table for those sub-models */
+int  smc_load_rcbk_tables(smc_ctx* ctx, const double* kt, const double* na, int maxq0, int maxy, int maxkt);
 /* install a table computed elsewhere (e.g. the reference's data/dNdyTable.dat) */
 int  smc_set_kln_table(smc_ctx* ctx, const double* table, int tmax, double dt);
 

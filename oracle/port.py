@@ -55,6 +55,8 @@ def lib():
         L.smc_o_density_kln.restype = C.c_double
         L.smc_o_kln_integrand.restype = C.c_double
         L.smc_o_kln_dndy.restype = C.c_double
+        L.smc_o_rcbk_func.restype = C.c_double
+        L.smc_o_rcbk_dndy.restype = C.c_double
         L.smc_o_populate.restype = C.c_long
         L.smc_o_populate_table.restype = C.c_long
         L.smc_o_populate_deuteron.restype = C.c_long
@@ -247,6 +249,35 @@ def eccentricities(cfg, dens, boxes4, from_order=1, to_order=9):
 def kln(ecm, lam, model=7, pt_order=1):
     k = Kln(); k.ecm = ecm; k.lambda_ = lam; k.siginNN200 = sigma_inel(200.0); k.model = model; k.pt_order = pt_order
     return k
+
+
+class Rcbk(C.Structure):
+    _fields_ = [("set", C.c_int), ("maxQ0", C.c_int), ("maxY", C.c_int), ("maxKt", C.c_int), ("dQ0", C.c_double),
+                ("kt", dp), ("na", dp), ("y2", dp)]
+
+
+def rcbk(sub_model, kt, na):
+    """tabulated rcBK uGD: kt, na arrays [maxQ0][maxY][maxKt]; second derivatives of the natural spline per (iq, iy)"""
+    kt = np.ascontiguousarray(kt, dtype=np.float64); na = np.ascontiguousarray(na, dtype=np.float64)
+    y2 = np.zeros_like(na)
+    nq, ny, nk = kt.shape
+    L = lib()
+    for iq in range(nq):
+        for iy in range(ny):
+            L.smc_o_spline_natural(_d(kt[iq, iy]), _d(na[iq, iy]), nk, _d(y2[iq, iy]))
+    t = Rcbk(); t.set = int(sub_model); t.maxQ0, t.maxY, t.maxKt = nq, ny, nk
+    t.dQ0 = 0.1 if sub_model == 100 else 0.168
+    t.kt, t.na, t.y2 = _d(kt), _d(na), _d(y2)
+    t._keep = (kt, na, y2)
+    return t
+
+
+def rcbk_func(t, qs2, x, kt2, alp):
+    return lib().smc_o_rcbk_func(C.byref(t), C.c_double(qs2), C.c_double(x), C.c_double(kt2), C.c_double(alp))
+
+
+def rcbk_dndy(k, t, y, ta, tb, npt=400, nkt=200, nphi=64):
+    return lib().smc_o_rcbk_dndy(C.byref(k), C.byref(t), C.c_double(y), C.c_double(ta), C.c_double(tb), npt, nkt, nphi)
 
 
 def kln_dndy(k, y, ta, tb, npt=400, nkt=200, nphi=64):

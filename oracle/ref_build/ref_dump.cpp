@@ -40,7 +40,7 @@ struct GdProbe : public GlueDensity { using GlueDensity::density; };
 struct MdProbe : public MakeDensity {
   MdProbe(ParameterReader* p) : MakeDensity(p) {}
   using MakeDensity::mc; using MakeDensity::Maxx; using MakeDensity::Maxy;
-  using MakeDensity::bmin; using MakeDensity::bmax; using MakeDensity::finalFactor; using MakeDensity::Npart;
+  using MakeDensity::bmin; using MakeDensity::bmax; using MakeDensity::finalFactor; using MakeDensity::Npart; using MakeDensity::wf;
 };
 
 struct PartProbe : public Particle { using Particle::baseBox; };
@@ -95,7 +95,7 @@ int main(int argc, char* argv[]) {
   ParameterReader paraRdr;
   paraRdr.readFromFile("parameters.dat");
   paraRdr.setVal("dump_grids", 0); paraRdr.setVal("dump_extra", 0);
-  paraRdr.setVal("dump_rotate", 0); paraRdr.setVal("dump_tries", 0); paraRdr.setVal("dump_text", 0);
+  paraRdr.setVal("dump_rotate", 0); paraRdr.setVal("dump_tries", 0); paraRdr.setVal("dump_text", 0); paraRdr.setVal("dump_ugd", 0);
   paraRdr.readFromArguments(argc, argv, "#", 3);
   int randomSeed = paraRdr.getVal("randomSeed");
   if (randomSeed < 0) randomSeed = 1;
@@ -117,6 +117,15 @@ int main(int argc, char* argv[]) {
     vector<double> c; c.push_back(mc->dT); c.push_back(mc->tmax); wr1("kln_consts", c);
   }
 
+  if ((int)paraRdr.getVal("dump_ugd") && dens->wf) {      // UnintegPartonDist::getFunc on a fixed lattice of arguments
+    const double qs[] = {0.05, 0.3, 0.41, 1.7, 5.5, 11.9, 14.0}, xs[] = {1e-5, 1e-3, 0.01, 0.05, 0.3}, ks[] = {0.01, 0.3, 2.5, 30., 120.};
+    vector<double> v;
+    for (int a = 0; a < 7; a++) for (int b2 = 0; b2 < 5; b2++) for (int c = 0; c < 5; c++) {
+      v.push_back(qs[a]); v.push_back(xs[b2]); v.push_back(ks[c]); v.push_back(0.3);
+      v.push_back(dens->wf->getFunc(qs[a], xs[b2], ks[c], 0.3));
+    }
+    wr2("ugd_samples", (long)(v.size() / 5), 5, v);
+  }
   double*** d1 = new double**[1]; d1[0] = new double*[dens->Maxx];
   for (int i = 0; i < dens->Maxx; i++) d1[0][i] = new double[dens->Maxy]();
   char eccfile[] = "data/h_ecc_%d.dat";

@@ -670,6 +670,72 @@ double smc_o_kln_integrand(const smc_o_kln* k, double rapidity, double ta, doubl
   return result;
 }
 
+/* ---- rcBK tabulated uGD (rcBKfunc.h:65-121, rcBKfunc.cpp:115-210; KLNModel.cpp:360-399) -------------------
+ * tables: kt[iq][iy][ik], N_A[iq][iy][ik]; natural cubic spline in kt (gsl_interp_cspline), nearest bin in
+ * Y = ln(x0/x) (dY = 0.1), linear in Q0^2 between neighbouring tables.  The table files are absent upstream:
+ * parity of this function is pinned only against the reference run on SYNTHETIC tables with the GSL stand-in. */
+void smc_o_spline_natural(const double* x, const double* y, int n, double* y2) {
+  double* u = (double*)calloc(n, sizeof(double));
+  y2[0] = 0.0; y2[n - 1] = 0.0;
+  for (int i = 1; i + 1 < n; i++) {
+    double sig = (x[i] - x[i - 1]) / (x[i + 1] - x[i - 1]);
+    double p = sig * y2[i - 1] + 2.0;
+    y2[i] = (sig - 1.0) / p;
+    u[i] = (y[i + 1] - y[i]) / (x[i + 1] - x[i]) - (y[i] - y[i - 1]) / (x[i] - x[i - 1]);
+    u[i] = (6.0 * u[i] / (x[i + 1] - x[i - 1]) - sig * u[i - 1]) / p;
+  }
+  for (int k = n - 2; k >= 0; k--) y2[k] = y2[k] * y2[k + 1] + u[k];
+  free(u);
+}
+static double spline_eval(const double* xa, const double* ya, const double* y2, int n, double x) {
+  int lo = 0, hi = n - 1;
+  while (hi - lo > 1) { int k = (hi + lo) >> 1; if (xa[k] > x) hi = k; else lo = k; }
+  double h = xa[hi] - xa[lo], a = (xa[hi] - x) / h, b = (x - xa[lo]) / h;
+  return a * ya[lo] + b * ya[hi] + ((a * a * a - a) * y2[lo] + (b * b * b - b) * y2[hi]) * (h * h) / 6.0;
+}
+double smc_o_rcbk_func(const smc_o_rcbk* t, double qs0_2, double x, double kt2, double alp) {
+  if (x < 0. || x > 1. || qs0_2 < 0) return 0.;
+  const double dY = 0.1, x0 = 0.01, lgXlambda = 0.3;
+  double Y = log(x0 / x);
+  if (Y < 0.0) { qs0_2 *= exp(lgXlambda * Y); Y = 0.; }
+  int iy = (int)(Y / dY + .5);
+  if (iy >= t->maxY) iy = t->maxY - 1;
+  double Q02 = 4. / 8. * qs0_2;
+  int iq = (int)(Q02 / t->dQ0); iq -= 1;
+  int iqoffset = 1;
+  if (t->set == 100) { iq -= 1; iqoffset++; }
+  if (iq == t->maxQ0 - 1) iq--; else if (iq > t->maxQ0 - 1) iq = t->maxQ0 - 2;
+  double fac = kt2 / (6. * M_PI * M_PI * M_PI) / alp, k = sqrt(kt2);
+  const int n = t->maxKt;
+#define TAB(arr, q) ((arr) + ((size_t)(q) * t->maxY + iy) * n)
+  if (iq >= 0) {
+    double val1 = spline_eval(TAB(t->kt, iq), TAB(t->na, iq), TAB(t->y2, iq), n, k);
+    double val2 = spline_eval(TAB(t->kt, iq + 1), TAB(t->na, iq + 1), TAB(t->y2, iq + 1), n, k);
+    return (val1 + (val2 - val1) * (Q02 - (iq + iqoffset) * t->dQ0) / t->dQ0) * fac;
+  }
+  double val2 = spline_eval(TAB(t->kt, 0), TAB(t->na, 0), TAB(t->y2, 0), n, k);
+  return (val2 * Q02 / (iqoffset * t->dQ0)) * fac;
+#undef TAB
+}
+/* KLNModel::func with model = rcBKalbacete / Set2 (KLNModel.cpp:219-277,360-399) */
+double smc_o_rcbk_integrand(const smc_o_kln* k, const smc_o_rcbk* t, double rapidity, double ta, double tb, const double x[3]) {
+  const double Ptmin = 0.1, Ptmax = 12.0;
+  double pt = Ptmin + x[0] * (Ptmax - Ptmin), ktmax = pt, kt = ktmax * x[1], phi = 2 * M_PI * x[2];
+  double ktsq1 = 0.25 * (pt * pt + kt * kt + 2 * kt * pt * cos(phi));
+  double ktsq2 = 0.25 * (pt * pt + kt * kt - 2 * pt * kt * cos(phi));
+  double mt = pt, x1 = mt / k->ecm * exp(rapidity), x2 = mt / k->ecm / exp(rapidity);
+  if (x1 > 1.0 || x2 > 1.0) return 0.0;
+  const double q0 = (t->set == 100) ? 0.399 : 0.336;
+  double qs2a = ta * k->siginNN200 / 10. * q0, qs2b = tb * k->siginNN200 / 10. * q0;
+  double f1 = smc_o_rcbk_func(t, qs2a, x1, ktsq1, kln_alpha_s(ktsq1)) * pow(1.0 - x1, 4.);
+  double f2 = smc_o_rcbk_func(t, qs2b, x2, ktsq2, kln_alpha_s(ktsq2)) * pow(1.0 - x2, 4.);
+  double scale = ktsq1 > ktsq2 ? ktsq1 : ktsq2, m2 = mt * mt;
+  double result = kln_alpha_s(scale > m2 ? scale : m2) * f1 * f2;
+  if (k->pt_order == 2) result *= (Ptmax - Ptmin) * pt * pt; else result *= 2.0 * M_PI * (Ptmax - Ptmin) * pt;
+  result /= mt * mt; result *= 2.0 * M_PI * kt * ktmax; result /= 4.0;
+  return result;
+}
+
 /* Gauss-Legendre nodes on [0,1] by Newton on P_n */
 static void gauleg01(int n, double* x, double* w) {
   for (int i = 0; i < (n + 1) / 2; i++) {
@@ -684,7 +750,10 @@ static void gauleg01(int n, double* x, double* w) {
   }
 }
 /* deterministic stand-in for KLNModel::ktF_MCintegral (BASES, KLNModel.cpp:177-213): product rule */
-double smc_o_kln_dndy(const smc_o_kln* k, double y, double ta, double tb, int npt, int nkt, int nphi) {
+static double kln_dndy_any(const smc_o_kln* k, const smc_o_rcbk* t, double y, double ta, double tb, int npt, int nkt, int nphi);
+double smc_o_kln_dndy(const smc_o_kln* k, double y, double ta, double tb, int npt, int nkt, int nphi) { return kln_dndy_any(k, 0, y, ta, tb, npt, nkt, nphi); }
+double smc_o_rcbk_dndy(const smc_o_kln* k, const smc_o_rcbk* t, double y, double ta, double tb, int npt, int nkt, int nphi) { return kln_dndy_any(k, t, y, ta, tb, npt, nkt, nphi); }
+static double kln_dndy_any(const smc_o_kln* k, const smc_o_rcbk* t, double y, double ta, double tb, int npt, int nkt, int nphi) {
   const double hbarC = 0.197327053, CF = (3.0 * 3.0 - 1.0) / (2 * 3.0), Norm = 2. / CF / (hbarC * hbarC);
   double *xp = malloc(sizeof(double) * npt), *wp = malloc(sizeof(double) * npt);
   double *xk = malloc(sizeof(double) * nkt), *wk = malloc(sizeof(double) * nkt);
@@ -692,7 +761,7 @@ double smc_o_kln_dndy(const smc_o_kln* k, double y, double ta, double tb, int np
   double sum = 0.0;
   for (int a = 0; a < npt; a++) for (int b = 0; b < nkt; b++) {
     double s = 0.0;
-    for (int p = 0; p < nphi; p++) { double x[3] = {xp[a], xk[b], (p + 0.5) / nphi}; s += smc_o_kln_integrand(k, y, ta, tb, x); }
+    for (int p = 0; p < nphi; p++) { double x[3] = {xp[a], xk[b], (p + 0.5) / nphi}; s += t ? smc_o_rcbk_integrand(k, t, y, ta, tb, x) : smc_o_kln_integrand(k, y, ta, tb, x); }
     sum += wp[a] * wk[b] * s / nphi;
   }
   free(xp); free(wp); free(xk); free(wk);

@@ -113,6 +113,12 @@ void smc_o_eccentricities(const smc_o_cfg* c, const double* dens, int nbox, cons
 typedef struct { double ecm, lambda, siginNN200; int model; int pt_order; } smc_o_kln;
 double smc_o_kln_integrand(const smc_o_kln* k, double y, double ta, double tb, const double x[3]);
 double smc_o_kln_dndy(const smc_o_kln* k, double y, double ta, double tb, int npt, int nkt, int nphi);
+/* rcBK tabulated uGD (rcBKfunc.h:65-121); set = 100 (59 tables, dQ0 0.1) or 101 (30 tables, dQ0 0.168) */
+typedef struct { int set, maxQ0, maxY, maxKt; double dQ0; const double *kt, *na, *y2; } smc_o_rcbk;
+void smc_o_spline_natural(const double* x, const double* y, int n, double* y2);
+double smc_o_rcbk_func(const smc_o_rcbk* t, double qs0_2, double x, double kt2, double alp);
+double smc_o_rcbk_integrand(const smc_o_kln* k, const smc_o_rcbk* t, double y, double ta, double tb, const double x[3]);
+double smc_o_rcbk_dndy(const smc_o_kln* k, const smc_o_rcbk* t, double y, double ta, double tb, int npt, int nkt, int nphi);
 
 #ifdef __cplusplus
 }

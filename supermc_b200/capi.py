@@ -144,6 +144,11 @@ class Context:
         ncfg, A = a.shape[0], a.shape[1] // 3 if a.ndim == 2 else a.shape[1]
         self._ck(lib().smc_load_config_table(self.h, int(which), a.ctypes.data_as(dp), ncfg, A))
 
+    def load_rcbk_tables(self, kt, na):
+        kt = np.ascontiguousarray(kt, dtype=np.float64); na = np.ascontiguousarray(na, dtype=np.float64)
+        q, y, k = kt.shape
+        self._ck(lib().smc_load_rcbk_tables(self.h, kt.ctypes.data_as(dp), na.ctypes.data_as(dp), q, y, k))
+
     def build_kln_table(self):
         t = np.zeros((self.k.kln_tmax, self.k.kln_tmax))
         self._ck(lib().smc_build_kln_table(self.h, t.ctypes.data_as(dp)))

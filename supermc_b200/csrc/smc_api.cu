@@ -51,6 +51,7 @@ extern "C" int smc_create(const smc_params* p, int device, smc_ctx** out) {
   smc_ctx* ctx = new smc_ctx();
   ctx->p = *p; ctx->device = device; ctx->launches = 0; ctx->last_ms = 0; ctx->last_n = 0; ctx->last_flags = 0;
   ctx->d_grids = nullptr; ctx->grids_bytes = 0; ctx->d_pair_u = nullptr; ctx->pair_u_bytes = 0; ctx->d_coll_w = nullptr; ctx->coll_w_bytes = 0;
+  ctx->d_rcbk = nullptr; ctx->rcbk_q = ctx->rcbk_y = ctx->rcbk_k = 0;
   ctx->d_quark = nullptr; ctx->d_cfgtab[0] = ctx->d_cfgtab[1] = nullptr; ctx->d_kln = nullptr; ctx->d_avg = nullptr; ctx->avg_doubles = 0; ctx->avg_count = 0;
   ctx->stream = nullptr; ctx->ev0 = ctx->ev1 = nullptr; ctx->profile = 0; ctx->cur_slot = 0;
   std::memset(ctx->slots, 0, sizeof ctx->slots);
@@ -67,7 +68,7 @@ extern "C" int smc_create(const smc_params* p, int device, smc_ctx** out) {
   // ---- parameter checks (the reference prints and exits) ----
   if (p->which_mc_model != 1 && p->which_mc_model != 5 && p->which_mc_model != 7) FAIL(SMC_ERR_PARAM, "which_mc_model must be 1, 5 or 7");
   if (p->which_mc_model == 5 && p->sub_model != 1 && p->sub_model != 2) FAIL(SMC_ERR_PARAM, "MC-Glauber sub_model must be 1 or 2 (MCnucl.cpp:718-721)");
-  if (p->which_mc_model == 1 && p->sub_model != 7) FAIL(SMC_ERR_PARAM, "MC-KLN: only sub_model 7 (KLN uGD) is built; rcBK tables are absent upstream");
+  if (p->which_mc_model == 1 && p->sub_model != 7 && p->sub_model != 100 && p->sub_model != 101) FAIL(SMC_ERR_PARAM, "MC-KLN sub_model must be 7 (KLN uGD), 100 or 101 (rcBK tables, src/ParamDefs.h)");
   if (p->shape_of_nucleons != 1 && p->shape_of_nucleons != 2 && p->shape_of_nucleons != 4) FAIL(SMC_ERR_PARAM, "shape_of_nucleons must be 1, 2 or 4");
   if (p->shape_of_entropy != 1 && p->shape_of_entropy != 2) FAIL(SMC_ERR_PARAM, "shape_of_entropy must be 1 or 2 (3 = quark substructure is out of scope)");
   if (p->aproj < 1 || p->atarg < 1 || p->aproj > 512 || p->atarg > 512) FAIL(SMC_ERR_PARAM, "Aproj/Atarg out of range");
@@ -153,6 +154,7 @@ extern "C" void smc_destroy(smc_ctx* ctx) {
   if (ctx->d_cfgtab[0]) cudaFree(ctx->d_cfgtab[0]);
   if (ctx->d_cfgtab[1]) cudaFree(ctx->d_cfgtab[1]);
   if (ctx->d_kln) cudaFree(ctx->d_kln);
+  if (ctx->d_rcbk) cudaFree(ctx->d_rcbk);
   if (ctx->d_avg) cudaFree(ctx->d_avg);
   if (ctx->slots[0].ready || ctx->slots[1].ready) {     // return the active view to its slot, then release the other one
     slot_store(ctx, ctx->slots[ctx->cur_slot]);
@@ -222,6 +224,35 @@ static void gauleg01(int n, std::vector<double>& x, std::vector<double>& w) {
   }
 }
 
+// rcBKfunc::rcBKfunc (src/rcBKfunc.cpp:15-210): the tabulated N_A(Y, kt) of every Q0^2 file + a natural cubic
+// spline in kt per (file, Y-bin) (gsl_interp_cspline)
+extern "C" int smc_load_rcbk_tables(smc_ctx* ctx, const double* kt, const double* na, int maxq0, int maxy, int maxkt) {
+  if (!ctx || !kt || !na || maxq0 < 2 || maxy < 1 || maxkt < 3) return SMC_ERR_PARAM;
+  if (ctx->p.sub_model != 100 && ctx->p.sub_model != 101) FAIL(SMC_ERR_STATE, "rcBK tables need sub_model 100 or 101");
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)maxq0 * maxy * maxkt;
+  std::vector<double> y2(n, 0.0), u(maxkt);
+  for (size_t t = 0; t < (size_t)maxq0 * maxy; t++) {
+    const double* x = kt + t * maxkt; const double* y = na + t * maxkt; double* d2 = y2.data() + t * maxkt;
+    d2[0] = 0.0; u[0] = 0.0;
+    for (int i = 1; i + 1 < maxkt; i++) {
+      const double sig = (x[i] - x[i - 1]) / (x[i + 1] - x[i - 1]), pp = sig * d2[i - 1] + 2.0;
+      d2[i] = (sig - 1.0) / pp;
+      u[i] = (y[i + 1] - y[i]) / (x[i + 1] - x[i]) - (y[i] - y[i - 1]) / (x[i] - x[i - 1]);
+      u[i] = (6.0 * u[i] / (x[i + 1] - x[i - 1]) - sig * u[i - 1]) / pp;
+    }
+    d2[maxkt - 1] = 0.0;
+    for (int k2 = maxkt - 2; k2 >= 0; k2--) d2[k2] = d2[k2] * d2[k2 + 1] + u[k2];
+  }
+  if (ctx->d_rcbk) { cudaFree(ctx->d_rcbk); ctx->d_rcbk = nullptr; }
+  CK(cudaMalloc(&ctx->d_rcbk, 3 * n * sizeof(double)));
+  CK(cudaMemcpy(ctx->d_rcbk, kt, n * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->d_rcbk + n, na, n * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->d_rcbk + 2 * n, y2.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+  ctx->rcbk_q = maxq0; ctx->rcbk_y = maxy; ctx->rcbk_k = maxkt;
+  return SMC_OK;
+}
+
 extern "C" int smc_set_kln_table(smc_ctx* ctx, const double* table, int tmax, double dt) {
   if (!ctx || !table || tmax < 3) return SMC_ERR_PARAM;
   CK(cudaSetDevice(ctx->device));
@@ -236,6 +267,7 @@ extern "C" int smc_build_kln_table(smc_ctx* ctx, double* host_out) {
   if (!ctx) return SMC_ERR_PARAM;
   CK(cudaSetDevice(ctx->device));
   const int tmax = ctx->k.kln_tmax;
+  if (ctx->p.sub_model >= 100 && !ctx->d_rcbk) FAIL(SMC_ERR_STATE, "rcBK uGD (sub_model 100/101) needs smc_load_rcbk_tables first (the javier/ table files, src/rcBKfunc.cpp:115-178)");
   const char* q = getenv("SMC_KLN_QUAD");     // "npt,nkt,nphi"
   int npt = 400, nkt = 200, nphi = 64;
   if (q) sscanf(q, "%d,%d,%d", &npt, &nkt, &nphi);
@@ -251,6 +283,9 @@ extern "C" int smc_build_kln_table(smc_ctx* ctx, double* host_out) {
   if (ctx->d_kln) { cudaFree(ctx->d_kln); ctx->d_kln = nullptr; }
   CK(cudaMalloc(&ctx->d_kln, (size_t)tmax * tmax * sizeof(double)));
   smc::KlnCfg kc; kc.ecm = ctx->p.ecm; kc.lambda = ctx->p.lambda; kc.y = 0.0; kc.dT = ctx->k.kln_dt; kc.tmax = tmax; kc.pt_order = ctx->p.pt_order > 0 ? ctx->p.pt_order : 1;
+  kc.model = ctx->p.sub_model; kc.maxQ0 = ctx->rcbk_q; kc.maxY = ctx->rcbk_y; kc.maxKt = ctx->rcbk_k; kc.dQ0 = ctx->p.sub_model == 100 ? 0.1 : 0.168;
+  kc.siginNN200 = ctx->k.siginnn200;
+  { const size_t nn2 = (size_t)ctx->rcbk_q * ctx->rcbk_y * ctx->rcbk_k; kc.rkt = ctx->d_rcbk; kc.rna = ctx->d_rcbk ? ctx->d_rcbk + nn2 : nullptr; kc.ry2 = ctx->d_rcbk ? ctx->d_rcbk + 2 * nn2 : nullptr; }
   kc.npt = npt; kc.nkt = nkt; kc.nphi = nphi; kc.xp = d; kc.wp = d + npt; kc.xk = d + 2 * npt; kc.wk = d + 2 * npt + nkt; kc.cphi = d + 2 * npt + 2 * nkt;
   CK(smc::launch_kln_table(kc, ctx->d_kln, ctx->stream)); ctx->launches++;
   CK(cudaStreamSynchronize(ctx->stream));

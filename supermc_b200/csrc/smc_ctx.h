@@ -11,7 +11,8 @@ cudaError_t launch_sample_collide(const DevCfg&, const Store&, int nev, bool giv
 cudaError_t launch_deposit(const DevCfg&, const Store&, const int* kinds, int nk, int nev, cudaStream_t);
 cudaError_t launch_combine(const DevCfg&, const Store&, int nev, cudaStream_t);
 cudaError_t launch_moments(const DevCfg&, const Store&, int nev, cudaStream_t);
-struct KlnCfg { double ecm, lambda, y, dT; int tmax; int pt_order; int npt, nkt, nphi; const double *xp, *wp, *xk, *wk, *cphi; };
+struct KlnCfg { double ecm, lambda, y, dT; int tmax; int pt_order; int npt, nkt, nphi; const double *xp, *wp, *xk, *wk, *cphi;
+                int model, maxQ0, maxY, maxKt; double dQ0, siginNN200; const double *rkt, *rna, *ry2; };
 cudaError_t launch_kln_table(const KlnCfg&, double* table, cudaStream_t);
 }  // namespace smc
 
@@ -34,6 +35,7 @@ struct smc_ctx {
   double* d_grids; size_t grids_bytes; bool need_zero;
   double* d_pair_u; size_t pair_u_bytes; double* d_coll_w; size_t coll_w_bytes;
   double* d_quark; double* d_cfgtab[2]; double* d_kln; int* d_redo;
+  double* d_rcbk; int rcbk_q, rcbk_y, rcbk_k;      // rcBK uGD tables: kt | N_A | y2, each [q][y][k]
   int* h_hdr_i; double* h_hdr_d; double* h_mom; uint64_t* h_evid; int* h_try; double* h_nuc;
   std::string err; int64_t launches; double last_ms; int last_n; unsigned last_flags;
   // averaged profiles (operation 3)

@@ -161,6 +161,25 @@ int MakeDensity::load_tables() {
       xyz[(c * A[s] + i) * 3 + d] = v[c * per_cfg + skip_head + (size_t)i * per_nucleon + d];
     if (ncfg == 0 || smc_load_config_table(ctx, s, xyz.data(), (int)ncfg, A[s]) != SMC_OK) { err = std::string("configuration table ") + file + ": " + smc_last_error(ctx); return 1; }
   }
+  if (params.which_mc_model == 1 && (params.sub_model == 100 || params.sub_model == 101)) {
+    // rcBKfunc::rcBKfunc (rcBKfunc.cpp:15-178): javier/ft_rcbk_mv_qs02_*.dat, 121 Y-bins x 101 rows "Y kt N_F N_A"
+    const int nq = params.sub_model == 100 ? 59 : 30, maxy = 121, maxkt = 101;
+    std::vector<double> kt((size_t)nq * maxy * maxkt), na(kt.size());
+    for (int iq = 0; iq < nq; iq++) {
+      char name[96];
+      if (params.sub_model == 100) {
+        const int q = iq + 2;
+        if (q % 10 == 0) std::snprintf(name, sizeof name, "javier/ft_rcbk_mv_qs02_%d_ad.dat", q / 10);
+        else std::snprintf(name, sizeof name, "javier/ft_rcbk_mv_qs02_%02d_ad.dat", q);
+      } else std::snprintf(name, sizeof name, "javier/ft_rcbk_mv_qs02_0168_g1_119_%d.dat", iq + 1);
+      if (!read_doubles(name, v)) { err = std::string("Error unable to open file ") + name; return 1; }
+      const size_t need = (size_t)maxy * maxkt * 4;
+      if (v.size() < need) { err = "ERROR reading phi(x,kt) tables, too few entries !"; return 1; }
+      if (v.size() > need) { err = "ERROR reading phi(x,kt) tables, too many entries !"; return 1; }
+      for (size_t r = 0; r < (size_t)maxy * maxkt; r++) { kt[(size_t)iq * maxy * maxkt + r] = v[4 * r + 1]; na[(size_t)iq * maxy * maxkt + r] = v[4 * r + 3]; }
+    }
+    if (smc_load_rcbk_tables(ctx, kt.data(), na.data(), nq, maxy, maxkt) != SMC_OK) { err = smc_last_error(ctx); return 1; }
+  }
   if (params.which_mc_model == 1) {                                       // MakeDensity.cpp:108-132
     std::cout << "MCnucl::makeTable(): precalculating dNdy for all combinations of Ta and Tb." << std::endl;
     std::vector<double> tab((size_t)k.kln_tmax * k.kln_tmax);

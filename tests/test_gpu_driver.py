@@ -87,3 +87,28 @@ def test_light_ion_tables_through_the_executable(tmp_path):
     subprocess.check_call([EXE, "which_mc_model=5", "sub_model=1", "Aproj=16", "Atarg=16", "ecm=200", "maxx=13", "maxy=13", "operation=9", "nev=50",
                            "randomSeed=2", "finalFactor=1", "bmax=8"], cwd=d, stdout=subprocess.DEVNULL)
     assert np.loadtxt(d / "data" / "sn_ecc_eccp_10.dat").shape == (50, 49)
+
+
+def test_rcbk_tables_read_from_javier_directory(tmp_path):
+    """sub_model=101: the executable reads javier/ft_rcbk_mv_qs02_0168_g1_119_*.dat (rcBKfunc.cpp:115-178) and appends
+    the dN/dy table to data/dNdyTable.dat (MCnucl.cpp:1027-1048); a missing file is the reference's fatal error."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import rcbk_synth
+    import supermc_b200 as smc
+    d = _rundir(tmp_path)
+    args = [EXE, "which_mc_model=1", "sub_model=101", "Aproj=1", "Atarg=1", "ecm=2760", "maxx=6", "maxy=6", "tmax=8", "tmax_subdivision=3",
+            "operation=9", "nev=20", "randomSeed=2", "finalFactor=1", "bmax=1", "cc_fluctuation_model=0"]
+    r = subprocess.run(args, cwd=d, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    assert r.returncode != 0 and b"unable to open file javier/" in r.stdout
+    kt, na = rcbk_synth.write_files(str(d / "javier"), 101)
+    subprocess.check_call(args, cwd=d, stdout=subprocess.DEVNULL)
+    tab = np.loadtxt(d / "data" / "dNdyTable.dat")
+    ctx = smc.Context(smc.capi.default_params(which_mc_model=1, sub_model=101, aproj=1, atarg=1, ecm=2760.0, maxx=6.0, maxy=6.0, tmax=8,
+                                              tmax_subdivision=3, cc_fluctuation_model=0, max_batch=8))
+    ctx.load_rcbk_tables(kt, na)
+    T = ctx.build_kln_table()
+    n = T.shape[0]
+    assert tab.shape == ((n - 1) * (n - 1), 4)
+    assert np.allclose(tab[:, 3].reshape(n - 1, n - 1), T[1:, 1:], rtol=0, atol=1e-11)      # %22.12f
+    assert np.loadtxt(d / "data" / "sn_ecc_eccp_10.dat").shape == (20, 49)

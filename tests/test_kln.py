@@ -82,3 +82,47 @@ def test_gpu_kln_events_match_reference(oracle_lib):
             assert rel_err(ctx.grid(it, smc.GRID_RHO), t["rho"]).max() < 1e-9
             assert rel_err(ctx.grid(it, smc.GRID_TA1), t["TA1"]).max() < 1e-9
     ctx.close()
+
+
+# ---- rcBK tabulated uGD (sub_model 100): table files are absent upstream, synthetic stand-ins (tests/rcbk_synth.py) ----
+def _rcbk_tables(tmp_path):
+    import rcbk_synth
+    return rcbk_synth.write_files(str(tmp_path / "javier"), 100)
+
+
+def test_oracle_rcbk_vs_reference_on_synthetic_tables(oracle_lib, tmp_path):
+    """rcBKfunc::getFunc (rcBKfunc.h:65-121) and the kT integral with it, against the unmodified reference run on the
+    same synthetic tables (tests/golden/rcbk_synth_ref.npz): uGD values to 1e-13, BASES table to its MC error"""
+    import os
+    from helpers import GOLDEN
+    port = oracle_lib
+    ref = np.load(os.path.join(GOLDEN, "rcbk_synth_ref.npz"))
+    kt, na = _rcbk_tables(tmp_path)
+    t = port.rcbk(100, kt, na)
+    for qs2, x, kt2, alp, val in ref["ugd"]:
+        got = port.rcbk_func(t, qs2, x, kt2, alp)
+        assert abs(got - val) <= 1e-13 * max(abs(val), 1e-30), (qs2, x, kt2, got, val)
+    T = ref["table"]; dT = float(ref["kln_consts"][0])
+    k = port.kln(2760.0, 0.138, model=100)
+    for i, j in [(1, 1), (3, 7), (10, 10), (21, 2), (21, 21)]:
+        v = port.rcbk_dndy(k, t, 0.0, dT * i, dT * j, 200, 100, 32)
+        assert abs(v / T[i, j] - 1) < 5e-3, (i, j, v, T[i, j])
+
+
+@pytest.mark.gpu
+def test_gpu_rcbk_table_equals_oracle(oracle_lib, tmp_path, monkeypatch):
+    import supermc_b200 as smc
+    port = oracle_lib
+    kt, na = _rcbk_tables(tmp_path)
+    t = port.rcbk(100, kt, na)
+    monkeypatch.setenv("SMC_KLN_QUAD", "100,50,16")
+    ctx = smc.Context(smc.capi.default_params(which_mc_model=1, sub_model=100, aproj=208, atarg=208, ecm=2760.0, tmax=8, tmax_subdivision=3,
+                                              maxx=13.0, maxy=13.0, cc_fluctuation_model=0, max_batch=8, **{"lambda": 0.138}))
+    ctx.load_rcbk_tables(kt, na)
+    T = ctx.build_kln_table()
+    dT = ctx.k.kln_dt
+    k = port.kln(2760.0, 0.138, model=100)
+    for i, j in [(1, 1), (3, 7), (10, 10), (21, 2), (21, 21)]:
+        v = port.rcbk_dndy(k, t, 0.0, dT * i, dT * j, 100, 50, 16)
+        assert abs(T[i, j] / v - 1) < 1e-9, (i, j, T[i, j], v)
+    ctx.close()
