@@ -114,6 +114,7 @@ extern "C" int smc_create(const smc_params* p, int device, smc_ctx** out) {
   c.ecc_from = p->ecc_from_order; c.ecc_to = p->ecc_to_order;
   c.kln_tmax = 0; c.kln_dT = k.kln_dt;
   { const double reach = std::max(c.dmax, std::sqrt(k.dsq)); c.wmax = (int)(2. * reach / std::min(p->dx, p->dy)) + 6; }
+  c.inv_dx_f = (float)(1.0 / p->dx); c.inv_dy_f = (float)(1.0 / p->dy);
   ctx->G = (size_t)c.Maxx * c.Maxy;
   if (c.Maxy > 1024) FAIL(SMC_ERR_PARAM, "grids wider than 1024 cells are not supported");
 

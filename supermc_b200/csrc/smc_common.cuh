@@ -52,6 +52,7 @@ struct DevCfg {
   int kln_tmax; double kln_dT;
   // deposit geometry
   int wmax;               // max window cells per axis (+ slack)
+  float inv_dx_f, inv_dy_f;   // single-precision 1/dx, 1/dy (interval estimates of the deposit masks)
 };
 
 // device-resident event records for one batch

@@ -92,24 +92,48 @@ __device__ void load_src(const DevCfg& c, const Store& st, int e, const int* hi,
 
 struct KindList { int n; int kind[8]; };
 
-// Deposit geometry: a CTA owns a band of DEP_BAND rows; warp (wr, stripe) keeps DEP_WROWS rows x 32
-// columns of it in registers.  Sources are processed in chunks of DEP_CH whose factor tables live in
-// shared memory:  xtab[r][t] = (W*exp(-dx^2/2w^2), dx^2)  and  ytab[t][c] = (exp(-dy^2/2w^2), dy^2).
+// Deposit geometry.  A CTA owns DEP_BAND rows x DEP_COLS columns of one event's lattice; warp (wr, ws) owns a
+// 16 x 32 tile of it and every lane a 4 x 4 register micro-tile (rows 4*lr..4*lr+3, columns 4*lc..4*lc+3 of the
+// tile), so one source costs a lane 5 shared-memory loads, 4 shifts, 4 R2P and 16 predicated DFMAs.  Sources are processed in chunks of DEP_CH whose tables live in shared memory:
+//   xg[t][r]      W * exp(-dx^2/2w^2) of row r            (two-multiply Gaussian recurrence, DEP_XP rows per item)
+//   yg[t][c]      exp(-dy^2/2w^2) of column c             (same, DEP_YP columns per item)
+//   mk[t][s][r]   32-bit mask of row r over stripe s: window  AND  the reference's circle test
+// The circle test  (x-xg)^2 + (y-yg)^2 <= thr  (each term rounded as the reference rounds it) is monotone in
+// |y-yg|, so per (source,row) it is a column interval.  Its end points come from a single-precision estimate and
+// are settled with the exact double-precision predicate whenever the estimate lies within 2e-3 cells of a cell
+// boundary (the estimate's own error is < 1e-4 cells), i.e. the masks are the reference's, bit for bit.
 #ifndef DEP_BAND
 #define DEP_BAND 32
 #endif
 #define DEP_WROWS 16
 #define DEP_NWR (DEP_BAND / DEP_WROWS)
+#ifndef DEP_NSTR
+#define DEP_NSTR 4
+#endif
+#define DEP_COLS (DEP_NSTR * 32)
 #ifndef DEP_CH
-#define DEP_CH 32
+#define DEP_CH 16
+#endif
+#define DEP_XP 4
+#ifndef DEP_YP
+#define DEP_YP 16
 #endif
 #ifndef DEP_MINCTA
-#define DEP_MINCTA 2
+#define DEP_MINCTA 3
 #endif
-#ifndef DEP_PART
-#define DEP_PART 16
-#endif
-#define DEP_MAXSTRIPES 4
+#define DEP_THREADS (DEP_NWR * DEP_NSTR * 32)
+#define DEP_NXI (DEP_BAND / DEP_XP)
+#define DEP_NYI (DEP_COLS / DEP_YP)
+#define DEP_NITEMS (DEP_CH * (DEP_NXI + DEP_NYI))
+
+// rows are padded by 16 bytes: builder lanes work on different sources t at the same row/column, and a row
+// pitch that is a multiple of 128 bytes would put all of their stores into the same banks
+struct DepTab {
+  double xg[DEP_CH][DEP_BAND + 2];
+  uint32_t mk[DEP_CH][DEP_NSTR * DEP_BAND + 4];     // [t][s * DEP_BAND + r]
+  double yg[DEP_CH][DEP_COLS + 2];
+  int4 desc[DEP_CH];                         // iL, iR, jL, jR
+};
 
 // bounding rectangle (cells) of every source window of the participant/collision deposits of one event
 __global__ void bbox_kernel(DevCfg c, Store st, KindList kl, int nev) {
@@ -143,187 +167,252 @@ __global__ void bbox_kernel(DevCfg c, Store st, KindList kl, int nev) {
   }
 }
 
-struct DepSmem {
-  double2* xtab;      // [2][DEP_BAND][DEP_CH]   (double-buffered)
-  double2* ytab;      // [2][DEP_CH][CS]
-  double* sthr;       // [2][DEP_CH] chunk descriptors
-  int* siL; int* siR; int* sjL; int* sjR;   // [2][DEP_CH]
-  int* wtot;          // [32]
-  unsigned short* act;
-};
+// position and reach of source k in cells, single precision: enough for the (conservative) band/column-group test
+__device__ __forceinline__ void src_cell_f(const DevCfg& c, const Store& st, int e, const int* hi, int kind, int k, float& fi, float& fj) {
+  const int Amax = c.Amax, np1 = hi[H_NP1], np2 = hi[H_NP2];
+  const double* row = nullptr;
+  const double* nuc = st.nuc + (size_t)e * 2 * Amax * NROW;
+  int id = -1;
+  if (kind == GK_RHO) {
+    const int nwn = (c.sub_model == 1) ? np1 + np2 : 0;
+    if (k < nwn) id = st.part_idx[(size_t)e * 2 * Amax + k];
+    else row = st.coll + ((size_t)e * c.ncoll_cap + (k - nwn)) * CROW;
+  } else if (kind == GK_RHOA || kind == GK_TA1) id = st.part_idx[(size_t)e * 2 * Amax + k];
+  else if (kind == GK_RHOB || kind == GK_TA2) id = st.part_idx[(size_t)e * 2 * Amax + np1 + k];
+  else if (kind == GK_RHO_BINARY) row = st.coll + ((size_t)e * c.ncoll_cap + k) * CROW;
+  else id = st.spec_idx[(size_t)e * 2 * Amax + (kind == GK_SPEC_B ? (c.A[0] - np1) : 0) + k];
+  if (id >= 0) row = nuc + ((size_t)(id >> 16) * Amax + (id & 0xffff)) * NROW;
+  fi = (float)(row[0] - c.Xmin) * c.inv_dx_f; fj = (float)(row[1] - c.Ymin) * c.inv_dy_f;
+}
 
-__global__ void __launch_bounds__(DEP_NWR * DEP_MAXSTRIPES * 32, DEP_MINCTA) deposit_kernel(DevCfg c, Store st, KindList kl, int nev, int nbands, int CS) {
-  extern __shared__ double2 smem_d2[];
+__device__ __forceinline__ uint32_t ones_below(int n) {      // bits [0, n) of a word, n clamped to [0, 32]
+  return __funnelshift_lc(0xffffffffu, 0u, (uint32_t)n);
+}
+
+// one row of a lane's micro-tile: four DFMAs guarded by bits 0..3 of the (pre-shifted) row mask.  Written as PTX
+// *branches*: ptxas turns those into predicated DFMAs fed by one R2P, whereas `if (bit) a = fma(..)` (or a PTX
+// `@p fma`) comes out as an unconditional DFMA plus two FSELs per cell.
+__device__ __forceinline__ void row_fma(double (&a)[4], double gx, double y0, double y1, double y2, double y3, uint32_t m) {
+  asm volatile("{\n\t.reg .pred p0, p1, p2, p3;\n\t.reg .b32 t;\n\t"
+      "and.b32 t, %9, 1; setp.eq.u32 p0, t, 0;\n\t"
+      "and.b32 t, %9, 2; setp.eq.u32 p1, t, 0;\n\t"
+      "and.b32 t, %9, 4; setp.eq.u32 p2, t, 0;\n\t"
+      "and.b32 t, %9, 8; setp.eq.u32 p3, t, 0;\n\t"
+      "@p0 bra L0;\n\t fma.rn.f64 %0, %4, %5, %0;\n\tL0:\n\t"
+      "@p1 bra L1;\n\t fma.rn.f64 %1, %4, %6, %1;\n\tL1:\n\t"
+      "@p2 bra L2;\n\t fma.rn.f64 %2, %4, %7, %2;\n\tL2:\n\t"
+      "@p3 bra L3;\n\t fma.rn.f64 %3, %4, %8, %3;\n\tL3:\n\t}"
+      : "+d"(a[0]), "+d"(a[1]), "+d"(a[2]), "+d"(a[3])
+      : "d"(gx), "d"(y0), "d"(y1), "d"(y2), "d"(y3), "r"(m));
+}
+// position of column c (0..31 of a stripe) in yg: lane lc owns columns 4*lc..4*lc+3 and reads them with two
+// 128-bit loads; this order makes both conflict-free (8 lanes x 16 B contiguous each)
+__device__ __forceinline__ int yg_pos(int c) { return ((c >> 1) & 1) * 16 + (c >> 2) * 2 + (c & 1); }
+
+__global__ void __launch_bounds__(DEP_THREADS, DEP_MINCTA) deposit_kernel(DevCfg c, Store st, KindList kl, int nev, int nbands) {
+  extern __shared__ __align__(16) unsigned char dep_smem[];
   const int e = blockIdx.x, band = blockIdx.y % nbands, sgroup = blockIdx.y / nbands, kind = kl.kind[blockIdx.z];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nwarps = nthreads >> 5;
-  const int nstr = nwarps / DEP_NWR;                  // stripes handled by this CTA
-  const int wr = warp / nstr;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (st.redo && !st.redo[e]) return;
   const int* hi = st.hdr_i + (size_t)e * HDR_I;
-  const int slot = st.kind_slot[kind];
-  double* grid = st.grids + ((size_t)e * st.nkinds + slot) * (size_t)c.Maxx * c.Maxy;
   // bands and column groups are laid out from the corner of the event's own bounding rectangle (bbox_kernel),
   // so a CTA is either inside the populated region or exits at once; spectator grids span the whole lattice
   const bool whole = (kind == GK_SPEC_A || kind == GK_SPEC_B);
   const int r_org = whole ? 0 : hi[H_RLO], r_end = whole ? c.Maxx : hi[H_RHI];
   const int c_org = whole ? 0 : hi[H_CLO], c_end = whole ? c.Maxy : hi[H_CHI];
-  const int r0 = r_org + band * DEP_BAND, rw0 = r0 + wr * DEP_WROWS;
-  const int c0 = c_org + sgroup * nstr * 32;
+  const int r0 = r_org + band * DEP_BAND, c0 = c_org + sgroup * DEP_COLS;
   if (r0 >= r_end || c0 >= c_end) return;
-  const int sc0 = c0 + (warp % nstr) * 32;            // first column of this warp's stripe
-  const int j = sc0 + lane;
-  DepSmem sm;
-  sm.xtab = smem_d2; sm.ytab = sm.xtab + 2 * DEP_BAND * DEP_CH;
-  sm.sthr = (double*)(sm.ytab + (size_t)2 * DEP_CH * CS);
-  sm.siL = (int*)(sm.sthr + 2 * DEP_CH); sm.siR = sm.siL + 2 * DEP_CH; sm.sjL = sm.siR + 2 * DEP_CH; sm.sjR = sm.sjL + 2 * DEP_CH;
-  sm.wtot = sm.sjR + 2 * DEP_CH; sm.act = (unsigned short*)(sm.wtot + 32);
+  const int wr = warp / DEP_NSTR, ws = warp % DEP_NSTR, lr = lane >> 3, lc = lane & 7;
+  const int rw0 = r0 + wr * DEP_WROWS, sc0 = c0 + ws * 32;
+  DepTab* tab = reinterpret_cast<DepTab*>(dep_smem);
+  Src* srcs = reinterpret_cast<Src*>(tab + 2);                 // [2][DEP_CH]
+  int* wtot = reinterpret_cast<int*>(srcs + 2 * DEP_CH);       // [32]
+  unsigned short* act = reinterpret_cast<unsigned short*>(wtot + 32);
+  const int slot = st.kind_slot[kind];
+  double* grid = st.grids + ((size_t)e * st.nkinds + slot) * (size_t)c.Maxx * c.Maxy;
 
-  double acc[DEP_WROWS];
+  double acc[4][4];
 #pragma unroll
-  for (int r = 0; r < DEP_WROWS; r++) acc[r] = 0.0;
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
 
   const int status = hi[H_STATUS];
   const int nsrc = (status == 0 || status == 4) ? src_count(c, hi, kind) : 0;
-  // ---- ordered compaction of the sources that touch this band ----
+  // ---- ordered compaction of the sources that can touch this CTA (conservative single-precision test) ----
   int nact = 0;
-  for (int base = 0; base < nsrc; base += nthreads) {
-    const int k = base + tid;
-    bool on = false;
-    if (k < nsrc) { Src s; load_src(c, st, e, hi, kind, k, s); on = (s.iL < s.iR) && (s.jL < s.jR) && (s.iL < r0 + DEP_BAND) && (s.iR > r0) && (s.jL < c0 + nstr * 32) && (s.jR > c0); }
-    const unsigned m = __ballot_sync(0xffffffffu, on);
-    if (lane == 0) sm.wtot[warp] = __popc(m);
-    __syncthreads();
-    int off = nact;
-    for (int w2 = 0; w2 < warp; w2++) off += sm.wtot[w2];
-    if (on) sm.act[off + __popc(m & ((1u << lane) - 1u))] = (unsigned short)k;
-    for (int w2 = 0; w2 < nwarps; w2++) nact += sm.wtot[w2];
-    __syncthreads();
+  {
+    const float reach_i = (float)fmax(c.dmax, c.rclip_flat) * c.inv_dx_f + 3.0f, reach_j = (float)fmax(c.dmax, c.rclip_flat) * c.inv_dy_f + 3.0f;
+    for (int base = 0; base < nsrc; base += DEP_THREADS) {
+      const int k = base + tid;
+      bool on = false;
+      if (k < nsrc) {
+        float fi, fj; src_cell_f(c, st, e, hi, kind, k, fi, fj);
+        on = (fi + reach_i >= (float)r0) && (fi - reach_i <= (float)(r0 + DEP_BAND)) && (fj + reach_j >= (float)c0) && (fj - reach_j <= (float)(c0 + DEP_COLS));
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, on);
+      if (lane == 0) wtot[warp] = __popc(m);
+      __syncthreads();
+      int off = nact;
+      for (int w2 = 0; w2 < warp; w2++) off += wtot[w2];
+      if (on) act[off + __popc(m & ((1u << lane) - 1u))] = (unsigned short)k;
+      for (int w2 = 0; w2 < DEP_THREADS / 32; w2++) nact += wtot[w2];
+      __syncthreads();
+    }
   }
-  const int nxp = DEP_BAND / DEP_PART, nyp = (CS + DEP_PART - 1) / DEP_PART, nitems = (nxp + nyp) * DEP_CH;
   const int nchunks = (nact + DEP_CH - 1) / DEP_CH;
-  // One table item = (source t of the chunk, part): DEP_PART consecutive rows or columns of its separable
-  // factors, started by 2 exps and continued by the two-multiply Gaussian recurrence.  Items of chunk n+1 are
-  // handed out dynamically (shared counter) into the *other* table buffer while chunk n is being consumed, so
-  // warps whose stripe holds few sources spend their slack building tables: one barrier per chunk.
-  auto build_items = [&](int chunk, int first, int stride_all) {
-    const int buf = chunk & 1, cb = chunk * DEP_CH, nch = min(DEP_CH, nact - cb);
-    double2* xtab = sm.xtab + (size_t)buf * DEP_BAND * DEP_CH; double2* ytab = sm.ytab + (size_t)buf * DEP_CH * CS;
-    for (int wk = first; wk < nitems; wk += stride_all) {
-      const int t = wk % DEP_CH, part = wk / DEP_CH;
-      if (t >= nch) continue;
-      Src s; load_src(c, st, e, hi, kind, sm.act[cb + t], s);
-      if (part == 0) {
-        const int o = buf * DEP_CH + t;
-        sm.sthr[o] = s.thr; sm.siL[o] = s.iL; sm.siR[o] = s.iR; sm.sjL[o] = s.jL; sm.sjR[o] = s.jR;
+
+  // One table item = DEP_XP rows or DEP_YP columns of one source of the chunk (or, ids >= DEP_NITEMS, the source
+  // record of the chunk after it).  Items of chunk n+1 are handed out dynamically (shared counter) into the
+  // *other* table buffer while chunk n is being consumed: warps whose tile holds few sources spend their slack
+  // building tables, and there is one barrier per chunk.
+  const int nyq = min(DEP_NYI, (c.wmax + 2 * DEP_YP - 2) / DEP_YP), nitems = DEP_CH * (DEP_NXI + nyq);
+  auto build_item = [&](int chunk, int id) {
+    DepTab& T = tab[chunk & 1];
+    const int nch = min(DEP_CH, nact - chunk * DEP_CH);
+    if (id < DEP_CH * DEP_NXI) {                                            // ---- rows: xg + masks ----
+      const int t = id % DEP_CH, part = id / DEP_CH;
+      if (t >= nch) return;
+      const Src s = srcs[(chunk & 1) * DEP_CH + t];
+      if (part == 0) T.desc[t] = make_int4(s.iL, s.iR, s.jL, s.jR);
+      const int rb = part * DEP_XP, i0 = r0 + rb;
+      const int ka = max(s.iL - i0, 0), kb = min(s.iR - i0, DEP_XP);
+      double g = 0.0, q = 0.0;
+      if (ka < kb && !s.flat) {
+        const double d = __dadd_rn(s.x, -xg_of(c, i0 + ka));
+        g = s.W * exp(-__dmul_rn(d, d) * c.inv2w2); q = exp((2.0 * d * c.dx - c.dx * c.dx) * c.inv2w2);
       }
-      if (part < nxp) {
-        double g = 0, q = 0; bool started = false;
-#pragma unroll 4
-        for (int k = 0; k < DEP_PART; k++) {
-          const int r = part * DEP_PART + k, i = r0 + r;
-          double2 v = make_double2(0.0, 1e300);
-          if (i >= s.iL && i < s.iR) {
-            const double d = __dadd_rn(s.x, -xg_of(c, i));
-            const double d2 = __dmul_rn(d, d);
-            if (s.flat) v.x = s.W;
-            else {
-              if (!started) { g = s.W * exp(-d2 * c.inv2w2); q = exp((2.0 * d * c.dx - c.dx * c.dx) * c.inv2w2); started = true; }
-              v.x = g; g *= q; q *= c.recx;
+      const float fyf = (float)(s.y - c.Ymin) * c.inv_dy_f;
+      double v[DEP_XP]; uint32_t w[DEP_NSTR][DEP_XP];
+#pragma unroll
+      for (int k = 0; k < DEP_XP; k++) {
+        v[k] = 0.0;
+#pragma unroll
+        for (int s2 = 0; s2 < DEP_NSTR; s2++) w[s2][k] = 0u;
+        if (k >= ka && k < kb) {
+          const double d = __dadd_rn(s.x, -xg_of(c, i0 + k));
+          const double d2 = __dmul_rn(d, d);
+          if (s.flat) v[k] = s.W; else { v[k] = g; g *= q; q *= c.recx; }
+          const double rem = __dadd_rn(s.thr, -d2);
+          if (rem >= 0.0) {
+            float hf; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(hf) : "f"((float)rem));
+            hf *= c.inv_dy_f;
+            const float tl = fyf - hf, th = fyf + hf, rl = rintf(tl), rh = rintf(th);
+            int lo = (int)ceilf(tl), hi2 = (int)floorf(th) + 1;
+            if (fabsf(tl - rl) < 2e-3f) {                                   // exact predicate at the doubtful cell
+              const int cn = (int)rl; const double dy = __dadd_rn(s.y, -yg_of(c, cn));
+              lo = (__dadd_rn(d2, __dmul_rn(dy, dy)) <= s.thr) ? cn : cn + 1;
             }
-            v.y = d2;
-          }
-          xtab[r * DEP_CH + t] = v;
-        }
-      } else {
-        const int p = part - nxp, ncol = s.jR - s.jL;
-        double g = 0, q = 0;
-#pragma unroll 4
-        for (int k = 0; k < DEP_PART; k++) {
-          const int cc = p * DEP_PART + k;
-          if (cc < ncol && cc < CS) {
-            const double d = __dadd_rn(s.y, -yg_of(c, s.jL + cc));
-            const double d2 = __dmul_rn(d, d);
-            double2 v = make_double2(1.0, d2);
-            if (!s.flat) {
-              if (k == 0) { g = exp(-d2 * c.inv2w2); q = exp((2.0 * d * c.dy - c.dy * c.dy) * c.inv2w2); }
-              v.x = g; g *= q; q *= c.recy;
+            if (fabsf(th - rh) < 2e-3f) {
+              const int cn = (int)rh; const double dy = __dadd_rn(s.y, -yg_of(c, cn));
+              hi2 = (__dadd_rn(d2, __dmul_rn(dy, dy)) <= s.thr) ? cn + 1 : cn;
             }
-            ytab[(size_t)t * CS + cc] = v;
+            lo = max(lo, s.jL); hi2 = min(hi2, s.jR);
+            const int a = lo - c0, b = hi2 - c0;
+            if (a < b) {
+#pragma unroll
+              for (int s2 = 0; s2 < DEP_NSTR; s2++)
+                w[s2][k] = ones_below(__viaddmax_s32(b, -32 * s2, 0)) & ~ones_below(__viaddmax_s32(a, -32 * s2, 0));
+            }
           }
         }
       }
+      *reinterpret_cast<double2*>(&T.xg[t][rb]) = make_double2(v[0], v[1]);
+      *reinterpret_cast<double2*>(&T.xg[t][rb + 2]) = make_double2(v[2], v[3]);
+#pragma unroll
+      for (int s2 = 0; s2 < DEP_NSTR; s2++) *reinterpret_cast<uint4*>(&T.mk[t][s2 * DEP_BAND + rb]) = make_uint4(w[s2][0], w[s2][1], w[s2][2], w[s2][3]);
+    } else if (id < nitems) {                                               // ---- columns: yg ----
+      const int id2 = id - DEP_CH * DEP_NXI, t = id2 % DEP_CH;
+      if (t >= nch) return;
+      const Src s = srcs[(chunk & 1) * DEP_CH + t];
+      const int part = max(s.jL - c0, 0) / DEP_YP + id2 / DEP_CH;          // a window spans at most nyq parts
+      if (part >= DEP_NYI) return;
+      const int cb = part * DEP_YP, j0 = c0 + cb;
+      const int ka = max(s.jL - j0, 0) & ~1, kb = min(s.jR - j0, DEP_YP);   // pairs of columns (an extra one is masked off)
+      if (ka >= kb) return;
+      double g = 1.0, q = 1.0, rec = 1.0;
+      if (!s.flat) {
+        const double d = __dadd_rn(s.y, -yg_of(c, j0 + ka));
+        g = exp(-__dmul_rn(d, d) * c.inv2w2); q = exp((2.0 * d * c.dy - c.dy * c.dy) * c.inv2w2); rec = c.recy;
+      }
+      for (int k = ka; k < kb; k += 2) {
+        const int cc = cb + k;
+        const double v0 = g; g *= q; q *= rec;
+        const double v1 = g; g *= q; q *= rec;
+        *reinterpret_cast<double2*>(&T.yg[t][(cc & ~31) + yg_pos(cc & 31)]) = make_double2(v0, v1);
+      }
+    } else {                                                                // ---- source records of chunk+1 ----
+      const int t = id - nitems, q = chunk + 1;
+      if (t < DEP_CH && q * DEP_CH + t < nact) load_src(c, st, e, hi, kind, act[q * DEP_CH + t], srcs[(q & 1) * DEP_CH + t]);
     }
   };
-  if (tid < 2) sm.wtot[tid] = 0;                      // wtot[0..1] double as the item counters from here on
-  if (nchunks > 0) build_items(0, tid, nthreads);
+
+  if (tid < 2) wtot[tid] = 0;                                   // wtot[0..1] double as the item counters from here on
+  if (tid < 2 * DEP_CH && tid < nact) load_src(c, st, e, hi, kind, act[tid], srcs[tid]);
   __syncthreads();
+  if (nchunks > 0) for (int id = tid; id < nitems; id += DEP_THREADS) build_item(0, id);
+  __syncthreads();
+  const int sh = 4 * lc;
   for (int n = 0; n < nchunks; n++) {
-    const int buf = n & 1, nch = min(DEP_CH, nact - n * DEP_CH);
-    const double2* xtab = sm.xtab + (size_t)buf * DEP_BAND * DEP_CH; const double2* ytab = sm.ytab + (size_t)buf * DEP_CH * CS;
-    // ---- accumulate: every warp walks the chunk, 32 sources per ballot ----
-    for (int tb = 0; tb < nch; tb += 32) {
-      const int tt = tb + lane, o = buf * DEP_CH + tt;
-      bool hit = false;
-      if (tt < nch) hit = (sm.sjR[o] > sc0) && (sm.sjL[o] < sc0 + 32) && (sm.siR[o] > rw0) && (sm.siL[o] < rw0 + DEP_WROWS);
-      unsigned m = __ballot_sync(0xffffffffu, hit);
-      while (m) {
-        const int t = tb + __ffs(m) - 1; m &= m - 1;
-        const int jL = sm.sjL[buf * DEP_CH + t], jR = sm.sjR[buf * DEP_CH + t];
-        const bool inw = (j >= jL) && (j < jR);
-        double2 yv = make_double2(0.0, 1e300);
-        if (inw) yv = ytab[(size_t)t * CS + (j - jL)];
-        const double th = sm.sthr[buf * DEP_CH + t];
-        const double2* xt = xtab + (wr * DEP_WROWS) * DEP_CH + t;
+    const DepTab& T = tab[n & 1];
+    const int nch = min(DEP_CH, nact - n * DEP_CH);
+    // ---- accumulate: every warp walks the sources of the chunk whose window meets its tile ----
+    bool hit = false;
+    if (lane < nch) { const int4 d = T.desc[lane]; hit = (d.y > rw0) && (d.x < rw0 + DEP_WROWS) && (d.w > sc0) && (d.z < sc0 + 32); }
+    unsigned m = __ballot_sync(0xffffffffu, hit);
+    while (m) {
+      const int t = __ffs(m) - 1; m &= m - 1;
+      const uint4 mw = *reinterpret_cast<const uint4*>(&T.mk[t][ws * DEP_BAND + wr * DEP_WROWS + 4 * lr]);
+      const double2 xa = *reinterpret_cast<const double2*>(&T.xg[t][wr * DEP_WROWS + 4 * lr]);
+      const double2 xb = *reinterpret_cast<const double2*>(&T.xg[t][wr * DEP_WROWS + 4 * lr + 2]);
+      const double2 ya = *reinterpret_cast<const double2*>(&T.yg[t][ws * 32 + 2 * lc]);          // columns 4lc, 4lc+1
+      const double2 yb = *reinterpret_cast<const double2*>(&T.yg[t][ws * 32 + 16 + 2 * lc]);     // columns 4lc+2, 4lc+3
+      const uint32_t mr[4] = {mw.x >> sh, mw.y >> sh, mw.z >> sh, mw.w >> sh};
+      const double gx[4] = {xa.x, xa.y, xb.x, xb.y};
 #pragma unroll
-        for (int r = 0; r < DEP_WROWS; r++) {
-          const double2 xv = xt[r * DEP_CH];
-          const double dc = __dadd_rn(xv.y, yv.y);                      // (x-xg)^2 + (y-yg)^2, reference rounding
-          if (dc <= th) acc[r] = fma(xv.x, yv.x, acc[r]);
-        }
-      }
+      for (int a = 0; a < 4; a++) row_fma(acc[a], gx[a], ya.x, ya.y, yb.x, yb.y, mr[a]);
     }
-    // ---- then help building the tables of the next chunk ----
+    // ---- then help building the tables of the next chunk (and the source records of the one after it) ----
     if (n + 1 < nchunks) {
-      int* counter = &sm.wtot[(n + 1) & 1];
+      int* counter = &wtot[(n + 1) & 1];
       for (;;) {
         int base = 0;
         if (lane == 0) base = atomicAdd(counter, 32);
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= nitems) break;
-        build_items(n + 1, base + lane, nitems);         // one item per lane
+        if (base >= nitems + DEP_CH) break;
+        build_item(n + 1, base + lane);
       }
     }
-    if (tid == 0) sm.wtot[n & 1] = 0;                      // counter of chunk n+2
+    if (tid == 0) wtot[n & 1] = 0;                         // counter of chunk n+2
     __syncthreads();
   }
-  if (j < c.Maxy) {
 #pragma unroll
-    for (int r = 0; r < DEP_WROWS; r++) if (rw0 + r < c.Maxx) grid[(size_t)(rw0 + r) * c.Maxy + j] = acc[r];
+  for (int a = 0; a < 4; a++) {
+    const int i = rw0 + 4 * lr + a;
+    if (i < c.Maxx) {
+      double* g = grid + (size_t)i * c.Maxy;
+      const int j = sc0 + 4 * lc;
+#pragma unroll
+      for (int b = 0; b < 4; b++) if (j + b < c.Maxy) g[j + b] = acc[a][b];
+    }
   }
 }
 
-static int dep_cs(const DevCfg& c) { int cs = c.wmax; while ((cs & 7) != 1) cs++; return cs; }
-
 size_t deposit_smem_bytes(const DevCfg& c, int nsrc_max) {
-  const int CS = dep_cs(c);
-  size_t b = (size_t)2 * (DEP_BAND * DEP_CH + (size_t)DEP_CH * CS) * sizeof(double2);
-  b += (size_t)2 * DEP_CH * sizeof(double) + (size_t)(8 * DEP_CH + 32) * sizeof(int);
+  size_t b = 2 * sizeof(DepTab) + 2 * DEP_CH * sizeof(Src) + 32 * sizeof(int);
   b += (size_t)(nsrc_max + 8) * sizeof(unsigned short);
   return (b + 15) & ~(size_t)15;
 }
 
-#define DEP_GS 4      // stripes (of 32 columns) per CTA
 cudaError_t launch_deposit(const DevCfg& c, const Store& st, const int* kinds, int nk, int nev, cudaStream_t s) {
   KindList kl; kl.n = nk; for (int i = 0; i < nk; i++) kl.kind[i] = kinds[i];
   bbox_kernel<<<nev, 128, 0, s>>>(c, st, kl, nev);
-  const int nstr = DEP_GS;
-  const int ngroups = (c.Maxy + nstr * 32 - 1) / (nstr * 32) + 1;      // +1: groups start at the event's own first column
+  const int ngroups = (c.Maxy + DEP_COLS - 1) / DEP_COLS + 1;      // +1: groups start at the event's own first column
   const int nbands = (c.Maxx + DEP_BAND - 1) / DEP_BAND + 1;
-  const int threads = DEP_NWR * nstr * 32;
   const size_t smem = deposit_smem_bytes(c, 2 * c.Amax + c.ncoll_cap);
   cudaFuncSetAttribute(deposit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 g(nev, nbands * ngroups, nk);
-  deposit_kernel<<<g, threads, smem, s>>>(c, st, kl, nev, nbands, dep_cs(c));
+  deposit_kernel<<<g, DEP_THREADS, smem, s>>>(c, st, kl, nev, nbands);
   return cudaGetLastError();
 }
 
