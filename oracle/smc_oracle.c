@@ -227,6 +227,7 @@ long smc_o_populate(const smc_o_nucleus* n, double xCenter, double yCenter,
   if (cx_phi) { cx_phi[0] = ctr; cx_phi[1] = phir; }
   part_t* P = (part_t*)malloc(sizeof(part_t) * (A > 0 ? A : 1));
   int cand = 0;
+  int nws = 0;   /* flat index of the Woods-Saxon rejection draws: the address the Philox callback uses (drand48 ignores it) */
   if (A == 1) {
     P[0].x = xCenter; P[0].y = yCenter; P[0].z = 0.0; P[0].idx = 0;
     particle_box(n, xCenter, yCenter, U, st, cand, &P[0].box); nu += 4;
@@ -238,25 +239,24 @@ long smc_o_populate(const smc_o_nucleus* n, double xCenter, double yCenter,
     do {
       double r = 0.0, cx = 1.0;
       if (n->deformed) {
-        double rad1, rwMax1; int k = 0;
+        double rad1, rwMax1;
         do {
-          r = n->rmaxCut * pow(U(st, 2, cand, 3 * k), 1.0 / 3.0);
-          cx = 1.0 - 2.0 * U(st, 2, cand, 3 * k + 1);
+          r = n->rmaxCut * pow(U(st, 2, nws, 0), 1.0 / 3.0);
+          cx = 1.0 - 2.0 * U(st, 2, nws, 1);
           double y20 = sph_harm(2, cx), y40 = sph_harm(4, cx);
           rad1 = n->rad * (1.0 + n->beta2 * y20 + n->beta4 * y40);
           rwMax1 = 1.0 / (1.0 + exp(-rad1 / n->dr));
           nu += 3;
-        } while (U(st, 2, cand, 3 * (k++) + 2) * rwMax1 > 1.0 / (1.0 + exp((r - rad1) / n->dr)));
+        } while (U(st, 2, nws++, 2) * rwMax1 > 1.0 / (1.0 + exp((r - rad1) / n->dr)));
         double sx = sqrt(1.0 - cx * cx);
         double phi = 2 * M_PI * U(st, 3, cand, 1); nu += 1;
         x = r * sx * cos(phi); y = r * sx * sin(phi); z = r * cx;
         rot3(ctr, phir, &x, &y, &z);
       } else {
-        int k = 0;
         do {
-          r = n->rmaxCut * pow(U(st, 2, cand, 2 * k), 1.0 / 3.0);
+          r = n->rmaxCut * pow(U(st, 2, nws, 0), 1.0 / 3.0);
           nu += 2;
-        } while (U(st, 2, cand, 2 * (k++) + 1) * n->rwMax > 1.0 / (1.0 + exp((r - n->rad) / n->dr)));
+        } while (U(st, 2, nws++, 1) * n->rwMax > 1.0 / (1.0 + exp((r - n->rad) / n->dr)));
         cx = 1.0 - 2.0 * U(st, 3, cand, 0);
         double sx = sqrt(1.0 - cx * cx);
         double phi = 2 * M_PI * U(st, 3, cand, 1); nu += 2;

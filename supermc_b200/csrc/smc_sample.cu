@@ -26,6 +26,7 @@ struct SampleSmem {
   int* firstB;      // [Amax]
   int* rowoff;      // [Amax+1]
   int* misc;        // [16]
+  double* wsq;      // [2][2][64] queue of accepted Woods-Saxon draws (r, cos theta) per warp
 };
 
 __device__ __forceinline__ void rot3(double cth, double phi, double& x, double& y, double& z) {
@@ -105,10 +106,20 @@ __device__ __forceinline__ void sort_by_xl(const DevCfg& c, const Store& st, con
   int rk[MK]; double key[MK];
 #pragma unroll
   for (int m = 0; m < MK; m++) { const int k = lane + 32 * m; rk[m] = 0; key[m] = (k < A) ? S_(sm, s, NXL, k) : 0.0; }
-  for (int j = 0; j < A; j++) {
-    const double o = S_(sm, s, NXL, j);
+  // rank = #{j : key_j < key_k or (key_j == key_k and j < k)}; for keys of another 32-block the index comparison is
+  // known at compile time, which leaves one compare per pair
 #pragma unroll
-    for (int m = 0; m < MK; m++) rk[m] += (o < key[m]) || (o == key[m] && j < lane + 32 * m);
+  for (int jb = 0; jb < MK; jb++) {
+    const int jend = min(32, A - 32 * jb);
+    for (int jj = 0; jj < jend; jj++) {
+      const double o = S_(sm, s, NXL, 32 * jb + jj);
+#pragma unroll
+      for (int m = 0; m < MK; m++) {
+        if (m > jb) rk[m] += (o <= key[m]);
+        else if (m < jb) rk[m] += (o < key[m]);
+        else rk[m] += (o < key[m]) || (o == key[m] && jj < lane);
+      }
+    }
   }
   __syncwarp();
 #pragma unroll 1
@@ -201,27 +212,47 @@ __device__ void sample_nucleus(const DevCfg& c, const Store& st, const SampleSme
     const smc_stream s_an = smc_make_stream(c.seed_lo, c.seed_hi, ev, tr, SMC_K_ANGLE, s);
     const double rad = c.rad[s], dr = c.dr[s], rmaxCut = c.rmaxCut[s], rwMax = c.rwMax[s];
     const double rmin = 0.9 * 0.9;
-    int placed = 0; uint32_t cand_base = 0;
+    // The Woods-Saxon rejection draws form ONE flat stream per nucleus (draw n -> Philox (WS, n)): whether draw n is
+    // accepted depends on nothing else, so 32 draws are tested at once and the accepted ones, in stream order, are
+    // exactly the radii a sequential do/while loop hands to candidates 0, 1, 2, ...  (queue in shared memory)
+    int placed = 0, nq = 0; uint32_t cand_base = 0, ndraw = 0;
+    double* qr = sm.wsq + (size_t)s * 128; double* qc = qr + 64;
+    const unsigned below = (1u << lane) - 1u;
     while (placed < A) {
+      while (nq < 32) {
+        const uint32_t n = ndraw + lane;
+        double r, cx = 0.0; bool ok;
+        if (c.deformed[s]) {                                    // Nucleus.cpp:585-607
+          double u0, u1; smc_uniform2(s_ws, n, 0, &u0, &u1);
+          const double u2 = smc_uniform(s_ws, n, 2);
+          r = rmaxCut * cbrt(u0); cx = 1.0 - 2.0 * u1;
+          const double rad1 = rad * (1.0 + c.beta2[s] * sph_harm2(cx) + c.beta4[s] * sph_harm4(cx));
+          const double rwMax1 = 1.0 / (1.0 + exp(-rad1 / dr));
+          ok = !(u2 * rwMax1 > 1.0 / (1.0 + exp((r - rad1) / dr)));
+        } else {                                                // Nucleus.cpp:610-613
+          double u1, u2; smc_uniform2(s_ws, n, 0, &u1, &u2);
+          r = rmaxCut * cbrt(u1);
+          ok = !(u2 * rwMax > 1.0 / (1.0 + exp((r - rad) / dr)));
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (ok) { const int pos = nq + __popc(m & below); qr[pos] = r; qc[pos] = cx; }
+        nq += __popc(m); ndraw += 32;
+        __syncwarp();
+      }
       const uint32_t cand = cand_base + lane;
+      const double r = qr[lane], cxq = qc[lane];
+      { double t0 = 0, t1 = 0; const bool mv = lane + 32 < nq;
+        if (mv) { t0 = qr[lane + 32]; t1 = qc[lane + 32]; }
+        __syncwarp();
+        if (mv) { qr[lane] = t0; qc[lane] = t1; }
+        nq -= 32; __syncwarp(); }
       double x, y, z;
-      if (c.deformed[s]) {                                      // Nucleus.cpp:585-607
-        double r, cx, rad1, rwMax1, u3; uint32_t k = 0;
-        do {
-          r = rmaxCut * cbrt(smc_uniform(s_ws, cand, 3 * k));
-          cx = 1.0 - 2.0 * smc_uniform(s_ws, cand, 3 * k + 1);
-          rad1 = rad * (1.0 + c.beta2[s] * sph_harm2(cx) + c.beta4[s] * sph_harm4(cx));
-          rwMax1 = 1.0 / (1.0 + exp(-rad1 / dr));
-          u3 = smc_uniform(s_ws, cand, 3 * k + 2); k++;
-        } while (u3 * rwMax1 > 1.0 / (1.0 + exp((r - rad1) / dr)));
-        double sx = sqrt(1.0 - cx * cx), sp, cp;
+      if (c.deformed[s]) {
+        const double cx = cxq, sx = sqrt(1.0 - cx * cx); double sp, cp;
         sincos(2 * SMC_PI * smc_uniform(s_an, cand, 1), &sp, &cp);
         x = r * sx * cp; y = r * sx * sp; z = r * cx;
         rot3(ctr, phir, x, y, z);
-      } else {                                                  // Nucleus.cpp:610-619
-        double r, u1, u2; uint32_t k = 0;
-        do { smc_uniform2(s_ws, cand, k, &u1, &u2); r = rmaxCut * cbrt(u1); k++; }
-        while (u2 * rwMax > 1.0 / (1.0 + exp((r - rad) / dr)));
+      } else {                                                  // Nucleus.cpp:614-619
         double ua, ub; smc_uniform2(s_an, cand, 0, &ua, &ub);
         double cx = 1.0 - 2.0 * ua, sx = sqrt(1.0 - cx * cx), sp, cp;
         sincos(2 * SMC_PI * ub, &sp, &cp);
@@ -311,8 +342,9 @@ __global__ void __launch_bounds__(64, 6) sample_collide_kernel(DevCfg c, Store s
   const int A = c.A[0], B = c.A[1], Amax = c.Amax, HW = (Amax + 31) / 32;
   SampleSmem sm;
   sm.soa = smem_d; sm.Amax = Amax;
-  sm.hit = (uint32_t*)(sm.soa + 2 * Amax * NROW);
+  sm.hit = (uint32_t*)(sm.soa + 2 * Amax * NROW + 256);
   sm.ncB = (int*)(sm.hit + (size_t)Amax * HW); sm.firstB = sm.ncB + Amax; sm.rowoff = sm.firstB + Amax; sm.misc = sm.rowoff + Amax + 1;
+  sm.wsq = smem_d + 2 * Amax * NROW;
   const uint64_t ev = st.event_id[e];
   double* gn = st.nuc + (size_t)e * 2 * Amax * NROW;
   int* hi = st.hdr_i + (size_t)e * HDR_I;
@@ -420,23 +452,15 @@ __global__ void __launch_bounds__(64, 6) sample_collide_kernel(DevCfg c, Store s
   }
   __syncthreads();
   const bool givenw = GIVEN && hi[H_GIVENW];
-  // nucleon weights (selectFluctFactors: re-drawn at every hit, last wins => one draw per wounded nucleon)
   for (int k = tid; k < A + B; k += 64) {
     const int s = k >= A, i = s ? k - A : k;
     const int nc = s ? sm.ncB[i] : (sm.rowoff[i + 1] - sm.rowoff[i]);
-    double wv = 1.0;
-    if (givenw) wv = S_(sm, s, NW, i);
-    else if (c.cc_fluct > 5 && nc > 0 && accepted) {
-      const smc_stream sg = smc_make_stream(c.seed_lo, c.seed_hi, ev, trw, SMC_K_GAMMA_PART, s);
-      wv = gamma_variate(sg, (uint32_t)i, c.gam_k_part, c.gam_th_part);
-    }
-    S_(sm, s, NW, i) = wv;
+    if (!givenw) S_(sm, s, NW, i) = 1.0;
     st.nuc_ncoll[((size_t)e * 2 + s) * Amax + i] = nc;
     if (s) st.nuc_first[(size_t)e * Amax + i] = sm.firstB[i];
   }
-  __syncthreads();
-  for (int k = tid; k < 2 * Amax * NROW; k += 64) { const int sd = k / (Amax * NROW), i = (k / NROW) % Amax, f = k % NROW; gn[k] = S_(sm, sd, f, i); }
   // compact participant / spectator lists (ordered), warp 0 = proj, warp 1 = targ
+  int* pidx = st.part_idx + (size_t)e * 2 * Amax;
   {
     const int s = warp, n = c.A[s];
     int npart = 0, nspec = 0;
@@ -447,46 +471,60 @@ __global__ void __launch_bounds__(64, 6) sample_collide_kernel(DevCfg c, Store s
       const int nc = in ? (s ? sm.ncB[i] : (sm.rowoff[i + 1] - sm.rowoff[i])) : 0;
       const unsigned mp = __ballot_sync(0xffffffffu, in && nc > 0), ms = __ballot_sync(0xffffffffu, in && nc == 0);
       const unsigned below = (1u << lane) - 1u;
-      if (in && nc > 0) st.part_idx[(size_t)e * 2 * Amax + pbase + npart + __popc(mp & below)] = (s << 16) | i;
+      if (in && nc > 0) pidx[pbase + npart + __popc(mp & below)] = (s << 16) | i;
       if (in && nc == 0) st.spec_idx[(size_t)e * 2 * Amax + sbase + nspec + __popc(ms & below)] = (s << 16) | i;
       npart += __popc(mp); nspec += __popc(ms);
     }
     if (lane == 0) hi[s ? H_NSPEC2 : H_NSPEC1] = nspec;
   }
-  // collisions: midpoints + weights
+  // collision list in (i,j) order (createBinaryCollisions, MCnucl.cpp:326-352): the sparse pass only records the pair
+  int* cij = st.coll_ij + (size_t)e * c.ncoll_cap;
   if (accepted) {
-    const smc_stream sgc = smc_make_stream(c.seed_lo, c.seed_hi, ev, trw, SMC_K_GAMMA_COLL, 0);
-    const double* cw = (GIVEN && st.coll_w) ? st.coll_w + (size_t)e * c.ncoll_cap * 2 : nullptr;
     for (int i = warp; i < A; i += 2) {
       int off = sm.rowoff[i];
-      const int nci = sm.rowoff[i + 1] - off;
-      if (nci == 0) continue;
+      if (sm.rowoff[i + 1] == off) continue;
       for (int wj = 0; wj < HW; wj++) {
         const unsigned hm = sm.hit[(size_t)i * HW + wj];
-        if ((hm >> lane) & 1u) {
-          const int j = wj * 32 + lane, k = off + __popc(hm & ((1u << lane) - 1u));
-          if (k < c.ncoll_cap) {
-            double* cr = st.coll + ((size_t)e * c.ncoll_cap + k) * CROW;
-            cr[CX] = (S_(sm, 0, NX, i) + S_(sm, 1, NX, j)) / 2.0;                                           // MCnucl.cpp:339-340
-            cr[CY] = (S_(sm, 0, NY, i) + S_(sm, 1, NY, j)) / 2.0;
-            double wv = 1.0, addw = 0.0;
-            if (c.which_mc_model == 5 && c.sub_model == 2)                                           // integer division in the reference,
-              addw = (double)((nci == 1 ? 1 : 0) + (sm.ncB[j] == 1 ? 1 : 0));                        // MCnucl.cpp:345-348
-            if (cw) { wv = cw[2 * k]; addw = cw[2 * k + 1]; }
-            else if (c.cc_fluct > 5) wv = gamma_variate(sgc, (uint32_t)k, c.gam_k_bin, c.gam_th_bin);
-            cr[CW] = wv; cr[CADDW] = addw;
-            st.coll_ij[(size_t)e * c.ncoll_cap + k] = (i << 16) | j;
-          }
-        }
+        if ((hm >> lane) & 1u) { const int k = off + __popc(hm & ((1u << lane) - 1u)); if (k < c.ncoll_cap) cij[k] = (i << 16) | (wj * 32 + lane); }
         off += __popc(hm);
       }
     }
   }
+  __syncthreads();
+  // Gamma multiplicity weights, one variate per lane (dense over the compact lists).  Nucleon weights
+  // (selectFluctFactors, MCnucl.cpp:310-324) are re-drawn at every hit, last wins => one draw per wounded nucleon.
+  if (!givenw && c.cc_fluct > 5 && accepted) {
+    for (int k = tid; k < np1 + np2; k += 64) {
+      const int id = pidx[k], s = id >> 16, i = id & 0xffff;
+      const smc_stream sg = smc_make_stream(c.seed_lo, c.seed_hi, ev, trw, SMC_K_GAMMA_PART, s);
+      S_(sm, s, NW, i) = gamma_variate(sg, (uint32_t)i, c.gam_k_part, c.gam_th_part);
+    }
+  }
+  // collisions: midpoints + weights
+  if (accepted) {
+    const smc_stream sgc = smc_make_stream(c.seed_lo, c.seed_hi, ev, trw, SMC_K_GAMMA_COLL, 0);
+    const double* cw = (GIVEN && st.coll_w) ? st.coll_w + (size_t)e * c.ncoll_cap * 2 : nullptr;
+    const int nck = min(ncoll, c.ncoll_cap);
+    for (int k = tid; k < nck; k += 64) {
+      const int ij = cij[k], i = ij >> 16, j = ij & 0xffff;
+      double* cr = st.coll + ((size_t)e * c.ncoll_cap + k) * CROW;
+      cr[CX] = (S_(sm, 0, NX, i) + S_(sm, 1, NX, j)) / 2.0;                                           // MCnucl.cpp:339-340
+      cr[CY] = (S_(sm, 0, NY, i) + S_(sm, 1, NY, j)) / 2.0;
+      double wv = 1.0, addw = 0.0;
+      if (c.which_mc_model == 5 && c.sub_model == 2)                                           // integer division in the reference,
+        addw = (double)((sm.rowoff[i + 1] - sm.rowoff[i] == 1 ? 1 : 0) + (sm.ncB[j] == 1 ? 1 : 0));   // MCnucl.cpp:345-348
+      if (cw) { wv = cw[2 * k]; addw = cw[2 * k + 1]; }
+      else if (c.cc_fluct > 5) wv = gamma_variate(sgc, (uint32_t)k, c.gam_k_bin, c.gam_th_bin);
+      cr[CW] = wv; cr[CADDW] = addw;
+    }
+  }
+  __syncthreads();
+  for (int k = tid; k < 2 * Amax * NROW; k += 64) { const int sd = k / (Amax * NROW), i = (k / NROW) % Amax, f = k % NROW; gn[k] = S_(sm, sd, f, i); }
 }
 
 size_t sample_smem_bytes(int Amax) {
   const int HW = (Amax + 31) / 32;
-  size_t d = (size_t)(2 * Amax * NROW);
+  size_t d = (size_t)(2 * Amax * NROW) + 256;
   size_t i = (size_t)Amax * HW + 3 * Amax + 1 + 16;
   return d * sizeof(double) + i * sizeof(int);
 }
