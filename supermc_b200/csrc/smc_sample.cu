@@ -111,6 +111,7 @@ __device__ __forceinline__ void sort_by_xl(const DevCfg& c, const Store& st, con
 #pragma unroll
   for (int jb = 0; jb < MK; jb++) {
     const int jend = min(32, A - 32 * jb);
+#pragma unroll 4
     for (int jj = 0; jj < jend; jj++) {
       const double o = S_(sm, s, NXL, 32 * jb + jj);
 #pragma unroll
@@ -218,6 +219,8 @@ __device__ void sample_nucleus(const DevCfg& c, const Store& st, const SampleSme
     int placed = 0, nq = 0; uint32_t cand_base = 0, ndraw = 0;
     double* qr = sm.wsq + (size_t)s * 128; double* qc = qr + 64;
     const unsigned below = (1u << lane) - 1u;
+    float4* pf = reinterpret_cast<float4*>(&S_(sm, s, NXL, 0));           // [Amax] placed nucleons, single precision (the box fields are not live yet)
+    float4* bq = reinterpret_cast<float4*>(sm.hit) + s * 32;               // [32] this batch's candidates (the hit masks are not live yet)
     while (placed < A) {
       while (nq < 32) {
         const uint32_t n = ndraw + lane;
@@ -258,23 +261,56 @@ __device__ void sample_nucleus(const DevCfg& c, const Store& st, const SampleSme
         sincos(2 * SMC_PI * ub, &sp, &cp);
         x = r * sx * cp; y = r * sx * sp; z = r * cx;
       }
-      bool bad = false;
-      for (int i = 0; i < placed; i++) {                        // Nucleus.cpp:284-293
-        double ax = x - S_(sm, s, NX, i), ay = y - S_(sm, s, NY, i), az = z - S_(sm, s, NZ, i);
-        double r2 = ax * ax + ay * ay + az * az;
-        bad |= (r2 < rmin);
+      // Hard core (Nucleus.cpp:284-293).  The distance tests run in single precision on float4 copies of the
+      // positions; a squared distance within 1e-4 of 0.81 (the single-precision error is < 1e-5) is settled by the
+      // reference's double-precision expression, so every decision is the reference's.
+      const float xf = (float)x, yf = (float)y, zf = (float)z;
+      float r2min = 1e30f;
+      for (int i = 0; i < placed; i++) {
+        const float4 p = pf[i];
+        const float ax = xf - p.x, ay = yf - p.y, az = zf - p.z;
+        r2min = fminf(r2min, ax * ax + ay * ay + az * az);
       }
-      int nacc = 0;
-      unsigned okmask = __ballot_sync(0xffffffffu, !bad);
-      for (int l = 0; l < 32 && okmask; l++) {                  // in-batch conflicts, candidate order
-        if (!((okmask >> l) & 1u)) continue;
-        if (placed + nacc >= A) break;
-        double lx = __shfl_sync(0xffffffffu, x, l), ly = __shfl_sync(0xffffffffu, y, l), lz = __shfl_sync(0xffffffffu, z, l);
-        if (lane > l) { double ax = x - lx, ay = y - ly, az = z - lz; bad |= (ax * ax + ay * ay + az * az < rmin); }
-        if (lane == l) { const int q = placed + nacc; S_(sm, s, NX, q) = x; S_(sm, s, NY, q) = y; S_(sm, s, NZ, q) = z; S_(sm, s, NW, q) = (double)cand; }
-        nacc++;
-        okmask = __ballot_sync(0xffffffffu, !bad) & ~((2u << l) - 1u);
+      bool bad = r2min < 0.81f - 1e-4f;
+      if (__any_sync(0xffffffffu, !bad && r2min < 0.81f + 1e-4f)) {
+        for (int i = 0; i < placed; i++) {
+          double ax = x - S_(sm, s, NX, i), ay = y - S_(sm, s, NY, i), az = z - S_(sm, s, NZ, i);
+          bad |= (ax * ax + ay * ay + az * az < rmin);
+        }
       }
+      // conflicts inside the batch: cm = earlier lanes closer than the core
+      bq[lane] = make_float4(xf, yf, zf, 0.f);
+      __syncwarp();
+      unsigned cm = 0, dm = 0;
+#pragma unroll
+      for (int j = 0; j < 31; j++) {
+        const float4 p = bq[j];
+        const float ax = xf - p.x, ay = yf - p.y, az = zf - p.z, r2 = ax * ax + ay * ay + az * az;
+        if (r2 < 0.81f + 1e-4f) { if (r2 < 0.81f - 1e-4f) cm |= 1u << j; else dm |= 1u << j; }
+      }
+      cm &= below; dm &= below;
+      while (__any_sync(0xffffffffu, dm != 0)) {                // doubtful pairs: exact
+        const int j = dm ? __ffs(dm) - 1 : lane;
+        const double lx = __shfl_sync(0xffffffffu, x, j), ly = __shfl_sync(0xffffffffu, y, j), lz = __shfl_sync(0xffffffffu, z, j);
+        if (dm) { const double ax = x - lx, ay = y - ly, az = z - lz; if (ax * ax + ay * ay + az * az < rmin) cm |= 1u << j; dm &= dm - 1; }
+      }
+      // sequential acceptance in candidate order: a lane without a conflict among the earlier admissible lanes is in;
+      // the (few) others are in iff none of the lanes they conflict with was accepted
+      const unsigned okb = __ballot_sync(0xffffffffu, !bad);
+      unsigned todo = __ballot_sync(0xffffffffu, !bad && (cm & okb) != 0);
+      unsigned acc = okb & ~todo;
+      while (todo) {
+        const int l = __ffs(todo) - 1; todo &= todo - 1;
+        const unsigned cml = __shfl_sync(0xffffffffu, cm, l);
+        if (!(cml & acc)) acc |= 1u << l;
+      }
+      const int rank = __popc(acc & below);
+      if (((acc >> lane) & 1u) && placed + rank < A) {
+        const int q = placed + rank;
+        S_(sm, s, NX, q) = x; S_(sm, s, NY, q) = y; S_(sm, s, NZ, q) = z; S_(sm, s, NW, q) = (double)cand;
+        pf[q] = make_float4(xf, yf, zf, 0.f);
+      }
+      const int nacc = min(__popc(acc), A - placed);
       placed += nacc; cand_base += 32;
       __syncwarp();
     }
@@ -343,7 +379,7 @@ __global__ void __launch_bounds__(64, 6) sample_collide_kernel(DevCfg c, Store s
   SampleSmem sm;
   sm.soa = smem_d; sm.Amax = Amax;
   sm.hit = (uint32_t*)(sm.soa + 2 * Amax * NROW + 256);
-  sm.ncB = (int*)(sm.hit + (size_t)Amax * HW); sm.firstB = sm.ncB + Amax; sm.rowoff = sm.firstB + Amax; sm.misc = sm.rowoff + Amax + 1;
+  sm.ncB = (int*)(sm.hit + max((size_t)Amax * HW, (size_t)256)); sm.firstB = sm.ncB + Amax; sm.rowoff = sm.firstB + Amax; sm.misc = sm.rowoff + Amax + 1;
   sm.wsq = smem_d + 2 * Amax * NROW;
   const uint64_t ev = st.event_id[e];
   double* gn = st.nuc + (size_t)e * 2 * Amax * NROW;
@@ -363,22 +399,37 @@ __global__ void __launch_bounds__(64, 6) sample_collide_kernel(DevCfg c, Store s
       sample_nucleus(c, st, sm, e, warp, ev, tr, warp == 0 ? b / 2.0 : -b / 2.0, 0.0);                 // MCnucl.cpp:208-214
     }
     for (int k = tid; k < Amax; k += 64) { sm.ncB[k] = 0; sm.firstB[k] = 0x7fffffff; }
+    for (int k = tid; k < Amax * HW; k += 64) sm.hit[k] = 0;
     __syncthreads();
     // ---- collisions: rows of the projectile, 32 target nucleons per step ----
     const smc_stream s_p = smc_make_stream(c.seed_lo, c.seed_hi, ev, tr, SMC_K_PAIR, 0);
     const float hit_c1f = (float)(c.sigma_gg / (4. * SMC_PI * c.w * c.w)), hit_c2f = (float)(1.0 / (4. * c.w * c.w));
     const double* pu = (GIVEN && st.pair_u) ? st.pair_u + (size_t)e * A * B : nullptr;
+    // pairs whose uniform is below a single-precision over-estimate of the hit probability wait in a per-warp queue
+    // and are settled 32 at a time by the double-precision expression of the reference (dense lanes)
+    double* qu = sm.wsq + (size_t)warp * 128; int* qij = reinterpret_cast<int*>(qu + 64);
+    const unsigned below = (1u << lane) - 1u;
+    int nq = 0;
+    auto record_hit = [&](int i, int j) { atomicOr(&sm.hit[(size_t)i * HW + (j >> 5)], 1u << (j & 31)); atomicAdd(&sm.ncB[j], 1); atomicMin(&sm.firstB[j], i); };
+    auto settle = [&](int cnt) {
+      if (lane < cnt) {
+        const int ij = qij[lane], i = ij >> 16, j = ij & 0xffff; const double u = qu[lane];
+        const double ddx = S_(sm, 1, NX, j) - S_(sm, 0, NX, i), ddy = S_(sm, 1, NY, j) - S_(sm, 0, NY, i);
+        const double bb = sqrt(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)));              // MCnucl.cpp:359-360
+        const double prob = 1. - exp(-c.sigma_gg * exp(-bb * bb / (4. * c.w * c.w)) / (4. * SMC_PI * c.w * c.w));
+        if (u < prob) record_hit(i, j);
+      }
+      __syncwarp();
+    };
     int start_carry = 0;                                        // start(i) is non-decreasing in i (x-sorted sweep)
     for (int i = warp; i < A; i += 2) {
       const double px = S_(sm, 0, NX, i), py = S_(sm, 0, NY, i);
       const double pXL = S_(sm, 0, NXL, i), pXR = S_(sm, 0, NXR, i), pYL = S_(sm, 0, NYL, i), pYR = S_(sm, 0, NYR, i);
-      int start = -1; int rowhits = 0;
+      int start = -1;
       const int jbeg = start_carry & ~31;
-      if (lane < (jbeg >> 5)) sm.hit[(size_t)i * HW + lane] = 0;
       for (int j0 = jbeg; j0 < B; j0 += 32) {
         const int j = j0 + lane; const bool in = j < B;
         const int jj = in ? j : 0;
-        uint32_t hitbit = 0;
         if (start < 0) {                                        // skip loop of the sweep, MCnucl.cpp:255-261
           unsigned m = __ballot_sync(0xffffffffu, in && j >= start_carry && (S_(sm, 1, NXR, jj) >= pXL));
           if (m) { start = j0 + __ffs(m) - 1; start_carry = start; }
@@ -388,33 +439,40 @@ __global__ void __launch_bounds__(64, 6) sample_collide_kernel(DevCfg c, Store s
           bool tst = in && j >= start;
           if (tst) { int jp = j - 1 > start ? j - 1 : start; tst = pXR >= S_(sm, 1, NXL, jp); }
           const unsigned alive = __ballot_sync(0xffffffffu, tst);
+          bool maybe = false; double u = 0.0;
           if (tst && pYL <= S_(sm, 1, NYR, jj) && pYR >= S_(sm, 1, NYL, jj)) {
             const double ddx = S_(sm, 1, NX, jj) - px, ddy = S_(sm, 1, NY, jj) - py;
-            const double bb = sqrt(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)));          // MCnucl.cpp:359-360
-            if (c.crit == 1) hitbit = (__dmul_rn(bb, bb) <= c.dsq);
-            else {
-              const double u = pu ? pu[(size_t)i * B + j] : smc_uniform(s_p, (uint32_t)i, (uint32_t)j);
-              // P = 1 - exp(-t) <= t: a single-precision over-estimate of t settles almost every pair;
-              // only u below it pays for the double-precision evaluation the reference does
-              const float tub = hit_c1f * __expf(-(float)(bb * bb) * hit_c2f) * 1.01f;
-              if (u <= (double)tub) {
-                const double prob = 1. - exp(-c.sigma_gg * exp(-bb * bb / (4. * c.w * c.w)) / (4. * SMC_PI * c.w * c.w));
-                hitbit = (u < prob);
-              }
+            if (c.crit == 1) {
+              const double bb = sqrt(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)));        // MCnucl.cpp:359-366
+              if (__dmul_rn(bb, bb) <= c.dsq) record_hit(i, j);
+            } else {
+              u = pu ? pu[(size_t)i * B + j] : smc_uniform(s_p, (uint32_t)i, (uint32_t)j);
+              // P = 1 - exp(-t) <= t
+              const float tub = hit_c1f * __expf(-(float)(ddx * ddx + ddy * ddy) * hit_c2f) * 1.01f;
+              maybe = (u <= (double)tub);
             }
           }
-          const unsigned hm = __ballot_sync(0xffffffffu, hitbit);
-          if (lane == 0) sm.hit[(size_t)i * HW + (j0 >> 5)] = hm;
-          rowhits += __popc(hm);
-          if (hitbit) { atomicAdd(&sm.ncB[j], 1); atomicMin(&sm.firstB[j], i); }
-          if (!alive && j0 + 32 > start) {                     // x-sorted: nothing further can be tested
-            { const int w0 = (j0 >> 5) + 1 + lane; if (w0 < HW && w0 * 32 < B) sm.hit[(size_t)i * HW + w0] = 0; }
-            break;
+          const unsigned mm = __ballot_sync(0xffffffffu, maybe);
+          if (mm) {
+            if (maybe) { const int pos = nq + __popc(mm & below); qij[pos] = (i << 16) | j; qu[pos] = u; }
+            nq += __popc(mm);
+            __syncwarp();
+            if (nq >= 32) {
+              settle(32);
+              int t0 = 0; double t1 = 0.0; const bool mv = lane + 32 < nq;
+              if (mv) { t0 = qij[lane + 32]; t1 = qu[lane + 32]; }
+              __syncwarp();
+              if (mv) { qij[lane] = t0; qu[lane] = t1; }
+              nq -= 32; __syncwarp();
+            }
           }
-        } else if (lane == 0) sm.hit[(size_t)i * HW + (j0 >> 5)] = 0;
+          if (!alive && j0 + 32 > start) break;                // x-sorted: nothing further can be tested
+        }
       }
-      if (lane == 0) sm.rowoff[i] = rowhits;
     }
+    settle(nq);
+    __syncthreads();
+    for (int i = tid; i < A; i += 64) { int r = 0; for (int w = 0; w < HW; w++) r += __popc(sm.hit[(size_t)i * HW + w]); sm.rowoff[i] = r; }
     __syncthreads();
     // ---- counts ----
     if (warp == 0) {
@@ -525,7 +583,7 @@ __global__ void __launch_bounds__(64, 6) sample_collide_kernel(DevCfg c, Store s
 size_t sample_smem_bytes(int Amax) {
   const int HW = (Amax + 31) / 32;
   size_t d = (size_t)(2 * Amax * NROW) + 256;
-  size_t i = (size_t)Amax * HW + 3 * Amax + 1 + 16;
+  size_t i = std::max((size_t)Amax * HW, (size_t)256) + 3 * Amax + 1 + 16;
   return d * sizeof(double) + i * sizeof(int);
 }
 
