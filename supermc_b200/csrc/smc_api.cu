@@ -330,12 +330,21 @@ int smc_run_grid_stages(smc_ctx* ctx, int m, const int* kinds, int nd) {
   if (ctx->profile) CK(cudaEventRecord(ctx->pev[1], ctx->stream));
   // deposit CTAs only cover each event's bounding rectangle: whoever reads whole grids needs zeros elsewhere
   if (ctx->need_zero) CK(cudaMemsetAsync(ctx->d_grids, 0, (size_t)m * ctx->st.nkinds * ctx->G * sizeof(double), ctx->stream));
-  CK(smc::launch_deposit(c, ctx->st, kinds, nd, m, ctx->stream)); ctx->launches += 2;
-  if (ctx->profile) CK(cudaEventRecord(ctx->pev[2], ctx->stream));
-  if (c.which_mc_model != 5) { CK(smc::launch_combine(c, ctx->st, m, ctx->stream)); ctx->launches++; }
-  if (ctx->profile) CK(cudaEventRecord(ctx->pev[3], ctx->stream));
-  CK(smc::launch_moments(c, ctx->st, m, ctx->stream)); ctx->launches++;
-  if (ctx->profile) CK(cudaEventRecord(ctx->pev[4], ctx->stream));
+  // Sub-batches sized so that the density tiles a deposit launch writes are still in the 126 MB L2 when the
+  // moments launch reads them back (profiling mode keeps whole-batch launches: one event pair per stage)
+  static const int sub_env = getenv("SMC_SUBBATCH") ? atoi(getenv("SMC_SUBBATCH")) : 0;
+  const int sub = (!ctx->profile && sub_env > 0) ? sub_env : m;
+  for (int e0 = 0; e0 < m; e0 += sub) {
+    const int mm = std::min(sub, m - e0);
+    ctx->st.e0 = e0;
+    CK(smc::launch_deposit(c, ctx->st, kinds, nd, mm, ctx->stream)); ctx->launches += 2;
+    if (ctx->profile) CK(cudaEventRecord(ctx->pev[2], ctx->stream));
+    if (c.which_mc_model != 5) { CK(smc::launch_combine(c, ctx->st, mm, ctx->stream)); ctx->launches++; }
+    if (ctx->profile) CK(cudaEventRecord(ctx->pev[3], ctx->stream));
+    CK(smc::launch_moments(c, ctx->st, mm, ctx->stream)); ctx->launches++;
+    if (ctx->profile) CK(cudaEventRecord(ctx->pev[4], ctx->stream));
+  }
+  ctx->st.e0 = 0;
   return SMC_OK;
 }
 

@@ -81,6 +81,7 @@ struct Store {
   int nkinds;
   double* mom_out;    // [batch][MOM_OUT]
   double* kln_table;  // [tmax][tmax]
+  int e0;             // first event of the launch (the grid stages run in L2-sized sub-batches)
 };
 enum { H_NP1 = 0, H_NP2, H_NCOLL, H_TRIES, H_NSPEC1, H_NSPEC2, H_STATUS, H_RLO, H_RHI, H_CLO, H_CHI, H_GIVENW, HDR_I = 16 };
 enum { HD_B = 0, HDR_D = 4 };

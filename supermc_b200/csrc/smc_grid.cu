@@ -15,6 +15,7 @@
 // rounded dx^2, dy^2 the reference's circle masks are made of; every lane then does one DADD + compare
 // (the reference's `dc <= 25 w^2` / `r <= 5w` decision, bit for bit) and one DFMA per (source, cell).
 // Deposits are deterministic (fixed summation order) and each grid cell is written exactly once.
+#include <cuda_pipeline.h>
 #include "smc_common.cuh"
 
 namespace smc {
@@ -138,7 +139,7 @@ struct DepTab {
 // bounding rectangle (cells) of every source window of the participant/collision deposits of one event
 __global__ void bbox_kernel(DevCfg c, Store st, KindList kl, int nev) {
   __shared__ int red[4][4];
-  const int e = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int e = blockIdx.x + st.e0, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (st.redo && !st.redo[e]) return;
   int* hi = st.hdr_i + (size_t)e * HDR_I;
   int ilo = c.Maxx, ihi = 0, jlo = c.Maxy, jhi = 0;
@@ -211,7 +212,7 @@ __device__ __forceinline__ int yg_pos(int c) { return ((c >> 1) & 1) * 16 + (c >
 
 __global__ void __launch_bounds__(DEP_THREADS, DEP_MINCTA) deposit_kernel(DevCfg c, Store st, KindList kl, int nev, int nbands) {
   extern __shared__ __align__(16) unsigned char dep_smem[];
-  const int e = blockIdx.x, band = blockIdx.y % nbands, sgroup = blockIdx.y / nbands, kind = kl.kind[blockIdx.z];
+  const int e = blockIdx.x + st.e0, band = blockIdx.y % nbands, sgroup = blockIdx.y / nbands, kind = kl.kind[blockIdx.z];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (st.redo && !st.redo[e]) return;
   const int* hi = st.hdr_i + (size_t)e * HDR_I;
@@ -374,6 +375,9 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_MINCTA) deposit_kernel(DevCfg
     }
     // ---- then help building the tables of the next chunk (and the source records of the one after it) ----
     if (n + 1 < nchunks) {
+#ifdef DEP_STATIC
+      for (int id = tid; id < nitems + DEP_CH; id += DEP_THREADS) build_item(n + 1, id);
+#else
       int* counter = &wtot[(n + 1) & 1];
       for (;;) {
         int base = 0;
@@ -382,6 +386,7 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_MINCTA) deposit_kernel(DevCfg
         if (base >= nitems + DEP_CH) break;
         build_item(n + 1, base + lane);
       }
+#endif
     }
     if (tid == 0) wtot[n & 1] = 0;                         // counter of chunk n+2
     __syncthreads();
@@ -420,7 +425,7 @@ cudaError_t launch_deposit(const DevCfg& c, const Store& st, const int* kinds, i
 // which_mc_model 7: rho = sqrt(rhoA*rhoB) (MCnucl.cpp:797-803); which_mc_model 1: 6-point table lookup
 // (MCnucl.cpp:654-687, arsenal.cpp:33-54)
 __global__ void combine_kernel(DevCfg c, Store st, int nev) {
-  const int e = blockIdx.y;
+  const int e = blockIdx.y + st.e0;
   if (st.redo && !st.redo[e]) return;
   const size_t G = (size_t)c.Maxx * c.Maxy;
   int* hi = st.hdr_i + (size_t)e * HDR_I;
@@ -455,6 +460,9 @@ cudaError_t launch_combine(const DevCfg& c, const Store& st, int nev, cudaStream
 #ifndef MOM_THREADS
 #define MOM_THREADS 256
 #endif
+#ifndef MOM_LD
+#define MOM_LD 8      // density loads a lane keeps in flight
+#endif
 #ifndef MOM_MINCTA
 #define MOM_MINCTA 2
 #endif
@@ -479,15 +487,16 @@ __device__ __forceinline__ double block_min(double v, double* red, int tid) {
 
 __global__ void __launch_bounds__(MOM_THREADS, MOM_MINCTA) moments_kernel(DevCfg c, Store st, int nev) {
   extern __shared__ double smem_d[];
-  const int e = blockIdx.x, tid = threadIdx.x;
+  const int e = blockIdx.x + st.e0, tid = threadIdx.x;
   if (st.redo && !st.redo[e]) return;
   const int* hi = st.hdr_i + (size_t)e * HDR_I;
   double* out = st.mom_out + (size_t)e * MOM_OUT;
   const int status = hi[H_STATUS];
   if (!(status == 0 || status == 4)) { if (tid < MOM_OUT) out[tid] = 0.0; return; }
   const int Maxx = c.Maxx, Maxy = c.Maxy, MW = (Maxy + 31) / 32;
-  double* red = smem_d;                       // [64]
-  uint32_t* mask = (uint32_t*)(red + 64);     // [Maxx][MW]
+  double* red = smem_d;                       // [MOM_THREADS/32 + 1][64]
+  double* stage = red + (MOM_THREADS / 32 + 1) * 64;                   // [2][MOM_LD][MOM_THREADS] density staging
+  uint32_t* mask = (uint32_t*)(stage + 2 * MOM_LD * MOM_THREADS);      // [Maxx][MW]
   const size_t G = (size_t)Maxx * Maxy;
   const double* rho = st.grids + ((size_t)e * st.nkinds + st.kind_slot[GK_RHO]) * G;
   const int Amax = c.Amax, np = hi[H_NP1] + hi[H_NP2];
@@ -528,13 +537,24 @@ __global__ void __launch_bounds__(MOM_THREADS, MOM_MINCTA) moments_kernel(DevCfg
   // bounding rectangle of non-zero density = union of the source windows (bbox_kernel); MC-KLN: whole lattice
   int ilo = hi[H_RLO], ihi = hi[H_RHI], jlo = hi[H_CLO], jhi = hi[H_CHI];
   if (c.which_mc_model == 1) { ilo = 0; ihi = Maxx; jlo = 0; jhi = Maxy; }
-  const int nj = max(jhi - jlo, 0), ncell = max(ihi - ilo, 0) * nj;
+  const int lane = tid & 31, warp = tid >> 5;
+  // warp w walks rows ilo + w, ilo + w + 8, ...; lanes walk the columns of the row (no index divisions, the
+  // row coordinate is hoisted)
   // ---- pass 1: centre of mass (MakeDensity.cpp:2273-2282) ----
   double s0 = 0, sx = 0, sy = 0;
-  for (int k = tid; k < ncell; k += MOM_THREADS) {
-    const int i = ilo + k / nj, j = jlo + k % nj;
-    const double d = rho[(size_t)i * Maxy + j] * c.finalFactor;
-    s0 += d; sx += xg_of(c, i) * d; sy += yg_of(c, j) * d;
+  for (int i = ilo + warp; i < ihi; i += MOM_THREADS / 32) {
+    const double xg = xg_of(c, i); const double* row = rho + (size_t)i * Maxy;
+    for (int jb = jlo + lane; jb < jhi; jb += 32 * MOM_LD) {
+      double dv[MOM_LD];
+#pragma unroll
+      for (int u = 0; u < MOM_LD; u++) { const int j = jb + 32 * u; dv[u] = (j < jhi) ? row[j] : 0.0; }   // MOM_LD loads in flight
+#pragma unroll
+      for (int u = 0; u < MOM_LD; u++) {
+        const int j = jb + 32 * u;
+        const double d = dv[u] * c.finalFactor;
+        s0 += d; sx += xg * d; sy += yg_of(c, j) * d;
+      }
+    }
   }
   const double total = block_sum(s0, red, tid);
   const double xc = block_sum(sx, red, tid) / total, yc = block_sum(sy, red, tid) / total;
@@ -542,44 +562,87 @@ __global__ void __launch_bounds__(MOM_THREADS, MOM_MINCTA) moments_kernel(DevCfg
   double rn[10], mr[10], mi[10], pr[10], pi[10], npw[10], nrm = 0, nnz = 0;
 #pragma unroll
   for (int n = 0; n < 10; n++) { rn[n] = 0; mr[n] = 0; mi[n] = 0; pr[n] = 0; pi[n] = 0; npw[n] = 0; }
-  double dnext = (tid < ncell) ? rho[(size_t)(ilo + tid / nj) * Maxy + (jlo + tid % nj)] : 0.0;
-  for (int k = tid; k < ncell; k += MOM_THREADS) {
-    const int i = ilo + k / nj, j = jlo + k % nj;
-    const double d = dnext * c.finalFactor;
-    { const int k2 = k + MOM_THREADS; if (k2 < ncell) dnext = rho[(size_t)(ilo + k2 / nj) * Maxy + (jlo + k2 % nj)]; }   // prefetch
-    if (d == 0.0) continue;
-    nnz += 1.0;
-    const double x = xg_of(c, i) - xc, y = yg_of(c, j) - yc;
-    const double r2 = x * x + y * y, r = sqrt(r2);
-    double ux = 1.0, uy = 0.0;                                   // atan2(0,0) = 0
-    if (r > 0.0) { const double ri = 1.0 / r; ux = x * ri; uy = y * ri; }
-    const bool in = (mask[i * MW + (j >> 5)] >> (j & 31)) & 1u;
-    const double d2 = d * r2, d3 = d2 * r;
-    rn[0] += d;
-    if (in) nrm += d2;
-    double an = 1.0, bn = 0.0, p = d;
+  // The density of chunk t+1 (MOM_LD column steps of one row) streams into shared memory with cp.async while
+  // chunk t is being processed: the loads of a lane never wait in registers
+  const int nj = max(jhi - jlo, 0), cpr = (nj + 32 * MOM_LD - 1) / (32 * MOM_LD);
+  const int nrows_w = (ihi - ilo - warp + MOM_THREADS / 32 - 1) / (MOM_THREADS / 32), T = max(nrows_w, 0) * cpr;
+  auto issue = [&](int t) {
+    const int i = ilo + warp + (t / cpr) * (MOM_THREADS / 32), jb = jlo + lane + (t % cpr) * 32 * MOM_LD;
+    const double* row = rho + (size_t)i * Maxy; double* dst = stage + (size_t)(t & 1) * MOM_LD * MOM_THREADS + tid;
 #pragma unroll
-    for (int n = 1; n < 10; n++) {
-      const double a2 = an * ux - bn * uy; bn = an * uy + bn * ux; an = a2;
-      p *= r;
-      rn[n] += p;
-      if (in) {
-        mr[n] += d2 * an; mi[n] += d2 * bn;
-        const double pm = (n == 1) ? d3 : p;
+    for (int u = 0; u < MOM_LD; u++) {
+      const int j = jb + 32 * u;
+      if (j < jhi) __pipeline_memcpy_async(dst + u * MOM_THREADS, row + j, sizeof(double)); else dst[u * MOM_THREADS] = 0.0;
+    }
+    __pipeline_commit();
+  };
+  if (T > 0) issue(0);
+  for (int t = 0; t < T; t++) {
+    if (t + 1 < T) { issue(t + 1); __pipeline_wait_prior(1); } else __pipeline_wait_prior(0);
+    const int i = ilo + warp + (t / cpr) * (MOM_THREADS / 32), jb = jlo + lane + (t % cpr) * 32 * MOM_LD;
+    const double x = xg_of(c, i) - xc, xx = x * x;
+    const uint32_t* mrow = mask + i * MW;
+    const double* src = stage + (size_t)(t & 1) * MOM_LD * MOM_THREADS + tid;
+    {
+#pragma unroll 1
+      for (int u = 0; u < MOM_LD; u++) {
+      const int j = jb + 32 * u;
+      const double d = src[u * MOM_THREADS] * c.finalFactor;
+      if (d == 0.0) continue;
+      nnz += 1.0;
+      const double y = yg_of(c, j) - yc;
+      const double r2 = xx + y * y;
+      double ux = 1.0, uy = 0.0, r = 0.0;                          // atan2(0,0) = 0
+      if (r2 > 0.0) { const double ri = rsqrt(r2); r = r2 * ri; ux = x * ri; uy = y * ri; }
+      // hot-spot mask as a 0/1 weight: the masked sums take w * (...) instead of five predicated updates per order
+      const double w = (double)((mrow[j >> 5] >> (j & 31)) & 1u);
+      const double d2 = d * r2, d2m = d2 * w;
+      rn[0] += d;
+      nrm += d2m;
+      double an = 1.0, bn = 0.0, p = d, q = d * w;
+#pragma unroll
+      for (int n = 1; n < 10; n++) {
+        const double a2 = an * ux - bn * uy; bn = an * uy + bn * ux; an = a2;
+        p *= r; q *= r;
+        rn[n] += p;
+        mr[n] += d2m * an; mi[n] += d2m * bn;
+        const double pm = (n == 1) ? d2m * r : q;
         pr[n] += pm * an; pi[n] += pm * bn; npw[n] += pm;
+      }
       }
     }
   }
-  const double eps = 1e-15;
-  const double dn = block_sum(rn[0], red, tid);
-  const double nrmS = block_sum(nrm, red, tid);
-  const double nnzS = block_sum(nnz, red, tid);
-  if (tid == 0) { out[45] = dn / dn; out[46] = total * c.dx * c.dy; out[47] = xc; out[48] = yc; out[49] = (total / c.finalFactor) * c.dx * c.dy; out[50] = nnzS; }
+  // ---- one reduction for all 57 sums: a transposing butterfly leaves every lane with two fully warp-reduced
+  // values (5 stages, 62 shuffles instead of 57 x 5), then one pass over the per-warp partials in shared memory
+  double v[64];
 #pragma unroll
-  for (int n = 1; n < 10; n++) {
-    const double a = block_sum(mr[n], red, tid), b = block_sum(mi[n], red, tid), cc = block_sum(pr[n], red, tid);
-    const double dd = block_sum(pi[n], red, tid), ee = block_sum(npw[n], red, tid), ff = block_sum(rn[n], red, tid);
-    if (tid == 0) {
+  for (int n = 0; n < 10; n++) v[n] = rn[n];
+  v[10] = nrm; v[11] = nnz;
+#pragma unroll
+  for (int n = 1; n < 10; n++) { v[12 + (n - 1) * 5] = mr[n]; v[13 + (n - 1) * 5] = mi[n]; v[14 + (n - 1) * 5] = pr[n]; v[15 + (n - 1) * 5] = pi[n]; v[16 + (n - 1) * 5] = npw[n]; }
+#pragma unroll
+  for (int k = 57; k < 64; k++) v[k] = 0.0;
+#pragma unroll
+  for (int off = 16, cnt = 32; off > 0; off >>= 1, cnt >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < cnt; i++) {
+      const double keep = up ? v[2 * i + 1] : v[2 * i], send = up ? v[2 * i] : v[2 * i + 1];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  const int bl = (int)(__brev((unsigned)lane) >> 27);          // lane holds sums number bl and 32 + bl
+  __syncthreads();
+  red[warp * 64 + bl] = v[0]; red[warp * 64 + 32 + bl] = v[1];
+  __syncthreads();
+  double* fin = red + (MOM_THREADS / 32) * 64;
+  if (tid < 64) { double t = 0; for (int w = 0; w < MOM_THREADS / 32; w++) t += red[w * 64 + tid]; fin[tid] = t; }
+  __syncthreads();
+  if (tid == 0) {
+    const double eps = 1e-15, dn = fin[0], nrmS = fin[10], nnzS = fin[11];
+    out[45] = dn / dn; out[46] = total * c.dx * c.dy; out[47] = xc; out[48] = yc; out[49] = (total / c.finalFactor) * c.dx * c.dy; out[50] = nnzS;
+    for (int n = 1; n < 10; n++) {
+      const double a = fin[12 + (n - 1) * 5], b = fin[13 + (n - 1) * 5], cc = fin[14 + (n - 1) * 5], dd = fin[15 + (n - 1) * 5], ee = fin[16 + (n - 1) * 5], ff = fin[n];
       const bool on = (n >= c.ecc_from && n <= c.ecc_to);        // orders outside [from,to] stay 0 (MakeDensity.cpp:2389,2475)
       double* o = out + (n - 1) * 5;
       o[0] = on ? -a / (nrmS + eps) : 0.0; o[1] = on ? -b / (nrmS + eps) : 0.0;
@@ -590,7 +653,7 @@ __global__ void __launch_bounds__(MOM_THREADS, MOM_MINCTA) moments_kernel(DevCfg
 }
 
 cudaError_t launch_moments(const DevCfg& c, const Store& st, int nev, cudaStream_t s) {
-  const size_t smem = 64 * sizeof(double) + (size_t)c.Maxx * ((c.Maxy + 31) / 32) * sizeof(uint32_t);
+  const size_t smem = ((MOM_THREADS / 32 + 1) * 64 + 2 * MOM_LD * MOM_THREADS) * sizeof(double) + (size_t)c.Maxx * ((c.Maxy + 31) / 32) * sizeof(uint32_t);
   cudaFuncSetAttribute(moments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   moments_kernel<<<nev, MOM_THREADS, smem, s>>>(c, st, nev);
   return cudaGetLastError();
