@@ -55,6 +55,9 @@ struct DevCfg {
   float inv_dx_f, inv_dy_f;   // single-precision 1/dx, 1/dy (interval estimates of the deposit masks)
 };
 
+// one deposit source, expanded once per event by bbox_kernel: position, folded weight, mask threshold, window
+struct SrcRec { double x, y, W, thr; short iL, iR, jL, jR; int flat; int pad; };   // 48 bytes
+
 // device-resident event records for one batch
 struct Store {
   double* nuc;        // [batch][2][Amax][NROW]
@@ -81,6 +84,8 @@ struct Store {
   int nkinds;
   double* mom_out;    // [batch][MOM_OUT]
   double* kln_table;  // [tmax][tmax]
+  SrcRec* src_rec;    // [batch][deposit kinds][src_stride]
+  int src_stride;
   int e0;             // first event of the launch (the grid stages run in L2-sized sub-batches)
 };
 enum { H_NP1 = 0, H_NP2, H_NCOLL, H_TRIES, H_NSPEC1, H_NSPEC2, H_STATUS, H_RLO, H_RHI, H_CLO, H_CHI, H_GIVENW, HDR_I = 16 };

@@ -22,7 +22,7 @@ struct smc_slot {
   bool ready;
   double* nuc; int* nuc_ncoll; int* nuc_first; double* coll; int* coll_ij; int* part_idx; int* spec_idx;
   int* hdr_i; double* hdr_d; double* mom_out; uint64_t* event_id; int* try_start; double* cm; int* d_redo;
-  double* d_grids; size_t grids_bytes;
+  double* d_grids; size_t grids_bytes; void* d_srcrec; size_t srcrec_bytes;
   cudaStream_t stream; cudaEvent_t done; cudaEvent_t pev[8];
   int* h_hdr_i; double* h_hdr_d; double* h_mom; uint64_t* h_evid; int* h_try;
 };
@@ -33,6 +33,7 @@ struct smc_ctx {
   int batch; size_t G;
   std::vector<void*> owned;
   double* d_grids; size_t grids_bytes; bool need_zero;
+  void* d_srcrec; size_t srcrec_bytes;             // expanded deposit sources (smc::SrcRec), [batch][deposit kinds][src_stride]
   double* d_pair_u; size_t pair_u_bytes; double* d_coll_w; size_t coll_w_bytes;
   double* d_quark; double* d_cfgtab[2]; double* d_kln; int* d_redo;
   double* d_rcbk; int rcbk_q, rcbk_y, rcbk_k;      // rcBK uGD tables: kt | N_A | y2, each [q][y][k]

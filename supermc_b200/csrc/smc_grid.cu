@@ -147,11 +147,14 @@ __global__ void bbox_kernel(DevCfg c, Store st, KindList kl, int nev) {
   if (status == 0 || status == 4) {
     for (int q = 0; q < kl.n; q++) {
       const int kind = kl.kind[q];
-      if (kind == GK_SPEC_A || kind == GK_SPEC_B) continue;
+      const bool whole = (kind == GK_SPEC_A || kind == GK_SPEC_B);      // spectator grids span the whole lattice
       const int ns = src_count(c, hi, kind);
+      SrcRec* recs = st.src_rec + ((size_t)e * kl.n + q) * st.src_stride;
       for (int k = tid; k < ns; k += blockDim.x) {
         Src s; load_src(c, st, e, hi, kind, k, s);
-        if (s.iL < s.iR && s.jL < s.jR) { ilo = min(ilo, s.iL); ihi = max(ihi, s.iR); jlo = min(jlo, s.jL); jhi = max(jhi, s.jR); }
+        SrcRec r; r.x = s.x; r.y = s.y; r.W = s.W; r.thr = s.thr; r.iL = (short)s.iL; r.iR = (short)s.iR; r.jL = (short)s.jL; r.jR = (short)s.jR; r.flat = s.flat; r.pad = 0;
+        recs[k] = r;
+        if (!whole && s.iL < s.iR && s.jL < s.jR) { ilo = min(ilo, s.iL); ihi = max(ihi, s.iR); jlo = min(jlo, s.jL); jhi = max(jhi, s.jR); }
       }
     }
   }
@@ -166,24 +169,6 @@ __global__ void bbox_kernel(DevCfg c, Store st, KindList kl, int nev) {
     if (ihi <= ilo || jhi <= jlo) { ilo = ihi = jlo = jhi = 0; }
     hi[H_RLO] = ilo; hi[H_RHI] = ihi; hi[H_CLO] = jlo; hi[H_CHI] = jhi;
   }
-}
-
-// position and reach of source k in cells, single precision: enough for the (conservative) band/column-group test
-__device__ __forceinline__ void src_cell_f(const DevCfg& c, const Store& st, int e, const int* hi, int kind, int k, float& fi, float& fj) {
-  const int Amax = c.Amax, np1 = hi[H_NP1], np2 = hi[H_NP2];
-  const double* row = nullptr;
-  const double* nuc = st.nuc + (size_t)e * 2 * Amax * NROW;
-  int id = -1;
-  if (kind == GK_RHO) {
-    const int nwn = (c.sub_model == 1) ? np1 + np2 : 0;
-    if (k < nwn) id = st.part_idx[(size_t)e * 2 * Amax + k];
-    else row = st.coll + ((size_t)e * c.ncoll_cap + (k - nwn)) * CROW;
-  } else if (kind == GK_RHOA || kind == GK_TA1) id = st.part_idx[(size_t)e * 2 * Amax + k];
-  else if (kind == GK_RHOB || kind == GK_TA2) id = st.part_idx[(size_t)e * 2 * Amax + np1 + k];
-  else if (kind == GK_RHO_BINARY) row = st.coll + ((size_t)e * c.ncoll_cap + k) * CROW;
-  else id = st.spec_idx[(size_t)e * 2 * Amax + (kind == GK_SPEC_B ? (c.A[0] - np1) : 0) + k];
-  if (id >= 0) row = nuc + ((size_t)(id >> 16) * Amax + (id & 0xffff)) * NROW;
-  fi = (float)(row[0] - c.Xmin) * c.inv_dx_f; fj = (float)(row[1] - c.Ymin) * c.inv_dy_f;
 }
 
 __device__ __forceinline__ uint32_t ones_below(int n) {      // bits [0, n) of a word, n clamped to [0, 32]
@@ -226,9 +211,10 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_MINCTA) deposit_kernel(DevCfg
   const int wr = warp / DEP_NSTR, ws = warp % DEP_NSTR, lr = lane >> 3, lc = lane & 7;
   const int rw0 = r0 + wr * DEP_WROWS, sc0 = c0 + ws * 32;
   DepTab* tab = reinterpret_cast<DepTab*>(dep_smem);
-  Src* srcs = reinterpret_cast<Src*>(tab + 2);                 // [2][DEP_CH]
+  SrcRec* srcs = reinterpret_cast<SrcRec*>(tab + 2);           // [2][DEP_CH]
   int* wtot = reinterpret_cast<int*>(srcs + 2 * DEP_CH);       // [32]
   unsigned short* act = reinterpret_cast<unsigned short*>(wtot + 32);
+  const SrcRec* recs = st.src_rec + ((size_t)e * kl.n + blockIdx.z) * st.src_stride;
   const int slot = st.kind_slot[kind];
   double* grid = st.grids + ((size_t)e * st.nkinds + slot) * (size_t)c.Maxx * c.Maxy;
 
@@ -240,26 +226,23 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_MINCTA) deposit_kernel(DevCfg
 
   const int status = hi[H_STATUS];
   const int nsrc = (status == 0 || status == 4) ? src_count(c, hi, kind) : 0;
-  // ---- ordered compaction of the sources that can touch this CTA (conservative single-precision test) ----
+  // ---- ordered compaction of the sources whose window meets this CTA (records written by bbox_kernel) ----
   int nact = 0;
-  {
-    const float reach_i = (float)fmax(c.dmax, c.rclip_flat) * c.inv_dx_f + 3.0f, reach_j = (float)fmax(c.dmax, c.rclip_flat) * c.inv_dy_f + 3.0f;
-    for (int base = 0; base < nsrc; base += DEP_THREADS) {
-      const int k = base + tid;
-      bool on = false;
-      if (k < nsrc) {
-        float fi, fj; src_cell_f(c, st, e, hi, kind, k, fi, fj);
-        on = (fi + reach_i >= (float)r0) && (fi - reach_i <= (float)(r0 + DEP_BAND)) && (fj + reach_j >= (float)c0) && (fj - reach_j <= (float)(c0 + DEP_COLS));
-      }
-      const unsigned m = __ballot_sync(0xffffffffu, on);
-      if (lane == 0) wtot[warp] = __popc(m);
-      __syncthreads();
-      int off = nact;
-      for (int w2 = 0; w2 < warp; w2++) off += wtot[w2];
-      if (on) act[off + __popc(m & ((1u << lane) - 1u))] = (unsigned short)k;
-      for (int w2 = 0; w2 < DEP_THREADS / 32; w2++) nact += wtot[w2];
-      __syncthreads();
+  for (int base = 0; base < nsrc; base += DEP_THREADS) {
+    const int k = base + tid;
+    bool on = false;
+    if (k < nsrc) {
+      const short4 w = *reinterpret_cast<const short4*>(&recs[k].iL);
+      on = (w.x < w.y) && (w.z < w.w) && (w.x < r0 + DEP_BAND) && (w.y > r0) && (w.z < c0 + DEP_COLS) && (w.w > c0);
     }
+    const unsigned m = __ballot_sync(0xffffffffu, on);
+    if (lane == 0) wtot[warp] = __popc(m);
+    __syncthreads();
+    int off = nact;
+    for (int w2 = 0; w2 < warp; w2++) off += wtot[w2];
+    if (on) act[off + __popc(m & ((1u << lane) - 1u))] = (unsigned short)k;
+    for (int w2 = 0; w2 < DEP_THREADS / 32; w2++) nact += wtot[w2];
+    __syncthreads();
   }
   const int nchunks = (nact + DEP_CH - 1) / DEP_CH;
 
@@ -274,7 +257,7 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_MINCTA) deposit_kernel(DevCfg
     if (id < DEP_CH * DEP_NXI) {                                            // ---- rows: xg + masks ----
       const int t = id % DEP_CH, part = id / DEP_CH;
       if (t >= nch) return;
-      const Src s = srcs[(chunk & 1) * DEP_CH + t];
+      const SrcRec s = srcs[(chunk & 1) * DEP_CH + t];
       if (part == 0) T.desc[t] = make_int4(s.iL, s.iR, s.jL, s.jR);
       const int rb = part * DEP_XP, i0 = r0 + rb;
       const int ka = max(s.iL - i0, 0), kb = min(s.iR - i0, DEP_XP);
@@ -325,7 +308,7 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_MINCTA) deposit_kernel(DevCfg
     } else if (id < nitems) {                                               // ---- columns: yg ----
       const int id2 = id - DEP_CH * DEP_NXI, t = id2 % DEP_CH;
       if (t >= nch) return;
-      const Src s = srcs[(chunk & 1) * DEP_CH + t];
+      const SrcRec s = srcs[(chunk & 1) * DEP_CH + t];
       const int part = max(s.jL - c0, 0) / DEP_YP + id2 / DEP_CH;          // a window spans at most nyq parts
       if (part >= DEP_NYI) return;
       const int cb = part * DEP_YP, j0 = c0 + cb;
@@ -344,12 +327,12 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_MINCTA) deposit_kernel(DevCfg
       }
     } else {                                                                // ---- source records of chunk+1 ----
       const int t = id - nitems, q = chunk + 1;
-      if (t < DEP_CH && q * DEP_CH + t < nact) load_src(c, st, e, hi, kind, act[q * DEP_CH + t], srcs[(q & 1) * DEP_CH + t]);
+      if (t < DEP_CH && q * DEP_CH + t < nact) srcs[(q & 1) * DEP_CH + t] = recs[act[q * DEP_CH + t]];
     }
   };
 
   if (tid < 2) wtot[tid] = 0;                                   // wtot[0..1] double as the item counters from here on
-  if (tid < 2 * DEP_CH && tid < nact) load_src(c, st, e, hi, kind, act[tid], srcs[tid]);
+  if (tid < 2 * DEP_CH && tid < nact) srcs[tid] = recs[act[tid]];
   __syncthreads();
   if (nchunks > 0) for (int id = tid; id < nitems; id += DEP_THREADS) build_item(0, id);
   __syncthreads();
@@ -404,7 +387,7 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_MINCTA) deposit_kernel(DevCfg
 }
 
 size_t deposit_smem_bytes(const DevCfg& c, int nsrc_max) {
-  size_t b = 2 * sizeof(DepTab) + 2 * DEP_CH * sizeof(Src) + 32 * sizeof(int);
+  size_t b = 2 * sizeof(DepTab) + 2 * DEP_CH * sizeof(SrcRec) + 32 * sizeof(int);
   b += (size_t)(nsrc_max + 8) * sizeof(unsigned short);
   return (b + 15) & ~(size_t)15;
 }
