@@ -117,15 +117,18 @@ struct KindList { int n; int kind[8]; };
 #endif
 #define DEP_XP 4
 #ifndef DEP_YP
-#define DEP_YP 16
+#define DEP_YP 32
 #endif
 #ifndef DEP_MINCTA
 #define DEP_MINCTA 3
 #endif
+#ifndef DEP_GRAB
+#define DEP_GRAB 32     // items a warp takes per shared-counter grab
+#endif
 #define DEP_THREADS (DEP_NWR * DEP_NSTR * 32)
+#define DEP_NXG (DEP_BAND / 16)
 #define DEP_NXI (DEP_BAND / DEP_XP)
 #define DEP_NYI (DEP_COLS / DEP_YP)
-#define DEP_NITEMS (DEP_CH * (DEP_NXI + DEP_NYI))
 
 // rows are padded by 16 bytes: builder lanes work on different sources t at the same row/column, and a row
 // pitch that is a multiple of 128 bytes would put all of their stores into the same banks
@@ -246,37 +249,43 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_MINCTA) deposit_kernel(DevCfg
   }
   const int nchunks = (nact + DEP_CH - 1) / DEP_CH;
 
-  // One table item = DEP_XP rows or DEP_YP columns of one source of the chunk (or, ids >= DEP_NITEMS, the source
+  // One table item = DEP_XP rows or DEP_YP columns of one source of the chunk (or, last, the source
   // record of the chunk after it).  Items of chunk n+1 are handed out dynamically (shared counter) into the
   // *other* table buffer while chunk n is being consumed: warps whose tile holds few sources spend their slack
   // building tables, and there is one barrier per chunk.
-  const int nyq = min(DEP_NYI, (c.wmax + 2 * DEP_YP - 2) / DEP_YP), nitems = DEP_CH * (DEP_NXI + nyq);
+  const int nyq = min(DEP_NYI, (c.wmax + 2 * DEP_YP - 2) / DEP_YP), nitems = DEP_CH * (DEP_NXG + DEP_NXI + nyq);
   auto build_item = [&](int chunk, int id) {
     DepTab& T = tab[chunk & 1];
     const int nch = min(DEP_CH, nact - chunk * DEP_CH);
-    if (id < DEP_CH * DEP_NXI) {                                            // ---- rows: xg + masks ----
+    if (id < DEP_CH * DEP_NXG) {                                            // ---- rows: xg, 16 rows per item ----
       const int t = id % DEP_CH, part = id / DEP_CH;
+      if (t >= nch) return;
+      const SrcRec s = srcs[(chunk & 1) * DEP_CH + t];
+      const int rb = part * 16, i0 = r0 + rb;
+      const int ka = max(s.iL - i0, 0), kb = min(s.iR - i0, 16);
+      if (ka >= kb) return;
+      double g = s.W, q = 1.0, rec = 1.0;
+      if (!s.flat) {
+        const double d = __dadd_rn(s.x, -xg_of(c, i0 + ka));
+        g = s.W * exp(-__dmul_rn(d, d) * c.inv2w2); q = exp((2.0 * d * c.dx - c.dx * c.dx) * c.inv2w2); rec = c.recx;
+      }
+      for (int k = ka; k < kb; k++) { T.xg[t][rb + k] = g; g *= q; q *= rec; }
+    } else if (id < DEP_CH * (DEP_NXG + DEP_NXI)) {                         // ---- rows: masks, DEP_XP rows per item ----
+      const int id1 = id - DEP_CH * DEP_NXG, t = id1 % DEP_CH, part = id1 / DEP_CH;
       if (t >= nch) return;
       const SrcRec s = srcs[(chunk & 1) * DEP_CH + t];
       if (part == 0) T.desc[t] = make_int4(s.iL, s.iR, s.jL, s.jR);
       const int rb = part * DEP_XP, i0 = r0 + rb;
       const int ka = max(s.iL - i0, 0), kb = min(s.iR - i0, DEP_XP);
-      double g = 0.0, q = 0.0;
-      if (ka < kb && !s.flat) {
-        const double d = __dadd_rn(s.x, -xg_of(c, i0 + ka));
-        g = s.W * exp(-__dmul_rn(d, d) * c.inv2w2); q = exp((2.0 * d * c.dx - c.dx * c.dx) * c.inv2w2);
-      }
       const float fyf = (float)(s.y - c.Ymin) * c.inv_dy_f;
-      double v[DEP_XP]; uint32_t w[DEP_NSTR][DEP_XP];
+      uint32_t w[DEP_NSTR][DEP_XP];
 #pragma unroll
       for (int k = 0; k < DEP_XP; k++) {
-        v[k] = 0.0;
 #pragma unroll
         for (int s2 = 0; s2 < DEP_NSTR; s2++) w[s2][k] = 0u;
         if (k >= ka && k < kb) {
           const double d = __dadd_rn(s.x, -xg_of(c, i0 + k));
           const double d2 = __dmul_rn(d, d);
-          if (s.flat) v[k] = s.W; else { v[k] = g; g *= q; q *= c.recx; }
           const double rem = __dadd_rn(s.thr, -d2);
           if (rem >= 0.0) {
             float hf; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(hf) : "f"((float)rem));
@@ -291,7 +300,7 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_MINCTA) deposit_kernel(DevCfg
               const int cn = (int)rh; const double dy = __dadd_rn(s.y, -yg_of(c, cn));
               hi2 = (__dadd_rn(d2, __dmul_rn(dy, dy)) <= s.thr) ? cn + 1 : cn;
             }
-            lo = max(lo, s.jL); hi2 = min(hi2, s.jR);
+            lo = max(lo, (int)s.jL); hi2 = min(hi2, (int)s.jR);
             const int a = lo - c0, b = hi2 - c0;
             if (a < b) {
 #pragma unroll
@@ -301,12 +310,10 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_MINCTA) deposit_kernel(DevCfg
           }
         }
       }
-      *reinterpret_cast<double2*>(&T.xg[t][rb]) = make_double2(v[0], v[1]);
-      *reinterpret_cast<double2*>(&T.xg[t][rb + 2]) = make_double2(v[2], v[3]);
 #pragma unroll
       for (int s2 = 0; s2 < DEP_NSTR; s2++) *reinterpret_cast<uint4*>(&T.mk[t][s2 * DEP_BAND + rb]) = make_uint4(w[s2][0], w[s2][1], w[s2][2], w[s2][3]);
     } else if (id < nitems) {                                               // ---- columns: yg ----
-      const int id2 = id - DEP_CH * DEP_NXI, t = id2 % DEP_CH;
+      const int id2 = id - DEP_CH * (DEP_NXG + DEP_NXI), t = id2 % DEP_CH;
       if (t >= nch) return;
       const SrcRec s = srcs[(chunk & 1) * DEP_CH + t];
       const int part = max(s.jL - c0, 0) / DEP_YP + id2 / DEP_CH;          // a window spans at most nyq parts
@@ -364,10 +371,11 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_MINCTA) deposit_kernel(DevCfg
       int* counter = &wtot[(n + 1) & 1];
       for (;;) {
         int base = 0;
-        if (lane == 0) base = atomicAdd(counter, 32);
+        if (lane == 0) base = atomicAdd(counter, DEP_GRAB);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= nitems + DEP_CH) break;
-        build_item(n + 1, base + lane);
+#pragma unroll 1
+        for (int g2 = 0; g2 < DEP_GRAB; g2 += 32) if (base + g2 < nitems + DEP_CH) build_item(n + 1, base + g2 + lane);
       }
 #endif
     }
