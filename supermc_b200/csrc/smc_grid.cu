@@ -117,7 +117,7 @@ struct KindList { int n; int kind[8]; };
 #endif
 #define DEP_XP 4
 #ifndef DEP_YP
-#define DEP_YP 32
+#define DEP_YP 16
 #endif
 #ifndef DEP_MINCTA
 #define DEP_MINCTA 3

@@ -422,9 +422,13 @@ __global__ void __launch_bounds__(64, 6) sample_collide_kernel(DevCfg c, Store s
       __syncwarp();
     };
     int start_carry = 0;                                        // start(i) is non-decreasing in i (x-sorted sweep)
+    double tXRmax = -1e300;                                     // no target box reaches beyond it: rows further right test nothing
+    for (int j = lane; j < B; j += 32) tXRmax = fmax(tXRmax, S_(sm, 1, NXR, j));
+    for (int o = 16; o > 0; o >>= 1) tXRmax = fmax(tXRmax, __shfl_xor_sync(0xffffffffu, tXRmax, o));
     for (int i = warp; i < A; i += 2) {
       const double px = S_(sm, 0, NX, i), py = S_(sm, 0, NY, i);
       const double pXL = S_(sm, 0, NXL, i), pXR = S_(sm, 0, NXR, i), pYL = S_(sm, 0, NYL, i), pYR = S_(sm, 0, NYR, i);
+      if (pXL > tXRmax) break;                                  // rows are sorted by xL: the skip loop of the sweep finds no start
       int start = -1;
       const int jbeg = start_carry & ~31;
       for (int j0 = jbeg; j0 < B; j0 += 32) {
