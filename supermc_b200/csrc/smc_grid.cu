@@ -6,15 +6,18 @@
 // K4 replaces MakeDensity::dumpEccentricities / MCnucl::getHotSpots (src/MakeDensity.cpp:2244-2430,
 // src/MCnucl.cpp:1303-1323) and GlueDensity::calcCMAngle (src/GlueDensity.cpp:87-144).
 //
-// B200 mapping of K3 (gather, no atomics): the reference scatters every source over its window with
-// one exp per (source, cell).  Here one CTA owns a band of DEP_ROWS grid rows of one event; each warp
-// owns a 32-column stripe and keeps its DEP_ROWS x 32 cells in registers.  Sources that touch the band
-// are compacted in order, then processed in chunks: a few threads expand each source's *separable*
-// factors  W*exp(-dx^2/2w^2)  (per row) and  exp(-dy^2/2w^2)  (per column) into shared memory with a
-// two-multiply Gaussian recurrence (4 exps per source instead of ~2000), together with the exactly
-// rounded dx^2, dy^2 the reference's circle masks are made of; every lane then does one DADD + compare
-// (the reference's `dc <= 25 w^2` / `r <= 5w` decision, bit for bit) and one DFMA per (source, cell).
-// Deposits are deterministic (fixed summation order) and each grid cell is written exactly once.
+// B200 mapping of K3 (gather, no atomics): the reference scatters every source over its window with one
+// exp per (source, cell).  Here bbox_kernel expands every source once per event into a record (position,
+// folded weight, exact window); a deposit CTA owns DEP_BAND rows x DEP_COLS columns of one event, each warp a
+// 16 x 32 tile and each lane a 4 x 4 micro-tile in registers.  Sources whose window meets the CTA are compacted
+// in order and processed in chunks: per chunk the CTA builds, in shared memory, the *separable* factors
+// W*exp(-dx^2/2w^2) (rows) and exp(-dy^2/2w^2) (columns) with a two-multiply Gaussian recurrence (a few exps
+// per source instead of ~2000) and, per (source, row), the column interval of the reference's circle test
+// `(x-xg)^2 + (y-yg)^2 <= thr` as bit masks (single-precision estimate, settled by the exact double predicate
+// near cell boundaries: the masks are the reference's bit for bit).  A lane then spends 5 shared loads,
+// 4 shifts, 4 R2P and 16 predicated DFMAs per (source, tile).  Tables of chunk n+1 are built by whichever warps
+// finish chunk n first (shared item counter, one barrier per chunk).  Deposits are deterministic (fixed
+// summation order) and each grid cell is written exactly once.
 #include <cuda_pipeline.h>
 #include "smc_common.cuh"
 

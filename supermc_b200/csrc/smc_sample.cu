@@ -5,14 +5,19 @@
 // AABB (src/Particle.cpp:16-99), MCnucl::getBinaryCollision / hit / createBinaryCollisions
 // (src/MCnucl.cpp:217-385) and the Gamma multiplicity weights (src/MCnucl.cpp:1271-1301).
 //
-// B200 mapping: warp s owns nucleus s.  The reference's strictly sequential hard-core rejection
-// ("nucleon k depends on 0..k-1") is kept *exactly* but evaluated 32 candidates at a time: each lane
-// draws one Woods-Saxon candidate from its own Philox counter, tests it against the nucleons already
-// placed (shared-memory broadcast reads), and a 32-step shuffle pass resolves conflicts inside the
-// batch in candidate order -- the accepted set equals what a sequential loop over the same candidate
-// stream produces.  Collisions are an all-pairs test, one projectile row per warp step, 32 target
-// nucleons per instruction, with the reference's AABB sweep restated as a closed-form predicate so the
-// set of pairs that consume a uniform is the reference's.
+// B200 mapping: warp s owns nucleus s.  The Woods-Saxon rejection draws of a nucleus form one flat Philox
+// stream: 32 draws are tested per step and the accepted radii, in stream order, are exactly what the
+// reference's sequential do/while hands to candidates 0, 1, 2, ... (no divergent rejection loop).  The strictly
+// sequential hard-core rejection ("nucleon k depends on 0..k-1") is kept *exactly* but evaluated 32 candidates
+// at a time: distances to the nucleons already placed in single precision on float4 copies (a squared
+// distance within 1e-4 of 0.81 falls back to the reference's double expression), conflicts inside the batch as
+// bit masks resolved in candidate order -- the accepted set equals what a sequential loop over the same
+// candidate stream produces.  Collisions are an all-pairs test, one projectile row per warp step, 32 target
+// nucleons per instruction, with the reference's AABB sweep restated as a closed-form predicate so the set of
+// pairs that consume a uniform is the reference's; pairs whose uniform is below a
+// single-precision over-estimate of the hit probability queue up and are settled 32 at a time by the
+// reference's double-precision expression.  Gamma weights are drawn densely over the compact participant and
+// collision lists.
 #include "smc_common.cuh"
 
 namespace smc {
