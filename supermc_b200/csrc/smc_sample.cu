@@ -45,6 +45,19 @@ __device__ __forceinline__ void rot3(double cth, double phi, double& x, double& 
 
 #define S_(sm, side, f, i) (sm).soa[((size_t)(side) * NROW + (f)) * (sm).Amax + (i)]
 #define SMC_MAXK 16      // ceil(512 / 32): nucleons per lane
+#ifndef SMC_SORT_UNROLL
+#define SMC_SORT_UNROLL 1
+#endif
+#ifndef SMC_BATCH_UNROLL
+#define SMC_BATCH_UNROLL 4
+#endif
+constexpr int kSortUnroll = SMC_SORT_UNROLL, kBatchUnroll = SMC_BATCH_UNROLL;   // (macros are not expanded inside #pragma unroll)
+#ifndef SMC_SORT_UNROLL
+#define SMC_SORT_UNROLL 1
+#endif
+#ifndef SMC_BATCH_UNROLL
+#define SMC_BATCH_UNROLL 4
+#endif
 
 struct Box { double xL, xR, yL, yR, xC, yC; };
 __device__ __forceinline__ void box_center(Box& b, double x, double y) {   // Box2D::setCenter, src/Box2D.cpp:24-33
@@ -116,7 +129,7 @@ __device__ __forceinline__ void sort_by_xl(const DevCfg& c, const Store& st, con
 #pragma unroll
   for (int jb = 0; jb < MK; jb++) {
     const int jend = min(32, A - 32 * jb);
-#pragma unroll 4
+#pragma unroll kSortUnroll
     for (int jj = 0; jj < jend; jj++) {
       const double o = S_(sm, s, NXL, 32 * jb + jj);
 #pragma unroll
@@ -287,7 +300,7 @@ __device__ void sample_nucleus(const DevCfg& c, const Store& st, const SampleSme
       bq[lane] = make_float4(xf, yf, zf, 0.f);
       __syncwarp();
       unsigned cm = 0, dm = 0;
-#pragma unroll
+#pragma unroll kBatchUnroll
       for (int j = 0; j < 31; j++) {
         const float4 p = bq[j];
         const float ax = xf - p.x, ay = yf - p.y, az = zf - p.z, r2 = ax * ax + ay * ay + az * az;
