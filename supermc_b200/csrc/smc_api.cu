@@ -50,7 +50,7 @@ extern "C" int smc_create(const smc_params* p, int device, smc_ctx** out) {
   *out = nullptr;
   smc_ctx* ctx = new smc_ctx();
   ctx->p = *p; ctx->device = device; ctx->launches = 0; ctx->last_ms = 0; ctx->last_n = 0; ctx->last_flags = 0;
-  ctx->d_grids = nullptr; ctx->grids_bytes = 0; ctx->d_srcrec = nullptr; ctx->srcrec_bytes = 0; ctx->d_pair_u = nullptr; ctx->pair_u_bytes = 0; ctx->d_coll_w = nullptr; ctx->coll_w_bytes = 0;
+  ctx->d_grids = nullptr; ctx->grids_bytes = 0; ctx->d_srcrec = nullptr; ctx->srcrec_bytes = 0; ctx->d_cmpart = nullptr; ctx->d_pair_u = nullptr; ctx->pair_u_bytes = 0; ctx->d_coll_w = nullptr; ctx->coll_w_bytes = 0;
   ctx->d_rcbk = nullptr; ctx->rcbk_q = ctx->rcbk_y = ctx->rcbk_k = 0;
   ctx->d_quark = nullptr; ctx->d_cfgtab[0] = ctx->d_cfgtab[1] = nullptr; ctx->d_kln = nullptr; ctx->d_avg = nullptr; ctx->avg_doubles = 0; ctx->avg_count = 0;
   ctx->stream = nullptr; ctx->ev0 = ctx->ev1 = nullptr; ctx->profile = 0; ctx->cur_slot = 0;
@@ -150,6 +150,7 @@ extern "C" void smc_destroy(smc_ctx* ctx) {
   for (void* v : ctx->owned) cudaFree(v);
   if (ctx->d_grids) cudaFree(ctx->d_grids);
   if (ctx->d_srcrec) cudaFree(ctx->d_srcrec);
+  if (ctx->d_cmpart) cudaFree(ctx->d_cmpart);
   if (ctx->d_pair_u) cudaFree(ctx->d_pair_u);
   if (ctx->d_coll_w) cudaFree(ctx->d_coll_w);
   if (ctx->d_quark) cudaFree(ctx->d_quark);
@@ -164,6 +165,7 @@ extern "C" void smc_destroy(smc_ctx* ctx) {
     if (o.ready && o.stream) {
       if (o.d_grids) cudaFree(o.d_grids);
       if (o.d_srcrec) cudaFree(o.d_srcrec);
+      if (o.d_cmpart) cudaFree(o.d_cmpart);
       cudaFreeHost(o.h_hdr_i); cudaFreeHost(o.h_hdr_d); cudaFreeHost(o.h_mom); cudaFreeHost(o.h_evid); cudaFreeHost(o.h_try);
       for (int i = 0; i < 8; i++) if (o.pev[i]) cudaEventDestroy(o.pev[i]);
       cudaStreamDestroy(o.stream);
@@ -331,6 +333,12 @@ int smc_plan_kinds(smc_ctx* ctx, unsigned flags, int* kinds, int* nk_dep) {
     ctx->srcrec_bytes = need_rec;
   }
   st.src_rec = (smc::SrcRec*)ctx->d_srcrec;
+  st.cm_slots = smc::deposit_cm_slots(c);
+  if (!ctx->d_cmpart) {
+    cudaError_t e = cudaMalloc(&ctx->d_cmpart, (size_t)ctx->batch * st.cm_slots * 32 * 4 * sizeof(double));
+    if (e != cudaSuccess) { ctx->err = std::string("cm partial sums: ") + cudaGetErrorString(e); return SMC_ERR_NOMEM; }
+  }
+  st.cm_part = ctx->d_cmpart;
   return SMC_OK;
 }
 
@@ -392,7 +400,7 @@ static void slot_store(smc_ctx* ctx, smc_slot& sl) {          // ctx (active vie
   sl.nuc = st.nuc; sl.nuc_ncoll = st.nuc_ncoll; sl.nuc_first = st.nuc_first; sl.coll = st.coll; sl.coll_ij = st.coll_ij;
   sl.part_idx = st.part_idx; sl.spec_idx = st.spec_idx; sl.hdr_i = st.hdr_i; sl.hdr_d = st.hdr_d; sl.mom_out = st.mom_out;
   sl.event_id = (uint64_t*)st.event_id; sl.try_start = st.try_start; sl.cm = st.cm; sl.d_redo = ctx->d_redo;
-  sl.d_grids = ctx->d_grids; sl.grids_bytes = ctx->grids_bytes; sl.d_srcrec = ctx->d_srcrec; sl.srcrec_bytes = ctx->srcrec_bytes; sl.stream = ctx->stream;
+  sl.d_grids = ctx->d_grids; sl.grids_bytes = ctx->grids_bytes; sl.d_srcrec = ctx->d_srcrec; sl.srcrec_bytes = ctx->srcrec_bytes; sl.d_cmpart = ctx->d_cmpart; sl.stream = ctx->stream;
   for (int i = 0; i < 8; i++) sl.pev[i] = ctx->pev[i];
   sl.h_hdr_i = ctx->h_hdr_i; sl.h_hdr_d = ctx->h_hdr_d; sl.h_mom = ctx->h_mom; sl.h_evid = ctx->h_evid; sl.h_try = ctx->h_try;
 }
@@ -403,6 +411,7 @@ static void slot_load(smc_ctx* ctx, const smc_slot& sl) {     // slot -> ctx (ac
   st.event_id = sl.event_id; st.try_start = sl.try_start; st.cm = sl.cm; ctx->d_redo = sl.d_redo;
   ctx->d_grids = sl.d_grids; ctx->grids_bytes = sl.grids_bytes; st.grids = sl.d_grids; ctx->stream = sl.stream;
   ctx->d_srcrec = sl.d_srcrec; ctx->srcrec_bytes = sl.srcrec_bytes; st.src_rec = (smc::SrcRec*)sl.d_srcrec;
+  ctx->d_cmpart = sl.d_cmpart; st.cm_part = sl.d_cmpart;
   for (int i = 0; i < 8; i++) ctx->pev[i] = sl.pev[i];
   ctx->h_hdr_i = sl.h_hdr_i; ctx->h_hdr_d = sl.h_hdr_d; ctx->h_mom = sl.h_mom; ctx->h_evid = sl.h_evid; ctx->h_try = sl.h_try;
 }
@@ -422,7 +431,7 @@ static int slot_alloc(smc_ctx* ctx, smc_slot& sl) {            // the second slo
   if ((rc = dalloc(ctx, &sl.try_start, (size_t)B))) return rc;
   if ((rc = dalloc(ctx, &sl.cm, (size_t)B * 4))) return rc;
   if ((rc = dalloc(ctx, &sl.d_redo, (size_t)B))) return rc;
-  sl.d_grids = nullptr; sl.grids_bytes = 0; sl.d_srcrec = nullptr; sl.srcrec_bytes = 0;
+  sl.d_grids = nullptr; sl.grids_bytes = 0; sl.d_srcrec = nullptr; sl.srcrec_bytes = 0; sl.d_cmpart = nullptr;
   CK(cudaStreamCreate(&sl.stream));
   for (int i = 0; i < 8; i++) CK(cudaEventCreate(&sl.pev[i]));
   CK(cudaMallocHost(&sl.h_hdr_i, (size_t)B * smc::HDR_I * sizeof(int)));

@@ -86,6 +86,8 @@ struct Store {
   double* kln_table;  // [tmax][tmax]
   SrcRec* src_rec;    // [batch][deposit kinds][src_stride]
   int src_stride;
+  double* cm_part;    // [batch][cm_slots][4] per deposit CTA: sum rho, sum x rho, sum y rho of its tile (MC-Glauber rho only)
+  int cm_slots;
   int e0;             // first event of the launch (the grid stages run in L2-sized sub-batches)
 };
 enum { H_NP1 = 0, H_NP2, H_NCOLL, H_TRIES, H_NSPEC1, H_NSPEC2, H_STATUS, H_RLO, H_RHI, H_CLO, H_CHI, H_GIVENW, HDR_I = 16 };

@@ -11,6 +11,7 @@ cudaError_t launch_sample_collide(const DevCfg&, const Store&, int nev, bool giv
 cudaError_t launch_deposit(const DevCfg&, const Store&, const int* kinds, int nk, int nev, cudaStream_t);
 cudaError_t launch_combine(const DevCfg&, const Store&, int nev, cudaStream_t);
 cudaError_t launch_moments(const DevCfg&, const Store&, int nev, cudaStream_t);
+int deposit_cm_slots(const DevCfg&);
 struct KlnCfg { double ecm, lambda, y, dT; int tmax; int pt_order; int npt, nkt, nphi; const double *xp, *wp, *xk, *wk, *cphi;
                 int model, maxQ0, maxY, maxKt; double dQ0, siginNN200; const double *rkt, *rna, *ry2; };
 cudaError_t launch_kln_table(const KlnCfg&, double* table, cudaStream_t);
@@ -22,7 +23,7 @@ struct smc_slot {
   bool ready;
   double* nuc; int* nuc_ncoll; int* nuc_first; double* coll; int* coll_ij; int* part_idx; int* spec_idx;
   int* hdr_i; double* hdr_d; double* mom_out; uint64_t* event_id; int* try_start; double* cm; int* d_redo;
-  double* d_grids; size_t grids_bytes; void* d_srcrec; size_t srcrec_bytes;
+  double* d_grids; size_t grids_bytes; void* d_srcrec; size_t srcrec_bytes; double* d_cmpart;
   cudaStream_t stream; cudaEvent_t done; cudaEvent_t pev[8];
   int* h_hdr_i; double* h_hdr_d; double* h_mom; uint64_t* h_evid; int* h_try;
 };
@@ -33,6 +34,7 @@ struct smc_ctx {
   int batch; size_t G;
   std::vector<void*> owned;
   double* d_grids; size_t grids_bytes; bool need_zero;
+  double* d_cmpart;                                // per deposit CTA partial sums for the centre of mass
   void* d_srcrec; size_t srcrec_bytes;             // expanded deposit sources (smc::SrcRec), [batch][deposit kinds][src_stride]
   double* d_pair_u; size_t pair_u_bytes; double* d_coll_w; size_t coll_w_bytes;
   double* d_quark; double* d_cfgtab[2]; double* d_kln; int* d_redo;

@@ -395,7 +395,29 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_MINCTA) deposit_kernel(DevCfg
       for (int b = 0; b < 4; b++) if (j + b < c.Maxy) g[j + b] = acc[a][b];
     }
   }
+  // The moments kernel needs sum(rho), sum(x rho), sum(y rho) before it can do anything else (centre of mass,
+  // MakeDensity.cpp:2273-2282).  The tile is still in registers here: every warp leaves its three partial sums in a
+  // fixed slot and the moments kernel adds the slots of the event in a fixed order (deterministic, no atomics).
+  if (kind == GK_RHO && st.cm_part) {
+    double s0 = 0, sx = 0, sy = 0;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      double cs = 0;
+#pragma unroll
+      for (int a = 0; a < 4; a++) { cs += acc[a][b]; }
+      s0 += cs; sy += yg_of(c, sc0 + 4 * lc + b) * cs;
+    }
+#pragma unroll
+    for (int a = 0; a < 4; a++) sx += xg_of(c, rw0 + 4 * lr + a) * ((acc[a][0] + acc[a][1]) + (acc[a][2] + acc[a][3]));
+    s0 = warp_sum(s0); sx = warp_sum(sx); sy = warp_sum(sy);
+    if (lane == 0) {
+      double* o = st.cm_part + (((size_t)e * st.cm_slots + blockIdx.y) * (DEP_THREADS / 32) + warp) * 4;
+      o[0] = s0; o[1] = sx; o[2] = sy;
+    }
+  }
 }
+
+int deposit_cm_slots(const DevCfg& c) { return ((c.Maxy + DEP_COLS - 1) / DEP_COLS + 1) * ((c.Maxx + DEP_BAND - 1) / DEP_BAND + 1); }
 
 size_t deposit_smem_bytes(const DevCfg& c, int nsrc_max) {
   size_t b = 2 * sizeof(DepTab) + 2 * DEP_CH * sizeof(SrcRec) + 32 * sizeof(int);
@@ -535,23 +557,40 @@ __global__ void __launch_bounds__(MOM_THREADS, MOM_MINCTA) moments_kernel(DevCfg
   // warp w walks rows ilo + w, ilo + w + 8, ...; lanes walk the columns of the row (no index divisions, the
   // row coordinate is hoisted)
   // ---- pass 1: centre of mass (MakeDensity.cpp:2273-2282) ----
-  double s0 = 0, sx = 0, sy = 0;
-  for (int i = ilo + warp; i < ihi; i += MOM_THREADS / 32) {
-    const double xg = xg_of(c, i); const double* row = rho + (size_t)i * Maxy;
-    for (int jb = jlo + lane; jb < jhi; jb += 32 * MOM_LD) {
-      double dv[MOM_LD];
+  double total, xc, yc;
+  if (c.which_mc_model == 5 && st.cm_part) {
+    // MC-Glauber: the deposit CTAs left sum(rho), sum(x rho), sum(y rho) of their tiles; add them in slot order
+    const int nbands = (Maxx + DEP_BAND - 1) / DEP_BAND + 1;
+    const int nb = (max(ihi - ilo, 0) + DEP_BAND - 1) / DEP_BAND, ng = (max(jhi - jlo, 0) + DEP_COLS - 1) / DEP_COLS;
+    const int NWD = DEP_THREADS / 32, nslot = nb * ng * NWD;
+    const double* part = st.cm_part + (size_t)e * st.cm_slots * NWD * 4;
+    double s0 = 0, sx = 0, sy = 0;
+    for (int q = tid; q < nslot; q += MOM_THREADS) {
+      const int w2 = q % NWD, b2 = (q / NWD) % nb, g2 = q / (NWD * nb);
+      const double* o = part + ((size_t)(g2 * nbands + b2) * NWD + w2) * 4;
+      s0 += o[0]; sx += o[1]; sy += o[2];
+    }
+    const double t0 = block_sum(s0, red, tid);
+    total = t0 * c.finalFactor; xc = block_sum(sx, red, tid) / t0; yc = block_sum(sy, red, tid) / t0;
+  } else {
+    double s0 = 0, sx = 0, sy = 0;
+    for (int i = ilo + warp; i < ihi; i += MOM_THREADS / 32) {
+      const double xg = xg_of(c, i); const double* row = rho + (size_t)i * Maxy;
+      for (int jb = jlo + lane; jb < jhi; jb += 32 * MOM_LD) {
+        double dv[MOM_LD];
 #pragma unroll
-      for (int u = 0; u < MOM_LD; u++) { const int j = jb + 32 * u; dv[u] = (j < jhi) ? row[j] : 0.0; }   // MOM_LD loads in flight
+        for (int u = 0; u < MOM_LD; u++) { const int j = jb + 32 * u; dv[u] = (j < jhi) ? row[j] : 0.0; }   // MOM_LD loads in flight
 #pragma unroll
-      for (int u = 0; u < MOM_LD; u++) {
-        const int j = jb + 32 * u;
-        const double d = dv[u] * c.finalFactor;
-        s0 += d; sx += xg * d; sy += yg_of(c, j) * d;
+        for (int u = 0; u < MOM_LD; u++) {
+          const int j = jb + 32 * u;
+          const double d = dv[u] * c.finalFactor;
+          s0 += d; sx += xg * d; sy += yg_of(c, j) * d;
+        }
       }
     }
+    total = block_sum(s0, red, tid);
+    xc = block_sum(sx, red, tid) / total; yc = block_sum(sy, red, tid) / total;
   }
-  const double total = block_sum(s0, red, tid);
-  const double xc = block_sum(sx, red, tid) / total, yc = block_sum(sy, red, tid) / total;
   // ---- pass 2: <r^n>, eps_n, eps'_n (MakeDensity.cpp:2285-2298, 2389-2430) ----
   double rn[10], mr[10], mi[10], pr[10], pi[10], npw[10], nrm = 0, nnz = 0;
 #pragma unroll
