@@ -474,13 +474,13 @@ cudaError_t launch_combine(const DevCfg& c, const Store& st, int nev, cudaStream
 
 // ---- K4: moments --------------------------------------------------------------------------------
 #ifndef MOM_THREADS
-#define MOM_THREADS 256
+#define MOM_THREADS 128    // 3 CTAs/SM leave 170 registers per thread: the 57 accumulators stay in registers
 #endif
 #ifndef MOM_LD
 #define MOM_LD 8      // density loads a lane keeps in flight
 #endif
 #ifndef MOM_MINCTA
-#define MOM_MINCTA 2
+#define MOM_MINCTA 3
 #endif
 __device__ __forceinline__ double block_sum(double v, double* red, int tid) {
   v = warp_sum(v);
