@@ -36,6 +36,11 @@ REF_ARGS = ["which_mc_model=5", "sub_model=1", "Aproj=208", "Atarg=208", "ecm=27
             "bmin=0", "bmax=20", "Npmin=2", "Npmax=500", "shape_of_nucleons=2", "collision_criterion=2", "shape_of_entropy=2",
             "ecc_from_order=1", "ecc_to_order=9", "use_sd=1", "use_ed=1"]
 WORKLOAD_NAME = "MC-Glauber Pb+Pb 2.76 TeV min-bias eccentricity scan (operation 9), 261x261 grid, orders 1-9"
+# second half of the BASELINE.json metric ("MC-Glauber & MC-KLN Pb+Pb"): same scan with the kT-factorised MC-KLN density
+# (SURVEY.md 8(d) input 4 without the rcBK tables: KLN uGD, lambda = 0.138 as scripts/generateAvgprofile.py:211-222 sets it
+# for 2.76 TeV; no multiplicity fluctuations).  `--workload kln`; the default bench line stays MC-Glauber.
+WORKLOAD_KLN = dict(WORKLOAD, which_mc_model=1, sub_model=7, cc_fluctuation_model=0, **{"lambda": 0.138})
+WORKLOAD_KLN_NAME = "MC-KLN Pb+Pb 2.76 TeV min-bias eccentricity scan (operation 9), 261x261 grid, orders 1-9, 211x211 dN/dy table built on the device"
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -84,13 +89,14 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def algorithmic_flops(ev, width, dx):
+def algorithmic_flops(ev, width, dx, kln=False):
     """F_dep = 2[Np n4^2 (rho_WN) + Nc n5^2 (rho_BC)] (operation 9 with MC-Glauber needs no
-    TA1/TA2, so that term is not claimed), F_mom = 200 per non-zero cell."""
+    TA1/TA2, so that term is not claimed), F_mom = 200 per non-zero cell.  MC-KLN: F_dep = 2 Np n5^2 (TA1 + TA2,
+    participants only -- quirk Q6); the 6-point table lookup (~30 FLOP per cell) is counted with the moments."""
     import numpy as np
     n5, n4 = 2 * 5 * width / dx, 8 * width / dx
     npart = (ev["npart1"] + ev["npart2"]).astype(np.float64); nc = ev["ncoll"].astype(np.float64)
-    f_dep = 2.0 * (npart * n4 * n4 + nc * n5 * n5)
+    f_dep = 2.0 * (npart * n5 * n5) if kln else 2.0 * (npart * n4 * n4 + nc * n5 * n5)
     f_mom = 200.0 * ev["nonzero_cells"].astype(np.float64)
     # collisions 6AB FLOP per try, hard-core scan 3A^2 per nucleus per try (A = B = 208)
     f_smp = ev["tries"].astype(np.float64) * (6.0 * 208 * 208 + 2 * 3.0 * 208 * 208)
@@ -157,6 +163,8 @@ def main():
     ap.add_argument("--batch", type=int, default=2048, help="events resident per launch wave")
     ap.add_argument("--cpu-sample-events", type=int, default=150)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="glauber", choices=["glauber", "kln"],
+                    help="glauber = BASELINE.json configs[1] (the headline line); kln = the same scan with the MC-KLN density")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
 
@@ -196,7 +204,12 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    ctx = smc.Context(smc.capi.default_params(max_batch=a.batch, randomseed=20261017, **WORKLOAD), device=local)
+    kln = a.workload == "kln"
+    wl, wl_name = (WORKLOAD_KLN, WORKLOAD_KLN_NAME) if kln else (WORKLOAD, WORKLOAD_NAME)
+    ctx = smc.Context(smc.capi.default_params(max_batch=a.batch, randomseed=20261017, **wl), device=local)
+    table_s = None
+    if kln:      # one-off start-up (MCnucl::makeTable, 12.5 min on one reference core), outside the timed region
+        t_tab = time.perf_counter(); kln_table = ctx.build_kln_table(); table_s = time.perf_counter() - t_tab
     n = a.events_per_step
     out = np.zeros(n, dtype=smc.capi.EVENT_OUT_DTYPE)
 
@@ -223,7 +236,7 @@ def main():
     f_dep = f_mom = f_smp = 0.0
     for _ in range(a.steps):
         dev_ms += step()
-        fd, fm, fs = algorithmic_flops(out, ctx.k.width, WORKLOAD["dx"]); f_dep += fd; f_mom += fm; f_smp += fs
+        fd, fm, fs = algorithmic_flops(out, ctx.k.width, WORKLOAD["dx"], kln); f_dep += fd; f_mom += fm; f_smp += fs
     barrier()
     wall = time.perf_counter() - t0
     launches = ctx.launches - l0
@@ -258,6 +271,8 @@ def main():
     dom_flops = flops[dom]
     traffic = None
     try:      # DRAM bytes per event of each kernel from the committed `ncu --set full` capture of this command
+        if kln:
+            raise KeyError("the committed capture is of the MC-Glauber workload")
         tj = json.load(open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json")))
         traffic = tj[dom + "_kernel"]["dram_bytes_per_event"] * a.batch      # per launch (one launch = one batch)
     except Exception:
@@ -269,8 +284,8 @@ def main():
         "metric": "events/sec", "value": total_events / dev_max, "unit": "events/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": 1e3 * dev_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD_NAME, "events_per_step_per_gpu": n, "batch": a.batch, "sharding": "event-id ranges per rank, no collective",
-                   "l2": "per-step working set (rho scratch %d MB + event records) exceeds the 126 MB L2" % int(8 * ctx.G * a.batch / 1e6)},
+        "config": {"workload": wl_name, "events_per_step_per_gpu": n, "batch": a.batch, "sharding": "event-id ranges per rank, no collective",
+                   "l2": "per-step working set (%s scratch %d MB + event records) exceeds the 126 MB L2" % ("TA1/TA2/rho" if kln else "rho", int((3 if kln else 1) * 8 * ctx.G * a.batch / 1e6))},
         "e2e": {"value": total_events / wall_max, "unit": "events/s", "h2d_bytes_per_step": 12 * n, "d2h_bytes_per_step": int(out.itemsize) * n},
         "gpu_launches": int(launches),
         "clocks": ck,
@@ -283,11 +298,21 @@ def main():
                      "stage_note": "kernel durations from a second, serial pass over the same steps (CUDA events around every launch); the timed region overlaps consecutive batches on two streams",
                      "hbm": {"achieved_gbs": 2 * grid_bytes / (dev_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak, "note": "rho scratch write+read; not the binding resource"}},
     }
+    if kln:
+        line["config"]["kln_table_build_s"] = table_s
+        # zero-fill + two thickness grids + rho written, thickness grids and rho read back
+        line["roofline"]["hbm"] = {"achieved_gbs": (3 + 3 + 3) * grid_bytes / (dev_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                                   "note": "memset of 3 grids, TA1/TA2/rho written, TA1/TA2/rho read back (whole lattice: MC-KLN has no bounding-rectangle shortcut)"}
     if not a.no_cpu_baseline and world == 1:       # reported at N=1 only
-        cb = cpu_baseline(1, a.cpu_sample_events)
-        if cb is None:
-            # the unmodified reference binary is not on this box: time the oracle port instead
-            cb = port_baseline(a.cpu_sample_events)
+        if kln:
+            # the reference rebuilds its dN/dy table at every start (12.5 min, MCnucl.cpp:911-960), so its binary cannot
+            # be sampled within the bench budget: the per-event loop is timed with the oracle port on the same table
+            cb = port_baseline(min(a.cpu_sample_events, 60), kln_table=kln_table, kln_dt=ctx.k.kln_dt)
+        else:
+            cb = cpu_baseline(1, a.cpu_sample_events)
+            if cb is None:
+                # the unmodified reference binary is not on this box: time the oracle port instead
+                cb = port_baseline(a.cpu_sample_events)
         line["cpu_baseline"] = cb
     print(json.dumps(line))
     ctx.close()
@@ -296,11 +321,11 @@ def main():
     return 0
 
 
-def port_baseline(nev):
+def port_baseline(nev, kln_table=None, kln_dt=None):
     """oracle port (scalar C restatement) timed on one core: sample+collide+deposit+moments per event."""
     import numpy as np
     from oracle import port
-    cfg = port.make_cfg(ecm=2760.0, alpha=0.118)
+    cfg = port.make_cfg(ecm=2760.0, alpha=0.118) if kln_table is None else port.make_cfg(ecm=2760.0, alpha=0.118, which_mc_model=1, sub_model=7, cc_fluct_model=0)
     nA = port.nucleus(208, cfg.width); nB = port.nucleus(208, cfg.width)
     st = port.Stream48(seed=5)
     t0 = time.perf_counter(); done = 0
@@ -314,12 +339,16 @@ def port_baseline(nev):
         p8 = np.zeros((len(ia), 8)); p8[:, :2] = p[ia, :2]; p8[:, 2:6] = p[ia, 3:7]; p8[:, 6] = 1
         t8 = np.zeros((len(ib), 8)); t8[:, :2] = t[ib, :2]; t8[:, 2:6] = t[ib, 3:7]; t8[:, 6] = 1
         c8 = np.zeros((r["ncoll"], 8)); c8[:, 0] = (p[r["pairs"][:, 0], 0] + t[r["pairs"][:, 1], 0]) / 2; c8[:, 1] = (p[r["pairs"][:, 0], 1] + t[r["pairs"][:, 1], 1]) / 2; c8[:, 6] = 1
-        rho, _ = port.density(cfg, p8, t8, c8)
+        if kln_table is None:
+            rho, _ = port.density(cfg, p8, t8, c8)
+        else:
+            rho, _ = port.density_kln(cfg, port.thickness(cfg, p8), port.thickness(cfg, t8), kln_table, kln_dt)
         boxes = np.concatenate([p8[:, 2:6], t8[:, 2:6], np.zeros((1, 4))])
         port.eccentricities(cfg, rho, boxes); port.eccentricities(cfg, rho, boxes)     # sd + ed
         done += 1
     dt = time.perf_counter() - t0
-    return dict(value=nev / dt, unit="events/s", cores=1, kind="port", sample="%d accepted events, oracle/smc_oracle.c, one core" % nev)
+    return dict(value=nev / dt, unit="events/s", cores=1, kind="port",
+                sample="%d accepted events, oracle/smc_oracle.c, one core%s" % (nev, "" if kln_table is None else "; dN/dy table taken as given (the reference spends 12.5 min building it at every start)"))
 
 
 if __name__ == "__main__":

@@ -313,7 +313,10 @@ int smc_plan_kinds(smc_ctx* ctx, unsigned flags, int* kinds, int* nk_dep) {
   if (flags & SMC_RUN_RHO_BINARY) add(smc::GK_RHO_BINARY, true);
   if (flags & SMC_RUN_SPECTATORS) { add(smc::GK_SPEC_A, true); add(smc::GK_SPEC_B, true); }
   st.nkinds = n; *nk_dep = nd;
-  ctx->need_zero = !(c.which_mc_model == 5 && (flags & ~(unsigned)SMC_RUN_MOMENTS) == 0);
+  // Scan mode (moments only): deposit tiles, combine and moments all work on the event's bounding rectangle, so the
+  // lattice outside it is never read on the device and the getters blank it on the host (smc_get_grid).  Profile
+  // modes hand whole grids to the host and to the averaging kernels: those start from zeros.
+  ctx->need_zero = (flags & ~(unsigned)SMC_RUN_MOMENTS) != 0;
   const size_t need = (size_t)ctx->batch * n * ctx->G * sizeof(double);
   if (need > ctx->grids_bytes) {
     if (ctx->d_grids) cudaFree(ctx->d_grids);
@@ -349,7 +352,12 @@ int smc_run_grid_stages(smc_ctx* ctx, int m, const int* kinds, int nd) {
   if (c.which_mc_model == 1 && !ctx->st.kln_table) FAIL(SMC_ERR_STATE, "MC-KLN density requires smc_build_kln_table / smc_set_kln_table first (MCnucl.cpp:636-640)");
   if (ctx->profile) CK(cudaEventRecord(ctx->pev[1], ctx->stream));
   // deposit CTAs only cover each event's bounding rectangle: whoever reads whole grids needs zeros elsewhere
-  if (ctx->need_zero) CK(cudaMemsetAsync(ctx->d_grids, 0, (size_t)m * ctx->st.nkinds * ctx->G * sizeof(double), ctx->stream));
+  if (ctx->need_zero) {
+    const size_t ev_bytes = (size_t)ctx->st.nkinds * ctx->G * sizeof(double);
+    if (!ctx->st.redo) CK(cudaMemsetAsync(ctx->d_grids, 0, (size_t)m * ev_bytes, ctx->stream));
+    else      // dS/dy-window re-runs touch only the flagged events (h_try holds the flags): the others keep their grids
+      for (int e = 0; e < m; e++) if (ctx->h_try[e]) CK(cudaMemsetAsync(ctx->d_grids + (size_t)e * ctx->st.nkinds * ctx->G, 0, ev_bytes, ctx->stream));
+  }
   // Sub-batches sized so that the density tiles a deposit launch writes are still in the 126 MB L2 when the
   // moments launch reads them back (profiling mode keeps whole-batch launches: one event pair per stage)
   static const int sub_env = getenv("SMC_SUBBATCH") ? atoi(getenv("SMC_SUBBATCH")) : 0;
@@ -652,6 +660,14 @@ extern "C" int smc_get_grid(smc_ctx* ctx, int slot, int which, double* host) {
   if (ks < 0) FAIL(SMC_ERR_STATE, "that grid was not requested in the flags of the last run");
   CK(cudaSetDevice(ctx->device));
   CK(cudaMemcpy(host, ctx->d_grids + ((size_t)slot * ctx->st.nkinds + ks) * ctx->G, ctx->G * sizeof(double), cudaMemcpyDeviceToHost));
+  if (!ctx->need_zero) {       // scan mode: only the event's bounding rectangle was written (all else is 0 by construction)
+    int hi[smc::HDR_I];
+    CK(cudaMemcpy(hi, ctx->st.hdr_i + (size_t)slot * smc::HDR_I, sizeof hi, cudaMemcpyDeviceToHost));
+    const int My = ctx->cfg.Maxy;
+    for (int i = 0; i < ctx->cfg.Maxx; i++)
+      for (int j = 0; j < My; j++)
+        if (i < hi[smc::H_RLO] || i >= hi[smc::H_RHI] || j < hi[smc::H_CLO] || j >= hi[smc::H_CHI]) host[(size_t)i * My + j] = 0.0;
+  }
   return SMC_OK;
 }
 

@@ -417,7 +417,9 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_MINCTA) deposit_kernel(DevCfg
   }
 }
 
-int deposit_cm_slots(const DevCfg& c) { return ((c.Maxy + DEP_COLS - 1) / DEP_COLS + 1) * ((c.Maxx + DEP_BAND - 1) / DEP_BAND + 1); }
+// Bands / column groups start at the event's own first row / column (>= 0), so ceil(Maxx / DEP_BAND) bands and
+// ceil(Maxy / DEP_COLS) groups always reach the end of the rectangle
+int deposit_cm_slots(const DevCfg& c) { return ((c.Maxy + DEP_COLS - 1) / DEP_COLS) * ((c.Maxx + DEP_BAND - 1) / DEP_BAND); }
 
 size_t deposit_smem_bytes(const DevCfg& c, int nsrc_max) {
   size_t b = 2 * sizeof(DepTab) + 2 * DEP_CH * sizeof(SrcRec) + 32 * sizeof(int);
@@ -428,8 +430,8 @@ size_t deposit_smem_bytes(const DevCfg& c, int nsrc_max) {
 cudaError_t launch_deposit(const DevCfg& c, const Store& st, const int* kinds, int nk, int nev, cudaStream_t s) {
   KindList kl; kl.n = nk; for (int i = 0; i < nk; i++) kl.kind[i] = kinds[i];
   bbox_kernel<<<nev, 128, 0, s>>>(c, st, kl, nev);
-  const int ngroups = (c.Maxy + DEP_COLS - 1) / DEP_COLS + 1;      // +1: groups start at the event's own first column
-  const int nbands = (c.Maxx + DEP_BAND - 1) / DEP_BAND + 1;
+  const int ngroups = (c.Maxy + DEP_COLS - 1) / DEP_COLS;
+  const int nbands = (c.Maxx + DEP_BAND - 1) / DEP_BAND;
   const size_t smem = deposit_smem_bytes(c, 2 * c.Amax + c.ncoll_cap);
   cudaFuncSetAttribute(deposit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 g(nev, nbands * ngroups, nk);
@@ -447,24 +449,33 @@ __global__ void combine_kernel(DevCfg c, Store st, int nev) {
   int* hi = st.hdr_i + (size_t)e * HDR_I;
   double* base = st.grids + (size_t)e * st.nkinds * G;
   double* rho = base + (size_t)st.kind_slot[GK_RHO] * G;
-  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < G; k += (size_t)gridDim.x * blockDim.x) {
-    if (c.which_mc_model == 7) {
-      const double a = base[(size_t)st.kind_slot[GK_RHOA] * G + k], b = base[(size_t)st.kind_slot[GK_RHOB] * G + k];
-      rho[k] = sqrt(a * b);
-    } else {
-      const double ta = base[(size_t)st.kind_slot[GK_TA1] * G + k], tb = base[(size_t)st.kind_slot[GK_TA2] * G + k];
-      const double di = ta / c.kln_dT, dj = tb / c.kln_dT;
-      if (di < 0 || di >= c.kln_tmax - 2 || dj < 0 || dj >= c.kln_tmax - 2) { hi[H_STATUS] = 4; rho[k] = 0.0; continue; }
-      const int i = (int)floor(di), jj = (int)floor(dj);
-      const double x = di - i, y = dj - jj;
-      const double* T = st.kln_table; const int tm = c.kln_tmax;
-      const double v00 = T[i * tm + jj], v01 = T[i * tm + jj + 1], v02 = T[i * tm + jj + 2];
-      const double v10 = T[(i + 1) * tm + jj], v11 = T[(i + 1) * tm + jj + 1], v20 = T[(i + 2) * tm + jj];
-      const double axx = 1.0 / 2.0 * (v00 - 2 * v10 + v20), axy = v00 - v01 - v10 + v11, ayy = 1.0 / 2.0 * (v00 - 2 * v01 + v02);
-      const double bx = 1.0 / 2.0 * (-3.0 * v00 + 4 * v10 - v20), by = 1.0 / 2.0 * (-3.0 * v00 + 4 * v01 - v02);
-      rho[k] = axx * x * x + axy * x * y + ayy * y * y + bx * x + by * y + v00;
+  // Only the event's bounding rectangle (bbox_kernel: union of the source windows of every deposited kind) can
+  // hold a non-zero input: outside it rho is 0 in the reference too (sqrt(0 * 0); table[0][j] = table[i][0] = 0,
+  // MCnucl.cpp:937-944), and nothing downstream reads it (moments walk the same rectangle, getters zero the rest)
+  const int ilo = hi[H_RLO], ihi = hi[H_RHI], jlo = hi[H_CLO], jhi = hi[H_CHI];
+  const double* ga = base + (size_t)st.kind_slot[c.which_mc_model == 7 ? GK_RHOA : GK_TA1] * G;
+  const double* gb = base + (size_t)st.kind_slot[c.which_mc_model == 7 ? GK_RHOB : GK_TA2] * G;
+  bool overflow = false;
+  for (int i = ilo + blockIdx.x; i < ihi; i += gridDim.x) {
+    for (int j = jlo + threadIdx.x; j < jhi; j += blockDim.x) {
+      const size_t k = (size_t)i * c.Maxy + j;
+      if (c.which_mc_model == 7) {
+        rho[k] = sqrt(ga[k] * gb[k]);
+      } else {
+        const double di = ga[k] / c.kln_dT, dj = gb[k] / c.kln_dT;
+        if (di < 0 || di >= c.kln_tmax - 2 || dj < 0 || dj >= c.kln_tmax - 2) { overflow = true; rho[k] = 0.0; continue; }
+        const int ii = (int)floor(di), jj = (int)floor(dj);
+        const double x = di - ii, y = dj - jj;
+        const double* T = st.kln_table; const int tm = c.kln_tmax;
+        const double v00 = T[ii * tm + jj], v01 = T[ii * tm + jj + 1], v02 = T[ii * tm + jj + 2];
+        const double v10 = T[(ii + 1) * tm + jj], v11 = T[(ii + 1) * tm + jj + 1], v20 = T[(ii + 2) * tm + jj];
+        const double axx = 1.0 / 2.0 * (v00 - 2 * v10 + v20), axy = v00 - v01 - v10 + v11, ayy = 1.0 / 2.0 * (v00 - 2 * v01 + v02);
+        const double bx = 1.0 / 2.0 * (-3.0 * v00 + 4 * v10 - v20), by = 1.0 / 2.0 * (-3.0 * v00 + 4 * v01 - v02);
+        rho[k] = axx * x * x + axy * x * y + ayy * y * y + bx * x + by * y + v00;
+      }
     }
   }
+  if (overflow) hi[H_STATUS] = 4;
 }
 cudaError_t launch_combine(const DevCfg& c, const Store& st, int nev, cudaStream_t s) {
   dim3 g(32, nev);
@@ -550,9 +561,9 @@ __global__ void __launch_bounds__(MOM_THREADS, MOM_MINCTA) moments_kernel(DevCfg
       }
     }
   }
-  // bounding rectangle of non-zero density = union of the source windows (bbox_kernel); MC-KLN: whole lattice
-  int ilo = hi[H_RLO], ihi = hi[H_RHI], jlo = hi[H_CLO], jhi = hi[H_CHI];
-  if (c.which_mc_model == 1) { ilo = 0; ihi = Maxx; jlo = 0; jhi = Maxy; }
+  // bounding rectangle of non-zero density = union of the source windows (bbox_kernel); the derived densities
+  // (sqrt(rhoA rhoB), the MC-KLN table lookup) vanish outside it as well (combine_kernel)
+  const int ilo = hi[H_RLO], ihi = hi[H_RHI], jlo = hi[H_CLO], jhi = hi[H_CHI];
   const int lane = tid & 31, warp = tid >> 5;
   // warp w walks rows ilo + w, ilo + w + 8, ...; lanes walk the columns of the row (no index divisions, the
   // row coordinate is hoisted)
@@ -560,7 +571,7 @@ __global__ void __launch_bounds__(MOM_THREADS, MOM_MINCTA) moments_kernel(DevCfg
   double total, xc, yc;
   if (c.which_mc_model == 5 && st.cm_part) {
     // MC-Glauber: the deposit CTAs left sum(rho), sum(x rho), sum(y rho) of their tiles; add them in slot order
-    const int nbands = (Maxx + DEP_BAND - 1) / DEP_BAND + 1;
+    const int nbands = (Maxx + DEP_BAND - 1) / DEP_BAND;
     const int nb = (max(ihi - ilo, 0) + DEP_BAND - 1) / DEP_BAND, ng = (max(jhi - jlo, 0) + DEP_COLS - 1) / DEP_COLS;
     const int NWD = DEP_THREADS / 32, nslot = nb * ng * NWD;
     const double* part = st.cm_part + (size_t)e * st.cm_slots * NWD * 4;

@@ -3,7 +3,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import Golden, ROOT
+from helpers import Golden, ROOT, event_in_from
 
 pytestmark = pytest.mark.gpu
 
@@ -86,4 +86,32 @@ def test_deuteron_sampling_equals_oracle(oracle_lib):
                 break
         assert out[e]["tries"] == tr + 1 and out[e]["ncoll"] == r["ncoll"]
         assert np.abs(ctx.nucleons(e, 0)[:, [0, 1, 3, 4, 5, 6]] - p[:, [0, 1, 3, 4, 5, 6]]).max() < 1e-10
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", ["pbpb2760_glb", "pbpb2760_sqrt_disk", "auau200_kln"])
+def test_scan_mode_equals_profile_mode(name, oracle_lib):
+    """Moments-only runs skip the zero fill and work on each event's bounding rectangle only (deposit tiles,
+    combine, moments); the profile modes start from zeroed lattices.  Both must give the same rows and -- through
+    the getter, which blanks what the device never wrote -- the same grids, bit for bit, also when the grid pool
+    still holds a different, larger event from the run before."""
+    import supermc_b200 as smc
+    port = oracle_lib
+    g = Golden(name); cfg = g.oracle_cfg(port)
+    ctx = smc.Context(g.smc_params(smc.capi, max_batch=8))
+    if name == "auau200_kln":
+        ctx.set_kln_table(g.z["kln_table"], float(g.z["kln_consts"][0]))
+    evs = [event_in_from(t, port, cfg) for t in g.tries()]
+    acc = [i for i, t in enumerate(g.tries()) if int(t["hdr"][4])]
+    assert len(acc) >= 2
+    full = ctx.run_from_positions(evs, smc.RUN_MOMENTS | smc.RUN_KEEP_RHO | smc.RUN_THICKNESS)
+    ref_rho = {i: ctx.grid(i, smc.GRID_RHO).copy() for i in acc}
+    # dirty the pool: the accepted events in reverse order land in the slots of other (different-sized) events
+    ctx.run_from_positions([evs[i] for i in acc[::-1]], smc.RUN_MOMENTS)
+    scan = ctx.run_from_positions(evs, smc.RUN_MOMENTS)
+    for i in acc:
+        assert np.array_equal(scan[i]["mom"], full[i]["mom"]), (name, i)
+        assert scan[i]["total"] == full[i]["total"] and scan[i]["dsdy"] == full[i]["dsdy"]
+        assert scan[i]["nonzero_cells"] == full[i]["nonzero_cells"]
+        assert np.array_equal(ctx.grid(i, smc.GRID_RHO), ref_rho[i]), (name, i)
     ctx.close()
