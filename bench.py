@@ -300,9 +300,8 @@ def main():
     }
     if kln:
         line["config"]["kln_table_build_s"] = table_s
-        # zero-fill + two thickness grids + rho written, thickness grids and rho read back
-        line["roofline"]["hbm"] = {"achieved_gbs": (3 + 3 + 3) * grid_bytes / (dev_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
-                                   "note": "memset of 3 grids, TA1/TA2/rho written, TA1/TA2/rho read back (whole lattice: MC-KLN has no bounding-rectangle shortcut)"}
+        line["roofline"]["hbm"] = {"achieved_gbs": (3 + 2 + 2) * grid_bytes / (dev_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                                   "note": "upper bound (whole lattices): TA1/TA2/rho written, TA1/TA2 read by the lookup, rho read twice by the moments; the kernels only touch each event's bounding rectangle"}
     if not a.no_cpu_baseline and world == 1:       # reported at N=1 only
         if kln:
             # the reference rebuilds its dN/dy table at every start (12.5 min, MCnucl.cpp:911-960), so its binary cannot

@@ -1,9 +1,10 @@
 #!/usr/bin/env python3
 """Join an ncu `--page source --csv` dump with `nvdisasm -g -c` line info: samples and executed
-instructions per CUDA source line.  usage: line_profile.py src.csv dis.txt mangled_kernel_name [topN]"""
+instructions per CUDA source line.  usage: line_profile.py src.csv dis.txt mangled_kernel_name [topN] [kernel-name substring in the csv]"""
 import csv, re, sys
 src_csv, dis, mangled = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+want = sys.argv[5] if len(sys.argv) > 5 else ""
 # offset -> (file, line) from nvdisasm
 off2line = {}; cur = None; inside = False
 for ln in open(dis, errors="ignore"):
@@ -25,7 +26,7 @@ while i < len(rows):
             if len(rows[j]) == len(hdr): data.append(rows[j])
             j += 1
         si = hdr.index("# Samples"); tot = sum(int(r[si] or 0) for r in data)
-        if best is None or tot > best[0]: best = (tot, hdr, data)
+        if want in rows[i][1] and (best is None or tot > best[0]): best = (tot, hdr, data)
         i = j
     else: i += 1
 tot, hdr, data = best

@@ -327,7 +327,9 @@ int smc_plan_kinds(smc_ctx* ctx, unsigned flags, int* kinds, int* nk_dep) {
   }
   st.grids = ctx->d_grids;
   st.src_stride = 2 * c.Amax + c.ncoll_cap;
-  const size_t need_rec = (size_t)ctx->batch * std::max(nd, 1) * st.src_stride * sizeof(smc::SrcRec);
+  st.work_off = (((size_t)ctx->batch * std::max(nd, 1) * st.src_stride * sizeof(smc::SrcRec)) + 15) & ~(size_t)15;
+  st.work_cap = ctx->batch * std::max(nd, 1) * smc::deposit_cm_slots(c);
+  const size_t need_rec = st.work_off + smc::deposit_work_bytes(c, ctx->batch, std::max(nd, 1));
   if (need_rec > ctx->srcrec_bytes) {
     if (ctx->d_srcrec) cudaFree(ctx->d_srcrec);
     ctx->d_srcrec = nullptr; ctx->srcrec_bytes = 0;

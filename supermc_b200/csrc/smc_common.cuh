@@ -86,6 +86,8 @@ struct Store {
   double* kln_table;  // [tmax][tmax]
   SrcRec* src_rec;    // [batch][deposit kinds][src_stride]
   int src_stride;
+  size_t work_off;    // byte offset, from src_rec, of the deposit tile list (int2 items[work_cap], then two counters)
+  int work_cap;
   double* cm_part;    // [batch][cm_slots][4] per deposit CTA: sum rho, sum x rho, sum y rho of its tile (MC-Glauber rho only)
   int cm_slots;
   int e0;             // first event of the launch (the grid stages run in L2-sized sub-batches)

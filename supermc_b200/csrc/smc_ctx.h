@@ -12,6 +12,7 @@ cudaError_t launch_deposit(const DevCfg&, const Store&, const int* kinds, int nk
 cudaError_t launch_combine(const DevCfg&, const Store&, int nev, cudaStream_t);
 cudaError_t launch_moments(const DevCfg&, const Store&, int nev, cudaStream_t);
 int deposit_cm_slots(const DevCfg&);
+size_t deposit_work_bytes(const DevCfg&, int batch, int nk);
 struct KlnCfg { double ecm, lambda, y, dT; int tmax; int pt_order; int npt, nkt, nphi; const double *xp, *wp, *xk, *wk, *cphi;
                 int model, maxQ0, maxY, maxKt; double dQ0, siginNN200; const double *rkt, *rna, *ry2; };
 cudaError_t launch_kln_table(const KlnCfg&, double* table, cudaStream_t);

@@ -18,6 +18,8 @@
 // 4 shifts, 4 R2P and 16 predicated DFMAs per (source, tile).  Tables of chunk n+1 are built by whichever warps
 // finish chunk n first (shared item counter, one barrier per chunk).  Deposits are deterministic (fixed
 // summation order) and each grid cell is written exactly once.
+#include <algorithm>
+#include <cstdlib>
 #include <cuda_pipeline.h>
 #include "smc_common.cuh"
 
@@ -129,6 +131,9 @@ struct KindList { int n; int kind[8]; };
 #define DEP_GRAB 32     // items a warp takes per shared-counter grab
 #endif
 #define DEP_THREADS (DEP_NWR * DEP_NSTR * 32)
+#ifndef SMC_DEP_PERSIST_DEFAULT
+#define SMC_DEP_PERSIST_DEFAULT 1     // 1: persistent CTAs over bbox_kernel's tile list; k > 1: k x as many CTAs as fit
+#endif
 #define DEP_NXG (DEP_BAND / 16)
 #define DEP_NXI (DEP_BAND / DEP_XP)
 #define DEP_NYI (DEP_COLS / DEP_YP)
@@ -142,9 +147,18 @@ struct DepTab {
   int4 desc[DEP_CH];                         // iL, iR, jL, jR
 };
 
+// Tile list of the persistent deposit launch: (event, kind index, column group, band) of every tile that exists.
+// bbox_kernel appends the tiles of its event (one atomicAdd per event); the order of the list does not matter,
+// every tile is written by exactly one CTA and its result does not depend on who computes it or when.
+struct DepWork { int2* items; int* ctr; };      // ctr[0] = tiles listed, ctr[1] = next tile to hand out
+__device__ __forceinline__ DepWork dep_work(const Store& st) {
+  DepWork w; w.items = reinterpret_cast<int2*>(reinterpret_cast<char*>(st.src_rec) + st.work_off); w.ctr = reinterpret_cast<int*>(w.items + st.work_cap); return w;
+}
+
 // bounding rectangle (cells) of every source window of the participant/collision deposits of one event
-__global__ void bbox_kernel(DevCfg c, Store st, KindList kl, int nev) {
+__global__ void bbox_kernel(DevCfg c, Store st, KindList kl, int nev, int list_tiles) {
   __shared__ int red[4][4];
+  __shared__ int s_cnt[10], s_base, s_nb;
   const int e = blockIdx.x + st.e0, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (st.redo && !st.redo[e]) return;
   int* hi = st.hdr_i + (size_t)e * HDR_I;
@@ -174,6 +188,29 @@ __global__ void bbox_kernel(DevCfg c, Store st, KindList kl, int nev) {
     for (int w = 1; w < (int)(blockDim.x >> 5); w++) { ilo = min(ilo, red[w][0]); ihi = max(ihi, red[w][1]); jlo = min(jlo, red[w][2]); jhi = max(jhi, red[w][3]); }
     if (ihi <= ilo || jhi <= jlo) { ilo = ihi = jlo = jhi = 0; }
     hi[H_RLO] = ilo; hi[H_RHI] = ihi; hi[H_CLO] = jlo; hi[H_CHI] = jhi;
+    if (list_tiles) {
+      const int nb = (ihi - ilo + DEP_BAND - 1) / DEP_BAND, ng = (jhi - jlo + DEP_COLS - 1) / DEP_COLS;
+      const int nbF = (c.Maxx + DEP_BAND - 1) / DEP_BAND, ngF = (c.Maxy + DEP_COLS - 1) / DEP_COLS;
+      int tot = 0;
+      for (int q = 0; q < kl.n; q++) {
+        const bool whole = (kl.kind[q] == GK_SPEC_A || kl.kind[q] == GK_SPEC_B);
+        s_cnt[q] = tot;
+        if (status == 0 || status == 4) tot += whole ? nbF * ngF : nb * ng;
+      }
+      s_cnt[kl.n] = tot; s_nb = nb;
+      s_base = tot ? atomicAdd(dep_work(st).ctr, tot) : 0;
+    }
+  }
+  if (!list_tiles) return;
+  __syncthreads();
+  const int tot = s_cnt[kl.n], nbF = (c.Maxx + DEP_BAND - 1) / DEP_BAND;
+  int2* items = dep_work(st).items + s_base;
+  for (int k = tid; k < tot; k += blockDim.x) {
+    int q = 0;
+    while (k >= s_cnt[q + 1]) q++;
+    const bool whole = (kl.kind[q] == GK_SPEC_A || kl.kind[q] == GK_SPEC_B);
+    const int t = k - s_cnt[q], nb = whole ? nbF : s_nb;
+    items[k] = make_int2(e, (q << 16) | ((t / nb) << 8) | (t % nb));
   }
 }
 
@@ -201,11 +238,32 @@ __device__ __forceinline__ void row_fma(double (&a)[4], double gx, double y0, do
 // 128-bit loads; this order makes both conflict-free (8 lanes x 16 B contiguous each)
 __device__ __forceinline__ int yg_pos(int c) { return ((c >> 1) & 1) * 16 + (c >> 2) * 2 + (c & 1); }
 
+// PERSIST: one resident CTA per slot of the GPU walks the tile list of bbox_kernel (shared counter) instead of one
+// CTA per possible tile of every event: most possible tiles lie outside their event's bounding rectangle, and those
+// CTAs cost a launch slot with 74 KB of shared memory each just to find that out.
+template <bool PERSIST>
 __global__ void __launch_bounds__(DEP_THREADS, DEP_MINCTA) deposit_kernel(DevCfg c, Store st, KindList kl, int nev, int nbands) {
   extern __shared__ __align__(16) unsigned char dep_smem[];
-  const int e = blockIdx.x + st.e0, band = blockIdx.y % nbands, sgroup = blockIdx.y / nbands, kind = kl.kind[blockIdx.z];
+  __shared__ int s_item;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (st.redo && !st.redo[e]) return;
+  bool first_tile = true; int next_item = 0;
+ for (;;) {
+  int e, band, sgroup, kq;
+  if (PERSIST) {
+    const DepWork wk = dep_work(st);
+    if (first_tile) { if (tid == 0) s_item = atomicAdd(wk.ctr + 1, 1); first_tile = false; }
+    else if (tid == 0) s_item = next_item;      // fetched while the previous tile was being processed
+    __syncthreads();
+    const int it = s_item;
+    if (it >= wk.ctr[0]) return;
+    if (tid == 0) next_item = atomicAdd(wk.ctr + 1, 1);
+    const int2 w = wk.items[it];
+    e = w.x; kq = w.y >> 16; sgroup = (w.y >> 8) & 0xff; band = w.y & 0xff;
+  } else {
+    e = blockIdx.x + st.e0; band = blockIdx.y % nbands; sgroup = blockIdx.y / nbands; kq = blockIdx.z;
+    if (st.redo && !st.redo[e]) return;
+  }
+  const int kind = kl.kind[kq], tile_slot = sgroup * nbands + band;
   const int* hi = st.hdr_i + (size_t)e * HDR_I;
   // bands and column groups are laid out from the corner of the event's own bounding rectangle (bbox_kernel),
   // so a CTA is either inside the populated region or exits at once; spectator grids span the whole lattice
@@ -213,14 +271,14 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_MINCTA) deposit_kernel(DevCfg
   const int r_org = whole ? 0 : hi[H_RLO], r_end = whole ? c.Maxx : hi[H_RHI];
   const int c_org = whole ? 0 : hi[H_CLO], c_end = whole ? c.Maxy : hi[H_CHI];
   const int r0 = r_org + band * DEP_BAND, c0 = c_org + sgroup * DEP_COLS;
-  if (r0 >= r_end || c0 >= c_end) return;
+  if (!PERSIST && (r0 >= r_end || c0 >= c_end)) return;
   const int wr = warp / DEP_NSTR, ws = warp % DEP_NSTR, lr = lane >> 3, lc = lane & 7;
   const int rw0 = r0 + wr * DEP_WROWS, sc0 = c0 + ws * 32;
   DepTab* tab = reinterpret_cast<DepTab*>(dep_smem);
   SrcRec* srcs = reinterpret_cast<SrcRec*>(tab + 2);           // [2][DEP_CH]
   int* wtot = reinterpret_cast<int*>(srcs + 2 * DEP_CH);       // [32]
   unsigned short* act = reinterpret_cast<unsigned short*>(wtot + 32);
-  const SrcRec* recs = st.src_rec + ((size_t)e * kl.n + blockIdx.z) * st.src_stride;
+  const SrcRec* recs = st.src_rec + ((size_t)e * kl.n + kq) * st.src_stride;
   const int slot = st.kind_slot[kind];
   double* grid = st.grids + ((size_t)e * st.nkinds + slot) * (size_t)c.Maxx * c.Maxy;
 
@@ -411,10 +469,13 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_MINCTA) deposit_kernel(DevCfg
     for (int a = 0; a < 4; a++) sx += xg_of(c, rw0 + 4 * lr + a) * ((acc[a][0] + acc[a][1]) + (acc[a][2] + acc[a][3]));
     s0 = warp_sum(s0); sx = warp_sum(sx); sy = warp_sum(sy);
     if (lane == 0) {
-      double* o = st.cm_part + (((size_t)e * st.cm_slots + blockIdx.y) * (DEP_THREADS / 32) + warp) * 4;
+      double* o = st.cm_part + (((size_t)e * st.cm_slots + tile_slot) * (DEP_THREADS / 32) + warp) * 4;
       o[0] = s0; o[1] = sx; o[2] = sy;
     }
   }
+  if (!PERSIST) return;
+  __syncthreads();          // the next tile reuses the tables and s_item
+ }
 }
 
 // Bands / column groups start at the event's own first row / column (>= 0), so ceil(Maxx / DEP_BAND) bands and
@@ -427,18 +488,35 @@ size_t deposit_smem_bytes(const DevCfg& c, int nsrc_max) {
   return (b + 15) & ~(size_t)15;
 }
 
+size_t deposit_work_bytes(const DevCfg& c, int batch, int nk) { return ((size_t)batch * nk * deposit_cm_slots(c)) * sizeof(int2) + 16; }
+
 cudaError_t launch_deposit(const DevCfg& c, const Store& st, const int* kinds, int nk, int nev, cudaStream_t s) {
   KindList kl; kl.n = nk; for (int i = 0; i < nk; i++) kl.kind[i] = kinds[i];
-  bbox_kernel<<<nev, 128, 0, s>>>(c, st, kl, nev);
+  static const int persist = getenv("SMC_DEP_PERSIST") ? atoi(getenv("SMC_DEP_PERSIST")) : SMC_DEP_PERSIST_DEFAULT;
+  static int n_sm = 0;
+  if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
   const int ngroups = (c.Maxy + DEP_COLS - 1) / DEP_COLS;
   const int nbands = (c.Maxx + DEP_BAND - 1) / DEP_BAND;
+  const bool use_list = persist && nbands < 256 && ngroups < 256;
+  if (use_list) cudaMemsetAsync(reinterpret_cast<char*>(st.src_rec) + st.work_off + (size_t)st.work_cap * sizeof(int2), 0, 2 * sizeof(int), s);
+  bbox_kernel<<<nev, 128, 0, s>>>(c, st, kl, nev, use_list ? 1 : 0);
   const size_t smem = deposit_smem_bytes(c, 2 * c.Amax + c.ncoll_cap);
-  cudaFuncSetAttribute(deposit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  dim3 g(nev, nbands * ngroups, nk);
-  deposit_kernel<<<g, DEP_THREADS, smem, s>>>(c, st, kl, nev, nbands);
+  if (use_list) {
+    cudaFuncSetAttribute(deposit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const long want = (long)nev * nbands * ngroups * nk;
+    const int grid = (int)std::min<long>(want, (long)n_sm * DEP_MINCTA * persist);
+    deposit_kernel<true><<<grid, DEP_THREADS, smem, s>>>(c, st, kl, nev, nbands);
+  } else {
+    cudaFuncSetAttribute(deposit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dim3 g(nev, nbands * ngroups, nk);
+    deposit_kernel<false><<<g, DEP_THREADS, smem, s>>>(c, st, kl, nev, nbands);
+  }
   return cudaGetLastError();
 }
 
+#define COMB_BLOCKS 32      // blocks per event of combine_kernel (= centre-of-mass partial-sum slots it leaves)
+#define COMB_THREADS 256
+#define COMB_ILP 4
 // ---- pointwise combinations -------------------------------------------------------------------
 // which_mc_model 7: rho = sqrt(rhoA*rhoB) (MCnucl.cpp:797-803); which_mc_model 1: 6-point table lookup
 // (MCnucl.cpp:654-687, arsenal.cpp:33-54)
@@ -456,13 +534,33 @@ __global__ void combine_kernel(DevCfg c, Store st, int nev) {
   const double* ga = base + (size_t)st.kind_slot[c.which_mc_model == 7 ? GK_RHOA : GK_TA1] * G;
   const double* gb = base + (size_t)st.kind_slot[c.which_mc_model == 7 ? GK_RHOB : GK_TA2] * G;
   bool overflow = false;
-  for (int i = ilo + blockIdx.x; i < ihi; i += gridDim.x) {
-    for (int j = jlo + threadIdx.x; j < jhi; j += blockDim.x) {
-      const size_t k = (size_t)i * c.Maxy + j;
-      if (c.which_mc_model == 7) {
-        rho[k] = sqrt(ga[k] * gb[k]);
+  double s0 = 0, sx = 0, sy = 0;          // centre-of-mass sums of this block's cells (MakeDensity.cpp:2273-2282)
+  // the rectangle as a linear list of cells, COMB_ILP cells per thread in flight: the kernel is bound by the latency
+  // of the dependent loads (thicknesses -> table entries), not by their volume
+  const int wj = max(jhi - jlo, 0), ncell = max(ihi - ilo, 0) * wj, stride = gridDim.x * blockDim.x;
+  for (int base = blockIdx.x * blockDim.x + threadIdx.x; base < ncell; base += COMB_ILP * stride) {
+    double a[COMB_ILP], b[COMB_ILP]; int ci[COMB_ILP], cj[COMB_ILP];
+#pragma unroll
+    for (int u = 0; u < COMB_ILP; u++) {
+      const int idx = base + u * stride;
+      a[u] = 0.0; b[u] = 0.0; ci[u] = -1; cj[u] = 0;
+      if (idx < ncell) {
+        const int ir = idx / wj; ci[u] = ilo + ir; cj[u] = jlo + (idx - ir * wj);
+        const size_t k = (size_t)ci[u] * c.Maxy + cj[u];
+        a[u] = ga[k]; b[u] = gb[k];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < COMB_ILP; u++) {
+      if (ci[u] < 0) continue;
+      const size_t k = (size_t)ci[u] * c.Maxy + cj[u];
+      double r;
+      if (a[u] == 0.0 || b[u] == 0.0) {
+        r = 0.0;           // sqrt(0) and the lookup at the table's zero row / column (table[0][j] = table[i][0] = 0) are exactly 0
+      } else if (c.which_mc_model == 7) {
+        r = sqrt(a[u] * b[u]);
       } else {
-        const double di = ga[k] / c.kln_dT, dj = gb[k] / c.kln_dT;
+        const double di = a[u] / c.kln_dT, dj = b[u] / c.kln_dT;
         if (di < 0 || di >= c.kln_tmax - 2 || dj < 0 || dj >= c.kln_tmax - 2) { overflow = true; rho[k] = 0.0; continue; }
         const int ii = (int)floor(di), jj = (int)floor(dj);
         const double x = di - ii, y = dj - jj;
@@ -471,15 +569,30 @@ __global__ void combine_kernel(DevCfg c, Store st, int nev) {
         const double v10 = T[(ii + 1) * tm + jj], v11 = T[(ii + 1) * tm + jj + 1], v20 = T[(ii + 2) * tm + jj];
         const double axx = 1.0 / 2.0 * (v00 - 2 * v10 + v20), axy = v00 - v01 - v10 + v11, ayy = 1.0 / 2.0 * (v00 - 2 * v01 + v02);
         const double bx = 1.0 / 2.0 * (-3.0 * v00 + 4 * v10 - v20), by = 1.0 / 2.0 * (-3.0 * v00 + 4 * v01 - v02);
-        rho[k] = axx * x * x + axy * x * y + ayy * y * y + bx * x + by * y + v00;
+        r = axx * x * x + axy * x * y + ayy * y * y + bx * x + by * y + v00;
       }
+      rho[k] = r;
+      s0 += r; sx += xg_of(c, ci[u]) * r; sy += yg_of(c, cj[u]) * r;
     }
   }
   if (overflow) hi[H_STATUS] = 4;
+  // per-block partial sums in a fixed slot; the moments kernel adds the COMB_BLOCKS slots in order (deterministic)
+  if (st.cm_part) {
+    __shared__ double red[3][COMB_THREADS / 32];
+    s0 = warp_sum(s0); sx = warp_sum(sx); sy = warp_sum(sy);
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s0; red[1][threadIdx.x >> 5] = sx; red[2][threadIdx.x >> 5] = sy; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t0 = 0, tx = 0, ty = 0;
+      for (int w = 0; w < COMB_THREADS / 32; w++) { t0 += red[0][w]; tx += red[1][w]; ty += red[2][w]; }
+      double* o = st.cm_part + ((size_t)e * st.cm_slots * (DEP_THREADS / 32) + blockIdx.x) * 4;
+      o[0] = t0; o[1] = tx; o[2] = ty;
+    }
+  }
 }
 cudaError_t launch_combine(const DevCfg& c, const Store& st, int nev, cudaStream_t s) {
-  dim3 g(32, nev);
-  combine_kernel<<<g, 256, 0, s>>>(c, st, nev);
+  dim3 g(COMB_BLOCKS, nev);
+  combine_kernel<<<g, COMB_THREADS, 0, s>>>(c, st, nev);
   return cudaGetLastError();
 }
 
@@ -581,6 +694,13 @@ __global__ void __launch_bounds__(MOM_THREADS, MOM_MINCTA) moments_kernel(DevCfg
       const double* o = part + ((size_t)(g2 * nbands + b2) * NWD + w2) * 4;
       s0 += o[0]; sx += o[1]; sy += o[2];
     }
+    const double t0 = block_sum(s0, red, tid);
+    total = t0 * c.finalFactor; xc = block_sum(sx, red, tid) / t0; yc = block_sum(sy, red, tid) / t0;
+  } else if (st.cm_part && st.cm_slots * (DEP_THREADS / 32) >= COMB_BLOCKS) {
+    // derived densities (sqrt scaling, MC-KLN): combine_kernel left the sums of its row blocks
+    const double* part = st.cm_part + (size_t)e * st.cm_slots * (DEP_THREADS / 32) * 4;
+    double s0 = 0, sx = 0, sy = 0;
+    if (tid < COMB_BLOCKS) { s0 = part[tid * 4]; sx = part[tid * 4 + 1]; sy = part[tid * 4 + 2]; }
     const double t0 = block_sum(s0, red, tid);
     total = t0 * c.finalFactor; xc = block_sum(sx, red, tid) / t0; yc = block_sum(sy, red, tid) / t0;
   } else {

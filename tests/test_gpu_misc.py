@@ -93,12 +93,12 @@ def test_deuteron_sampling_equals_oracle(oracle_lib):
 def test_scan_mode_equals_profile_mode(name, oracle_lib):
     """Moments-only runs skip the zero fill and work on each event's bounding rectangle only (deposit tiles,
     combine, moments); the profile modes start from zeroed lattices.  Both must give the same rows and -- through
-    the getter, which blanks what the device never wrote -- the same grids, bit for bit, also when the grid pool
+    the getter, which blanks what the device never wrote -- the same grids, cell by cell bit for bit, also when the grid pool
     still holds a different, larger event from the run before."""
     import supermc_b200 as smc
     port = oracle_lib
     g = Golden(name); cfg = g.oracle_cfg(port)
-    ctx = smc.Context(g.smc_params(smc.capi, max_batch=8))
+    ctx = smc.Context(g.smc_params(smc.capi, max_batch=64))      # the getters address the last batch: keep all tries in one
     if name == "auau200_kln":
         ctx.set_kln_table(g.z["kln_table"], float(g.z["kln_consts"][0]))
     evs = [event_in_from(t, port, cfg) for t in g.tries()]
@@ -110,8 +110,10 @@ def test_scan_mode_equals_profile_mode(name, oracle_lib):
     ctx.run_from_positions([evs[i] for i in acc[::-1]], smc.RUN_MOMENTS)
     scan = ctx.run_from_positions(evs, smc.RUN_MOMENTS)
     for i in acc:
-        assert np.array_equal(scan[i]["mom"], full[i]["mom"]), (name, i)
-        assert scan[i]["total"] == full[i]["total"] and scan[i]["dsdy"] == full[i]["dsdy"]
+        # the rectangle (hence the tiling, hence the order of the centre-of-mass partial sums) depends on which grids
+        # were asked for: rows agree to rounding, cells bit for bit
+        assert np.allclose(scan[i]["mom"], full[i]["mom"], rtol=1e-11, atol=1e-13), (name, i)
+        assert abs(scan[i]["total"] / full[i]["total"] - 1) < 1e-13 and abs(scan[i]["dsdy"] / full[i]["dsdy"] - 1) < 1e-13
         assert scan[i]["nonzero_cells"] == full[i]["nonzero_cells"]
         assert np.array_equal(ctx.grid(i, smc.GRID_RHO), ref_rho[i]), (name, i)
     ctx.close()
