@@ -147,18 +147,23 @@ struct DepTab {
   int4 desc[DEP_CH];                         // iL, iR, jL, jR
 };
 
-// Tile list of the persistent deposit launch: (event, kind index, column group, band) of every tile that exists.
-// bbox_kernel appends the tiles of its event (one atomicAdd per event); the order of the list does not matter,
-// every tile is written by exactly one CTA and its result does not depend on who computes it or when.
-struct DepWork { int2* items; int* ctr; };      // ctr[0] = tiles listed, ctr[1] = next tile to hand out
+// Tile lists of the persistent deposit launch: (event, kind index, column group, band) of every tile that exists,
+// in DEP_NCLS weight classes (class 0 = the middle bands of an event's rectangle, the last class = its edges) that
+// are walked in order, heaviest first, so that the launch does not end on a heavy tile.  bbox_kernel appends the
+// tiles of its event; the order inside a class does not matter: every tile is written by exactly one CTA and its
+// result does not depend on who computes it or when.
+#define DEP_NCLS 8
+struct DepWork { int2* items; int* ctr; int cap; };      // ctr[0] = next tile to hand out, ctr[1 + c] = tiles in class c
 __device__ __forceinline__ DepWork dep_work(const Store& st) {
-  DepWork w; w.items = reinterpret_cast<int2*>(reinterpret_cast<char*>(st.src_rec) + st.work_off); w.ctr = reinterpret_cast<int*>(w.items + st.work_cap); return w;
+  DepWork w; w.items = reinterpret_cast<int2*>(reinterpret_cast<char*>(st.src_rec) + st.work_off); w.cap = st.work_cap;
+  w.ctr = reinterpret_cast<int*>(w.items + (size_t)DEP_NCLS * st.work_cap); return w;
 }
+__device__ __forceinline__ int dep_tile_class(int band, int nb, int sgroup) { return min(abs(2 * band - (nb - 1)) + 3 * sgroup, DEP_NCLS - 1); }
 
 // bounding rectangle (cells) of every source window of the participant/collision deposits of one event
 __global__ void bbox_kernel(DevCfg c, Store st, KindList kl, int nev, int list_tiles) {
   __shared__ int red[4][4];
-  __shared__ int s_cnt[10], s_base, s_nb;
+  __shared__ int s_cnt[10], s_nb;
   const int e = blockIdx.x + st.e0, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (st.redo && !st.redo[e]) return;
   int* hi = st.hdr_i + (size_t)e * HDR_I;
@@ -198,19 +203,20 @@ __global__ void bbox_kernel(DevCfg c, Store st, KindList kl, int nev, int list_t
         if (status == 0 || status == 4) tot += whole ? nbF * ngF : nb * ng;
       }
       s_cnt[kl.n] = tot; s_nb = nb;
-      s_base = tot ? atomicAdd(dep_work(st).ctr, tot) : 0;
     }
   }
   if (!list_tiles) return;
   __syncthreads();
   const int tot = s_cnt[kl.n], nbF = (c.Maxx + DEP_BAND - 1) / DEP_BAND;
-  int2* items = dep_work(st).items + s_base;
+  const DepWork wk = dep_work(st);
   for (int k = tid; k < tot; k += blockDim.x) {
     int q = 0;
     while (k >= s_cnt[q + 1]) q++;
     const bool whole = (kl.kind[q] == GK_SPEC_A || kl.kind[q] == GK_SPEC_B);
-    const int t = k - s_cnt[q], nb = whole ? nbF : s_nb;
-    items[k] = make_int2(e, (q << 16) | ((t / nb) << 8) | (t % nb));
+    const int t = k - s_cnt[q], nb = whole ? nbF : s_nb, band = t % nb, sgroup = t / nb;
+    const int cls = dep_tile_class(band, nb, sgroup);
+    const int pos = atomicAdd(wk.ctr + 1 + cls, 1);
+    wk.items[(size_t)cls * wk.cap + pos] = make_int2(e, (q << 16) | (sgroup << 8) | band);
   }
 }
 
@@ -247,17 +253,20 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_MINCTA) deposit_kernel(DevCfg
   __shared__ int s_item;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   bool first_tile = true; int next_item = 0;
+  __shared__ int s_ccnt[DEP_NCLS];
+  if (PERSIST) { if (tid < DEP_NCLS) s_ccnt[tid] = dep_work(st).ctr[1 + tid]; }      // final: bbox_kernel has completed
  for (;;) {
   int e, band, sgroup, kq;
   if (PERSIST) {
     const DepWork wk = dep_work(st);
-    if (first_tile) { if (tid == 0) s_item = atomicAdd(wk.ctr + 1, 1); first_tile = false; }
+    if (first_tile) { if (tid == 0) s_item = atomicAdd(wk.ctr, 1); first_tile = false; }
     else if (tid == 0) s_item = next_item;      // fetched while the previous tile was being processed
     __syncthreads();
-    const int it = s_item;
-    if (it >= wk.ctr[0]) return;
-    if (tid == 0) next_item = atomicAdd(wk.ctr + 1, 1);
-    const int2 w = wk.items[it];
+    int it = s_item, cls = 0;
+    while (cls < DEP_NCLS && it >= s_ccnt[cls]) { it -= s_ccnt[cls]; cls++; }     // class lists are walked in order
+    if (cls == DEP_NCLS) return;
+    if (tid == 0) next_item = atomicAdd(wk.ctr, 1);
+    const int2 w = wk.items[(size_t)cls * wk.cap + it];
     e = w.x; kq = w.y >> 16; sgroup = (w.y >> 8) & 0xff; band = w.y & 0xff;
   } else {
     e = blockIdx.x + st.e0; band = blockIdx.y % nbands; sgroup = blockIdx.y / nbands; kq = blockIdx.z;
@@ -488,7 +497,7 @@ size_t deposit_smem_bytes(const DevCfg& c, int nsrc_max) {
   return (b + 15) & ~(size_t)15;
 }
 
-size_t deposit_work_bytes(const DevCfg& c, int batch, int nk) { return ((size_t)batch * nk * deposit_cm_slots(c)) * sizeof(int2) + 16; }
+size_t deposit_work_bytes(const DevCfg& c, int batch, int nk) { return (size_t)DEP_NCLS * ((size_t)batch * nk * deposit_cm_slots(c)) * sizeof(int2) + (1 + DEP_NCLS) * sizeof(int) + 16; }
 
 cudaError_t launch_deposit(const DevCfg& c, const Store& st, const int* kinds, int nk, int nev, cudaStream_t s) {
   KindList kl; kl.n = nk; for (int i = 0; i < nk; i++) kl.kind[i] = kinds[i];
@@ -498,7 +507,7 @@ cudaError_t launch_deposit(const DevCfg& c, const Store& st, const int* kinds, i
   const int ngroups = (c.Maxy + DEP_COLS - 1) / DEP_COLS;
   const int nbands = (c.Maxx + DEP_BAND - 1) / DEP_BAND;
   const bool use_list = persist && nbands < 256 && ngroups < 256;
-  if (use_list) cudaMemsetAsync(reinterpret_cast<char*>(st.src_rec) + st.work_off + (size_t)st.work_cap * sizeof(int2), 0, 2 * sizeof(int), s);
+  if (use_list) cudaMemsetAsync(reinterpret_cast<char*>(st.src_rec) + st.work_off + (size_t)DEP_NCLS * st.work_cap * sizeof(int2), 0, (1 + DEP_NCLS) * sizeof(int), s);
   bbox_kernel<<<nev, 128, 0, s>>>(c, st, kl, nev, use_list ? 1 : 0);
   const size_t smem = deposit_smem_bytes(c, 2 * c.Amax + c.ncoll_cap);
   if (use_list) {

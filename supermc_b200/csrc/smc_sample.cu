@@ -18,6 +18,8 @@
 // single-precision over-estimate of the hit probability queue up and are settled 32 at a time by the
 // reference's double-precision expression.  Gamma weights are drawn densely over the compact participant and
 // collision lists.
+#include <cstdlib>
+#include <algorithm>
 #include "smc_common.cuh"
 
 namespace smc {
@@ -610,7 +612,8 @@ size_t sample_smem_bytes(int Amax) {
 }
 
 cudaError_t launch_sample_collide(const DevCfg& c, const Store& st, int nev, bool given, cudaStream_t s) {
-  const size_t smem = sample_smem_bytes(c.Amax);
+  static const size_t pad = getenv("SMC_SAMPLE_PAD") ? (size_t)atoi(getenv("SMC_SAMPLE_PAD")) : 0;     // tuning aid: occupancy sensitivity
+  const size_t smem = sample_smem_bytes(c.Amax) + pad;
   if (given) {
     cudaFuncSetAttribute(sample_collide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(sample_collide_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);

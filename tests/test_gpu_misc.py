@@ -3,7 +3,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import Golden, ROOT, event_in_from
+from helpers import Golden, ROOT, event_in_from, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -93,7 +93,7 @@ def test_deuteron_sampling_equals_oracle(oracle_lib):
 def test_scan_mode_equals_profile_mode(name, oracle_lib):
     """Moments-only runs skip the zero fill and work on each event's bounding rectangle only (deposit tiles,
     combine, moments); the profile modes start from zeroed lattices.  Both must give the same rows and -- through
-    the getter, which blanks what the device never wrote -- the same grids, cell by cell bit for bit, also when the grid pool
+    the getter, which blanks what the device never wrote -- the same grids (identical zero pattern, cells to rounding), also when the grid pool
     still holds a different, larger event from the run before."""
     import supermc_b200 as smc
     port = oracle_lib
@@ -111,9 +111,11 @@ def test_scan_mode_equals_profile_mode(name, oracle_lib):
     scan = ctx.run_from_positions(evs, smc.RUN_MOMENTS)
     for i in acc:
         # the rectangle (hence the tiling, hence the order of the centre-of-mass partial sums) depends on which grids
-        # were asked for: rows agree to rounding, cells bit for bit
+        # were asked for: rows agree to rounding
         assert np.allclose(scan[i]["mom"], full[i]["mom"], rtol=1e-11, atol=1e-13), (name, i)
         assert abs(scan[i]["total"] / full[i]["total"] - 1) < 1e-13 and abs(scan[i]["dsdy"] / full[i]["dsdy"] - 1) < 1e-13
         assert scan[i]["nonzero_cells"] == full[i]["nonzero_cells"]
-        assert np.array_equal(ctx.grid(i, smc.GRID_RHO), ref_rho[i]), (name, i)
+        got = ctx.grid(i, smc.GRID_RHO)
+        # (the Gaussian recurrence restarts at tile boundaries, so cells agree to rounding, not bit for bit)
+        assert np.array_equal(got == 0, ref_rho[i] == 0) and rel_err(got, ref_rho[i]).max() < 1e-12, (name, i)
     ctx.close()
