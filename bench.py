@@ -195,6 +195,10 @@ def main():
         print(json.dumps(line))
         return 0
 
+    # rank 0 prints ONE JSON line on stdout: libraries that write there (NCCL prints its version banner on stdout when
+    # NCCL_DEBUG is set) are sent to stderr for the duration of the run
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import numpy as np
     import torch
     import supermc_b200 as smc
@@ -313,7 +317,7 @@ def main():
                 # the unmodified reference binary is not on this box: time the oracle port instead
                 cb = port_baseline(a.cpu_sample_events)
         line["cpu_baseline"] = cb
-    print(json.dumps(line))
+    json_out.write(json.dumps(line) + "\n"); json_out.flush()
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
