@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define SMC_ABI_VERSION 1
+#define SMC_ABI_VERSION 2
 
 enum {
   SMC_OK = 0,
@@ -40,7 +40,7 @@ typedef struct smc_params {
   int aproj, atarg;              /*                                            MCnucl.cpp:99-106 */
   int proj_deformed, targ_deformed;
   int include_nn_correlation;    /*                                            Nucleus.cpp:26 */
-  int shape_of_nucleons;         /* 1 disk, 2 gaussian(sigma_NN), 4 user width GaussianNucleonsCal.cpp:28-55 */
+  int shape_of_nucleons;         /* 1 disk, 2 gaussian(sigma_NN), 3 gaussian(gaussian_lambda), 4 user width  GaussianNucleonsCal.cpp:28-55 */
   int collision_criterion;       /* 1 disk, 2 gaussian, else from shape_of_entropy   MCnucl.cpp:357-385 */
   int shape_of_entropy;          /* 1 disk, 2 gaussian                         MCnucl.cpp:109 */
   double quark_width;            /*                                            Nucleus.cpp:29 */
@@ -55,6 +55,7 @@ typedef struct smc_params {
   int cc_fluctuation_model;      /* 0 none, 6 Gamma weights                    MCnucl.cpp:67-83 */
   double cc_fluctuation_gamma_theta;
   int pt_order;                  /* KLN pT weight, 1 unless PT_flag<0          MCnucl.cpp:52-55 */
+  double gaussian_lambda;        /* shape_of_nucleons == 3                     GaussianNucleonsCal.cpp:29,39-44 */
   /* capacities of the device-side event records (not reference parameters) */
   int max_batch;                 /* events resident per launch wave; 0 = default */
   int ncoll_cap;                 /* collision-list capacity per event; 0 = default */

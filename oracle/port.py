@@ -85,13 +85,13 @@ def gauss_params(shape, siginNN, lam=4.14, user_w=0.812):
 
 def make_cfg(maxx=13.0, maxy=13.0, dx=0.1, dy=0.1, ecm=2760.0, alpha=0.118, shape_of_nucleons=2,
              shape_of_entropy=2, collision_criterion=2, which_mc_model=5, sub_model=1, cc_fluct_model=6,
-             gauss_nucl_width=0.812):
+             gauss_nucl_width=0.812, gaussian_lambda=4.14):
     c = Cfg()
     c.Xmin, c.Ymin, c.dx, c.dy = -maxx, -maxy, dx, dy
     c.Maxx = int((2 * maxx) / dx + 0.1) + 1
     c.Maxy = int((2 * maxy) / dy + 0.1) + 1
     c.siginNN = sigma_inel(ecm)
-    c.width, c.sigma_gg = gauss_params(shape_of_nucleons, c.siginNN, user_w=gauss_nucl_width)
+    c.width, c.sigma_gg = gauss_params(shape_of_nucleons, c.siginNN, lam=gaussian_lambda, user_w=gauss_nucl_width)
     c.dsq = 0.1 * c.siginNN / np.pi
     c.alpha = alpha
     c.shape_of_nucleons, c.shape_of_entropy, c.collision_criterion = shape_of_nucleons, shape_of_entropy, collision_criterion

@@ -57,13 +57,40 @@ static double sig_eff(double siginNN, double width) {
   return sigeff;
 }
 
-/* GaussianNucleonsCal ctor (GaussianNucleonsCal.cpp:24-55); shape 3 (energy-dependent width) needs
- * the E1 integral of arsenal qiu_simpsons and is not part of any BASELINE config: not restated. */
+/* arsenal.cpp:531-571 qiu_simpsons applied to Gamma0Integrand (GaussianNucleonsCal.cpp:19-22): Simpson sums on
+ * 1, 2, 4, ... panels until two successive values differ by less than epsilon (depth cap 50) */
+static double gamma0_integrand(double t) { return 1. / t * exp(-t); }
+static double qiu_simpsons_gamma0(double a, double b, double epsilon) {
+  double f_1 = gamma0_integrand(a) + gamma0_integrand(b), f_2 = 0., f_4 = 0., sum_previous = 0., sum_current = 0.;
+  long count = 1, i;
+  double length = (b - a), step = length / count;
+  int currentRecursionDepth = 1;
+  f_4 = gamma0_integrand(a + 0.5 * step);
+  sum_current = (length / 6) * (f_1 + f_2 * 2. + f_4 * 4.);
+  do {
+    sum_previous = sum_current;
+    f_2 += f_4;
+    count *= 2;
+    step /= 2.0;
+    f_4 = 0.;
+    for (i = 0; i < count; i++) f_4 += gamma0_integrand(a + step * (i + 0.5));
+    sum_current = (length / 6 / count) * (f_1 + f_2 * 2. + f_4 * 4.);
+    if (currentRecursionDepth > 50) break;
+    else currentRecursionDepth++;
+  } while (fabs(sum_current - sum_previous) > epsilon);
+  return sum_current;
+}
+
+/* GaussianNucleonsCal ctor (GaussianNucleonsCal.cpp:24-55) */
 void smc_o_gauss_params(int shape, double siginNN, double gaussian_lambda, double gauss_nucl_width,
                         double* width, double* sigma_gg) {
-  (void)gaussian_lambda;
   double w = 0.0, sg = 0.0;
   if (shape == 1) { w = sqrt(0.1 * siginNN / (M_PI)) / 2.0; sg = sig_eff(siginNN, w); }
+  if (shape == 3) {                                                                      /* :39-44 */
+    double ratio = (0.5772156649 + qiu_simpsons_gamma0(gaussian_lambda, gaussian_lambda + 100., 1e-10) + log(gaussian_lambda)) / gaussian_lambda;
+    w = sqrt(siginNN * 0.1 / (4 * M_PI * gaussian_lambda * ratio));
+    sg = siginNN * 0.1 / ratio;
+  }
   else if (shape == 2) { w = sqrt(0.1 * siginNN / M_PI) / sqrt(8); sg = sig_eff(siginNN, w); }
   else if (shape == 4) { w = gauss_nucl_width; sg = sig_eff(siginNN, w); }
   *width = w; *sigma_gg = sg;

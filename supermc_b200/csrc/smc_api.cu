@@ -27,7 +27,7 @@ extern "C" void smc_params_default(smc_params* p) {   // reference parameters.da
   p->npmin = 2; p->npmax = 500; p->cutdsdy = 0; p->cutdsdy_lowerbound = 593.51; p->cutdsdy_upperbound = 889.53;
   p->randomseed = 1; p->finalfactor = 40.0; p->ecc_from_order = 1; p->ecc_to_order = 9;
   p->maxx = 15.; p->maxy = 15.; p->dx = 0.1; p->dy = 0.1; p->cc_fluctuation_model = 6; p->cc_fluctuation_gamma_theta = 0.75;
-  p->pt_order = 1; p->max_batch = 0; p->ncoll_cap = 0;
+  p->pt_order = 1; p->gaussian_lambda = 4.14; p->max_batch = 0; p->ncoll_cap = 0;
 }
 
 template <typename T> static int dalloc(smc_ctx* ctx, T** p, size_t n) {
@@ -69,7 +69,8 @@ extern "C" int smc_create(const smc_params* p, int device, smc_ctx** out) {
   if (p->which_mc_model != 1 && p->which_mc_model != 5 && p->which_mc_model != 7) FAIL(SMC_ERR_PARAM, "which_mc_model must be 1, 5 or 7");
   if (p->which_mc_model == 5 && p->sub_model != 1 && p->sub_model != 2) FAIL(SMC_ERR_PARAM, "MC-Glauber sub_model must be 1 or 2 (MCnucl.cpp:718-721)");
   if (p->which_mc_model == 1 && p->sub_model != 7 && p->sub_model != 100 && p->sub_model != 101) FAIL(SMC_ERR_PARAM, "MC-KLN sub_model must be 7 (KLN uGD), 100 or 101 (rcBK tables, src/ParamDefs.h)");
-  if (p->shape_of_nucleons != 1 && p->shape_of_nucleons != 2 && p->shape_of_nucleons != 4) FAIL(SMC_ERR_PARAM, "shape_of_nucleons must be 1, 2 or 4");
+  if (p->shape_of_nucleons < 1 || p->shape_of_nucleons > 4) FAIL(SMC_ERR_PARAM, "shape_of_nucleons must be 1, 2, 3 or 4");
+  if (p->shape_of_nucleons == 3 && !(p->gaussian_lambda > 0)) FAIL(SMC_ERR_PARAM, "shape_of_nucleons 3 needs gaussian_lambda > 0");
   if (p->shape_of_entropy != 1 && p->shape_of_entropy != 2) FAIL(SMC_ERR_PARAM, "shape_of_entropy must be 1 or 2 (3 = quark substructure is out of scope)");
   if (p->aproj < 1 || p->atarg < 1 || p->aproj > 512 || p->atarg > 512) FAIL(SMC_ERR_PARAM, "Aproj/Atarg out of range");
   if (!(p->dx > 0) || !(p->dy > 0) || !(p->maxx > 0) || !(p->maxy > 0)) FAIL(SMC_ERR_PARAM, "bad grid");
@@ -78,7 +79,7 @@ extern "C" int smc_create(const smc_params* p, int device, smc_ctx** out) {
   smc_constants& k = ctx->k; smc::DevCfg& c = ctx->cfg;
   std::memset(&c, 0, sizeof c); std::memset(&ctx->st, 0, sizeof ctx->st);
   k.siginnn = smc_host::sigma_inel(p->ecm); k.siginnn200 = smc_host::sigma_inel(200.0);
-  if (!smc_host::gaussian_nucleon(p->shape_of_nucleons, k.siginnn, p->gauss_nucl_width, &k.width, &k.sigma_gg)) FAIL(SMC_ERR_PARAM, "unsupported shape_of_nucleons");
+  if (!smc_host::gaussian_nucleon(p->shape_of_nucleons, k.siginnn, p->gauss_nucl_width, p->gaussian_lambda, &k.width, &k.sigma_gg)) FAIL(SMC_ERR_PARAM, "unsupported shape_of_nucleons");
   k.dsq = 0.1 * k.siginnn / M_PI;
   k.maxx_cells = (int)((p->maxx - (-p->maxx)) / p->dx + 0.1) + 1; k.maxy_cells = (int)((p->maxy - (-p->maxy)) / p->dy + 0.1) + 1;
   k.kln_dt = 10.0 / k.siginnn; k.kln_tmax = p->tmax;

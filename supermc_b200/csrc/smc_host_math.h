@@ -53,8 +53,39 @@ inline double sigma_gg_newton(double siginNN, double width) {
   return sg;
 }
 
-// returns false for shapes this build does not support (3: energy-dependent width)
-inline bool gaussian_nucleon(int shape, double siginNN, double user_width, double* width, double* sigma_gg) {
+// E1-type integral of exp(-t)/t over [a, b] by the reference's own doubling Simpson rule (src/arsenal.cpp:531-571,
+// called with epsilon 1e-10 and the default depth 50): the width of shape 3 inherits its rounding
+inline double simpson_exp_over_t(double a, double b, double epsilon) {
+  auto f = [](double t) { return 1. / t * std::exp(-t); };
+  double f_1 = f(a) + f(b), f_2 = 0., f_4 = 0.;
+  double sum_previous = 0., sum_current = 0.;
+  long count = 1;
+  const double length = (b - a);
+  double step = length / count;
+  int depth = 1;
+  f_4 = f(a + 0.5 * step);
+  sum_current = (length / 6) * (f_1 + f_2 * 2. + f_4 * 4.);
+  do {
+    sum_previous = sum_current;
+    f_2 += f_4;
+    count *= 2; step /= 2.0; f_4 = 0.;
+    for (long i = 0; i < count; i++) f_4 += f(a + step * (i + 0.5));
+    sum_current = (length / 6 / count) * (f_1 + f_2 * 2. + f_4 * 4.);
+    if (depth > 50) break;
+    depth++;
+  } while (std::fabs(sum_current - sum_previous) > epsilon);
+  return sum_current;
+}
+
+// GaussianNucleonsCal constructor (src/GaussianNucleonsCal.cpp:24-55); false for an unknown shape
+inline bool gaussian_nucleon(int shape, double siginNN, double user_width, double gaussian_lambda, double* width, double* sigma_gg) {
+  if (shape == 3) {                 // energy-dependent width from sigma_in / sigma_gg = (gamma_E + E1(lambda) + ln lambda) / lambda
+    const double lam = gaussian_lambda;
+    const double ratio = (0.5772156649 + simpson_exp_over_t(lam, lam + 100., 1e-10) + std::log(lam)) / lam;
+    *width = std::sqrt(siginNN * 0.1 / (4 * M_PI * lam * ratio));
+    *sigma_gg = siginNN * 0.1 / ratio;
+    return true;
+  }
   if (shape == 1) *width = std::sqrt(0.1 * siginNN / (M_PI)) / 2.0;
   else if (shape == 2) *width = std::sqrt(0.1 * siginNN / M_PI) / std::sqrt(8);
   else if (shape == 4) *width = user_width;

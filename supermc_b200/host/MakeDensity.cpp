@@ -95,7 +95,7 @@ MakeDensity::MakeDensity(ParameterReader* p, int device, smc_shard sh, const std
     params.include_nn_correlation = ival(p, "include_NN_correlation");
     params.shape_of_nucleons = ival(p, "shape_of_nucleons"); params.collision_criterion = ival(p, "collision_criterion");
     params.shape_of_entropy = ival(p, "shape_of_entropy"); params.quark_width = p->getVal("quark_width");
-    params.gauss_nucl_width = p->getVal("gauss_nucl_width"); params.ecm = p->getVal("ecm");
+    params.gauss_nucl_width = p->getVal("gauss_nucl_width"); params.gaussian_lambda = p->getVal("gaussian_lambda"); params.ecm = p->getVal("ecm");
     params.bmin = p->getVal("bmin"); params.bmax = p->getVal("bmax"); params.npmin = ival(p, "Npmin"); params.npmax = ival(p, "Npmax");
     params.cutdsdy = ival(p, "cutdSdy"); params.cutdsdy_lowerbound = p->getVal("cutdSdy_lowerBound"); params.cutdsdy_upperbound = p->getVal("cutdSdy_upperBound");
     long long seed = (long long)p->getVal("randomSeed");

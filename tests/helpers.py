@@ -7,7 +7,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 KLN_SYSTEM = "auau200_kln"
 SYSTEMS = ["pbpb2760_glb", "auau200_glb_quarks", "ppb5020_glb_quarks", "pbpb2760_sqrt_disk", "pbpb2760_uli",
-           "auau200_disk_nucleons", "he3au200_glb", "cc200_glb", "uu193_deformed", "pbpb2760_rotate"]
+           "auau200_disk_nucleons", "he3au200_glb", "cc200_glb", "uu193_deformed", "pbpb5020_lambda_width", "pbpb2760_rotate"]
 
 
 class Golden:
@@ -32,7 +32,8 @@ class Golden:
         return port.make_cfg(maxx=p["maxx"], maxy=p["maxy"], dx=p["dx"], dy=p["dy"], ecm=p["ecm"], alpha=p.get("alpha", 0.118),
                              shape_of_nucleons=int(p["shape_of_nucleons"]), shape_of_entropy=int(p["shape_of_entropy"]),
                              collision_criterion=int(p["collision_criterion"]), which_mc_model=int(p["which_mc_model"]),
-                             sub_model=int(p["sub_model"]), cc_fluct_model=int(p["cc_fluctuation_model"]))
+                             sub_model=int(p["sub_model"]), cc_fluct_model=int(p["cc_fluctuation_model"]),
+                             gaussian_lambda=p.get("gaussian_lambda", 4.14))
 
     def smc_params(self, capi, **over):
         p = self.par
@@ -44,6 +45,8 @@ class Golden:
                   finalfactor=p["finalfactor"], maxx=p["maxx"], maxy=p["maxy"], dx=p["dx"], dy=p["dy"],
                   cc_fluctuation_model=int(p["cc_fluctuation_model"]),
                   cc_fluctuation_gamma_theta=p.get("cc_fluctuation_gamma_theta", 0.75), randomseed=int(p["randomseed"]))
+        if "gaussian_lambda" in p:
+            kw["gaussian_lambda"] = p["gaussian_lambda"]
         if "lambda" in p:
             kw.update({"lambda": p["lambda"], "tmax": int(p["tmax"]), "tmax_subdivision": int(p["tmax_subdivision"])})
         kw.update(over)
