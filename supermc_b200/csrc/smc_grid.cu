@@ -543,6 +543,7 @@ __global__ void combine_kernel(DevCfg c, Store st, int nev) {
   const double* ga = base + (size_t)st.kind_slot[c.which_mc_model == 7 ? GK_RHOA : GK_TA1] * G;
   const double* gb = base + (size_t)st.kind_slot[c.which_mc_model == 7 ? GK_RHOB : GK_TA2] * G;
   bool overflow = false;
+  const double inv_dT = 1.0 / c.kln_dT;
   double s0 = 0, sx = 0, sy = 0;          // centre-of-mass sums of this block's cells (MakeDensity.cpp:2273-2282)
   // the rectangle as a linear list of cells, COMB_ILP cells per thread in flight: the kernel is bound by the latency
   // of the dependent loads (thicknesses -> table entries), not by their volume
@@ -569,9 +570,13 @@ __global__ void combine_kernel(DevCfg c, Store st, int nev) {
       } else if (c.which_mc_model == 7) {
         r = sqrt(a[u] * b[u]);
       } else {
-        const double di = a[u] / c.kln_dT, dj = b[u] / c.kln_dT;
+        // TA / dT (MCnucl.cpp:660-661) with the reciprocal of the constant divisor hoisted: q = a * (1/dT), then one
+        // exact-remainder correction step, q + fma(-q, dT, a) * (1/dT) -- Markstein's final division step, which returns
+        // the correctly rounded quotient when 1/dT is correctly rounded (3 instructions instead of a division each)
+        const double q1 = __dmul_rn(a[u], inv_dT), q2 = __dmul_rn(b[u], inv_dT);
+        const double di = __fma_rn(__fma_rn(-q1, c.kln_dT, a[u]), inv_dT, q1), dj = __fma_rn(__fma_rn(-q2, c.kln_dT, b[u]), inv_dT, q2);
         if (di < 0 || di >= c.kln_tmax - 2 || dj < 0 || dj >= c.kln_tmax - 2) { overflow = true; rho[k] = 0.0; continue; }
-        const int ii = (int)floor(di), jj = (int)floor(dj);
+        const int ii = (int)di, jj = (int)dj;               // floor of a non-negative number
         const double x = di - ii, y = dj - jj;
         const double* T = st.kln_table; const int tm = c.kln_tmax;
         const double v00 = T[ii * tm + jj], v01 = T[ii * tm + jj + 1], v02 = T[ii * tm + jj + 2];
