@@ -52,10 +52,11 @@ typedef struct smc_params {
   double finalfactor;            /*                                            MakeDensity.cpp:30 */
   int ecc_from_order, ecc_to_order;  /*                                        MakeDensity.cpp:2112 */
   double maxx, maxy, dx, dy;     /* grid                                       MCnucl.cpp:33-40 */
-  int cc_fluctuation_model;      /* 0 none, 6 Gamma weights                    MCnucl.cpp:67-83 */
+  int cc_fluctuation_model;      /* 0 none, 1/2 NBD per cell (constant k / k from TA,TB), 6 Gamma weights   MCnucl.cpp:67-83,868-905 */
   double cc_fluctuation_gamma_theta;
   int pt_order;                  /* KLN pT weight, 1 unless PT_flag<0          MCnucl.cpp:52-55 */
   double gaussian_lambda;        /* shape_of_nucleons == 3                     GaussianNucleonsCal.cpp:29,39-44 */
+  double cc_fluctuation_k;       /* NBD k of cc_fluctuation_model == 1         MCnucl.cpp:68,872-880 */
   /* capacities of the device-side event records (not reference parameters) */
   int max_batch;                 /* events resident per launch wave; 0 = default */
   int ncoll_cap;                 /* collision-list capacity per event; 0 = default */

@@ -287,3 +287,44 @@ def kln_dndy(k, y, ta, tb, npt=400, nkt=200, nphi=64):
 def kln_integrand(k, y, ta, tb, x3):
     x = (C.c_double * 3)(*x3)
     return lib().smc_o_kln_integrand(C.byref(k), C.c_double(y), C.c_double(ta), C.c_double(tb), x)
+
+
+# ---- NBD multiplicity fluctuations (MCnucl.cpp:868-905, NBD.cpp, RandomVariable.cpp) ----
+def nbd_rand(p, r, stream):
+    """NBD::rand(p, r) restated literally, consuming `stream` (Stream48) like the reference consumes drand48"""
+    L = lib(); L.smc_o_nbd_rand.restype = C.c_long; L.smc_o_nbd_rand.argtypes = [C.c_double, C.c_double, C.c_void_p]
+    return L.smc_o_nbd_rand(p, r, C.byref(stream.s))
+
+
+def nbd_law(p, r, cap=8192):
+    """-> (k0, probabilities): the closed-form law of NBD::rand (a truncated NBD with fractional end cells)"""
+    L = lib(); L.smc_o_nbd_law.argtypes = [C.c_double, C.c_double, C.POINTER(C.c_long), C.POINTER(C.c_double), C.c_int]
+    k0 = C.c_long(); w = (C.c_double * cap)()
+    n = L.smc_o_nbd_law(p, r, C.byref(k0), w, cap)
+    pr = np.array(w[:n]); return k0.value, pr / pr.sum()
+
+
+def nbd_quantile(p, r, u):
+    L = lib(); L.smc_o_nbd_quantile.restype = C.c_long; L.smc_o_nbd_quantile.argtypes = [C.c_double, C.c_double, C.c_double]
+    return L.smc_o_nbd_quantile(p, r, u)
+
+
+def fluctuate_density(cfg, model, cc_k, rho, u, TA1=None, TA2=None):
+    """MCnucl::fluctuateCurrentDensity with the per-cell uniforms given (row-major like the grids)"""
+    rho = np.array(rho, dtype=np.float64, order="C"); u = np.ascontiguousarray(u, dtype=np.float64)
+    z = np.zeros_like(rho)
+    a = np.ascontiguousarray(TA1 if TA1 is not None else z, dtype=np.float64); b = np.ascontiguousarray(TA2 if TA2 is not None else z, dtype=np.float64)
+    L = lib(); L.smc_o_fluctuate_density.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.smc_o_fluctuate_density(C.byref(cfg), int(model), C.c_double(cc_k), a.ctypes.data, b.ctypes.data, u.ctypes.data, rho.ctypes.data)
+    return rho
+
+
+def cell_uniforms(seed, event, npass, ncell):
+    """the CUDA path's per-cell NBD uniforms (smc_philox.h smc_uniform_cell): Philox(ctr = event lo/hi, pass<<8 | 10<<1, cell)"""
+    out = np.empty(ncell)
+    key = [seed & 0xffffffff, (seed >> 32) & 0xffffffff]
+    c2 = ((npass << 8) | (10 << 1)) & 0xffffffff
+    for q in range(ncell):
+        o = philox([event & 0xffffffff, (event >> 32) & 0xffffffff, c2, q], key)
+        out[q] = float((o[0] << 21) | (o[1] >> 11)) / 9007199254740992.0
+    return out

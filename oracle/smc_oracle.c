@@ -794,3 +794,143 @@ static double kln_dndy_any(const smc_o_kln* k, const smc_o_rcbk* t, double y, do
   free(xp); free(wp); free(xk); free(wk);
   return 2.0 * Norm * sum * 9. / 32.;
 }
+
+/* ======================================================================================
+ * NBD multiplicity fluctuations (cc_fluctuation_model 1, 2): MCnucl::fluctuateCurrentDensity
+ * (MCnucl.cpp:868-905) -> NBD::rand(p, r) (NBD.cpp:31-90) -> RandomVariable's step-function envelope
+ * (RandomVariable.cpp:190-216, 243-286).  log Gamma comes from libm instead of the reference's own
+ * rational approximation (arsenal.cpp log_gamma_function): pmf values agree to ~1e-15, which no sample sees.
+ * ====================================================================================== */
+/* NBD::pdf (NBD.cpp:31-40): pmf of floor(k_in) for success probability p and r failures */
+double smc_o_nbd_pdf(double p, double r, double k_in) {
+  if (k_in < 0) return 0;
+  int k = (int)floor(k_in);
+  double prefactor = exp(lgamma(k + r) - lgamma(k + 1.0) - lgamma(r));      /* binomial_coefficient(k+r-1, k), arsenal.cpp:886-891 */
+  return prefactor * pow(1 - p, r) * pow(p, k);
+}
+
+/* NBD::recalculateMode + RandomVariable::constructEnvelopTab: M = step_left + 6 intervals of width std starting at
+ * mode - step_left*std; edge[0..M], height[m] = larger pmf of the two ends.  Returns M. */
+int smc_o_nbd_envelope(double p, double r, double* edge, double* height) {
+  double mode = (r <= 1) ? 1e-30 : p * (r - 1) / (1 - p);
+  double std = sqrt(p * r) / (1 - p);
+  int step_left;
+  for (step_left = 6; step_left > 0; step_left--) if (mode - std * step_left >= 0) break;
+  double LB = mode - step_left * std, RB = LB + std;
+  double pdfLB = smc_o_nbd_pdf(p, r, LB), pdfRB = smc_o_nbd_pdf(p, r, RB);
+  int M = step_left + 6;
+  edge[0] = LB;
+  for (int ii = 0; ii < M; ii++) {
+    height[ii] = pdfLB > pdfRB ? pdfLB : pdfRB;
+    edge[ii + 1] = RB;
+    LB = RB; RB += std;
+    pdfLB = smc_o_nbd_pdf(p, r, LB); pdfRB = smc_o_nbd_pdf(p, r, RB);
+  }
+  return M;
+}
+
+/* NBD::rand(p, r) literally: envelope tables, inverse-CDF draw, acceptance test; `next` yields the drand48 sequence */
+long smc_o_nbd_rand(double p, double r, smc_o_rand48* st) {
+  const double ZERO = 1e-15;
+  if (p < ZERO) return 0;
+  if (p + ZERO > 1.0) return 0;
+  double edge[16], height[16], cum[16], cen[16], hv[16];
+  int M = smc_o_nbd_envelope(p, r, edge, height);
+  double std = sqrt(p * r) / (1 - p), sum = 0;
+  cum[0] = 0;                                               /* envelopInvCDFTab: (sum, right edge) */
+  for (int m = 0; m < M; m++) { sum += std * height[m]; cum[m + 1] = sum; }
+  /* envelopPdfTab: centres edge[m] + std/2 with a zero cap on either side (nearest-neighbour lookup) */
+  cen[0] = edge[0] - std / 2; hv[0] = 0;
+  for (int m = 0; m < M; m++) { cen[m + 1] = edge[m] + std / 2; hv[m + 1] = height[m]; }
+  cen[M + 1] = edge[M] + std / 2; hv[M + 1] = 0;
+  double x = 0;
+  for (long it = 0; ; it++) {
+    /* RandomVariable::drand(LB, RB) on [0, sum] */
+    double width = cum[M] - cum[0], dw = width * 1e-30;
+    double y = cum[0] + dw + (width - 2 * dw) * smc_o_drand48(st);
+    /* interpLinearMono (arsenal.cpp:258-283) with binarySearch (:644-676) */
+    if (fabs(y - cum[0]) < (cum[1] - cum[0]) * 1e-30) x = edge[0];
+    else {
+      int i0 = 0, i1 = M, idx = (int)floor((i1 + i0) / 2.);
+      while (i1 - i0 > 1) { if (cum[idx] < y) i0 = idx; else i1 = idx; idx = (int)floor((i1 + i0) / 2.); }
+      x = edge[i0] + (edge[i0 + 1] - edge[i0]) / (cum[i0 + 1] - cum[i0]) * (y - cum[i0]);
+    }
+    /* interpNearestDirect (arsenal.cpp:141-166) on the equally spaced centres */
+    double env;
+    {
+      double dx = cen[1] - cen[0];
+      if (fabs(x - cen[0]) < dx * 1e-30) env = hv[0];
+      else { long idx = (long)floor((x - cen[0]) / dx); env = (x - cen[idx] > dx / 2) ? hv[idx + 1] : hv[idx]; }
+    }
+    if (smc_o_drand48(st) < smc_o_nbd_pdf(p, r, x) / (1.0 * env + 1e-60)) return (long)x;
+    if (it + 1 > 1000) return (long)x;                      /* MAXITER */
+  }
+}
+
+/* The law of that sampler in closed form: the envelope draw is uniform on interval m with probability ~ std*height[m]
+ * and survives with probability min(1, pmf/height[m]), so
+ *     P(k) ~ sum_m |[edge_m, edge_m+1) n [k, k+1)| * min(height[m], pmf(k)),   k = floor(edge_0) ... floor(edge_M)
+ * -- a NBD truncated to [mode - s*std, mode + 6*std) with fractional end cells (cells with 6 std < 1 always give 0).
+ * weights[i] for k = *k0 + i, i < n (not normalised); returns n (<= cap). */
+int smc_o_nbd_law(double p, double r, long* k0, double* weights, int cap) {
+  const double ZERO = 1e-15;
+  if (p < ZERO || p + ZERO > 1.0) { *k0 = 0; weights[0] = 1.0; return 1; }
+  double edge[16], height[16];
+  int M = smc_o_nbd_envelope(p, r, edge, height);
+  long ka = (long)floor(edge[0]), kb = (long)floor(edge[M]);
+  int n = 0;
+  *k0 = ka;
+  for (long k = ka; k <= kb && n < cap; k++, n++) {
+    double pk = smc_o_nbd_pdf(p, r, (double)k), w = 0;
+    for (int m = 0; m < M; m++) {
+      double lo = edge[m] > (double)k ? edge[m] : (double)k, hi = edge[m + 1] < (double)(k + 1) ? edge[m + 1] : (double)(k + 1);
+      if (hi > lo) w += (hi - lo) * (height[m] < pk ? height[m] : pk);
+    }
+    weights[n] = w;
+  }
+  return n;
+}
+
+/* inverse CDF of the closed-form law at u in [0,1): what the CUDA path evaluates per cell (one Philox uniform) */
+long smc_o_nbd_quantile(double p, double r, double u) {
+  const double ZERO = 1e-15;
+  if (p < ZERO || p + ZERO > 1.0) return 0;
+  double edge[16], height[16];
+  int M = smc_o_nbd_envelope(p, r, edge, height);
+  if (edge[M] <= 1.0) return 0;                              /* the whole envelope lies inside the cell k = 0 */
+  long ka = (long)floor(edge[0]), kb = (long)floor(edge[M]);
+  double tot = 0;
+  for (int pass = 0; pass < 2; pass++) {
+    double acc = 0, target = u * tot;
+    for (long k = ka; k <= kb; k++) {
+      double pk = smc_o_nbd_pdf(p, r, (double)k), w = 0;
+      for (int m = 0; m < M; m++) {
+        double lo = edge[m] > (double)k ? edge[m] : (double)k, hi = edge[m + 1] < (double)(k + 1) ? edge[m + 1] : (double)(k + 1);
+        if (hi > lo) w += (hi - lo) * (height[m] < pk ? height[m] : pk);
+      }
+      acc += w;
+      if (pass == 1 && acc > target) return k;
+    }
+    tot = acc;
+  }
+  return kb;
+}
+
+/* MCnucl::fluctuateCurrentDensity (MCnucl.cpp:868-905) with the per-cell uniforms supplied (u[cell] in [0,1)):
+ * model 1: k = cc_fluctuation_k; model 2: k = kpp * min(TA1, TA2) * siginNN / 10 */
+void smc_o_fluctuate_density(const smc_o_cfg* c, int model, double cc_k, const double* TA1, const double* TA2,
+                             const double* u, double* rho) {
+  const double HBARC = 0.197327053;
+  const double kpp = 1.0 / M_PI * c->dx * c->dy * 1.0 * (0.25 * 0.25 / HBARC / HBARC);
+  for (int ir = 0; ir < c->Maxx; ir++)
+    for (int jr = 0; jr < c->Maxy; jr++) {
+      const size_t q = (size_t)ir * c->Maxy + jr;
+      double nb = rho[q] * c->dx * c->dy, n;
+      if (model == 1) n = (double)smc_o_nbd_quantile(nb / (nb + cc_k), cc_k, u[q]);
+      else {
+        double k = kpp * (TA1[q] < TA2[q] ? TA1[q] : TA2[q]) * c->siginNN / 10;
+        if (nb < 1e-10) n = nb; else n = (double)smc_o_nbd_quantile(nb / (nb + k), k, u[q]);
+      }
+      rho[q] = n / (c->dx * c->dy);
+    }
+}

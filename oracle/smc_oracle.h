@@ -120,6 +120,15 @@ double smc_o_rcbk_func(const smc_o_rcbk* t, double qs0_2, double x, double kt2, 
 double smc_o_rcbk_integrand(const smc_o_kln* k, const smc_o_rcbk* t, double y, double ta, double tb, const double x[3]);
 double smc_o_rcbk_dndy(const smc_o_kln* k, const smc_o_rcbk* t, double y, double ta, double tb, int npt, int nkt, int nphi);
 
+/* ---- NBD multiplicity fluctuations (MCnucl.cpp:868-905, NBD.cpp, RandomVariable.cpp:190-286) ---- */
+double smc_o_nbd_pdf(double p, double r, double k_in);
+int smc_o_nbd_envelope(double p, double r, double* edge, double* height);
+long smc_o_nbd_rand(double p, double r, smc_o_rand48* st);
+int smc_o_nbd_law(double p, double r, long* k0, double* weights, int cap);
+long smc_o_nbd_quantile(double p, double r, double u);
+void smc_o_fluctuate_density(const smc_o_cfg* c, int model, double cc_k, const double* TA1, const double* TA2,
+                             const double* u, double* rho);
+
 #ifdef __cplusplus
 }
 #endif

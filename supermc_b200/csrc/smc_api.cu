@@ -27,7 +27,7 @@ extern "C" void smc_params_default(smc_params* p) {   // reference parameters.da
   p->npmin = 2; p->npmax = 500; p->cutdsdy = 0; p->cutdsdy_lowerbound = 593.51; p->cutdsdy_upperbound = 889.53;
   p->randomseed = 1; p->finalfactor = 40.0; p->ecc_from_order = 1; p->ecc_to_order = 9;
   p->maxx = 15.; p->maxy = 15.; p->dx = 0.1; p->dy = 0.1; p->cc_fluctuation_model = 6; p->cc_fluctuation_gamma_theta = 0.75;
-  p->pt_order = 1; p->gaussian_lambda = 4.14; p->max_batch = 0; p->ncoll_cap = 0;
+  p->pt_order = 1; p->gaussian_lambda = 4.14; p->cc_fluctuation_k = 0.75; p->max_batch = 0; p->ncoll_cap = 0;
 }
 
 template <typename T> static int dalloc(smc_ctx* ctx, T** p, size_t n) {
@@ -74,7 +74,9 @@ extern "C" int smc_create(const smc_params* p, int device, smc_ctx** out) {
   if (p->shape_of_entropy != 1 && p->shape_of_entropy != 2) FAIL(SMC_ERR_PARAM, "shape_of_entropy must be 1 or 2 (3 = quark substructure is out of scope)");
   if (p->aproj < 1 || p->atarg < 1 || p->aproj > 512 || p->atarg > 512) FAIL(SMC_ERR_PARAM, "Aproj/Atarg out of range");
   if (!(p->dx > 0) || !(p->dy > 0) || !(p->maxx > 0) || !(p->maxy > 0)) FAIL(SMC_ERR_PARAM, "bad grid");
-  if (p->cc_fluctuation_model != 0 && p->cc_fluctuation_model != 6) FAIL(SMC_ERR_PARAM, "cc_fluctuation_model must be 0 or 6 (NBD models 1,2 are out of scope)");
+  if (p->cc_fluctuation_model != 0 && p->cc_fluctuation_model != 1 && p->cc_fluctuation_model != 2 && p->cc_fluctuation_model != 6)
+    FAIL(SMC_ERR_PARAM, "cc_fluctuation_model must be 0, 1, 2 or 6 (MCnucl.cpp:899-903)");
+  if (p->cc_fluctuation_model == 1 && !(p->cc_fluctuation_k > 0)) FAIL(SMC_ERR_PARAM, "cc_fluctuation_model 1 needs cc_fluctuation_k > 0");
 
   smc_constants& k = ctx->k; smc::DevCfg& c = ctx->cfg;
   std::memset(&c, 0, sizeof c); std::memset(&ctx->st, 0, sizeof ctx->st);
@@ -94,7 +96,7 @@ extern "C" int smc_create(const smc_params* p, int device, smc_ctx** out) {
   c.finalFactor = p->finalfactor;
   c.shape_of_nucleons = p->shape_of_nucleons; c.shape_of_entropy = p->shape_of_entropy;
   c.crit = (p->collision_criterion == 1 || p->collision_criterion == 2) ? p->collision_criterion : (p->shape_of_entropy == 2 ? 2 : 1);
-  c.which_mc_model = p->which_mc_model; c.sub_model = p->sub_model; c.cc_fluct = p->cc_fluctuation_model;
+  c.which_mc_model = p->which_mc_model; c.sub_model = p->sub_model; c.cc_fluct = p->cc_fluctuation_model; c.cc_k = p->cc_fluctuation_k;
   c.A[0] = p->aproj; c.A[1] = p->atarg; c.deformed[0] = p->proj_deformed; c.deformed[1] = p->targ_deformed;
   for (int s = 0; s < 2; s++) {
     smc_host::WoodsSaxon ws = smc_host::woods_saxon(c.A[s], c.deformed[s]);
@@ -310,7 +312,7 @@ int smc_plan_kinds(smc_ctx* ctx, unsigned flags, int* kinds, int* nk_dep) {
   if (c.which_mc_model == 5) add(smc::GK_RHO, true);
   else if (c.which_mc_model == 7) { add(smc::GK_RHO, false); add(smc::GK_RHOA, true); add(smc::GK_RHOB, true); }
   else { add(smc::GK_RHO, false); add(smc::GK_TA1, true); add(smc::GK_TA2, true); }
-  if (flags & SMC_RUN_THICKNESS) { add(smc::GK_TA1, true); add(smc::GK_TA2, true); }
+  if ((flags & SMC_RUN_THICKNESS) || c.cc_fluct == 2) { add(smc::GK_TA1, true); add(smc::GK_TA2, true); }     // NBD model 2: k from min(TA, TB)
   if (flags & SMC_RUN_RHO_BINARY) add(smc::GK_RHO_BINARY, true);
   if (flags & SMC_RUN_SPECTATORS) { add(smc::GK_SPEC_A, true); add(smc::GK_SPEC_B, true); }
   st.nkinds = n; *nk_dep = nd;
@@ -353,6 +355,7 @@ static int run_grid_stages(smc_ctx* ctx, int m, const int* kinds, int nd) { retu
 int smc_run_grid_stages(smc_ctx* ctx, int m, const int* kinds, int nd) {
   const smc::DevCfg& c = ctx->cfg;
   if (c.which_mc_model == 1 && !ctx->st.kln_table) FAIL(SMC_ERR_STATE, "MC-KLN density requires smc_build_kln_table / smc_set_kln_table first (MCnucl.cpp:636-640)");
+  ctx->st.nbd_pass = 0;            // the first density of an event; operation 3 counts its re-deposits from here
   if (ctx->profile) CK(cudaEventRecord(ctx->pev[1], ctx->stream));
   // deposit CTAs only cover each event's bounding rectangle: whoever reads whole grids needs zeros elsewhere
   if (ctx->need_zero) {
@@ -371,8 +374,13 @@ int smc_run_grid_stages(smc_ctx* ctx, int m, const int* kinds, int nd) {
     CK(smc::launch_deposit(c, ctx->st, kinds, nd, mm, ctx->stream)); ctx->launches += 2;
     if (ctx->profile) CK(cudaEventRecord(ctx->pev[2], ctx->stream));
     if (c.which_mc_model != 5) { CK(smc::launch_combine(c, ctx->st, mm, ctx->stream)); ctx->launches++; }
+    smc::Store stm = ctx->st;
+    if (c.cc_fluct == 1 || c.cc_fluct == 2) {          // MCnucl::fluctuateCurrentDensity, MCnucl.cpp:819,868-905
+      CK(smc::launch_fluctuate(c, ctx->st, mm, ctx->stream)); ctx->launches++;
+      stm.cm_part = nullptr;                           // the partial sums of the deposit describe the smooth density
+    }
     if (ctx->profile) CK(cudaEventRecord(ctx->pev[3], ctx->stream));
-    CK(smc::launch_moments(c, ctx->st, mm, ctx->stream)); ctx->launches++;
+    CK(smc::launch_moments(c, stm, mm, ctx->stream)); ctx->launches++;
     if (ctx->profile) CK(cudaEventRecord(ctx->pev[4], ctx->stream));
   }
   ctx->st.e0 = 0;

@@ -155,6 +155,7 @@ static int avg_sequence(smc_ctx* ctx, int m) {
     CK(cudaMemsetAsync(ctx->d_grids, 0, (size_t)m * st.nkinds * ctx->G * sizeof(double), ctx->stream));
     CK(smc::launch_deposit(c, st, kinds, nd, m, ctx->stream)); ctx->launches += 2;
     if (c.which_mc_model != 5) { CK(smc::launch_combine(c, st, m, ctx->stream)); ctx->launches++; }
+    if (c.cc_fluct == 1 || c.cc_fluct == 2) { st.nbd_pass++; CK(smc::launch_fluctuate(c, st, m, ctx->stream)); ctx->launches++; }   // fresh draws per setDensity
     return SMC_OK;
   };
   auto cm = [&](int order, double scale) -> int { smc::cm_angle_kernel<<<m, AVG_THREADS, 0, ctx->stream>>>(c, st, order, scale); ctx->launches++; CK(cudaGetLastError()); return SMC_OK; };

@@ -34,6 +34,7 @@ struct DevCfg {
   double finalFactor;
   int shape_of_nucleons, shape_of_entropy, crit;   // crit: 1 disk, 2 gaussian
   int which_mc_model, sub_model, cc_fluct;
+  double cc_k;            // NBD k of cc_fluctuation_model 1
   int A[2];               // mass numbers
   int deformed[2];
   int sampler[2];         // 0 WS, 1 single nucleon, 2 config table (no recentre), 3 config table (NN-corr), 4 deuteron
@@ -90,6 +91,7 @@ struct Store {
   int work_cap;
   double* cm_part;    // [batch][cm_slots][4] per deposit CTA: sum rho, sum x rho, sum y rho of its tile (MC-Glauber rho only)
   int cm_slots;
+  int nbd_pass;       // how often this batch has been (re)deposited: part of the NBD uniforms' address (operation 3)
   int e0;             // first event of the launch (the grid stages run in L2-sized sub-batches)
 };
 enum { H_NP1 = 0, H_NP2, H_NCOLL, H_TRIES, H_NSPEC1, H_NSPEC2, H_STATUS, H_RLO, H_RHI, H_CLO, H_CHI, H_GIVENW, HDR_I = 16 };

@@ -10,6 +10,7 @@ enum { GK_RHO = 0, GK_TA1 = 1, GK_TA2 = 2, GK_RHO_BINARY = 3, GK_SPEC_A = 4, GK_
 cudaError_t launch_sample_collide(const DevCfg&, const Store&, int nev, bool given, cudaStream_t);
 cudaError_t launch_deposit(const DevCfg&, const Store&, const int* kinds, int nk, int nev, cudaStream_t);
 cudaError_t launch_combine(const DevCfg&, const Store&, int nev, cudaStream_t);
+cudaError_t launch_fluctuate(const DevCfg&, const Store&, int nev, cudaStream_t);
 cudaError_t launch_moments(const DevCfg&, const Store&, int nev, cudaStream_t);
 int deposit_cm_slots(const DevCfg&);
 size_t deposit_work_bytes(const DevCfg&, int batch, int nk);

@@ -610,6 +610,92 @@ cudaError_t launch_combine(const DevCfg& c, const Store& st, int nev, cudaStream
   return cudaGetLastError();
 }
 
+// ---- NBD multiplicity fluctuations (cc_fluctuation_model 1, 2) ------------------------------------------
+// MCnucl::fluctuateCurrentDensity (MCnucl.cpp:868-905) replaces rho dx dy of every cell by a draw of NBD::rand(p, r)
+// (NBD.cpp:31-90).  That sampler works through RandomVariable's step-function envelope (RandomVariable.cpp:190-286):
+// M = s + 6 intervals of width std = sqrt(p r)/(1-p) from mode - s std on, interval m of height h_m = the larger pmf
+// of its two ends; a point is drawn uniformly from interval m with probability ~ std h_m and kept with probability
+// min(1, pmf/h_m); the integer part is returned.  Its law is therefore
+//     P(k) ~ sum_m |[e_m, e_m+1) n [k, k+1)| min(h_m, pmf(k)),     k = floor(e_0) ... floor(e_M)
+// (a truncated NBD: cells with 6 std < 1 always give 0).  The reference walks the lattice with one sequential drand48;
+// here every cell inverts that law at its own Philox uniform, which makes the draw addressable and exactly
+// reproducible by the oracle (smc_o_nbd_quantile).
+__device__ double nbd_pmf(double p, double r, double k_in) {
+  if (k_in < 0) return 0;
+  const int k = (int)floor(k_in);
+  return exp(lgamma(k + r) - lgamma(k + 1.0) - lgamma(r)) * pow(1 - p, r) * pow(p, (double)k);
+}
+__device__ long nbd_quantile(double p, double r, double u) {
+  const double ZERO = 1e-15;
+  if (p < ZERO || p + ZERO > 1.0) return 0;
+  const double mode = (r <= 1) ? 1e-30 : p * (r - 1) / (1 - p), sd = sqrt(p * r) / (1 - p);
+  int sl;
+  for (sl = 6; sl > 0; sl--) if (mode - sd * sl >= 0) break;
+  const int M = sl + 6;
+  double edge[13], hgt[12];
+  double LB = mode - sl * sd, RB = LB + sd;
+  if (sl == 0 && LB + 6.5 * sd <= 1.0) return 0;          // the whole envelope lies inside the cell k = 0 (with slack for the summed edge)
+  double pl = nbd_pmf(p, r, LB), pr = nbd_pmf(p, r, RB);
+  edge[0] = LB;
+  for (int m = 0; m < M; m++) {
+    hgt[m] = pl > pr ? pl : pr; edge[m + 1] = RB;
+    LB = RB; RB += sd;
+    pl = pr; pr = nbd_pmf(p, r, RB);
+  }
+  if (edge[M] <= 1.0) return 0;
+  const long ka = (long)floor(edge[0]), kb = (long)floor(edge[M]);
+  double tot = 0;
+  for (int pass = 0; pass < 2; pass++) {
+    double acc = 0; const double target = u * tot;
+    for (long k = ka; k <= kb; k++) {
+      const double pk = nbd_pmf(p, r, (double)k); double w = 0;
+      for (int m = 0; m < M; m++) {
+        const double lo = fmax(edge[m], (double)k), hi = fmin(edge[m + 1], (double)(k + 1));
+        if (hi > lo) w += (hi - lo) * fmin(hgt[m], pk);
+      }
+      acc += w;
+      if (pass == 1 && acc > target) return k;
+    }
+    tot = acc;
+  }
+  return kb;
+}
+__global__ void fluctuate_kernel(DevCfg c, Store st, int nev) {
+  const int e = blockIdx.y + st.e0;
+  if (st.redo && !st.redo[e]) return;
+  const int* hi = st.hdr_i + (size_t)e * HDR_I;
+  if (!(hi[H_STATUS] == 0 || hi[H_STATUS] == 4)) return;
+  const size_t G = (size_t)c.Maxx * c.Maxy;
+  double* base = st.grids + (size_t)e * st.nkinds * G;
+  double* rho = base + (size_t)st.kind_slot[GK_RHO] * G;
+  const double* ta = c.cc_fluct == 2 ? base + (size_t)st.kind_slot[GK_TA1] * G : nullptr;
+  const double* tb = c.cc_fluct == 2 ? base + (size_t)st.kind_slot[GK_TA2] * G : nullptr;
+  // outside the bounding rectangle rho = 0 and the draw is 0 (p = 0 / nb < 1e-10), MCnucl.cpp:877-894
+  const int ilo = hi[H_RLO], ihi = hi[H_RHI], jlo = hi[H_CLO], jhi = hi[H_CHI];
+  const int wj = max(jhi - jlo, 0), ncell = max(ihi - ilo, 0) * wj;
+  const double cell = c.dx * c.dy, kpp = 1.0 / SMC_PI * c.dx * c.dy * 1.0 * (0.25 * 0.25 / 0.197327053 / 0.197327053);
+  const uint64_t ev = st.event_id[e];
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < ncell; idx += gridDim.x * blockDim.x) {
+    const int ir = idx / wj, i = ilo + ir, j = jlo + (idx - ir * wj);
+    const size_t q = (size_t)i * c.Maxy + j;
+    const double nb = rho[q] * cell;
+    double n;
+    if (c.cc_fluct == 1) {
+      n = (nb == 0.0) ? 0.0 : (double)nbd_quantile(nb / (nb + c.cc_k), c.cc_k, smc_uniform_cell(c.seed_lo, c.seed_hi, ev, (uint32_t)st.nbd_pass, (uint32_t)q));
+    } else {
+      const double k = kpp * fmin(ta[q], tb[q]) * c.siginNN / 10;
+      if (nb < 1e-10) n = nb;
+      else n = (double)nbd_quantile(nb / (nb + k), k, smc_uniform_cell(c.seed_lo, c.seed_hi, ev, (uint32_t)st.nbd_pass, (uint32_t)q));
+    }
+    rho[q] = n / cell;
+  }
+}
+cudaError_t launch_fluctuate(const DevCfg& c, const Store& st, int nev, cudaStream_t s) {
+  dim3 g(COMB_BLOCKS, nev);
+  fluctuate_kernel<<<g, COMB_THREADS, 0, s>>>(c, st, nev);
+  return cudaGetLastError();
+}
+
 // ---- K4: moments --------------------------------------------------------------------------------
 #ifndef MOM_THREADS
 #define MOM_THREADS 128    // 3 CTAs/SM leave 170 registers per thread: the 57 accumulators stay in registers

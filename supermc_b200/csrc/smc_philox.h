@@ -19,7 +19,7 @@
 #endif
 
 enum { SMC_K_B = 0, SMC_K_ORIENT = 1, SMC_K_WS = 2, SMC_K_ANGLE = 3, SMC_K_QUARK = 4, SMC_K_PAIR = 5,
-       SMC_K_GAMMA_PART = 6, SMC_K_GAMMA_COLL = 7, SMC_K_CONFIG = 8, SMC_K_DEUT = 9 };
+       SMC_K_GAMMA_PART = 6, SMC_K_GAMMA_COLL = 7, SMC_K_CONFIG = 8, SMC_K_DEUT = 9, SMC_K_NBD = 10 };
 
 struct smc_u4 { uint32_t v[4]; };
 
@@ -63,4 +63,10 @@ SMC_HD void smc_uniform2(const smc_stream& s, uint32_t cand, uint32_t q, double*
 }
 SMC_HD double smc_uniform(const smc_stream& s, uint32_t cand, uint32_t slot) {
   double a, b; smc_uniform2(s, cand, slot >> 1, &a, &b); return (slot & 1) ? b : a;
+}
+// per-lattice-cell uniform of the NBD multiplicity fluctuations: ctr3 is the cell index itself (a lattice can have more
+// than 2^20 cells), ctr2 = pass << 8 | SMC_K_NBD << 1 where `pass` counts the re-deposits of an event (operation 3)
+SMC_HD double smc_uniform_cell(uint32_t seed_lo, uint32_t seed_hi, uint64_t event, uint32_t pass, uint32_t cell) {
+  smc_u4 o = smc_philox4x32_10((uint32_t)event, (uint32_t)(event >> 32), (pass << 8) | ((uint32_t)SMC_K_NBD << 1), cell, seed_lo, seed_hi);
+  return smc_u53(o.v[0], o.v[1]);
 }

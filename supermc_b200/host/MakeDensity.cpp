@@ -104,6 +104,7 @@ MakeDensity::MakeDensity(ParameterReader* p, int device, smc_shard sh, const std
     params.finalfactor = p->getVal("finalFactor"); params.ecc_from_order = ival(p, "ecc_from_order"); params.ecc_to_order = ival(p, "ecc_to_order");
     params.maxx = p->getVal("maxx"); params.maxy = p->getVal("maxy"); params.dx = p->getVal("dx"); params.dy = p->getVal("dy");
     params.cc_fluctuation_model = ival(p, "cc_fluctuation_model"); params.cc_fluctuation_gamma_theta = p->getVal("cc_fluctuation_Gamma_theta");
+    params.cc_fluctuation_k = p->getVal("cc_fluctuation_k");
     const double ptflag = p->getVal("PT_Flag");
     params.pt_order = ptflag < 0 ? ival(p, "PT_order") : 1;
     params.max_batch = (int)p->getVal("gpu_batch", 0);
