@@ -162,10 +162,13 @@ extern "C" void smc_destroy(smc_ctx* ctx) {
   if (ctx->d_kln) cudaFree(ctx->d_kln);
   if (ctx->d_rcbk) cudaFree(ctx->d_rcbk);
   if (ctx->d_avg) cudaFree(ctx->d_avg);
-  if (ctx->slots[0].ready || ctx->slots[1].ready) {     // return the active view to its slot, then release the other one
+  bool any_slot = false;
+  for (int q = 0; q < SMC_MAX_SLOTS; q++) any_slot |= ctx->slots[q].ready;
+  if (any_slot) {     // return the active view to its slot, then release the others
     slot_store(ctx, ctx->slots[ctx->cur_slot]);
-    smc_slot& o = ctx->slots[ctx->cur_slot ^ 1];
-    if (o.ready && o.stream) {
+    for (int q = 0; q < SMC_MAX_SLOTS; q++) {
+      smc_slot& o = ctx->slots[q];
+      if (q == ctx->cur_slot || !o.ready || !o.stream) continue;
       if (o.d_grids) cudaFree(o.d_grids);
       if (o.d_srcrec) cudaFree(o.d_srcrec);
       if (o.d_cmpart) cudaFree(o.d_cmpart);
@@ -173,7 +176,7 @@ extern "C" void smc_destroy(smc_ctx* ctx) {
       for (int i = 0; i < 8; i++) if (o.pev[i]) cudaEventDestroy(o.pev[i]);
       cudaStreamDestroy(o.stream);
     }
-    for (int q = 0; q < 2; q++) if (ctx->slots[q].ready && ctx->slots[q].done) cudaEventDestroy(ctx->slots[q].done);
+    for (int q = 0; q < SMC_MAX_SLOTS; q++) if (ctx->slots[q].ready && ctx->slots[q].done) cudaEventDestroy(ctx->slots[q].done);
   }
   if (ctx->h_hdr_i) cudaFreeHost(ctx->h_hdr_i);
   if (ctx->h_hdr_d) cudaFreeHost(ctx->h_hdr_d);
@@ -524,15 +527,17 @@ extern "C" int smc_run_events(smc_ctx* ctx, uint64_t first_event_id, int n, unsi
   if ((rc = smc_plan_kinds(ctx, flags, kinds, &nd))) return rc;
   const int nb = (n + ctx->batch - 1) / ctx->batch;
   if (nb >= 2 && ctx->p.cutdsdy != 1 && !ctx->profile && !getenv("SMC_NO_PIPELINE")) {
-    // two-slot software pipeline: batch i runs on stream (i & 1); its rows are read back when the slot comes
-    // round again, so K1/K2 of one batch overlap K3/K4 and the copies of the other
-    for (int sidx = 0; sidx < 2; sidx++) { if ((rc = smc_activate_slot(ctx, sidx))) return rc; if ((rc = smc_plan_kinds(ctx, flags, kinds, &nd))) return rc; }
+    // software pipeline over NS slots: batch i runs on the stream of slot i % NS; its rows are read back when the slot
+    // comes round again, so K1/K2 of one batch overlap K3/K4 and the copies of the others
+    static const int ns_env = getenv("SMC_SLOTS") ? atoi(getenv("SMC_SLOTS")) : 4;
+    const int NS = std::max(2, std::min(std::min(ns_env, SMC_MAX_SLOTS), nb));
+    for (int sidx = 0; sidx < NS; sidx++) { if ((rc = smc_activate_slot(ctx, sidx))) return rc; if ((rc = smc_plan_kinds(ctx, flags, kinds, &nd))) return rc; }
     CK(cudaEventRecord(ctx->ev0, ctx->slots[0].stream));
-    for (int i = 0; i < nb + 2; i++) {
-      if ((rc = smc_activate_slot(ctx, i & 1))) return rc;
-      if (i >= 2) {                                     // retire batch i-2 of this slot
-        CK(cudaEventSynchronize(ctx->slots[i & 1].done));
-        const int off = (i - 2) * ctx->batch, m = std::min(ctx->batch, n - off);
+    for (int i = 0; i < nb + NS; i++) {
+      if ((rc = smc_activate_slot(ctx, i % NS))) return rc;
+      if (i >= NS) {                                    // retire batch i-NS of this slot
+        CK(cudaEventSynchronize(ctx->slots[i % NS].done));
+        const int off = (i - NS) * ctx->batch, m = std::min(ctx->batch, n - off);
         smc_fill_out(ctx, m, out + off); ctx->last_n = m;
       }
       if (i < nb) {
@@ -542,13 +547,13 @@ extern "C" int smc_run_events(smc_ctx* ctx, uint64_t first_event_id, int n, unsi
         CK(cudaMemcpyAsync(ctx->h_hdr_i, ctx->st.hdr_i, (size_t)m * smc::HDR_I * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(ctx->h_hdr_d, ctx->st.hdr_d, (size_t)m * smc::HDR_D * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(ctx->h_mom, ctx->st.mom_out, (size_t)m * smc::MOM_OUT * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaEventRecord(ctx->slots[i & 1].done, ctx->stream));
+        CK(cudaEventRecord(ctx->slots[i % NS].done, ctx->stream));
       }
     }
-    if ((rc = smc_activate_slot(ctx, (nb - 1) & 1))) return rc;      // getters address the last batch
+    if ((rc = smc_activate_slot(ctx, (nb - 1) % NS))) return rc;      // getters address the last batch
     ctx->last_n = std::min(ctx->batch, n - (nb - 1) * ctx->batch);
-    // device time of the whole call: from the first operation of slot 0 to the end of both streams
-    CK(cudaStreamWaitEvent(ctx->stream, ctx->slots[(nb - 2) & 1].done, 0));
+    // device time of the whole call: from the first operation of slot 0 to the end of all streams
+    for (int q = 0; q < NS; q++) if (q != (nb - 1) % NS) CK(cudaStreamWaitEvent(ctx->stream, ctx->slots[q].done, 0));
     CK(cudaEventRecord(ctx->ev1, ctx->stream)); CK(cudaEventSynchronize(ctx->ev1));
     { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->last_ms = ms; }
     ctx->last_flags = flags;

@@ -30,6 +30,7 @@ struct smc_slot {
   int* h_hdr_i; double* h_hdr_d; double* h_mom; uint64_t* h_evid; int* h_try;
 };
 
+#define SMC_MAX_SLOTS 4
 struct smc_ctx {
   smc_params p; smc_constants k; smc::DevCfg cfg; smc::Store st;
   int device; cudaStream_t stream; cudaEvent_t ev0, ev1;
@@ -45,7 +46,7 @@ struct smc_ctx {
   std::string err; int64_t launches; double last_ms; int last_n; unsigned last_flags;
   // averaged profiles (operation 3)
   int profile; double stage_ms[8]; cudaEvent_t pev[8];
-  smc_slot slots[2]; int cur_slot;
+  smc_slot slots[SMC_MAX_SLOTS]; int cur_slot;
   double* d_avg; int64_t avg_doubles; int64_t avg_count; int avg_from, avg_to, avg_rp, avg_ed;
 };
 
