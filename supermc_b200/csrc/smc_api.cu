@@ -34,6 +34,7 @@ template <typename T> static int dalloc(smc_ctx* ctx, T** p, size_t n) {
   void* v = nullptr;
   cudaError_t e = cudaMalloc(&v, std::max<size_t>(n, 1) * sizeof(T));
   if (e != cudaSuccess) { ctx->err = std::string("cudaMalloc: ") + cudaGetErrorString(e); return SMC_ERR_NOMEM; }
+  cudaMemset(v, 0, std::max<size_t>(n, 1) * sizeof(T));      // record slots the kernels never write are copied to the host too
   ctx->owned.push_back(v); *p = (T*)v; return SMC_OK;
 }
 

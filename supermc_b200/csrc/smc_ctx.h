@@ -19,8 +19,8 @@ struct KlnCfg { double ecm, lambda, y, dT; int tmax; int pt_order; int npt, nkt,
 cudaError_t launch_kln_table(const KlnCfg&, double* table, cudaStream_t);
 }  // namespace smc
 
-// Per-batch device/host buffers of one pipeline slot.  Two slots let sample+collide of batch n+1 run on a
-// second stream while deposit/moments of batch n are still in flight (smc_run_events).
+// Per-batch device/host buffers of one pipeline slot.  Several slots let sample+collide of batch n+1 run on another
+// stream while deposit/moments of batch n are still in flight (smc_run_events rotates over up to SMC_MAX_SLOTS).
 struct smc_slot {
   bool ready;
   double* nuc; int* nuc_ncoll; int* nuc_first; double* coll; int* coll_ij; int* part_idx; int* spec_idx;

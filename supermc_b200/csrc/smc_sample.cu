@@ -418,6 +418,9 @@ __global__ void __launch_bounds__(64, 6) sample_collide_kernel(DevCfg c, Store s
       b = sqrt((c.bmax * c.bmax - c.bmin * c.bmin) * smc_uniform(s_b, 0, 0) + c.bmin * c.bmin);   // MakeDensity.cpp:2149
       sample_nucleus(c, st, sm, e, warp, ev, tr, warp == 0 ? b / 2.0 : -b / 2.0, 0.0);                 // MCnucl.cpp:208-214
     }
+    // both nuclei must be complete before the hit masks are cleared: while a warp samples, the candidates of its
+    // current batch live in that very region (bq in sample_nucleus) -- found by compute-sanitizer racecheck
+    __syncthreads();
     for (int k = tid; k < Amax; k += 64) { sm.ncB[k] = 0; sm.firstB[k] = 0x7fffffff; }
     for (int k = tid; k < Amax * HW; k += 64) sm.hit[k] = 0;
     __syncthreads();
