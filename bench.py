@@ -238,11 +238,14 @@ def main():
     t0 = time.perf_counter()
     dev_ms = 0.0
     f_dep = f_mom = f_smp = 0.0
+    kept = []
     for _ in range(a.steps):
         dev_ms += step()
-        fd, fm, fs = algorithmic_flops(out, ctx.k.width, WORKLOAD["dx"], kln); f_dep += fd; f_mom += fm; f_smp += fs
+        kept.append({k: out[k].copy() for k in ("npart1", "npart2", "ncoll", "nonzero_cells", "tries")})   # roofline bookkeeping, evaluated after the timed region
     barrier()
     wall = time.perf_counter() - t0
+    for cols in kept:
+        fd, fm, fs = algorithmic_flops(cols, ctx.k.width, WORKLOAD["dx"], kln); f_dep += fd; f_mom += fm; f_smp += fs
     launches = ctx.launches - l0
     ck = clocks.stop()
     # per-kernel durations: the same steps once more with CUDA events around every launch; this pass runs the
