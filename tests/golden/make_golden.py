@@ -45,6 +45,8 @@ SYSTEMS = {
                                      cc_fluctuation_Gamma_theta=0.61, randomSeed=18)),
     "uu193_deformed": ("zero", 3, 0, dict(which_mc_model=5, sub_model=1, Aproj=238, Atarg=238, ecm=193, alpha=0.14,
                                           proj_deformed=1, targ_deformed=1, randomSeed=19)),
+    "cuau200_glb": ("rand", 4, 0, dict(which_mc_model=5, sub_model=1, Aproj=63, Atarg=197, ecm=200, alpha=0.14,
+                                       cc_fluctuation_Gamma_theta=0.61, randomSeed=23)),
     "pbpb5020_lambda_width": ("zero", 3, 0, dict(which_mc_model=5, sub_model=1, Aproj=208, Atarg=208, ecm=5020, alpha=0.118,
                                                  shape_of_nucleons=3, gaussian_lambda=4.14, cc_fluctuation_Gamma_theta=0.75, randomSeed=22)),
     "auau200_kln": ("zero", 4, 1, dict(which_mc_model=1, sub_model=7, Aproj=197, Atarg=197, ecm=200, tmax=14, tmax_subdivision=3,

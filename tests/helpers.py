@@ -7,7 +7,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 KLN_SYSTEM = "auau200_kln"
 SYSTEMS = ["pbpb2760_glb", "auau200_glb_quarks", "ppb5020_glb_quarks", "pbpb2760_sqrt_disk", "pbpb2760_uli",
-           "auau200_disk_nucleons", "he3au200_glb", "cc200_glb", "uu193_deformed", "pbpb5020_lambda_width", "pbpb2760_rotate"]
+           "auau200_disk_nucleons", "he3au200_glb", "cc200_glb", "uu193_deformed", "pbpb5020_lambda_width", "cuau200_glb", "pbpb2760_rotate"]
 
 
 class Golden:
