@@ -24,13 +24,12 @@ elif which == "sqrt":
     p = dict(bench.WORKLOAD, which_mc_model=7)
     ctx = smc.Context(smc.capi.default_params(max_batch=48, randomseed=3, **p))
     ev = ctx.run_events(0, 150); print("sqrt", ev["dsdy"][:6], np.isfinite(ev["mom"]).all())
-elif which == "pos":          # the from-positions entry (oracle-supplied uniforms and weights), the getters, the device sort
+elif which == "pos":          # the from-positions entry (golden positions and weights), the getters, the device sort
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
     from helpers import Golden, event_in_from
-    from oracle import port
-    g = Golden("pbpb2760_glb"); cfg = g.oracle_cfg(port)
+    g = Golden("pbpb2760_glb")
     ctx = smc.Context(g.smc_params(smc.capi, max_batch=16))
-    evs = [event_in_from(t, port, cfg) for t in g.tries()]
+    evs = [event_in_from(t) for t in g.tries()]          # golden positions and weights; the pair uniforms come from Philox
     out = ctx.run_from_positions(evs, smc.RUN_MOMENTS | smc.RUN_THICKNESS | smc.RUN_RHO_BINARY | smc.RUN_SPECTATORS)
     print("pos", out["ncoll"][:6], ctx.collisions(3).shape, ctx.participants(3).shape, ctx.spectators(3).shape)
     ev = ctx.run_events(0, 300); print(ctx.centrality_sort(ev["total"])[:5])
