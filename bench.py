@@ -163,8 +163,9 @@ def main():
     ap.add_argument("--batch", type=int, default=2048, help="events resident per launch wave")
     ap.add_argument("--cpu-sample-events", type=int, default=150)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="glauber", choices=["glauber", "kln"],
-                    help="glauber = BASELINE.json configs[1] (the headline line); kln = the same scan with the MC-KLN density")
+    ap.add_argument("--workload", default="glauber", choices=["glauber", "kln", "ebe"],
+                    help="glauber = BASELINE.json configs[1] (the headline line); kln = the same scan with the MC-KLN density; "
+                         "ebe = BASELINE.json configs[0] through the drop-in executable, text output included (secondary line)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
 
@@ -195,6 +196,10 @@ def main():
         print(json.dumps(line))
         return 0
 
+    if a.workload == "ebe":
+        if rank == 0:
+            print(json.dumps(ebe_line(a)))
+        return 0
     # rank 0 prints ONE JSON line on stdout: libraries that write there (NCCL prints its version banner on stdout when
     # NCCL_DEBUG is set) are sent to stderr for the duration of the run
     json_out = os.fdopen(os.dup(1), "w")
@@ -325,6 +330,58 @@ def main():
     if dist is not None:
         dist.destroy_process_group()
     return 0
+
+
+EBE_ARGS = ["which_mc_model=5", "sub_model=1", "Aproj=197", "Atarg=197", "ecm=200", "alpha=0.14", "cc_fluctuation_model=6",
+            "cc_fluctuation_Gamma_theta=0.61", "maxx=13", "maxy=13", "dx=0.1", "dy=0.1", "finalFactor=1", "operation=1", "use_sd=1",
+            "use_ed=0", "use_block=1", "use_4col=0", "randomSeed=9"]
+
+
+def ebe_line(a):
+    """BASELINE.json configs[0]: MC-Glauber Au+Au 200 GeV, event-by-event entropy density (one 261^2 text block per event)
+    + eccentricities, through supermc_b200/superMC_b200.e -- wall clock of the whole process, start-up, CUDA
+    initialisation and text formatting included; next to it the unmodified reference binary (start-up run subtracted)."""
+    exe = os.path.join(ROOT, "supermc_b200", "superMC_b200.e")
+    nev = 1000
+
+    def ours(n):
+        d = tempfile.mkdtemp(prefix="smcebe_"); os.makedirs(os.path.join(d, "data"))
+        subprocess.check_call(["cp", os.path.join(ROOT, "supermc_b200", "parameters.dat"), d])
+        t0 = time.perf_counter()
+        so = subprocess.run([exe] + EBE_ARGS + ["nev=%d" % n], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, check=True).stdout
+        dt = time.perf_counter() - t0
+        loop = [float(l.split(":")[1]) for l in so.splitlines() if l.startswith("Time elapsed (in seconds)")]      # main.cpp:65-68
+        nfiles = len([f for f in os.listdir(os.path.join(d, "data")) if f.startswith("sd_event_")])
+        subprocess.call(["rm", "-rf", d])
+        return dt, nfiles, (loop[0] if loop else None)
+    for _ in range(max(a.warmup, 1)):
+        t_start, _, _ = ours(8)
+    tot, files, loops = 0.0, 0, []
+    for _ in range(a.steps):
+        dt, nf, lp = ours(nev); tot += dt; files += nf; loops.append(lp)
+    v = nev * a.steps / tot
+    line = {"metric": "events/sec", "value": v, "unit": "events/s", "n_gpus": 1, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * tot / a.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "MC-Glauber Au+Au 200 GeV event-by-event profiles (operation 1), 261x261 grid, one text block file per event, "
+                                   "whole-process wall clock incl. start-up (an 8-event run of the same binary takes %.2f s)" % t_start,
+                       "events_per_step": nev, "files_written": files, "event_loop_s_reported_by_the_program": loops},
+            "e2e": {"value": v, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8 * 261 * 261 * nev},
+            "roofline": None}
+    rexe, run = ref_paths()
+    if not a.no_cpu_baseline and os.path.exists(rexe):
+        def ref(n):
+            d = tempfile.mkdtemp(prefix="smcref_"); os.makedirs(os.path.join(d, "data"))
+            for f in ("parameters.dat", "EOS", "tables"):
+                os.symlink(os.path.join(run, f), os.path.join(d, f))
+            t0 = time.perf_counter()
+            subprocess.call([rexe] + EBE_ARGS + ["nev=%d" % n], cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            dt = time.perf_counter() - t0
+            subprocess.call(["rm", "-rf", d])
+            return dt
+        t1 = ref(1); t = ref(41)
+        line["cpu_baseline"] = dict(value=40 / max(t - t1, 1e-3), unit="events/s", cores=1, kind="reference",
+                                    sample="41 events of the same workload, oracle/_ref/superMC_ref.e, 1-event start-up run subtracted")
+    return line
 
 
 def port_baseline(nev, kln_table=None, kln_dt=None):

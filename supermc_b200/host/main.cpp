@@ -8,6 +8,8 @@
 #include "MakeDensity.h"
 
 int main(int argc, char* argv[]) {
+  const auto t_start = std::chrono::steady_clock::now();
+  const bool timing = std::getenv("SMC_TIMING") != nullptr;      // phase times on stderr (start-up is CUDA initialisation + memory pools)
   ParameterReader paraRdr;
   try {
     paraRdr.readFromFile("parameters.dat");
@@ -21,6 +23,7 @@ int main(int argc, char* argv[]) {
   if (sh.world > 1 && sh.rank > 0) dd = "data_rank" + std::to_string(sh.rank);
   MakeDensity dens(&paraRdr, device, sh, dd);
   if (!dens.ok()) { std::cerr << "superMC_b200: " << dens.error() << std::endl; return 255; }
+  if (timing) std::cerr << "# start-up (parameters, CUDA context, tables): " << std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() << " s" << std::endl;
   int nevent = 0, operation = 0;
   try { nevent = (int)paraRdr.getVal("nev"); operation = (int)paraRdr.getVal("operation"); }
   catch (std::exception& e) { std::cout << e.what() << std::endl; return 255; }
@@ -29,5 +32,6 @@ int main(int argc, char* argv[]) {
   const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   if (rc) std::cerr << "superMC_b200: " << dens.error() << std::endl;
   std::cout << "Time elapsed (in seconds): " << dt << std::endl;
+  if (timing) std::cerr << "# event loop: " << dt << " s; since process start: " << std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() << " s (context teardown follows)" << std::endl;
   return rc;
 }
