@@ -58,6 +58,9 @@ extern "C" int smc_create(const smc_params* p, int device, smc_ctx** out) {
   std::memset(ctx->slots, 0, sizeof ctx->slots);
   for (int i = 0; i < 8; i++) { ctx->stage_ms[i] = 0; ctx->pev[i] = nullptr; }
   *out = ctx;      // returned even on failure so the caller can read smc_last_error
+  const bool timing = getenv("SMC_TIMING") != nullptr;
+  const auto tc0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) { if (timing) std::fprintf(stderr, "#   smc_create %-28s %.3f s\n", what, std::chrono::duration<double>(std::chrono::steady_clock::now() - tc0).count()); };
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device >= ndev) FAIL(SMC_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
   CK(cudaSetDevice(device));
@@ -65,6 +68,7 @@ extern "C" int smc_create(const smc_params* p, int device, smc_ctx** out) {
   if (prop.major < 9) FAIL(SMC_ERR_CUDA, "device is not sm_100-class");
   CK(cudaStreamCreate(&ctx->stream)); CK(cudaEventCreate(&ctx->ev0)); CK(cudaEventCreate(&ctx->ev1));
   for (int i = 0; i < 8; i++) CK(cudaEventCreate(&ctx->pev[i]));
+  lap("CUDA context, stream, events");
 
   // ---- parameter checks (the reference prints and exits) ----
   if (p->which_mc_model != 1 && p->which_mc_model != 5 && p->which_mc_model != 7) FAIL(SMC_ERR_PARAM, "which_mc_model must be 1, 5 or 7");
@@ -138,6 +142,7 @@ extern "C" int smc_create(const smc_params* p, int device, smc_ctx** out) {
   if ((rc = dalloc(ctx, &st.try_start, (size_t)B))) return rc;
   if ((rc = dalloc(ctx, &ctx->d_redo, (size_t)B))) return rc;
   if ((rc = dalloc(ctx, &st.cm, (size_t)B * 4))) return rc;
+  lap("device record buffers");
   CK(cudaMallocHost(&ctx->h_hdr_i, (size_t)B * smc::HDR_I * sizeof(int)));
   CK(cudaMallocHost(&ctx->h_hdr_d, (size_t)B * smc::HDR_D * sizeof(double)));
   CK(cudaMallocHost(&ctx->h_mom, (size_t)B * smc::MOM_OUT * sizeof(double)));
@@ -145,6 +150,7 @@ extern "C" int smc_create(const smc_params* p, int device, smc_ctx** out) {
   CK(cudaMallocHost(&ctx->h_try, (size_t)B * sizeof(int)));
   CK(cudaMallocHost(&ctx->h_nuc, (size_t)B * 2 * c.Amax * smc::NROW * sizeof(double)));
   for (int i = 0; i < 8; i++) st.kind_slot[i] = -1;
+  lap("pinned host buffers");
   return SMC_OK;
 }
 
