@@ -112,3 +112,27 @@ def test_rcbk_tables_read_from_javier_directory(tmp_path):
     assert tab.shape == ((n - 1) * (n - 1), 4)
     assert np.allclose(tab[:, 3].reshape(n - 1, n - 1), T[1:, 1:], rtol=0, atol=1e-11)      # %22.12f
     assert np.loadtxt(d / "data" / "sn_ecc_eccp_10.dat").shape == (20, 49)
+
+
+def test_centrality_tools_end_to_end(tmp_path):
+    """minimum-bias run -> centrality table (sorted on the GPU) -> per-centrality averaged profiles through the wrapper
+    (scripts/centrality_cut_h5.py + generateAvgprofile.py, natively: python -m supermc_b200.centrality)"""
+    import sys
+    from supermc_b200 import centrality as cen
+    d = _rundir(tmp_path)
+    subprocess.check_call([EXE] + ARGS + ["operation=9", "nev=4000"], cwd=d, stdout=subprocess.DEVNULL)     # >= 3000: the 0.1 % bins must not be empty
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    subprocess.check_call([sys.executable, "-m", "supermc_b200.centrality", "table", "data"], cwd=d, env=env, stdout=subprocess.DEVNULL)
+    tab = np.loadtxt(d / "data" / "iebe_centralityCut_total_entropy_data.dat")
+    assert tab.shape == (110, 6) and np.all(np.diff(tab[1:, 1]) <= 0) and tab[-1, 0] == 100.0
+    rows = np.loadtxt(d / "data" / "sn_ecc_eccp_10.dat")
+    assert abs(tab[19, 1] - np.sort(rows[:, 47])[::-1][int(4000 * 0.10) - 2]) < 1e-3 * tab[19, 1]      # the 10 % row: smallest dS/dy of the 9-10 % bin
+    os.makedirs(d / "tabs")
+    shutil.copy(d / "data" / "iebe_centralityCut_total_entropy_data.dat", d / "tabs" / cen.table_file_name("total_entropy", 5, 208, 208, 2760.0, 6))
+    for f in os.listdir(d / "data"):
+        os.remove(d / "data" / f)
+    subprocess.check_call([sys.executable, "-m", "supermc_b200.centrality", "run", "--model", "MCGlb", "--ecm", "2760", "--collsys", "Pb", "Pb",
+                           "--cen", "0-10", "--tables", "tabs", "--nev", "12", "maxx=13", "maxy=13", "average_from_order=2", "average_to_order=2"],
+                          cwd=d, env=env, stdout=subprocess.DEVNULL)
+    g = np.loadtxt(d / "data" / "sdAvg_order_2_block.dat")
+    assert g.shape == (261, 261) and g.sum() * 0.01 > tab[19, 1] * 0.9          # every averaged event passed the 0-10 % dS/dy cut
