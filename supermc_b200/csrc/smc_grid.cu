@@ -625,6 +625,8 @@ __device__ double nbd_pmf(double p, double r, double k_in) {
   const int k = (int)floor(k_in);
   return exp(lgamma(k + r) - lgamma(k + 1.0) - lgamma(r)) * pow(1 - p, r) * pow(p, (double)k);
 }
+// pmf(k+1) = pmf(k) p (k + r) / (k + 1): one multiply chain serves all thirteen envelope edges and both passes over the
+// support, so a cell costs one pow (or three lgamma when the support starts far from 0) instead of ~20 pmf evaluations
 __device__ long nbd_quantile(double p, double r, double u) {
   const double ZERO = 1e-15;
   if (p < ZERO || p + ZERO > 1.0) return 0;
@@ -635,26 +637,33 @@ __device__ long nbd_quantile(double p, double r, double u) {
   double edge[13], hgt[12];
   double LB = mode - sl * sd, RB = LB + sd;
   if (sl == 0 && LB + 6.5 * sd <= 1.0) return 0;          // the whole envelope lies inside the cell k = 0 (with slack for the summed edge)
-  double pl = nbd_pmf(p, r, LB), pr = nbd_pmf(p, r, RB);
   edge[0] = LB;
-  for (int m = 0; m < M; m++) {
-    hgt[m] = pl > pr ? pl : pr; edge[m + 1] = RB;
-    LB = RB; RB += sd;
-    pl = pr; pr = nbd_pmf(p, r, RB);
-  }
+  for (int m = 0; m < M; m++) { edge[m + 1] = RB; RB += sd; }
   if (edge[M] <= 1.0) return 0;
   const long ka = (long)floor(edge[0]), kb = (long)floor(edge[M]);
+  double pka;                                              // pmf(ka)
+  if (ka <= 64) { pka = pow(1 - p, r); for (long k = 0; k < ka; k++) pka *= p * ((double)k + r) / (double)(k + 1); }
+  else pka = nbd_pmf(p, r, (double)ka);
+  {                                                        // heights: the larger pmf of the two ends of every interval
+    long kc = ka; double pc = pka, pl = pka;
+    for (int m = 0; m < M; m++) {
+      const long km = (long)floor(edge[m + 1]);
+      while (kc < km) { pc *= p * ((double)kc + r) / (double)(kc + 1); kc++; }
+      hgt[m] = pl > pc ? pl : pc; pl = pc;
+    }
+  }
   double tot = 0;
   for (int pass = 0; pass < 2; pass++) {
-    double acc = 0; const double target = u * tot;
+    double acc = 0, pk = pka; const double target = u * tot;
     for (long k = ka; k <= kb; k++) {
-      const double pk = nbd_pmf(p, r, (double)k); double w = 0;
+      double w = 0;
       for (int m = 0; m < M; m++) {
         const double lo = fmax(edge[m], (double)k), hi = fmin(edge[m + 1], (double)(k + 1));
         if (hi > lo) w += (hi - lo) * fmin(hgt[m], pk);
       }
       acc += w;
       if (pass == 1 && acc > target) return k;
+      pk *= p * ((double)k + r) / (double)(k + 1);
     }
     tot = acc;
   }
