@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define SMC_ABI_VERSION 2
+#define SMC_ABI_VERSION 3
 
 enum {
   SMC_OK = 0,
@@ -57,6 +57,7 @@ typedef struct smc_params {
   int pt_order;                  /* KLN pT weight, 1 unless PT_flag<0          MCnucl.cpp:52-55 */
   double gaussian_lambda;        /* shape_of_nucleons == 3                     GaussianNucleonsCal.cpp:29,39-44 */
   double cc_fluctuation_k;       /* NBD k of cc_fluctuation_model == 1         MCnucl.cpp:68,872-880 */
+  int ny; double ymax;           /* rapidity slices: rapMin = -ymax, rapMax = ymax  MakeDensity.cpp:54-58, MCnucl.cpp:33-38 */
   /* capacities of the device-side event records (not reference parameters) */
   int max_batch;                 /* events resident per launch wave; 0 = default */
   int ncoll_cap;                 /* collision-list capacity per event; 0 = default */
@@ -132,6 +133,9 @@ void smc_destroy(smc_ctx* ctx);
 /* replaces `cerr << ...; exit()` */
 const char* smc_last_error(const smc_ctx* ctx);
 int  smc_get_constants(const smc_ctx* ctx, smc_constants* c);
+/* events resident per device batch: the grid / list getters address the last batch of a run, so a caller that wants
+ * them asks for at most this many events per smc_run_events call */
+int  smc_max_batch(const smc_ctx* ctx);
 
 /* Nucleus::Nucleus reading tables/QuarkPos.txt into Particle::quark_pos (src/Nucleus.cpp:37-48):
  * n rows of (r1, r2, cos theta12).  Not loaded => r1 = r2 = 0 (every AABB is the +-4w base box). */

@@ -25,7 +25,8 @@ class Params(C.Structure):
                 ("ecc_from_order", C.c_int), ("ecc_to_order", C.c_int),
                 ("maxx", C.c_double), ("maxy", C.c_double), ("dx", C.c_double), ("dy", C.c_double),
                 ("cc_fluctuation_model", C.c_int), ("cc_fluctuation_gamma_theta", C.c_double),
-                ("pt_order", C.c_int), ("gaussian_lambda", C.c_double), ("cc_fluctuation_k", C.c_double), ("max_batch", C.c_int), ("ncoll_cap", C.c_int)]
+                ("pt_order", C.c_int), ("gaussian_lambda", C.c_double), ("cc_fluctuation_k", C.c_double),
+                ("ny", C.c_int), ("ymax", C.c_double), ("max_batch", C.c_int), ("ncoll_cap", C.c_int)]
 
 
 class Constants(C.Structure):

@@ -27,7 +27,7 @@ extern "C" void smc_params_default(smc_params* p) {   // reference parameters.da
   p->npmin = 2; p->npmax = 500; p->cutdsdy = 0; p->cutdsdy_lowerbound = 593.51; p->cutdsdy_upperbound = 889.53;
   p->randomseed = 1; p->finalfactor = 40.0; p->ecc_from_order = 1; p->ecc_to_order = 9;
   p->maxx = 15.; p->maxy = 15.; p->dx = 0.1; p->dy = 0.1; p->cc_fluctuation_model = 6; p->cc_fluctuation_gamma_theta = 0.75;
-  p->pt_order = 1; p->gaussian_lambda = 4.14; p->cc_fluctuation_k = 0.75; p->max_batch = 0; p->ncoll_cap = 0;
+  p->pt_order = 1; p->gaussian_lambda = 4.14; p->cc_fluctuation_k = 0.75; p->ny = 1; p->ymax = 0.0; p->max_batch = 0; p->ncoll_cap = 0;
 }
 
 template <typename T> static int dalloc(smc_ctx* ctx, T** p, size_t n) {
@@ -65,7 +65,7 @@ extern "C" int smc_create(const smc_params* p, int device, smc_ctx** out) {
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device >= ndev) FAIL(SMC_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
   CK(cudaSetDevice(device));
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
-  if (prop.major < 9) FAIL(SMC_ERR_CUDA, "device is not sm_100-class");
+  if (prop.major != 10) FAIL(SMC_ERR_CUDA, "device is not sm_100-class (this library holds sm_100a code only)");
   CK(cudaStreamCreate(&ctx->stream)); CK(cudaEventCreate(&ctx->ev0)); CK(cudaEventCreate(&ctx->ev1));
   for (int i = 0; i < 8; i++) CK(cudaEventCreate(&ctx->pev[i]));
   lap("CUDA context, stream, events");
@@ -74,6 +74,9 @@ extern "C" int smc_create(const smc_params* p, int device, smc_ctx** out) {
   if (p->which_mc_model != 1 && p->which_mc_model != 5 && p->which_mc_model != 7) FAIL(SMC_ERR_PARAM, "which_mc_model must be 1, 5 or 7");
   if (p->which_mc_model == 5 && p->sub_model != 1 && p->sub_model != 2) FAIL(SMC_ERR_PARAM, "MC-Glauber sub_model must be 1 or 2 (MCnucl.cpp:718-721)");
   if (p->which_mc_model == 1 && p->sub_model != 7 && p->sub_model != 100 && p->sub_model != 101) FAIL(SMC_ERR_PARAM, "MC-KLN sub_model must be 7 (KLN uGD), 100 or 101 (rcBK tables, src/ParamDefs.h)");
+  if (p->collision_criterion == 3 || p->collision_criterion == 4)
+    FAIL(SMC_ERR_PARAM, "collision_criterion 3 (quark overlap, GaussianNucleonsCal.cpp:70-97) and 4 (numeric overlap) are not built; the reference uses different hit tests for them (MCnucl.cpp:371-376)");
+  if (p->ny != 1) FAIL(SMC_ERR_PARAM, "ny != 1 (several rapidity slices) is not built");
   if (p->shape_of_nucleons < 1 || p->shape_of_nucleons > 4) FAIL(SMC_ERR_PARAM, "shape_of_nucleons must be 1, 2, 3 or 4");
   if (p->shape_of_nucleons == 3 && !(p->gaussian_lambda > 0)) FAIL(SMC_ERR_PARAM, "shape_of_nucleons 3 needs gaussian_lambda > 0");
   if (p->shape_of_entropy != 1 && p->shape_of_entropy != 2) FAIL(SMC_ERR_PARAM, "shape_of_entropy must be 1 or 2 (3 = quark substructure is out of scope)");
@@ -199,6 +202,7 @@ extern "C" void smc_destroy(smc_ctx* ctx) {
 }
 
 extern "C" const char* smc_last_error(const smc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" int smc_max_batch(const smc_ctx* ctx) { return ctx ? ctx->batch : 0; }
 extern "C" int smc_get_constants(const smc_ctx* ctx, smc_constants* c) { if (!ctx || !c) return SMC_ERR_PARAM; *c = ctx->k; return SMC_OK; }
 extern "C" int smc_set_profiling(smc_ctx* ctx, int on) { if (!ctx) return SMC_ERR_PARAM; ctx->profile = on; for (int i = 0; i < 8; i++) ctx->stage_ms[i] = 0; return SMC_OK; }
 extern "C" int smc_get_stage_ms(const smc_ctx* ctx, double* ms4) { if (!ctx || !ms4) return SMC_ERR_PARAM; for (int i = 0; i < 4; i++) ms4[i] = ctx->stage_ms[i]; return SMC_OK; }
@@ -300,7 +304,7 @@ extern "C" int smc_build_kln_table(smc_ctx* ctx, double* host_out) {
   CK(cudaMemcpy(d, h.data(), nn * sizeof(double), cudaMemcpyHostToDevice));
   if (ctx->d_kln) { cudaFree(ctx->d_kln); ctx->d_kln = nullptr; }
   CK(cudaMalloc(&ctx->d_kln, (size_t)tmax * tmax * sizeof(double)));
-  smc::KlnCfg kc; kc.ecm = ctx->p.ecm; kc.lambda = ctx->p.lambda; kc.y = 0.0; kc.dT = ctx->k.kln_dt; kc.tmax = tmax; kc.pt_order = ctx->p.pt_order > 0 ? ctx->p.pt_order : 1;
+  smc::KlnCfg kc; kc.ecm = ctx->p.ecm; kc.lambda = ctx->p.lambda; kc.y = -ctx->p.ymax;      /* rapMin, MakeDensity.cpp:54-56, MCnucl.cpp:932 */ kc.dT = ctx->k.kln_dt; kc.tmax = tmax; kc.pt_order = ctx->p.pt_order > 0 ? ctx->p.pt_order : 1;
   kc.model = ctx->p.sub_model; kc.maxQ0 = ctx->rcbk_q; kc.maxY = ctx->rcbk_y; kc.maxKt = ctx->rcbk_k; kc.dQ0 = ctx->p.sub_model == 100 ? 0.1 : 0.168;
   kc.siginNN200 = ctx->k.siginnn200;
   { const size_t nn2 = (size_t)ctx->rcbk_q * ctx->rcbk_y * ctx->rcbk_k; kc.rkt = ctx->d_rcbk; kc.rna = ctx->d_rcbk ? ctx->d_rcbk + nn2 : nullptr; kc.ry2 = ctx->d_rcbk ? ctx->d_rcbk + 2 * nn2 : nullptr; }
@@ -530,6 +534,8 @@ extern "C" int smc_run_events(smc_ctx* ctx, uint64_t first_event_id, int n, unsi
   CK(cudaSetDevice(ctx->device));
   const smc::DevCfg& c = ctx->cfg;
   for (int s = 0; s < 2; s++) if ((c.sampler[s] == 2 || c.sampler[s] == 3) && !ctx->st.cfg_table[s]) FAIL(SMC_ERR_STATE, "this nucleus needs a configuration table: call smc_load_config_table (Nucleus.cpp:150-169)");
+  if ((flags & ~(unsigned)SMC_RUN_MOMENTS) && n > ctx->batch)
+    FAIL(SMC_ERR_PARAM, "grids and lists are kept for one device batch: with KEEP_RHO / THICKNESS / RHO_BINARY / SPECTATORS / LISTS call smc_run_events with n <= smc_max_batch()");
   int kinds[8], nd = 0, rc;
   if ((rc = smc_plan_kinds(ctx, flags, kinds, &nd))) return rc;
   const int nb = (n + ctx->batch - 1) / ctx->batch;
@@ -600,12 +606,10 @@ int smc_stage_positions(smc_ctx* ctx, int off, int m, const smc_event_in* in, bo
       if (!ev.pair_uniform) FAIL(SMC_ERR_PARAM, "pair_uniform must be given for all events of a call or for none");
       CK(cudaMemcpyAsync(ctx->d_pair_u + (size_t)e * A * B, ev.pair_uniform, (size_t)A * B * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     }
-    if (any_w && ev.coll_weight) {     // an event without the array (e.g. no collisions) keeps weight 1, additional_weight 0
-      const int nw = std::min(ev.n_coll_weight, c.ncoll_cap);
-      CK(cudaMemcpyAsync(ctx->d_coll_w + (size_t)e * c.ncoll_cap * 2, ev.coll_weight, (size_t)nw * 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    } else if (any_w) {
+    if (any_w) {     // rows the caller does not supply (none at all, or fewer than the event's Ncoll) keep weight 1, additional_weight 0
       hw_default.assign((size_t)c.ncoll_cap * 2, 0.0);
       for (int q = 0; q < c.ncoll_cap; q++) hw_default[2 * q] = 1.0;
+      if (ev.coll_weight) std::memcpy(hw_default.data(), ev.coll_weight, (size_t)std::max(0, std::min(ev.n_coll_weight, c.ncoll_cap)) * 2 * sizeof(double));
       CK(cudaMemcpy(ctx->d_coll_w + (size_t)e * c.ncoll_cap * 2, hw_default.data(), hw_default.size() * sizeof(double), cudaMemcpyHostToDevice));
     }
     if (ctx->st.nuc_extra) {           // operation-3 state (stale base boxes, quark offsets), else derived from the rows
@@ -677,7 +681,8 @@ extern "C" int smc_run_from_positions(smc_ctx* ctx, int n, const smc_event_in* i
 
 // ---- getters -------------------------------------------------------------------------------------
 extern "C" int smc_get_grid(smc_ctx* ctx, int slot, int which, double* host) {
-  if (!ctx || !host || slot < 0 || slot >= ctx->last_n || which < 0 || which >= SMC_GRID_KINDS) return SMC_ERR_PARAM;
+  if (!ctx) return SMC_ERR_PARAM;
+  if (!host || slot < 0 || slot >= ctx->last_n || which < 0 || which >= SMC_GRID_KINDS) FAIL(SMC_ERR_PARAM, "smc_get_grid: slot outside the last device batch, or bad grid kind");
   static const int map[SMC_GRID_KINDS] = {smc::GK_RHO, smc::GK_TA1, smc::GK_TA2, smc::GK_RHO_BINARY, smc::GK_SPEC_A, smc::GK_SPEC_B};
   const int ks = ctx->st.kind_slot[map[which]];
   if (ks < 0) FAIL(SMC_ERR_STATE, "that grid was not requested in the flags of the last run");
@@ -706,7 +711,8 @@ static int fetch_event_lists(smc_ctx* ctx, int slot, std::vector<double>& nuc, s
 }
 
 extern "C" int smc_get_nucleons(smc_ctx* ctx, int slot, int which, double* host8, int* n) {
-  if (!ctx || !n || slot < 0 || slot >= ctx->last_n || which < 0 || which > 1) return SMC_ERR_PARAM;
+  if (!ctx) return SMC_ERR_PARAM;
+  if (!n || slot < 0 || slot >= ctx->last_n || which < 0 || which > 1) FAIL(SMC_ERR_PARAM, "smc_get_nucleons: slot outside the last device batch");
   *n = ctx->cfg.A[which];
   if (!host8) return SMC_OK;
   std::vector<double> nuc; std::vector<int> nc, fi; int hi[smc::HDR_I]; int rc;
@@ -720,7 +726,8 @@ extern "C" int smc_get_nucleons(smc_ctx* ctx, int slot, int which, double* host8
 
 // participants in the reference's order: projectile ascending i, target by first hit (Nucleus::markWounded)
 extern "C" int smc_get_participants(smc_ctx* ctx, int slot, double* host8, int* n) {
-  if (!ctx || !n || slot < 0 || slot >= ctx->last_n) return SMC_ERR_PARAM;
+  if (!ctx) return SMC_ERR_PARAM;
+  if (!n || slot < 0 || slot >= ctx->last_n) FAIL(SMC_ERR_PARAM, "smc_get_participants: slot outside the last device batch");
   std::vector<double> nuc; std::vector<int> nc, fi; int hi[smc::HDR_I]; int rc;
   if ((rc = fetch_event_lists(ctx, slot, nuc, nc, fi, hi))) return rc;
   *n = hi[smc::H_NP1] + hi[smc::H_NP2];
@@ -739,7 +746,8 @@ extern "C" int smc_get_participants(smc_ctx* ctx, int slot, double* host8, int* 
 }
 
 extern "C" int smc_get_collisions(smc_ctx* ctx, int slot, double* host6, int* n) {
-  if (!ctx || !n || slot < 0 || slot >= ctx->last_n) return SMC_ERR_PARAM;
+  if (!ctx) return SMC_ERR_PARAM;
+  if (!n || slot < 0 || slot >= ctx->last_n) FAIL(SMC_ERR_PARAM, "smc_get_collisions: slot outside the last device batch");
   CK(cudaSetDevice(ctx->device));
   int hi[smc::HDR_I];
   CK(cudaMemcpy(hi, ctx->st.hdr_i + (size_t)slot * smc::HDR_I, sizeof hi, cudaMemcpyDeviceToHost));
@@ -758,7 +766,8 @@ extern "C" int smc_get_collisions(smc_ctx* ctx, int slot, double* host6, int* n)
 
 // spectators: projectile nucleons first (Y>0), then target (MCnucl.cpp:1223-1249)
 extern "C" int smc_get_spectators(smc_ctx* ctx, int slot, double* host3, int* n) {
-  if (!ctx || !n || slot < 0 || slot >= ctx->last_n) return SMC_ERR_PARAM;
+  if (!ctx) return SMC_ERR_PARAM;
+  if (!n || slot < 0 || slot >= ctx->last_n) FAIL(SMC_ERR_PARAM, "smc_get_spectators: slot outside the last device batch");
   std::vector<double> nuc; std::vector<int> nc, fi; int hi[smc::HDR_I]; int rc;
   if ((rc = fetch_event_lists(ctx, slot, nuc, nc, fi, hi))) return rc;
   *n = hi[smc::H_NSPEC1] + hi[smc::H_NSPEC2];

@@ -77,18 +77,20 @@ __device__ __forceinline__ void box_union(Box& b, const Box& o) {          // Bo
 }
 
 // Particle::Particle -> generateQuarkPositions -> calculateBounds (src/Particle.cpp:16-99)
+template <bool NOQUARKS>
 __device__ void particle_box(const DevCfg& c, const Store& st, const smc_stream& sq, uint32_t cand,
                              double x0, double y0, Box& out, double* extra) {
   Box base = {0, 0, 0, 0, 0, 0};
   box_center(base, x0, y0); box_square(base, 8 * c.w);
   out = base;
   if (extra) { extra[XBXL] = base.xL; extra[XBXR] = base.xR; extra[XBYL] = base.yL; extra[XBYR] = base.yR; for (int q = 0; q < 9; q++) extra[XQ + q] = 0.0; }
-  if (c.quark_rows <= 0) {           // no table: r1 = r2 = 0, the three quark boxes sit on the nucleon
+  if (NOQUARKS || c.quark_rows <= 0) {           // no table: r1 = r2 = 0, the three quark boxes sit on the nucleon
     Box b = {0, 0, 0, 0, 0, 0};
     box_center(b, 0.0, 0.0); box_square(b, 8 * c.quark_width); box_center(b, x0, y0);
     box_union(out, b); box_union(out, b); box_union(out, b);
     return;
   }
+  if (NOQUARKS) return;
   double u0, u1, u2, u3;
   smc_uniform2(sq, cand, 0, &u0, &u1); smc_uniform2(sq, cand, 1, &u2, &u3);
   int index = (int)(250000 * u0);
@@ -187,6 +189,11 @@ __device__ double hulthen_inv_cdf(double y) {
 }
 
 // One nucleus by warp `s` (side).  Leaves A sorted rows in sm.pos[s].
+// SPEC: 0 = every sampler; 1 = spherical Woods-Saxon on both sides; 2 = the same without a valence-quark table.  The
+// specialised kernels do not carry the deformed / configuration-table / deuteron / quark-offset code at all: the hot
+// instruction stream of the generic kernel (26 k SASS lines) did not fit the instruction cache (ncu: no_instruction
+// 0.66 stalls per issue).  MK = nucleons per lane of the rank sort.
+template <int SPEC, int MK>
 __device__ void sample_nucleus(const DevCfg& c, const Store& st, const SampleSmem& sm, int e, int s, uint64_t ev,
                                uint32_t tr, double xCenter, double yCenter) {
   const int lane = threadIdx.x & 31, A = c.A[s];
@@ -195,7 +202,8 @@ __device__ void sample_nucleus(const DevCfg& c, const Store& st, const SampleSme
   double uo0, uo1; smc_uniform2(s_or, 0, 0, &uo0, &uo1);
   double ctr = 1.0 - 2.0 * uo0, phir = 2 * SMC_PI * uo1;       // Nucleus.cpp:193-197
   bool recentre = true;
-  const int mode = c.sampler[s];
+  const int mode = SPEC ? 0 : c.sampler[s];
+  const bool deformed = SPEC ? false : (c.deformed[s] != 0);
   if (mode == 1) {                                              // single nucleon, Nucleus.cpp:201-202
     if (lane == 0) { S_(sm, s, NX, 0) = xCenter; S_(sm, s, NY, 0) = yCenter; S_(sm, s, NZ, 0) = 0.0; S_(sm, s, NW, 0) = 0.0; }
     recentre = false;
@@ -245,7 +253,7 @@ __device__ void sample_nucleus(const DevCfg& c, const Store& st, const SampleSme
       while (nq < 32) {
         const uint32_t n = ndraw + lane;
         double r, cx = 0.0; bool ok;
-        if (c.deformed[s]) {                                    // Nucleus.cpp:585-607
+        if (deformed) {                                    // Nucleus.cpp:585-607
           double u0, u1; smc_uniform2(s_ws, n, 0, &u0, &u1);
           const double u2 = smc_uniform(s_ws, n, 2);
           r = rmaxCut * cbrt(u0); cx = 1.0 - 2.0 * u1;
@@ -270,7 +278,7 @@ __device__ void sample_nucleus(const DevCfg& c, const Store& st, const SampleSme
         if (mv) { qr[lane] = t0; qc[lane] = t1; }
         nq -= 32; __syncwarp(); }
       double x, y, z;
-      if (c.deformed[s]) {
+      if (deformed) {
         const double cx = cxq, sx = sqrt(1.0 - cx * cx); double sp, cp;
         sincos(2 * SMC_PI * smc_uniform(s_an, cand, 1), &sp, &cp);
         x = r * sx * cp; y = r * sx * sp; z = r * cx;
@@ -347,7 +355,7 @@ __device__ void sample_nucleus(const DevCfg& c, const Store& st, const SampleSme
     double x0 = S_(sm, s, NX, k), y0 = S_(sm, s, NY, k), z0 = S_(sm, s, NZ, k);
     uint32_t cand = (uint32_t)S_(sm, s, NW, k);
     double* ex = st.nuc_extra_tmp ? st.nuc_extra_tmp + (((size_t)e * 2 + s) * c.Amax + k) * NEXTRA : nullptr;
-    Box bx; particle_box(c, st, s_q, cand, x0, y0, bx, ex);
+    Box bx; particle_box<SPEC == 2>(c, st, s_q, cand, x0, y0, bx, ex);
     if (recentre) {
       double x = x0 - mx / A + xCenter, y = y0 - my / A + yCenter, z = z0 - mz / A;
       box_center(bx, x, bx.yC); box_center(bx, bx.xC, y);       // Particle::setX / setY, src/Particle.cpp:176-185
@@ -359,8 +367,7 @@ __device__ void sample_nucleus(const DevCfg& c, const Store& st, const SampleSme
   }
   __syncwarp();
   if (A <= 32) sort_by_xl<1>(c, st, sm, e, s, A, lane);
-  else if (A <= 256) sort_by_xl<8>(c, st, sm, e, s, A, lane);
-  else sort_by_xl<SMC_MAXK>(c, st, sm, e, s, A, lane);
+  else sort_by_xl<MK>(c, st, sm, e, s, A, lane);
 }
 
 // Marsaglia-Tsang gamma(shape a, scale th); a<1 boosted by U^(1/a).  Law-equivalent to gsl_ran_gamma
@@ -388,7 +395,7 @@ __device__ double gamma_variate(const smc_stream& s, uint32_t cand, double a, do
   return a * th;
 }
 
-template <bool GIVEN>
+template <bool GIVEN, int SPEC, int MK>
 __global__ void __launch_bounds__(64, 6) sample_collide_kernel(DevCfg c, Store st, int nev) {
   extern __shared__ double smem_d[];
   const int e = blockIdx.x;
@@ -416,7 +423,7 @@ __global__ void __launch_bounds__(64, 6) sample_collide_kernel(DevCfg c, Store s
     } else {
       const smc_stream s_b = smc_make_stream(c.seed_lo, c.seed_hi, ev, tr, SMC_K_B, 0);
       b = sqrt((c.bmax * c.bmax - c.bmin * c.bmin) * smc_uniform(s_b, 0, 0) + c.bmin * c.bmin);   // MakeDensity.cpp:2149
-      sample_nucleus(c, st, sm, e, warp, ev, tr, warp == 0 ? b / 2.0 : -b / 2.0, 0.0);                 // MCnucl.cpp:208-214
+      sample_nucleus<SPEC, MK>(c, st, sm, e, warp, ev, tr, warp == 0 ? b / 2.0 : -b / 2.0, 0.0);                 // MCnucl.cpp:208-214
     }
     // both nuclei must be complete before the hit masks are cleared: while a warp samples, the candidates of its
     // current batch live in that very region (bq in sample_nucleus) -- found by compute-sanitizer racecheck
@@ -614,19 +621,24 @@ size_t sample_smem_bytes(int Amax) {
   return d * sizeof(double) + i * sizeof(int);
 }
 
+template <bool GIVEN, int SPEC, int MK>
+static cudaError_t launch_sc(const DevCfg& c, const Store& st, int nev, size_t smem, cudaStream_t s) {
+  cudaFuncSetAttribute(sample_collide_kernel<GIVEN, SPEC, MK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(sample_collide_kernel<GIVEN, SPEC, MK>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  sample_collide_kernel<GIVEN, SPEC, MK><<<nev, 64, smem, s>>>(c, st, nev);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_sample_collide(const DevCfg& c, const Store& st, int nev, bool given, cudaStream_t s) {
   static const size_t pad = getenv("SMC_SAMPLE_PAD") ? (size_t)atoi(getenv("SMC_SAMPLE_PAD")) : 0;     // tuning aid: occupancy sensitivity
+  static const bool generic = getenv("SMC_SAMPLE_GENERIC") != nullptr;                                   // A/B: the unspecialised kernel
   const size_t smem = sample_smem_bytes(c.Amax) + pad;
-  if (given) {
-    cudaFuncSetAttribute(sample_collide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(sample_collide_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    sample_collide_kernel<true><<<nev, 64, smem, s>>>(c, st, nev);
-  } else {
-    cudaFuncSetAttribute(sample_collide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(sample_collide_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    sample_collide_kernel<false><<<nev, 64, smem, s>>>(c, st, nev);
-  }
-  return cudaGetLastError();
+  const bool big = c.Amax > 256;
+  if (given) return big ? launch_sc<true, 0, SMC_MAXK>(c, st, nev, smem, s) : launch_sc<true, 0, 8>(c, st, nev, smem, s);
+  const bool ws = !generic && c.sampler[0] == 0 && c.sampler[1] == 0 && !c.deformed[0] && !c.deformed[1];
+  const int spec = ws ? (c.quark_rows > 0 ? 1 : 2) : 0;
+  if (big) return spec == 2 ? launch_sc<false, 2, SMC_MAXK>(c, st, nev, smem, s) : spec == 1 ? launch_sc<false, 1, SMC_MAXK>(c, st, nev, smem, s) : launch_sc<false, 0, SMC_MAXK>(c, st, nev, smem, s);
+  return spec == 2 ? launch_sc<false, 2, 8>(c, st, nev, smem, s) : spec == 1 ? launch_sc<false, 1, 8>(c, st, nev, smem, s) : launch_sc<false, 0, 8>(c, st, nev, smem, s);
 }
 
 }  // namespace smc

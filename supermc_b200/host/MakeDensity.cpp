@@ -110,6 +110,7 @@ MakeDensity::MakeDensity(ParameterReader* p, int device, smc_shard sh, const std
     params.max_batch = (int)p->getVal("gpu_batch", 0);
     binRapidity = ival(p, "ny");
     rapMin = -p->getVal("ymax"); rapMax = -rapMin;                       // MakeDensity.cpp:54-58
+    params.ny = binRapidity; params.ymax = p->getVal("ymax");
     p->setVal("rapMin", rapMin); p->setVal("rapMax", rapMax);
     finalFactor = params.finalfactor;
     deformed = (params.proj_deformed == 1 || params.targ_deformed == 1);
@@ -285,6 +286,8 @@ static int ebe_common(MakeDensity* self, smc_ctx* ctx, ParameterReader* paraRdr,
     return g;
   };
   const double ff = self->params.finalfactor;
+  batch = std::max(1, std::min(batch, smc_max_batch(ctx)));               // the getters address one device batch
+  auto ck = [&](int rc) { if (rc != SMC_OK && err.empty()) err = smc_last_error(ctx); return rc != SMC_OK; };
   for (int done = 0; done < count; done += batch) {
     const int n = std::min(batch, count - done);
     if (smc_run_events(ctx, first + done, n, flags, out.data()) != SMC_OK) { err = smc_last_error(ctx); return 1; }
@@ -293,21 +296,21 @@ static int ebe_common(MakeDensity* self, smc_ctx* ctx, ParameterReader* paraRdr,
       if (out[e].status != SMC_OK) { std::cerr << "event " << event << ": status " << out[e].status << std::endl; continue; }
       const double npart = out[e].npart1 + out[e].npart2;
       int np = 0, nc = 0, ns = 0;
-      smc_get_participants(ctx, e, nullptr, &np); smc_get_collisions(ctx, e, nullptr, &nc);
+      if (ck(smc_get_participants(ctx, e, nullptr, &np)) || ck(smc_get_collisions(ctx, e, nullptr, &nc))) return 1;
       std::vector<double> part((size_t)std::max(np, 1) * 8), coll((size_t)std::max(nc, 1) * 6);
-      smc_get_participants(ctx, e, part.data(), &np); smc_get_collisions(ctx, e, coll.data(), &nc);
+      if (ck(smc_get_participants(ctx, e, part.data(), &np)) || ck(smc_get_collisions(ctx, e, coll.data(), &nc))) return 1;
       if (jet) {
         write_file(P("ParticipantTable_event_%ld.dat", event), smc_fmt_participants(part.data(), np), true);
-        smc_get_spectators(ctx, e, nullptr, &ns);
-        std::vector<double> spec((size_t)std::max(ns, 1) * 3); smc_get_spectators(ctx, e, spec.data(), &ns);
+        if (ck(smc_get_spectators(ctx, e, nullptr, &ns))) return 1;
+        std::vector<double> spec((size_t)std::max(ns, 1) * 3); if (ck(smc_get_spectators(ctx, e, spec.data(), &ns))) return 1;
         write_file(P("Spectators_event_%ld.dat", event), smc_fmt_spectators(spec.data(), ns), false);
         write_file(P("BinaryCollisionTable_event_%ld.dat", event), smc_fmt_xy(coll.data(), nc, 6), true);
       } else write_file(data_dir + "/binary.dat", smc_fmt_xy(coll.data(), nc, 6), true);
       // dumpBinaryTable side files (MCnucl.cpp:1193-1209); quarks.data needs shape_of_entropy=3 state and is not written
       write_file(data_dir + "/wounded.data", smc_fmt_participants(part.data(), np), false);
       for (int s = 0; s < 2; s++) {
-        int na = 0; smc_get_nucleons(ctx, e, s, nullptr, &na);
-        std::vector<double> nu((size_t)std::max(na, 1) * 8); smc_get_nucleons(ctx, e, s, nu.data(), &na);
+        int na = 0; if (ck(smc_get_nucleons(ctx, e, s, nullptr, &na))) return 1;
+        std::vector<double> nu((size_t)std::max(na, 1) * 8); if (ck(smc_get_nucleons(ctx, e, s, nu.data(), &na))) return 1;
         write_file(data_dir + (s == 0 ? "/nucl1.data" : "/nucl2.data"), smc_fmt_xy(nu.data(), na, 8), false);
       }
       if (jet) for (int f = 0; f < 2; f++) {                              // per-event eccentricity files (:327-345)

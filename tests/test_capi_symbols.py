@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 25
     for n in names:
         assert hasattr(L, n), "missing export: " + n
-    assert L.smc_abi_version() == 2
+    assert L.smc_abi_version() == 3
 
 
 def test_struct_layouts_match_header():
