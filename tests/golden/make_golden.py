@@ -55,7 +55,7 @@ SYSTEMS = {
                                        cc_fluctuation_Gamma_theta=0.61, randomSeed=23)),
     "pbpb5020_lambda_width": ("zero", NEV, 0, dict(which_mc_model=5, sub_model=1, Aproj=208, Atarg=208, ecm=5020, alpha=0.118,
                                                  shape_of_nucleons=3, gaussian_lambda=4.14, cc_fluctuation_Gamma_theta=0.75, randomSeed=22)),
-    "auau200_kln": ("zero", 16, 1, dict(which_mc_model=1, sub_model=7, Aproj=197, Atarg=197, ecm=200, tmax=14, tmax_subdivision=3,
+    "auau200_kln": ("zero", 16, 1, dict(which_mc_model=1, sub_model=7, Aproj=197, Atarg=197, ecm=200, tmax=24, tmax_subdivision=3,
                                        cc_fluctuation_model=0, randomSeed=21, bmin=8)),
     # MC-KLN Pb+Pb 2.76 TeV, lambda = 0.138 (scripts/generateAvgprofile.py:211-222): the reference's full 211^2 BASES table
     # (MCnucl.cpp:911-960) + minimum-bias events; the second run holds central events (its table must be the same bits)

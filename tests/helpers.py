@@ -7,7 +7,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 KLN_SYSTEM = "auau200_kln"
 SYSTEMS = ["pbpb2760_glb", "auau200_glb_quarks", "ppb5020_glb_quarks", "pbpb2760_sqrt_disk", "pbpb2760_uli",
-           "auau200_disk_nucleons", "he3au200_glb", "cc200_glb", "uu193_deformed", "pbpb5020_lambda_width", "cuau200_glb", "pbpb2760_rotate"]
+           "auau200_disk_nucleons", "he3au200_glb", "cc200_glb", "uu193_deformed", "pbpb5020_lambda_width", "cuau200_glb", "oo200_glb", "auau200_nncorr", "pbpb2760_rotate"]
 
 
 class Golden:
@@ -44,7 +44,8 @@ class Golden:
                   ecm=p["ecm"], bmin=p["bmin"], bmax=p["bmax"], npmin=int(p["npmin"]), npmax=int(p["npmax"]),
                   finalfactor=p["finalfactor"], maxx=p["maxx"], maxy=p["maxy"], dx=p["dx"], dy=p["dy"],
                   cc_fluctuation_model=int(p["cc_fluctuation_model"]),
-                  cc_fluctuation_gamma_theta=p.get("cc_fluctuation_gamma_theta", 0.75), randomseed=int(p["randomseed"]))
+                  cc_fluctuation_gamma_theta=p.get("cc_fluctuation_gamma_theta", 0.75), randomseed=int(p["randomseed"]),
+                  include_nn_correlation=int(p.get("include_nn_correlation", 0)))
         if "gaussian_lambda" in p:
             kw["gaussian_lambda"] = p["gaussian_lambda"]
         if "lambda" in p:

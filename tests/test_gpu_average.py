@@ -45,6 +45,51 @@ def test_rotation_sequence_matches_reference(oracle_lib):
         ctx.close()
 
 
+AVG_FILES = [  # (file stem of src/MakeDensity.cpp:755-1228, variant 0 rotated / 1 reaction plane, quantity of SMC_AVG_*)
+    ("%sAvg_order_%d", 0, 0), ("%sAvg_RP_order_%d", 1, 0),
+    ("TATB_from%s_order_%d", 0, 1), ("TATB_from%s_RP_order_%d", 1, 1),
+    ("rho_binary_from%s_order_%d", 0, 2), ("rho_binary_from%s_RP_order_%d", 1, 2),
+    ("nuclear_thickness_TA_from%s_order_%d", 0, 3), ("nuclear_thickness_TA_from%s_RP_order_%d", 1, 3),
+    ("nuclear_thickness_TB_from%s_order_%d", 0, 4), ("nuclear_thickness_TB_from%s_RP_order_%d", 1, 4),
+    ("spectator_density_A_from%s_order_%d", 0, 5), ("spectator_density_B_from%s_order_%d", 0, 6)]
+
+
+def _avg3_events(g, port, cfg):
+    evs = []
+    for it in range(g.ntries):
+        t = g.tr(it)
+        ev = event_in_from(t, port, cfg)
+        ev["proj_extra"] = t["proj_x"]; ev["targ_extra"] = t["targ_x"]
+        evs.append(ev)
+    return evs
+
+
+def test_all_averaged_quantities_match_the_reference_files(oracle_lib):
+    """operation 3 end to end against the 48 files the unmodified reference wrote for the same five events
+    (tests/golden/make_avg_golden.py): entropy and energy branch, rotated and reaction-plane variants, all seven
+    averaged quantities, orders 2 and 3 -- 1e-8 per cell (the files carry 12 digits)"""
+    import supermc_b200 as smc
+    port = oracle_lib
+    g = Golden("pbpb2760_avg3"); cfg = g.oracle_cfg(port)
+    ctx = smc.Context(g.smc_params(smc.capi, max_batch=8))
+    ctx.avg_begin(2, 3, with_rp=True, branches=3)
+    out = ctx.avg_run_from_positions(_avg3_events(g, port, cfg))
+    assert ctx.avg_count() == g.ntries and (out["status"] == 0).all()
+    seen = 0
+    for order in (2, 3):
+        for branch, tag in ((0, "sd"), (1, "ed")):
+            for stem, variant, quantity in AVG_FILES:
+                name = stem % (tag if quantity == 0 else tag.capitalize(), order)
+                ref = g.z["avg/" + name]
+                got = ctx.avg_get(order, variant, quantity, branch)
+                assert np.array_equal(got == 0, ref == 0), (name, "zero pattern")
+                err = rel_err(got, ref).max()
+                assert err <= 1e-8, (name, err)
+                seen += 1
+    assert seen == 48 == len(g.z["files"])
+    ctx.close()
+
+
 def test_average_over_sampled_events_is_smooth():
     """statistical sanity of the sampled path: the order-2 rotated average is elongated along x or y
     consistently, normalised to <dS/dy>, and the reaction-plane average is left-right symmetric"""

@@ -38,30 +38,48 @@ def test_dsdy_window_redraws_until_inside():
     ctx.close()
 
 
-def test_he3_table_sampling_equals_oracle(oracle_lib):
+@pytest.mark.parametrize("name", ["he3au200_glb", "oo200_glb", "auau200_nncorr"])
+def test_table_nuclei_sampling_equals_oracle(name, oracle_lib):
+    """sampler modes 2 (He3 / O configurations: rotated, not recentred, Nucleus.cpp:555-574) and 3 (NN-correlated Au:
+    recentred, rotation re-drawn, recentred, Nucleus.cpp:623-666) on the same Philox streams as the oracle, whose
+    restatement equals the reference on whole drand48 + rand() streams (tests/test_oracle_vs_ref.py)"""
     import supermc_b200 as smc
+    import table_synth
     port = oracle_lib
-    g = Golden("he3au200_glb"); cfg = g.oracle_cfg(port)
-    raw = np.loadtxt(os.path.join(ROOT, "tests", "golden", "he3_configs_small.txt"))
+    g = Golden(name); cfg = g.oracle_cfg(port)
+    A, B = int(g.par["aproj"]), int(g.par["atarg"])
+    nn = int(g.par.get("include_nn_correlation", 0))
+    tabs = {3: lambda: np.loadtxt(os.path.join(ROOT, "tests", "golden", "he3_configs_small.txt")), 16: table_synth.oxygen, 197: table_synth.au197}
     seed = 11
     ctx = smc.Context(g.smc_params(smc.capi, max_batch=16, randomseed=seed))
-    ctx.load_config_table(0, raw)
-    nA = port.nucleus(3, cfg.width); nB = port.nucleus(197, cfg.width)
-    out = ctx.run_events(50, 4)
-    for e in range(4):
+    tab = [None, None]
+    for side, a in ((0, A), (1, B)):
+        if a in (3, 16) or nn:
+            tab[side] = tabs[a](); ctx.load_config_table(side, tab[side])
+    nuc = [port.nucleus(A, cfg.width), port.nucleus(B, cfg.width)]
+    n = 6
+    out = ctx.run_events(50, n)
+    for e in range(n):
         ev = 50 + e
-        for tr in range(200):
+        for tr in range(400):
             b = np.sqrt(400.0 * port.StreamPhilox(seed, ev, tr, 0).u(0, 0, 0))
-            icfg = int(port.StreamPhilox(seed, ev, tr, 0).u(8, 0, 0) * len(raw))
-            p = port.populate_table(nA, raw[icfg], 0, 0, b / 2, 0.0, stream=port.StreamPhilox(seed, ev, tr, 0))
-            t, _ = port.populate(nB, -b / 2, 0.0, stream=port.StreamPhilox(seed, ev, tr, 1))
-            r = port.collide(cfg, p, t, stream=port.StreamPhilox(seed, ev, tr, 0))
+            rows = []
+            for side in (0, 1):
+                xc = b / 2 if side == 0 else -b / 2
+                if tab[side] is None:
+                    rows.append(port.populate(nuc[side], xc, 0.0, stream=port.StreamPhilox(seed, ev, tr, side))[0])
+                else:
+                    icfg = int(port.StreamPhilox(seed, ev, tr, side).u(8, 0, 0) * len(tab[side]))
+                    rows.append(port.populate_table(nuc[side], tab[side][icfg], nn, nn, xc, 0.0, stream=port.StreamPhilox(seed, ev, tr, side)))
+            r = port.collide(cfg, rows[0], rows[1], stream=port.StreamPhilox(seed, ev, tr, 0))
             npart = int((r["ncollA"] > 0).sum() + (r["ncollB"] > 0).sum())
             if r["ncoll"] > 0 and npart >= 2:
                 break
-        assert out[e]["tries"] == tr + 1 and out[e]["ncoll"] == r["ncoll"]
-        got = ctx.nucleons(e, 0)
-        assert np.abs(got[:, [0, 1, 3, 4, 5, 6]] - p[:, [0, 1, 3, 4, 5, 6]]).max() < 1e-11
+        assert out[e]["tries"] == tr + 1 and out[e]["ncoll"] == r["ncoll"], (name, e)
+        for side in (0, 1):
+            got = ctx.nucleons(e, side)
+            assert np.abs(got[:, [0, 1, 3, 4, 5, 6]] - rows[side][:, [0, 1, 3, 4, 5, 6]]).max() < 1e-11, (name, e, side)
+        assert np.array_equal(ctx.collisions(e)[:, 4:6].astype(int), r["pairs"])
     ctx.close()
 
 

@@ -1,36 +1,42 @@
 """MC-KLN.
 
 CPU: the oracle's deterministic quadrature of the restated integrand against the reference's own BASES
-Monte-Carlo table (tests/golden/auau200_kln.npz, 40x40 entries built by the unmodified reference): the
-reference's stated MC accuracy is 0.1 %, observed differences are -0.02 .. -0.2 %, gate 0.5 %.
-GPU: (1) the device table against the oracle quadrature on the same nodes (1e-10), (2) the 6-point table
-look-up + moments on the reference's golden KLN events, with the reference's own table installed."""
+Monte-Carlo tables, built by the unmodified reference: tests/golden/auau200_kln.npz (Au+Au 200 GeV, lambda = 0.218,
+70 x 70) and tests/golden/pbpb2760_kln.npz (Pb+Pb 2.76 TeV, lambda = 0.138, the full 211 x 211 table of the BASELINE
+configuration).  The reference's stated MC accuracy is 0.1 %, observed differences are -0.02 .. -0.2 %, gate 0.5 %.
+GPU: (1) the device table against the oracle quadrature on the same nodes (1e-10) and against EVERY entry of the
+reference tables (0.5 %), (2) the 6-point table look-up + moments on the reference's golden KLN events (minimum-bias
+and central), with the reference's own table installed."""
 import numpy as np
 import pytest
 
 from helpers import Golden, KLN_SYSTEM, event_in_from, src8_from, rel_err
 
-ENTRIES = [(1, 1), (2, 17), (5, 9), (11, 3), (20, 20), (3, 30), (33, 12), (38, 38), (39, 1)]
+ENTRIES = {"auau200_kln": [(1, 1), (2, 17), (5, 9), (11, 3), (20, 20), (3, 30), (33, 12), (38, 38), (39, 1), (69, 69), (60, 7)],
+           "pbpb2760_kln": [(1, 1), (2, 170), (5, 9), (110, 3), (20, 20), (30, 130), (133, 12), (138, 138), (209, 1), (210, 210), (77, 201)]}
+KLN_SYSTEMS = [("auau200_kln", 70), ("pbpb2760_kln", 211)]
 
 
-def test_oracle_quadrature_vs_reference_bases_table(oracle_lib):
+@pytest.mark.parametrize("name,size", KLN_SYSTEMS)
+def test_oracle_quadrature_vs_reference_bases_table(name, size, oracle_lib):
     port = oracle_lib
-    g = Golden(KLN_SYSTEM)
+    g = Golden(name)
     T = g.z["kln_table"]; dT, tmax = g.z["kln_consts"]
-    assert T.shape == (40, 40) and (T[0] == 0).all() and (T[:, 0] == 0).all()         # MCnucl.cpp:937-944
+    assert T.shape == (size, size) and (T[0] == 0).all() and (T[:, 0] == 0).all()         # MCnucl.cpp:937-944
     k = port.kln(g.par["ecm"], g.par["lambda"])
-    for i, j in ENTRIES:
+    for i, j in ENTRIES[name]:
         v = port.kln_dndy(k, 0.0, dT * i, dT * j, 400, 200, 64)
         assert abs(v / T[i, j] - 1) < 5e-3, (i, j, v, T[i, j])
     # y = 0: dN/dy(TA,TB) = dN/dy(TB,TA)
     assert abs(port.kln_dndy(k, 0.0, dT * 4, dT * 9, 200, 100, 32) / port.kln_dndy(k, 0.0, dT * 9, dT * 4, 200, 100, 32) - 1) < 1e-12
 
 
-def test_oracle_kln_density_on_reference_events(oracle_lib):
+@pytest.mark.parametrize("name", ["auau200_kln", "pbpb2760_kln", "pbpb2760_kln_central"])
+def test_oracle_kln_density_on_reference_events(name, oracle_lib):
     """six-point look-up (MCnucl.cpp:654-687) with the reference's table on the reference's TA1/TA2: bit-exact rho"""
     port = oracle_lib
-    g = Golden(KLN_SYSTEM); cfg = g.oracle_cfg(port)
-    T = g.z["kln_table"]; dT, tmax = g.z["kln_consts"]
+    g = Golden(name); cfg = g.oracle_cfg(port)
+    T = Golden(name.replace("_central", "")).z["kln_table"]; dT, tmax = g.z["kln_consts"]
     done = 0
     for t in g.tries():
         if "rho" not in t:
@@ -42,32 +48,47 @@ def test_oracle_kln_density_on_reference_events(oracle_lib):
 
 
 @pytest.mark.gpu
-def test_gpu_table_equals_oracle_quadrature(oracle_lib, monkeypatch):
+@pytest.mark.parametrize("name,size", KLN_SYSTEMS)
+def test_gpu_table_equals_oracle_quadrature(name, size, oracle_lib, monkeypatch):
     import supermc_b200 as smc
     port = oracle_lib
-    g = Golden(KLN_SYSTEM)
+    g = Golden(name)
     monkeypatch.setenv("SMC_KLN_QUAD", "200,100,32")
     ctx = smc.Context(g.smc_params(smc.capi, max_batch=8))
     T = ctx.build_kln_table()
     dT = ctx.k.kln_dt
-    assert T.shape == (40, 40) and abs(dT - float(g.z["kln_consts"][0])) < 1e-15
+    assert T.shape == (size, size) and abs(dT - float(g.z["kln_consts"][0])) < 1e-15
     k = port.kln(g.par["ecm"], g.par["lambda"])
-    for i, j in ENTRIES:
+    for i, j in ENTRIES[name]:
         v = port.kln_dndy(k, 0.0, dT * i, dT * j, 200, 100, 32)
         assert abs(T[i, j] / v - 1) < 1e-10, (i, j, T[i, j], v)
     assert np.abs(T - T.T).max() <= 1e-12 * T.max() and (T[0] == 0).all()
     ref = g.z["kln_table"]
-    assert np.abs(T[1:, 1:] / ref[1:, 1:] - 1).max() < 5e-3          # the reference's BASES table, to its MC error
+    assert np.abs(T[1:, 1:] / ref[1:, 1:] - 1).max() < 5e-3          # EVERY entry of the reference's BASES table, to its MC error
     ctx.close()
 
 
 @pytest.mark.gpu
-def test_gpu_kln_events_match_reference(oracle_lib):
+def test_gpu_default_quadrature_vs_full_reference_table():
+    """the production quadrature (400 x 200 x 64 nodes) against all 210^2 non-trivial entries of the reference's
+    Pb+Pb 2.76 TeV lambda = 0.138 table"""
+    import supermc_b200 as smc
+    g = Golden("pbpb2760_kln")
+    ctx = smc.Context(g.smc_params(smc.capi, max_batch=8))
+    T = ctx.build_kln_table(); ref = g.z["kln_table"]
+    d = T[1:, 1:] / ref[1:, 1:] - 1
+    assert np.abs(d).max() < 5e-3 and abs(d.mean()) < 2.5e-3, (np.abs(d).max(), d.mean())
+    ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["auau200_kln", "pbpb2760_kln", "pbpb2760_kln_central"])
+def test_gpu_kln_events_match_reference(name, oracle_lib):
     import supermc_b200 as smc
     port = oracle_lib
-    g = Golden(KLN_SYSTEM); cfg = g.oracle_cfg(port)
-    ctx = smc.Context(g.smc_params(smc.capi, max_batch=8))
-    ctx.set_kln_table(g.z["kln_table"], float(g.z["kln_consts"][0]))
+    g = Golden(name); cfg = g.oracle_cfg(port)
+    ctx = smc.Context(g.smc_params(smc.capi, max_batch=32))
+    ctx.set_kln_table(Golden(name.replace("_central", "")).z["kln_table"], float(g.z["kln_consts"][0]))
     tries = g.tries()
     out = ctx.run_from_positions([event_in_from(t, port, cfg) for t in tries], smc.RUN_MOMENTS | smc.RUN_THICKNESS)
     for it, t in enumerate(tries):

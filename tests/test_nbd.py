@@ -81,8 +81,10 @@ def test_gpu_fluctuated_density_equals_oracle(model, oracle_lib):
             got = ctx.grid(e, smc.GRID_RHO)
             n_ref, n_got = np.rint(ref * cfg.dx * cfg.dy), np.rint(got * cfg.dx * cfg.dy)
             assert (n_ref > 0).sum() > 50 and n_ref.max() >= 2                                  # the event really fluctuates
-            # identical up to the (never observed, but possible) cell whose uniform sits within an ulp of a CDF step
-            assert (n_ref != n_got).sum() <= 2, (model, e, (n_ref != n_got).sum())
+            # integer output: equal cell by cell (the pmf recurrence of the kernel and the lgamma form of the oracle differ
+            # by ~1e-14 relative, so only a uniform within that distance of a CDF step could differ; none does here)
+            bad = np.argwhere(n_ref != n_got)
+            assert len(bad) == 0, (model, e, [(tuple(q), n_ref[tuple(q)], n_got[tuple(q)], u[tuple(q)]) for q in bad[:4]])
             assert abs(out[e]["dsdy"] - got.sum() * cfg.dx * cfg.dy) <= 1e-9 * max(out[e]["dsdy"], 1.0)
             # moments of the fluctuated lattice, by the oracle
             boxes = np.concatenate([tries[e]["proj"][tries[e]["proj_part"].astype(int), 3:7], tries[e]["targ"][tries[e]["targ_part"].astype(int), 3:7], np.zeros((1, 4))])
