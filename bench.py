@@ -163,39 +163,29 @@ def main():
     ap.add_argument("--batch", type=int, default=2048, help="events resident per launch wave")
     ap.add_argument("--cpu-sample-events", type=int, default=150)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="glauber", choices=["glauber", "kln", "ebe"],
+    ap.add_argument("--workload", default="glauber", choices=["glauber", "kln", "ebe", "scan-exe", "avg"],
                     help="glauber = BASELINE.json configs[1] (the headline line); kln = the same scan with the MC-KLN density; "
-                         "ebe = BASELINE.json configs[0] through the drop-in executable, text output included (secondary line)")
+                         "ebe = BASELINE.json configs[0] through the drop-in executable, text output included; "
+                         "scan-exe = configs[1] through the drop-in executable (superMC_b200.e operation=9, tables written); "
+                         "avg = configs[2]: MC-KLN Au+Au 200 GeV averaged profiles (operation 3), one centrality window, all-reduce in the timed region")
+    ap.add_argument("--ref-events-per-process", type=int, default=300,
+                    help="reference arm: accepted events per host process and step (BASELINE.md section 3 asks >= 2000 for quoted numbers: about 90 s per step)")
+    ap.add_argument("--exe-events", type=int, default=1000000, help="scan-exe: nev of one executable run")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
 
     if a.impl == "reference":
         if rank != 0:
             return 0
-        exe, _ = ref_paths()
-        if not os.path.exists(exe):
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/superMC_ref.e is not built (needs /root/reference at build time)"}))
-            return 0
-        cores = max(1, min(os.cpu_count() or 1, 64))
-        nev_each = 24
-        t1, _ = run_reference_once(cores, 1, 5)
-        for w in range(min(a.warmup, 1)):
-            run_reference_once(cores, 2, 50 + w)
-        tot_t, tot_n = 0.0, 0
-        for s in range(a.steps):
-            t, n = run_reference_once(cores, nev_each, 1000 + 100 * s)
-            tot_t += max(t - t1, 1e-3); tot_n += max(n - cores, 0)
-        v = tot_n / tot_t
-        line = {"metric": "events/sec", "value": v, "unit": "events/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-                "ms_per_step": 1e3 * tot_t / max(a.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic", "impl": "reference",
-                "config": {"workload": WORKLOAD_NAME, "events_per_step": cores * nev_each, "host_processes": cores},
-                "cpu_baseline": {"value": v, "unit": "events/s", "cores": cores, "kind": "reference",
-                                 "sample": "%d steps x %d processes x %d events, start-up run subtracted" % (a.steps, cores, nev_each)},
-                "e2e": {"value": v, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-        print(json.dumps(line))
+        print(json.dumps(reference_line(a)))
         return 0
 
+    if a.workload == "scan-exe":
+        if rank == 0:
+            print(json.dumps(scan_exe_line(a)))
+        return 0
+    if a.workload == "avg":
+        return avg_main(a, rank, world, local)
     if a.workload == "ebe":
         if rank == 0:
             print(json.dumps(ebe_line(a)))
@@ -330,6 +320,231 @@ def main():
     if dist is not None:
         dist.destroy_process_group()
     return 0
+
+
+def host_info():
+    model = ""
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                model = ln.split(":", 1)[1].strip(); break
+    except OSError:
+        pass
+    return {"cpu_model": model, "logical_cores": os.cpu_count(), "compiler": "g++ -std=gnu++11 -fpermissive -O3 (oracle/ref_build/Makefile), GSL replaced by the header shim"}
+
+
+def reference_modes(nev_each, repeats, modes):
+    """the unmodified reference as (a) one process, (b) its own 8-process mode
+    (CollectDataAccordingToSettings.py:110-115), (c) one process per logical core; event-loop rate = accepted events /
+    (wall clock - wall clock of a 1-event run of the same process count); min and median over `repeats` runs."""
+    out = {}
+    ncore = max(1, min(os.cpu_count() or 1, 64))
+    for name in modes:
+        nproc = {"1_process": 1, "8_process": 8, "all_cores": ncore}[name]
+        t1, _ = run_reference_once(nproc, 1, 5)
+        rates = []
+        for r in range(repeats):
+            t, n = run_reference_once(nproc, nev_each, 1000 + 100 * r)
+            rates.append(max(n - nproc, 0) / max(t - t1, 1e-3))
+        rates.sort()
+        out[name] = {"processes": nproc, "events_per_process": nev_each, "runs": repeats, "min": rates[0], "median": rates[len(rates) // 2],
+                     "startup_s": t1}
+    return out
+
+
+def reference_line(a):
+    exe, _ = ref_paths()
+    if not os.path.exists(exe):
+        return {"impl": "reference", "unavailable": "oracle/_ref/superMC_ref.e is not built (needs /root/reference at build time)"}
+    ncore = max(1, min(os.cpu_count() or 1, 64))
+    nev_each = a.ref_events_per_process
+    t1, _ = run_reference_once(ncore, 1, 5)
+    for w in range(min(a.warmup, 1)):
+        run_reference_once(ncore, 2, 50 + w)
+    rates, tot_t = [], 0.0
+    for s in range(a.steps):
+        t, n = run_reference_once(ncore, nev_each, 1000 + 100 * s)
+        tot_t += max(t - t1, 1e-3); rates.append(max(n - ncore, 0) / max(t - t1, 1e-3))
+    rates.sort()
+    v = rates[len(rates) // 2]
+    # the other two host configurations of BASELINE.md section 3, once each per call (median of 3 with --steps >= 3)
+    other = reference_modes(nev_each, min(3, max(1, a.steps)), ["1_process", "8_process"])
+    other["all_cores"] = {"processes": ncore, "events_per_process": nev_each, "runs": a.steps, "min": rates[0], "median": v, "startup_s": t1}
+    return {"metric": "events/sec", "value": v, "unit": "events/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1e3 * tot_t / max(a.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": WORKLOAD_NAME, "events_per_step": ncore * nev_each, "host_processes": ncore},
+            "cpu_baseline": {"value": v, "unit": "events/s", "cores": ncore, "kind": "reference",
+                             "sample": "median of %d steps x %d processes x %d events of the bench workload (sd+ed), start-up run subtracted; "
+                                       "BASELINE.md section 3 host configurations in `modes`" % (a.steps, ncore, nev_each),
+                             "modes": other, **host_info()},
+            "e2e": {"value": v, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+
+
+def clocks_of(fn, index=0):
+    ck = ClockSampler(index); ck.start()
+    r = fn()
+    return r, ck.stop()
+
+
+def scan_exe_line(a):
+    """BASELINE.json configs[1] through the product's front door: supermc_b200/superMC_b200.e operation=9 with its twenty
+    tables written (use_sd=1 use_ed=1, 130 formatted numbers per event and table set), whole-process wall clock; the event
+    loop the program reports (`Time elapsed`, src/main.cpp:65-68) next to it; the reference binary beside it."""
+    exe = os.path.join(ROOT, "supermc_b200", "superMC_b200.e")
+    nev = a.exe_events
+    args = [x for x in REF_ARGS] + ["gpu_batch=2048"]
+
+    def ours(n):
+        d = tempfile.mkdtemp(prefix="smcscan_"); os.makedirs(os.path.join(d, "data"))
+        subprocess.check_call(["cp", os.path.join(ROOT, "supermc_b200", "parameters.dat"), d])
+        t0 = time.perf_counter()
+        so = subprocess.run([exe] + args + ["nev=%d" % n, "randomSeed=20261017"], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, check=True).stdout
+        dt = time.perf_counter() - t0
+        loop = [float(l.split(":")[1]) for l in so.splitlines() if l.startswith("Time elapsed (in seconds)")]
+        rows = sum(1 for _ in open(os.path.join(d, "data", "sn_ecc_eccp_10.dat")))
+        nbytes = sum(os.path.getsize(os.path.join(d, "data", f)) for f in os.listdir(os.path.join(d, "data")))
+        subprocess.call(["rm", "-rf", d])
+        return dt, rows, (loop[0] if loop else None), nbytes
+    for _ in range(max(a.warmup, 1)):
+        t_start, _, _, _ = ours(64)
+
+    def timed():
+        tot, rows, loops, nb = 0.0, 0, [], 0
+        for _ in range(a.steps):
+            dt, r, lp, b = ours(nev); tot += dt; rows += r; loops.append(lp); nb += b
+        return tot, rows, loops, nb
+    (tot, rows, loops, nbytes), ck = clocks_of(timed)
+    v = rows / tot
+    loop_rate = nev * len(loops) / sum(loops) if all(loops) else None
+    line = {"metric": "events/sec", "value": v, "unit": "events/s", "n_gpus": 1, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * tot / a.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD_NAME + ", through superMC_b200.e with the sn_/en_ecc_eccp_1..10 tables written; whole-process wall clock "
+                                   "(a 64-event run of the same binary, i.e. start-up, takes %.2f s)" % t_start,
+                       "events_per_step": nev, "rows_written": rows, "text_bytes_per_step": nbytes // max(a.steps, 1),
+                       "event_loop_events_per_s": loop_rate, "event_loop_s_reported_by_the_program": loops},
+            "e2e": {"value": v, "unit": "events/s", "h2d_bytes_per_step": 12 * nev, "d2h_bytes_per_step": 440 * nev},
+            "gpu_launches": None, "clocks": ck, "roofline": None}
+    if not a.no_cpu_baseline:
+        cb = cpu_baseline(1, min(a.cpu_sample_events, 150))
+        if cb:
+            line["cpu_baseline"] = cb
+    return line
+
+
+AVG_WORKLOAD = dict(which_mc_model=1, sub_model=7, aproj=197, atarg=197, ecm=200.0, cc_fluctuation_model=0, maxx=13.0, maxy=13.0, dx=0.1, dy=0.1,
+                    shape_of_nucleons=2, collision_criterion=2, shape_of_entropy=2, finalfactor=1.0, ecc_from_order=1, ecc_to_order=9,
+                    # 20-30 % of scripts/centrality_cut_tables/iebe_centralityCut_total_entropy_MCKLNAuAu200_sigmaNN_gauss_d0.9_noMultFluct.dat
+                    # translated as scripts/generateAvgprofile.py:92-191 does (Npart and b windows of the two bounding rows)
+                    npmin=127, npmax=234, bmin=5.7851427, bmax=8.6297897, **{"lambda": 0.218})
+AVG_NAME = ("MC-KLN Au+Au 200 GeV averaged smooth profiles (operation 3), 261x261 grid, orders 2-3, sd+ed branches, rotated + reaction-plane, "
+            "all seven averaged quantities, one centrality window (20-30 %)")
+AVG_REF_ARGS = ["which_mc_model=1", "sub_model=7", "lambda=0.218", "Aproj=197", "Atarg=197", "ecm=200", "cc_fluctuation_model=0", "maxx=13", "maxy=13",
+                "dx=0.1", "dy=0.1", "finalFactor=1", "operation=3", "Npmin=127", "Npmax=234", "bmin=5.7851427", "bmax=8.6297897", "average_from_order=2",
+                "average_to_order=3", "use_sd=1", "use_ed=1", "use_block=1", "use_4col=0", "tmax=24", "tmax_subdivision=3"]
+
+
+def avg_main(a, rank, world, local):
+    """BASELINE.json configs[2].  One step = one averaged-profile run of `--events-per-step` accepted events per GPU:
+    smc_avg_begin -> smc_avg_run (per event and order: recentre / rotate / redeposit / accumulate, up to five density
+    evaluations per order and branch) -> smc_avg_allreduce over all ranks (N > 1) -> one averaged lattice read back."""
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    import numpy as np
+    import supermc_b200 as smc
+    n = a.events_per_step if a.events_per_step != 32768 else 2048
+    ctx = smc.Context(smc.capi.default_params(max_batch=min(a.batch, 1024), randomseed=20261017, **AVG_WORKLOAD), device=local)
+    backend = "single"
+    if world > 1:
+        backend = ctx.comm_init(rank, world, os.environ.get("MASTER_ADDR", "127.0.0.1"), int(os.environ.get("SMC_COMM_PORT", int(os.environ.get("MASTER_PORT", "29500")) + 1)))
+    t_tab = time.perf_counter(); ctx.build_kln_table(); table_s = time.perf_counter() - t_tab
+    G = ctx.G
+    step_id = [0]
+    ar_ms = []
+
+    def step():
+        first = (step_id[0] * world + rank) * n
+        ctx.avg_begin(2, 3, with_rp=True, branches=3)
+        out = ctx.avg_run(first, n)
+        if world > 1:
+            ar_ms.append(ctx.avg_allreduce())
+        g = ctx.avg_get(2, 0, 0, 0)              # the step's result leaves the device
+        step_id[0] += 1
+        return out, g
+    for _ in range(a.warmup):
+        step()
+    del ar_ms[:]
+    if world > 1:
+        ctx.comm_barrier()
+    clocks = ClockSampler(local); clocks.start()
+    l0 = ctx.launches
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        out, g = step()
+    if world > 1:
+        ctx.comm_barrier()
+    wall = time.perf_counter() - t0
+    launches = ctx.launches - l0
+    ck = clocks.stop()
+    if world > 1:      # max over ranks of the timed region
+        walls, _ = ctx.comm_gather(np.array([wall]), world)
+        wall = float(walls.max()) if rank == 0 else wall
+    if rank != 0:
+        ctx.close()
+        return 0
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    total = n * a.steps * world
+    # algorithmic HBM bytes per accepted event (SURVEY.md 8(d): 8 G per lattice written, 16 G per accumulator update):
+    # per order and branch two density evaluations (reaction plane, rotated) of 6 lattices (TA1 TA2 rho rho_binary spec_A
+    # spec_B) written and read once by the accumulation, + 5 / 7 accumulator lattices updated; + the first density
+    norders, nbranch = 2, 2
+    dens_evals = norders * (1 + nbranch * 2)
+    bytes_per_event = dens_evals * 6 * 8 * G + norders * nbranch * (6 * 8 * G + 7 * 8 * G) + norders * nbranch * (5 + 7) * 16 * G / max(min(a.batch, 1024), 1)
+    achieved = total * bytes_per_event / wall / 1e9
+    line = {"metric": "events/sec", "value": total / wall, "unit": "events/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1e3 * wall / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": AVG_NAME, "events_per_step_per_gpu": n, "batch": min(a.batch, 1024), "kln_table_build_s": table_s,
+                       "collective": "one all-reduce of %d doubles per step (%s)" % (2 * 4 * 7 * G, backend),
+                       "allreduce_ms": (sum(ar_ms) / len(ar_ms)) if ar_ms else None,
+                       "l2": "each density evaluation of a batch writes %d MB of lattices (> 126 MB L2)" % int(6 * 8 * G * min(a.batch, 1024) / 1e6)},
+            "e2e": {"value": total / wall, "unit": "events/s", "h2d_bytes_per_step": 12 * n, "d2h_bytes_per_step": int(out.itemsize) * n + 8 * G},
+            "gpu_launches": int(launches), "clocks": ck,
+            "roofline": {"bound": "hbm", "kernel": "deposit_kernel + accumulate_kernel (lattice writes and reads of the re-deposits)", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": None,
+                         "note": "algorithmic bytes = whole lattices (8 G per lattice written or read, 16 G per accumulator update); the kernels only touch each "
+                                 "event's bounding rectangle (~1/3 of the lattice), so the real traffic is lower; timing is wall clock of the C-ABI calls"}}
+    if not a.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = avg_cpu_baseline()
+    json_out.write(json.dumps(line) + "\n"); json_out.flush()
+    ctx.close()
+    return 0
+
+
+def avg_cpu_baseline(nev=12):
+    """the unmodified reference on the same window, one process; the table build (its start-up) is subtracted with a
+    1-event run (tmax=24: a 70x70 table, enough for this centrality window, keeps the start-up at ~25 s)"""
+    exe, run = ref_paths()
+    if not os.path.exists(exe):
+        return {"value": None, "unit": "events/s", "cores": 1, "kind": "reference", "sample": "oracle/_ref/superMC_ref.e not built on this box"}
+
+    def once(n):
+        d = tempfile.mkdtemp(prefix="smcavg_"); os.makedirs(os.path.join(d, "data"))
+        for f in ("parameters.dat", "EOS", "tables"):
+            os.symlink(os.path.join(run, f), os.path.join(d, f))
+        t0 = time.perf_counter()
+        subprocess.call([exe] + AVG_REF_ARGS + ["nev=%d" % n, "randomSeed=3"], cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        dt = time.perf_counter() - t0
+        subprocess.call(["rm", "-rf", d])
+        return dt
+    t1 = once(1); t = once(nev + 1)
+    return {"value": nev / max(t - t1, 1e-3), "unit": "events/s", "cores": 1, "kind": "reference",
+            "sample": "%d accepted events of the same window (operation 3, all outputs), oracle/_ref/superMC_ref.e, 1-event run (incl. the dN/dy table build, %.1f s) subtracted" % (nev, t1),
+            **host_info()}
 
 
 EBE_ARGS = ["which_mc_model=5", "sub_model=1", "Aproj=197", "Atarg=197", "ecm=200", "alpha=0.14", "cc_fluctuation_model=6",

@@ -136,6 +136,8 @@ int  smc_get_constants(const smc_ctx* ctx, smc_constants* c);
 /* events resident per device batch: the grid / list getters address the last batch of a run, so a caller that wants
  * them asks for at most this many events per smc_run_events call */
 int  smc_max_batch(const smc_ctx* ctx);
+/* srand(seed); srand48(seed) of src/main.cpp:32-33 after the fact: replaces the Philox key (all ranks of a run share one) */
+int  smc_set_seed(smc_ctx* ctx, int64_t seed);
 
 /* Nucleus::Nucleus reading tables/QuarkPos.txt into Particle::quark_pos (src/Nucleus.cpp:37-48):
  * n rows of (r1, r2, cos theta12).  Not loaded => r1 = r2 = 0 (every AABB is the +-4w base box). */
@@ -164,6 +166,11 @@ int  smc_run_from_positions(smc_ctx* ctx, int n, const smc_event_in* in, unsigne
 /* MCnucl::getRho/getTA1/getTA2/get_rho_binary/get_spectator_density (src/MCnucl.h:94-99,142) for the
  * event in batch slot `slot` of the last run; host receives Maxx*Maxy doubles, row index = ix */
 int  smc_get_grid(smc_ctx* ctx, int slot, int which, double* host);
+/* the same for n consecutive slots in one strided copy (operations 1 and 2 fetch a batch at once); host receives
+ * n * Maxx*Maxy doubles.  smc_pinned_alloc returns page-locked host memory for it (device->host copies at full PCIe rate). */
+int  smc_get_grids(smc_ctx* ctx, int first_slot, int n, int which, double* host);
+void* smc_pinned_alloc(size_t bytes);
+void smc_pinned_free(void* p);
 /* MCnucl::dumpparticipantTable / dumpBinaryTable / dumpSpectatorsTable payloads (src/MCnucl.cpp:1177-1269)
  * rows: participants (x, y, nucleus id, weight, xL, xR, yL, yR) ; collisions (x, y, weight, addw, i, j) ;
  * spectators (x, y, rapidity).  Returns the row count through *n; host may be NULL to query. */
@@ -188,6 +195,24 @@ int  smc_avg_count(smc_ctx* ctx, int64_t* count);
 int  smc_avg_set_count(smc_ctx* ctx, int64_t count);
 /* mean = sum / count for (order, variant, quantity, branch); host receives Maxx*Maxy doubles */
 int  smc_avg_get(smc_ctx* ctx, int order, int variant, int quantity, int branch, double* host);
+
+/* ---- several GPUs of one node, one process (rank) per GPU -------------------------------------------------------
+ * The reference only knows "start 8 copies with different seeds" (CollectDataAccordingToSettings.py:110-115).  Here the
+ * ranks own contiguous global event-id ranges of one run (smc_run_events takes the first id), and two things are combined:
+ * the operation-3 accumulators (MakeDensity.cpp:1299 running means, kept as sums) and per-event rows for the centrality
+ * sort.  smc_comm_init: rank 0 listens on addr:port (dotted IPv4, e.g. MASTER_ADDR / MASTER_PORT + 1), the others connect;
+ * the all-reduce then runs as ncclAllReduce over NVLink (libnccl.so.2 resolved at run time) or, when ranks share a GPU or
+ * NCCL is absent, as a peer-memory kernel over CUDA IPC.  SMC_COMM_BACKEND=nccl|ipc forces one.  All waits time out. */
+int  smc_comm_init(smc_ctx* ctx, int rank, int world, const char* addr, int port);
+void smc_comm_finalize(smc_ctx* ctx);                     /* also done by smc_destroy */
+const char* smc_comm_backend(const smc_ctx* ctx);         /* "nccl", "ipc", "single", or "none" before smc_comm_init */
+int  smc_comm_barrier(smc_ctx* ctx);
+int  smc_comm_bcast_i64(smc_ctx* ctx, int64_t* v);        /* rank 0's value to all (seed of randomSeed < 0, src/main.cpp:28-31) */
+/* rank 0 receives the rows of all ranks in rank order (`all` holds `cap` doubles); n_per_rank[world] optional */
+int  smc_comm_gather_doubles(smc_ctx* ctx, const double* mine, int64_t n, double* all, int64_t cap, int64_t* n_per_rank);
+/* in-place sum over all ranks of the accumulator block and of the accepted-event counter of smc_avg_* */
+int  smc_avg_allreduce(smc_ctx* ctx);
+double smc_comm_last_allreduce_ms(const smc_ctx* ctx);    /* device time of the last smc_avg_allreduce */
 
 /* scripts/centrality_cut_h5.py:36-110: sort n events descending by key; perm receives the order */
 int  smc_centrality_sort(smc_ctx* ctx, const double* key, int64_t n, int64_t* perm);

@@ -87,6 +87,17 @@ def lib():
         L.smc_avg_get.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.smc_get_grid.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.smc_centrality_sort.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        L.smc_get_grids.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.smc_set_seed.argtypes = [C.c_void_p, C.c_int64]
+        L.smc_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_int]
+        L.smc_comm_backend.restype = C.c_char_p
+        L.smc_comm_backend.argtypes = [C.c_void_p]
+        L.smc_comm_last_allreduce_ms.restype = C.c_double
+        L.smc_comm_last_allreduce_ms.argtypes = [C.c_void_p]
+        L.smc_comm_gather_doubles.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
+        L.smc_pinned_alloc.restype = C.c_void_p
+        L.smc_pinned_alloc.argtypes = [C.c_size_t]
+        L.smc_pinned_free.argtypes = [C.c_void_p]
         assert C.sizeof(EventOut) == EVENT_OUT_DTYPE.itemsize
         _LIB = L
     return _LIB
@@ -230,6 +241,43 @@ class Context:
         p = C.c_void_p(); n = C.c_int64()
         self._ck(lib().smc_avg_device_buffer(self.h, C.byref(p), C.byref(n)))
         return p.value, n.value
+
+    # ---- several GPUs (one process each) ----
+    def comm_init(self, rank, world, addr="127.0.0.1", port=29517):
+        self._ck(lib().smc_comm_init(self.h, int(rank), int(world), addr.encode(), int(port)))
+        return lib().smc_comm_backend(self.h).decode()
+
+    def comm_barrier(self):
+        self._ck(lib().smc_comm_barrier(self.h))
+
+    def avg_allreduce(self):
+        """-> device time of the all-reduce [ms]"""
+        self._ck(lib().smc_avg_allreduce(self.h))
+        return lib().smc_comm_last_allreduce_ms(self.h)
+
+    def comm_gather(self, rows, world):
+        """rank 0 receives every rank's rows (float64, any shape with a fixed trailing width) in rank order"""
+        a = np.ascontiguousarray(rows, dtype=np.float64)
+        cnt = np.zeros(world, dtype=np.int64)
+        # two-phase: the sizes first, then the rows into a buffer of the right size on rank 0
+        sizes = np.zeros(world)
+        self._ck(lib().smc_comm_gather_doubles(self.h, np.array([float(a.size)]).ctypes.data, 1, sizes.ctypes.data, world, None))
+        tot = int(sizes.sum()) if sizes.any() else a.size
+        out = np.zeros(max(tot, 1))
+        self._ck(lib().smc_comm_gather_doubles(self.h, a.ctypes.data, a.size, out.ctypes.data, out.size, cnt.ctypes.data))
+        return out[:tot], cnt
+
+    def set_seed(self, seed):
+        self._ck(lib().smc_set_seed(self.h, int(seed)))
+
+    @property
+    def max_batch(self):
+        return lib().smc_max_batch(self.h)
+
+    def grids(self, first_slot, n, which):
+        g = np.zeros((n, self.k.maxx_cells, self.k.maxy_cells))
+        self._ck(lib().smc_get_grids(self.h, int(first_slot), int(n), int(which), g.ctypes.data))
+        return g
 
     def grid(self, slot, which):
         g = np.zeros((self.k.maxx_cells, self.k.maxy_cells))

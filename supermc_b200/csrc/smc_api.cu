@@ -54,7 +54,7 @@ extern "C" int smc_create(const smc_params* p, int device, smc_ctx** out) {
   ctx->d_grids = nullptr; ctx->grids_bytes = 0; ctx->d_srcrec = nullptr; ctx->srcrec_bytes = 0; ctx->d_cmpart = nullptr; ctx->d_pair_u = nullptr; ctx->pair_u_bytes = 0; ctx->d_coll_w = nullptr; ctx->coll_w_bytes = 0;
   ctx->d_rcbk = nullptr; ctx->rcbk_q = ctx->rcbk_y = ctx->rcbk_k = 0;
   ctx->d_quark = nullptr; ctx->d_cfgtab[0] = ctx->d_cfgtab[1] = nullptr; ctx->d_kln = nullptr; ctx->d_avg = nullptr; ctx->avg_doubles = 0; ctx->avg_count = 0;
-  ctx->stream = nullptr; ctx->ev0 = ctx->ev1 = nullptr; ctx->profile = 0; ctx->cur_slot = 0;
+  ctx->stream = nullptr; ctx->ev0 = ctx->ev1 = nullptr; ctx->profile = 0; ctx->cur_slot = 0; ctx->comm = nullptr; ctx->epoch = 1; ctx->lists.epoch = 0; ctx->lists.n = 0;
   std::memset(ctx->slots, 0, sizeof ctx->slots);
   for (int i = 0; i < 8; i++) { ctx->stage_ms[i] = 0; ctx->pev[i] = nullptr; }
   *out = ctx;      // returned even on failure so the caller can read smc_last_error
@@ -157,9 +157,11 @@ extern "C" int smc_create(const smc_params* p, int device, smc_ctx** out) {
   return SMC_OK;
 }
 
+extern "C" void smc_comm_finalize(smc_ctx* ctx);
 extern "C" void smc_destroy(smc_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  smc_comm_finalize(ctx);
   for (void* v : ctx->owned) cudaFree(v);
   if (ctx->d_grids) cudaFree(ctx->d_grids);
   if (ctx->d_srcrec) cudaFree(ctx->d_srcrec);
@@ -202,6 +204,11 @@ extern "C" void smc_destroy(smc_ctx* ctx) {
 }
 
 extern "C" const char* smc_last_error(const smc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" int smc_set_seed(smc_ctx* ctx, int64_t seed) {
+  if (!ctx) return SMC_ERR_PARAM;
+  ctx->p.randomseed = seed; ctx->cfg.seed_lo = (uint32_t)((uint64_t)seed); ctx->cfg.seed_hi = (uint32_t)(((uint64_t)seed) >> 32);
+  return SMC_OK;
+}
 extern "C" int smc_max_batch(const smc_ctx* ctx) { return ctx ? ctx->batch : 0; }
 extern "C" int smc_get_constants(const smc_ctx* ctx, smc_constants* c) { if (!ctx || !c) return SMC_ERR_PARAM; *c = ctx->k; return SMC_OK; }
 extern "C" int smc_set_profiling(smc_ctx* ctx, int on) { if (!ctx) return SMC_ERR_PARAM; ctx->profile = on; for (int i = 0; i < 8; i++) ctx->stage_ms[i] = 0; return SMC_OK; }
@@ -488,6 +495,7 @@ int smc_activate_slot(smc_ctx* ctx, int s) {
 
 // one batch of sampled events: ids -> device, K1+K2
 int smc_sample_batch(smc_ctx* ctx, uint64_t first_event_id, int m) {
+  ctx->epoch++;
   for (int e = 0; e < m; e++) { ctx->h_evid[e] = first_event_id + (uint64_t)e; ctx->h_try[e] = 0; }
   CK(cudaMemcpyAsync((void*)ctx->st.event_id, ctx->h_evid, (size_t)m * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->st.try_start, ctx->h_try, (size_t)m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
@@ -591,6 +599,7 @@ extern "C" int smc_run_events(smc_ctx* ctx, uint64_t first_event_id, int n, unsi
 // host nuclei -> device for events [off, off+m), then K2 only
 int smc_stage_positions(smc_ctx* ctx, int off, int m, const smc_event_in* in, bool any_u, bool any_w) {
   const smc::DevCfg& c = ctx->cfg;
+  ctx->epoch++;
   const int A = c.A[0], B = c.A[1], Amax = c.Amax;
   std::vector<double> hw_default;
   std::memset(ctx->h_nuc, 0, (size_t)m * 2 * Amax * smc::NROW * sizeof(double));
@@ -659,6 +668,7 @@ int smc_check_positions(smc_ctx* ctx, int n, const smc_event_in* in, bool* any_u
 
 extern "C" int smc_run_from_positions(smc_ctx* ctx, int n, const smc_event_in* in, unsigned flags, smc_event_out* out) {
   if (!ctx || n < 0 || (n > 0 && (!in || !out))) return SMC_ERR_PARAM;
+  if ((flags & ~(unsigned)SMC_RUN_MOMENTS) && n > ctx->batch) FAIL(SMC_ERR_PARAM, "smc_run_from_positions: grids and lists are kept for one device batch, n exceeds smc_max_batch()");
   CK(cudaSetDevice(ctx->device));
   int kinds[8], nd = 0, rc;
   if ((rc = smc_plan_kinds(ctx, flags, kinds, &nd))) return rc;
@@ -699,14 +709,55 @@ extern "C" int smc_get_grid(smc_ctx* ctx, int slot, int which, double* host) {
   return SMC_OK;
 }
 
-static int fetch_event_lists(smc_ctx* ctx, int slot, std::vector<double>& nuc, std::vector<int>& ncoll, std::vector<int>& first, int hi[smc::HDR_I]) {
-  const int Amax = ctx->cfg.Amax;
-  nuc.resize((size_t)2 * Amax * smc::NROW); ncoll.resize((size_t)2 * Amax); first.resize(Amax);
+// n grids of one kind, slots first_slot .. first_slot+n-1 of the last batch, in ONE strided device->host copy (the
+// event-by-event modes fetch a whole batch at once; `host` is best allocated with smc_pinned_alloc)
+extern "C" int smc_get_grids(smc_ctx* ctx, int first_slot, int n, int which, double* host) {
+  if (!ctx) return SMC_ERR_PARAM;
+  if (!host || n < 0 || first_slot < 0 || first_slot + n > ctx->last_n || which < 0 || which >= SMC_GRID_KINDS) FAIL(SMC_ERR_PARAM, "smc_get_grids: slots outside the last device batch, or bad grid kind");
+  static const int map[SMC_GRID_KINDS] = {smc::GK_RHO, smc::GK_TA1, smc::GK_TA2, smc::GK_RHO_BINARY, smc::GK_SPEC_A, smc::GK_SPEC_B};
+  const int ks = ctx->st.kind_slot[map[which]];
+  if (ks < 0) FAIL(SMC_ERR_STATE, "that grid was not requested in the flags of the last run");
+  if (!ctx->need_zero) FAIL(SMC_ERR_STATE, "smc_get_grids needs a profile run (SMC_RUN_KEEP_RHO ...): scan mode only writes each event's bounding rectangle");
+  if (n == 0) return SMC_OK;
   CK(cudaSetDevice(ctx->device));
-  CK(cudaMemcpy(nuc.data(), ctx->st.nuc + (size_t)slot * 2 * Amax * smc::NROW, nuc.size() * sizeof(double), cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(ncoll.data(), ctx->st.nuc_ncoll + (size_t)slot * 2 * Amax, ncoll.size() * sizeof(int), cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(first.data(), ctx->st.nuc_first + (size_t)slot * Amax, first.size() * sizeof(int), cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(hi, ctx->st.hdr_i + (size_t)slot * smc::HDR_I, smc::HDR_I * sizeof(int), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy2DAsync(host, ctx->G * sizeof(double), ctx->d_grids + ((size_t)first_slot * ctx->st.nkinds + ks) * ctx->G, (size_t)ctx->st.nkinds * ctx->G * sizeof(double),
+                       ctx->G * sizeof(double), (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return SMC_OK;
+}
+extern "C" void* smc_pinned_alloc(size_t bytes) { void* p = nullptr; return cudaMallocHost(&p, bytes) == cudaSuccess ? p : nullptr; }
+extern "C" void smc_pinned_free(void* p) { if (p) cudaFreeHost(p); }
+
+// The list getters serve single events, but callers walk whole batches (operations 1 and 2 write several lists per event):
+// the first getter after a run mirrors the batch's records on the host in a few large copies, the others read the mirror.
+static int cache_lists(smc_ctx* ctx) {
+  smc_list_cache& lc = ctx->lists;
+  if (lc.epoch == ctx->epoch && lc.n == ctx->last_n) return SMC_OK;
+  const int Amax = ctx->cfg.Amax, n = ctx->last_n;
+  CK(cudaSetDevice(ctx->device));
+  lc.nuc.resize((size_t)n * 2 * Amax * smc::NROW); lc.ncoll.resize((size_t)n * 2 * Amax); lc.first.resize((size_t)n * Amax); lc.hdr.resize((size_t)n * smc::HDR_I);
+  CK(cudaMemcpy(lc.nuc.data(), ctx->st.nuc, lc.nuc.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(lc.ncoll.data(), ctx->st.nuc_ncoll, lc.ncoll.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(lc.first.data(), ctx->st.nuc_first, lc.first.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(lc.hdr.data(), ctx->st.hdr_i, lc.hdr.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  int mx = 0;
+  for (int e = 0; e < n; e++) mx = std::max(mx, std::min(lc.hdr[(size_t)e * smc::HDR_I + smc::H_NCOLL], ctx->cfg.ncoll_cap));
+  lc.coll_stride = mx; lc.coll.resize((size_t)n * mx * smc::CROW); lc.ij.resize((size_t)n * mx);
+  if (mx > 0) {
+    CK(cudaMemcpy2D(lc.coll.data(), (size_t)mx * smc::CROW * sizeof(double), ctx->st.coll, (size_t)ctx->cfg.ncoll_cap * smc::CROW * sizeof(double), (size_t)mx * smc::CROW * sizeof(double), n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy2D(lc.ij.data(), (size_t)mx * sizeof(int), ctx->st.coll_ij, (size_t)ctx->cfg.ncoll_cap * sizeof(int), (size_t)mx * sizeof(int), n, cudaMemcpyDeviceToHost));
+  }
+  lc.epoch = ctx->epoch; lc.n = n;
+  return SMC_OK;
+}
+static int fetch_event_lists(smc_ctx* ctx, int slot, std::vector<double>& nuc, std::vector<int>& ncoll, std::vector<int>& first, int hi[smc::HDR_I]) {
+  const int Amax = ctx->cfg.Amax; int rc;
+  if ((rc = cache_lists(ctx))) return rc;
+  const smc_list_cache& lc = ctx->lists;
+  nuc.assign(lc.nuc.begin() + (size_t)slot * 2 * Amax * smc::NROW, lc.nuc.begin() + (size_t)(slot + 1) * 2 * Amax * smc::NROW);
+  ncoll.assign(lc.ncoll.begin() + (size_t)slot * 2 * Amax, lc.ncoll.begin() + (size_t)(slot + 1) * 2 * Amax);
+  first.assign(lc.first.begin() + (size_t)slot * Amax, lc.first.begin() + (size_t)(slot + 1) * Amax);
+  std::memcpy(hi, lc.hdr.data() + (size_t)slot * smc::HDR_I, smc::HDR_I * sizeof(int));
   return SMC_OK;
 }
 
@@ -748,15 +799,12 @@ extern "C" int smc_get_participants(smc_ctx* ctx, int slot, double* host8, int* 
 extern "C" int smc_get_collisions(smc_ctx* ctx, int slot, double* host6, int* n) {
   if (!ctx) return SMC_ERR_PARAM;
   if (!n || slot < 0 || slot >= ctx->last_n) FAIL(SMC_ERR_PARAM, "smc_get_collisions: slot outside the last device batch");
-  CK(cudaSetDevice(ctx->device));
-  int hi[smc::HDR_I];
-  CK(cudaMemcpy(hi, ctx->st.hdr_i + (size_t)slot * smc::HDR_I, sizeof hi, cudaMemcpyDeviceToHost));
-  const int nc = std::min(hi[smc::H_NCOLL], ctx->cfg.ncoll_cap);
+  { int rc; if ((rc = cache_lists(ctx))) return rc; }
+  const smc_list_cache& lc = ctx->lists;
+  const int nc = std::min(lc.hdr[(size_t)slot * smc::HDR_I + smc::H_NCOLL], ctx->cfg.ncoll_cap);
   *n = nc;
   if (!host6 || nc == 0) return SMC_OK;
-  std::vector<double> c4((size_t)nc * smc::CROW); std::vector<int> ij(nc);
-  CK(cudaMemcpy(c4.data(), ctx->st.coll + (size_t)slot * ctx->cfg.ncoll_cap * smc::CROW, c4.size() * sizeof(double), cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(ij.data(), ctx->st.coll_ij + (size_t)slot * ctx->cfg.ncoll_cap, ij.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  const double* c4 = lc.coll.data() + (size_t)slot * lc.coll_stride * smc::CROW; const int* ij = lc.ij.data() + (size_t)slot * lc.coll_stride;
   for (int k = 0; k < nc; k++) {
     double* o = host6 + (size_t)k * 6;
     o[0] = c4[(size_t)k * 4]; o[1] = c4[(size_t)k * 4 + 1]; o[2] = c4[(size_t)k * 4 + 2]; o[3] = c4[(size_t)k * 4 + 3]; o[4] = ij[k] >> 16; o[5] = ij[k] & 0xffff;

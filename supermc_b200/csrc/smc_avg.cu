@@ -36,22 +36,24 @@ __global__ void __launch_bounds__(AVG_THREADS) cm_angle_kernel(DevCfg c, Store s
   if (hi[H_STATUS] != 0) return;
   const size_t G = (size_t)c.Maxx * c.Maxy;
   const double* rho = st.grids + ((size_t)e * st.nkinds + st.kind_slot[GK_RHO]) * G;
+  // rho vanishes outside the event's bounding rectangle (bbox_kernel) and that part of the lattice is not even written
+  const int ilo = hi[H_RLO], jlo = hi[H_CLO], wj = max(hi[H_CHI] - jlo, 0), ncell = max(hi[H_RHI] - ilo, 0) * wj;
   double w = 0, sx = 0, sy = 0;
-  for (size_t k = tid; k < G; k += AVG_THREADS) {
-    const int i = (int)(k / c.Maxy), j = (int)(k % c.Maxy);
-    const double wei = rho[k] * scale * c.dx * c.dy;
+  for (int q = tid; q < ncell; q += AVG_THREADS) {
+    const int i = ilo + q / wj, j = jlo + q % wj;
+    const double wei = rho[(size_t)i * c.Maxy + j] * scale * c.dx * c.dy;
     w += wei; sx += xg_of(c, i) * wei; sy += yg_of(c, j) * wei;
   }
   const double weight = bsum(w, red, tid);
   const double xc = bsum(sx, red, tid) / weight, yc = bsum(sy, red, tid) / weight;
   double nr = 0, ni = 0;
-  for (size_t k = tid; k < G; k += AVG_THREADS) {
-    const double d = rho[k] * scale;
+  for (int q = tid; q < ncell; q += AVG_THREADS) {
+    const int i = ilo + q / wj, j = jlo + q % wj;
+    const double d = rho[(size_t)i * c.Maxy + j] * scale;
     if (d == 0.0) continue;
-    const int i = (int)(k / c.Maxy), j = (int)(k % c.Maxy);
     const double x = xg_of(c, i) - xc, y = yg_of(c, j) - yc;
     double a = 1.0, b = 0.0;                 // (x + i y)^n = r^n e^{i n theta}
-    for (int q = 0; q < order; q++) { const double a2 = a * x - b * y; b = a * y + b * x; a = a2; }
+    for (int k2 = 0; k2 < order; k2++) { const double a2 = a * x - b * y; b = a * y + b * x; a = a2; }
     nr += a * d; ni += b * d;
   }
   const double Nr = bsum(nr, red, tid), Ni = bsum(ni, red, tid);
@@ -106,22 +108,40 @@ __global__ void transform_kernel(DevCfg c, Store st, int rotate) {
   }
 }
 
-struct AccList { int n; int dst[8]; int srcA[8]; int srcB[8]; double scale[8]; };
-// acc[dst] += sum over the batch of grid[srcA] (* grid[srcB]) * scale, event order fixed => deterministic
-__global__ void accumulate_kernel(DevCfg c, Store st, AccList al, double* acc, int nev) {
+struct AccList { int n; int dst[8]; int srcA[8]; int srcB[8]; int whole[8]; double scale[8]; };
+// acc[dst] += sum over the batch of grid[srcA] (* grid[srcB]) * scale, event order fixed => deterministic.  The deposits only
+// write each event's bounding rectangle (no zero fill in this mode), so a cell takes the events whose rectangle holds it;
+// the rectangles of the batch sit in shared memory.  Spectator lattices are written whole.
+#define ACC_EV 2048
+__global__ void __launch_bounds__(256) accumulate_kernel(DevCfg c, Store st, AccList al, double* acc, int nev) {
+  __shared__ short rect[ACC_EV][4];
   const size_t G = (size_t)c.Maxx * c.Maxy;
   const int q = blockIdx.y;
-  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < G; k += (size_t)gridDim.x * blockDim.x) {
-    double s = 0.0;
-    for (int e = 0; e < nev; e++) {
-      if (st.hdr_i[(size_t)e * HDR_I + H_STATUS] != 0) continue;
-      const double* base = st.grids + (size_t)e * st.nkinds * G;
-      double v = base[(size_t)st.kind_slot[al.srcA[q]] * G + k];
-      if (al.srcB[q] >= 0) v *= base[(size_t)st.kind_slot[al.srcB[q]] * G + k];
-      s += v * al.scale[q];
+  const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (int)(k / c.Maxy), j = (int)(k % c.Maxy);
+  const int sa = st.kind_slot[al.srcA[q]], sb = al.srcB[q] >= 0 ? st.kind_slot[al.srcB[q]] : -1;
+  double s = 0.0;
+  for (int e0 = 0; e0 < nev; e0 += ACC_EV) {
+    const int ne = min(ACC_EV, nev - e0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < ne; e += blockDim.x) {
+      const int* hi = st.hdr_i + (size_t)(e0 + e) * HDR_I;
+      const bool ok = hi[H_STATUS] == 0;
+      if (al.whole[q]) { rect[e][0] = 0; rect[e][1] = ok ? (short)c.Maxx : 0; rect[e][2] = 0; rect[e][3] = (short)c.Maxy; }
+      else { rect[e][0] = (short)hi[H_RLO]; rect[e][1] = ok ? (short)hi[H_RHI] : 0; rect[e][2] = (short)hi[H_CLO]; rect[e][3] = (short)hi[H_CHI]; }
     }
-    acc[(size_t)al.dst[q] * G + k] += s;
+    __syncthreads();
+    if (k < G) {
+      for (int e = 0; e < ne; e++) {
+        if (i < rect[e][0] || i >= rect[e][1] || j < rect[e][2] || j >= rect[e][3]) continue;
+        const double* base = st.grids + (size_t)(e0 + e) * st.nkinds * G;
+        double v = base[(size_t)sa * G + k];
+        if (sb >= 0) v *= base[(size_t)sb * G + k];
+        s += v * al.scale[q];
+      }
+    }
   }
+  if (k < G) acc[(size_t)al.dst[q] * G + k] += s;
 }
 }  // namespace smc
 
@@ -150,9 +170,11 @@ static int avg_sequence(smc_ctx* ctx, int m) {
   const smc::DevCfg& c = ctx->cfg; smc::Store& st = ctx->st;
   int kinds[8], nd = 0, rc;
   if ((rc = smc_plan_kinds(ctx, SMC_RUN_THICKNESS | SMC_RUN_RHO_BINARY | SMC_RUN_SPECTATORS, kinds, &nd))) return rc;
+  ctx->need_zero = false;
   if (c.which_mc_model == 1 && !st.kln_table) FAIL(SMC_ERR_STATE, "MC-KLN needs its table first");
   auto density = [&]() -> int {          // calculateThickness + setDensity + calculate_rho_binary + calculate_spectator_density
-    CK(cudaMemsetAsync(ctx->d_grids, 0, (size_t)m * st.nkinds * ctx->G * sizeof(double), ctx->stream));
+    // no zero fill: deposit, combine, cm_angle and accumulate all work on the event's bounding rectangle (spectator
+    // lattices are written whole)
     CK(smc::launch_deposit(c, st, kinds, nd, m, ctx->stream)); ctx->launches += 2;
     if (c.which_mc_model != 5) { CK(smc::launch_combine(c, st, m, ctx->stream)); ctx->launches++; }
     if (c.cc_fluct == 1 || c.cc_fluct == 2) { st.nbd_pass++; CK(smc::launch_fluctuate(c, st, m, ctx->stream)); ctx->launches++; }   // fresh draws per setDensity
@@ -162,16 +184,18 @@ static int avg_sequence(smc_ctx* ctx, int m) {
   auto tf = [&](int rot) -> int { smc::transform_kernel<<<m, 128, 0, ctx->stream>>>(c, st, rot); ctx->launches++; CK(cudaGetLastError()); return SMC_OK; };
   auto acc = [&](int io, int variant, int branch) -> int {
     smc::AccList al; int n = 0;
-    auto add = [&](int quantity, int a, int b, double scale) { al.dst[n] = avg_slot(io, variant, branch, quantity); al.srcA[n] = a; al.srcB[n] = b; al.scale[n] = scale; n++; };
+    auto add = [&](int quantity, int a, int b, double scale) { al.dst[n] = avg_slot(io, variant, branch, quantity); al.srcA[n] = a; al.srcB[n] = b; al.scale[n] = scale;
+                                                               al.whole[n] = (a == smc::GK_SPEC_A || a == smc::GK_SPEC_B); n++; };
     add(SMC_AVG_SD, smc::GK_RHO, -1, c.finalFactor);                                  // setSd/setEd: rho * finalFactor
     add(SMC_AVG_TATB, smc::GK_TA1, smc::GK_TA2, 1.0); add(SMC_AVG_RHO_BINARY, smc::GK_RHO_BINARY, -1, 1.0);
     add(SMC_AVG_TA, smc::GK_TA1, -1, 1.0); add(SMC_AVG_TB, smc::GK_TA2, -1, 1.0);
     if (variant == 0) { add(SMC_AVG_SPEC_A, smc::GK_SPEC_A, -1, 1.0); add(SMC_AVG_SPEC_B, smc::GK_SPEC_B, -1, 1.0); }
     al.n = n;
-    dim3 g(64, n);
+    dim3 g((unsigned)((ctx->G + 255) / 256), n);
     smc::accumulate_kernel<<<g, 256, 0, ctx->stream>>>(c, st, al, ctx->d_avg, m); ctx->launches++; CK(cudaGetLastError());
     return SMC_OK;
   };
+  ctx->epoch++;                          // positions and boxes are about to move: host mirrors of the lists are stale
   for (int order = ctx->avg_from; order <= ctx->avg_to; order++) {
     const int io = order - ctx->avg_from;
     if ((rc = density())) return rc;                                                   // MakeDensity.cpp:1275
@@ -199,6 +223,7 @@ extern "C" int smc_avg_run(smc_ctx* ctx, uint64_t first_event_id, int n, smc_eve
   for (int off = 0; off < n; off += ctx->batch) {
     const int m = std::min(ctx->batch, n - off);
     if ((rc = smc_plan_kinds(ctx, SMC_RUN_THICKNESS | SMC_RUN_RHO_BINARY | SMC_RUN_SPECTATORS, kinds, &nd))) return rc;
+    ctx->need_zero = false;                // every consumer of this mode walks rectangles (smc_get_grid blanks the rest)
     if ((rc = smc_sample_batch(ctx, first_event_id + (uint64_t)off, m))) return rc;
     // the un-rotated event: moments for the caller, sum(rho) for the dS/dy window
     if ((rc = smc_events_first_pass(ctx, m, kinds, nd))) return rc;
@@ -220,6 +245,7 @@ extern "C" int smc_avg_run_from_positions(smc_ctx* ctx, int n, const smc_event_i
   for (int off = 0; off < n; off += ctx->batch) {
     const int m = std::min(ctx->batch, n - off);
     if ((rc = smc_plan_kinds(ctx, SMC_RUN_THICKNESS | SMC_RUN_RHO_BINARY | SMC_RUN_SPECTATORS, kinds, &nd))) return rc;
+    ctx->need_zero = false;
     if ((rc = smc_stage_positions(ctx, off, m, in, any_u, any_w))) return rc;
     if ((rc = smc_run_grid_stages(ctx, m, kinds, nd))) return rc;
     if ((rc = smc_fetch_results(ctx, m))) return rc;

@@ -30,6 +30,9 @@ struct smc_slot {
   int* h_hdr_i; double* h_hdr_d; double* h_mom; uint64_t* h_evid; int* h_try;
 };
 
+// host mirror of the last batch's event records, filled by the first list getter after a run (smc_api.cu: cache_lists)
+struct smc_list_cache { uint64_t epoch; int n; int coll_stride; std::vector<double> nuc, coll; std::vector<int> ncoll, first, hdr, ij; };
+
 #define SMC_MAX_SLOTS 4
 struct smc_ctx {
   smc_params p; smc_constants k; smc::DevCfg cfg; smc::Store st;
@@ -48,6 +51,8 @@ struct smc_ctx {
   int profile; double stage_ms[8]; cudaEvent_t pev[8];
   smc_slot slots[SMC_MAX_SLOTS]; int cur_slot;
   double* d_avg; int64_t avg_doubles; int64_t avg_count; int avg_from, avg_to, avg_rp, avg_ed;
+  void* comm;                                      // multi-GPU state (smc_comm.cu)
+  uint64_t epoch; smc_list_cache lists;            // epoch: bumped whenever the device records change
 };
 
 #define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(_e); return SMC_ERR_CUDA; } } while (0)

@@ -452,14 +452,16 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_MINCTA) deposit_kernel(DevCfg
     if (tid == 0) wtot[n & 1] = 0;                         // counter of chunk n+2
     __syncthreads();
   }
+  // only the event's bounding rectangle is ever read back (moments / combine walk the rectangle, the getters blank the
+  // rest, profile modes start from a zeroed lattice): cells of the tile beyond it are exact zeros and are not stored
 #pragma unroll
   for (int a = 0; a < 4; a++) {
     const int i = rw0 + 4 * lr + a;
-    if (i < c.Maxx) {
+    if (i < r_end) {
       double* g = grid + (size_t)i * c.Maxy;
       const int j = sc0 + 4 * lc;
 #pragma unroll
-      for (int b = 0; b < 4; b++) if (j + b < c.Maxy) g[j + b] = acc[a][b];
+      for (int b = 0; b < 4; b++) if (j + b < c_end) g[j + b] = acc[a][b];
     }
   }
   // The moments kernel needs sum(rho), sum(x rho), sum(y rho) before it can do anything else (centre of mass,

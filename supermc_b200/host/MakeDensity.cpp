@@ -1,17 +1,21 @@
 #include "MakeDensity.h"
 #include <algorithm>
 #include <cmath>
+#include <charconv>
 #include <chrono>
 #include <condition_variable>
 #include <memory>
 #include <cstdio>
 #include <cstring>
 #include <deque>
+#include <dirent.h>
+#include <unistd.h>
 #include <fstream>
 #include <functional>
 #include <iostream>
 #include <mutex>
 #include <sstream>
+#include <sys/stat.h>
 #include <thread>
 
 // ---- a small pool of writer threads: text formatting caps operations 1/2 in the reference ----------
@@ -44,31 +48,41 @@ void write_file(const std::string& name, const std::string& text, bool append) {
   std::fwrite(text.data(), 1, text.size(), f); std::fclose(f);
 }
 inline void put(std::string& s, const char* fmt, double v) { char b[64]; int n = std::snprintf(b, sizeof b, fmt, v); s.append(b, n); }
+// "%<width>.<prec>g" without printf: std::to_chars(general, prec) is specified to produce what printf("%.<prec>g") produces in
+// the C locale (shortest of %e / %f at that precision, trailing zeros removed) and is several times faster; the text
+// formatting is what bounds operations 1, 2 and 9 once the physics runs on the GPU
+inline void put_g(std::string& s, double v, int width, int prec) {
+  char b[64];
+  const auto r = std::to_chars(b, b + sizeof b, v, std::chars_format::general, prec);
+  const int n = (int)(r.ptr - b);
+  if (n < width) s.append((size_t)(width - n), ' ');
+  s.append(b, (size_t)n);
+}
 int ival(ParameterReader* p, const char* n) { return (int)p->getVal(n); }
 }  // namespace
 
 // ---- formatting (printf %g == iostream default floatfield with the same precision) -----------------
 std::string MakeDensity::formatEccRow(const smc_event_out& ev, int order, bool deformed) {
   std::string s; const double* m = ev.mom[order - 1];
-  for (int k = 0; k < 5; k++) put(s, "%16.8g", m[k]);
-  put(s, "%10.5g", (double)(ev.npart1 + ev.npart2)); put(s, "%10.5g", (double)ev.ncoll);
-  put(s, "%16.8g", ev.total); put(s, "%16.8g", ev.b);
-  if (deformed) for (int k = 0; k < 4; k++) put(s, "%16.8g", 0.0);   // mc->lastCx1.. are never assigned upstream (quirk Q9)
+  for (int k = 0; k < 5; k++) put_g(s, m[k], 16, 8);
+  put_g(s, (double)(ev.npart1 + ev.npart2), 10, 5); put_g(s, (double)ev.ncoll, 10, 5);
+  put_g(s, ev.total, 16, 8); put_g(s, ev.b, 16, 8);
+  if (deformed) for (int k = 0; k < 4; k++) put_g(s, 0.0, 16, 8);   // mc->lastCx1.. are never assigned upstream (quirk Q9)
   s += "\n"; return s;
 }
 std::string MakeDensity::formatEccRowAll(const smc_event_out& ev, bool deformed) {
   std::string s;
-  for (int n = 1; n < 10; n++) for (int k = 0; k < 5; k++) put(s, "%16.8g", ev.mom[n - 1][k]);
-  put(s, "%10.5g", (double)(ev.npart1 + ev.npart2)); put(s, "%10.5g", (double)ev.ncoll);
-  put(s, "%16.8g", ev.total); put(s, "%16.8g", ev.b);
-  if (deformed) for (int k = 0; k < 4; k++) put(s, "%16.8g", 0.0);
+  s.reserve(49 * 16 + 8);
+  for (int n = 1; n < 10; n++) for (int k = 0; k < 5; k++) put_g(s, ev.mom[n - 1][k], 16, 8);
+  put_g(s, (double)(ev.npart1 + ev.npart2), 10, 5); put_g(s, (double)ev.ncoll, 10, 5);
+  put_g(s, ev.total, 16, 8); put_g(s, ev.b, 16, 8);
+  if (deformed) for (int k = 0; k < 4; k++) put_g(s, 0.0, 16, 8);
   s += "\n"; return s;
 }
 void MakeDensity::formatDensityBlock(const double* g, int Maxx, int Maxy, std::string& out) {
   out.clear(); out.reserve((size_t)Maxx * (Maxy * 22 + 1));
-  char b[64];
   for (int i = 0; i < Maxx; i++) {
-    for (int j = 0; j < Maxy; j++) { int n = std::snprintf(b, sizeof b, "%22.12g", g[(size_t)i * Maxy + j]); out.append(b, n); }
+    for (int j = 0; j < Maxy; j++) put_g(out, g[(size_t)i * Maxy + j], 22, 12);
     out += "\n";
   }
 }
@@ -77,15 +91,23 @@ void MakeDensity::formatDensity4Col(const double* g, int Maxx, int Maxy, double 
   out.clear(); out.reserve((size_t)Maxx * Maxy * 53 + 64);
   char b[160];
   int n = std::snprintf(b, sizeof b, "# <npart>= %g xmax= %d ymax= %d\n", npart, Maxx, Maxy); out.append(b, n);
-  for (int i = 0; i < Maxx; i++) for (int j = 0; j < Maxy; j++) {
-    n = std::snprintf(b, sizeof b, "%10.3g%10.3g%10.3g%22.12g\n", rap, Xmin + i * dx, Ymin + j * dy, g[(size_t)i * Maxy + j]);
-    out.append(b, n);
+  std::string head; put_g(head, rap, 10, 3);
+  for (int i = 0; i < Maxx; i++) {
+    std::string xs; put_g(xs, Xmin + i * dx, 10, 3);
+    for (int j = 0; j < Maxy; j++) {
+      out += head; out += xs; put_g(out, Ymin + j * dy, 10, 3); put_g(out, g[(size_t)i * Maxy + j], 22, 12); out += "\n";
+    }
   }
 }
 
 // ---- construction: parameters.dat keys -> smc_params (consumers listed in SURVEY.md appendix A) ------
 MakeDensity::MakeDensity(ParameterReader* p, int device, smc_shard sh, const std::string& dd)
-    : paraRdr(p), ctx(nullptr), ctx_ok(false), data_dir(dd), shard(sh) {
+    : paraRdr(p), ctx(nullptr), ctx_ok(false), data_dir(dd), root_data_dir(dd), shard(sh) {
+  if (shard.world > 1 && shard.rank > 0) {               // private output directory per rank, merged by rank 0 at the end
+    data_dir = dd + "_rank" + std::to_string(shard.rank);
+    mkdir(data_dir.c_str(), 0777);
+  }
+  bool seed_from_clock = false;
   try {
     smc_params_default(&params);
     params.which_mc_model = ival(p, "which_mc_model"); params.sub_model = ival(p, "sub_model");
@@ -99,7 +121,7 @@ MakeDensity::MakeDensity(ParameterReader* p, int device, smc_shard sh, const std
     params.bmin = p->getVal("bmin"); params.bmax = p->getVal("bmax"); params.npmin = ival(p, "Npmin"); params.npmax = ival(p, "Npmax");
     params.cutdsdy = ival(p, "cutdSdy"); params.cutdsdy_lowerbound = p->getVal("cutdSdy_lowerBound"); params.cutdsdy_upperbound = p->getVal("cutdSdy_upperBound");
     long long seed = (long long)p->getVal("randomSeed");
-    if (seed < 0) seed = (long long)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::system_clock::now().time_since_epoch()).count() % 1000000;  // main.cpp:28-31
+    if (seed < 0) { seed_from_clock = true; seed = (long long)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::system_clock::now().time_since_epoch()).count() % 1000000; }  // main.cpp:28-31
     params.randomseed = seed;
     params.finalfactor = p->getVal("finalFactor"); params.ecc_from_order = ival(p, "ecc_from_order"); params.ecc_to_order = ival(p, "ecc_to_order");
     params.maxx = p->getVal("maxx"); params.maxy = p->getVal("maxy"); params.dx = p->getVal("dx"); params.dy = p->getVal("dy");
@@ -121,6 +143,16 @@ MakeDensity::MakeDensity(ParameterReader* p, int device, smc_shard sh, const std
   if (rc != SMC_OK) { err = std::string("smc_create: ") + (ctx ? smc_last_error(ctx) : "failed"); return; }
   smc_get_constants(ctx, &k);
   p->setVal("siginNN", k.siginnn);                                        // MCnucl.cpp:93
+  if (shard.world > 1) {                                                   // one run over several GPUs: rendezvous, one seed for all
+    const char* addr = std::getenv("MASTER_ADDR"); const char* mp = std::getenv("MASTER_PORT"); const char* cp = std::getenv("SMC_COMM_PORT");
+    const int port = cp ? std::atoi(cp) : (mp ? std::atoi(mp) + 1 : 29517);
+    if (smc_comm_init(ctx, shard.rank, shard.world, addr ? addr : "127.0.0.1", port) != SMC_OK) { err = std::string("smc_comm_init: ") + smc_last_error(ctx); return; }
+    if (seed_from_clock) {
+      int64_t sd = params.randomseed;
+      if (smc_comm_bcast_i64(ctx, &sd) != SMC_OK || smc_set_seed(ctx, sd) != SMC_OK) { err = smc_last_error(ctx); return; }
+      params.randomseed = sd;
+    }
+  }
   Maxx = k.maxx_cells; Maxy = k.maxy_cells; Xmin = -params.maxx; Ymin = -params.maxy; dx = params.dx; dy = params.dy;
   if (load_tables() != 0) return;
   ctx_ok = true;
@@ -214,32 +246,108 @@ int MakeDensity::run(int operation, int nevent) {
 }
 
 // ---- operation 9: minimum-bias eccentricity table ---------------------------------------------------
+// The GPU produces ~0.75 M rows/s; one thread formats ~50 k rows/s.  So the loop is a pipeline: the main thread keeps the
+// GPU busy (smc_run_events on chunk k+1) while a writer thread takes chunk k, formats its rows on all host cores
+// (contiguous slices, so the files keep event order) and appends them to the ten/twenty tables.
 int MakeDensity::generateEccTable(int nevent) {
   const int from_order = ival(paraRdr, "ecc_from_order"), to_order = ival(paraRdr, "ecc_to_order");
   const bool use_sd = paraRdr->getVal("use_sd") != 0, use_ed = paraRdr->getVal("use_ed") != 0;
+  const bool binary = paraRdr->getVal("output_binary", 0) != 0;          // extension: raw smc_event_out rows next to the text tables
   uint64_t first; int count; shard_range(nevent, &first, &count);
-  const int chunk = 16384;
-  std::vector<smc_event_out> out(std::min(count, chunk) > 0 ? std::min(count, chunk) : 1);
-  std::vector<std::string> rows(11);
+  const int chunk = std::max(1, (int)paraRdr->getVal("host_chunk", 32768));
+  const int lo = std::max(from_order, 1), hi = std::min(to_order, 9);
+  const unsigned nthr = std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
+  struct Chunk { std::vector<smc_event_out> out; int n = 0; long done = 0; };
+  Chunk buf[3]; for (auto& b : buf) b.out.resize(std::max(1, std::min(count, chunk)));
+  std::mutex m; std::condition_variable cv; std::deque<Chunk*> full, empty; bool finished = false; long failed = 0;
+  for (auto& b : buf) empty.push_back(&b);
   const char* base[2] = {"sn_ecc_eccp_%d.dat", "en_ecc_eccp_%d.dat"};     // en == sn numerically (quirk Q2)
-  for (int done = 0; done < count; done += chunk) {
+  std::thread writer([&] {
+    std::vector<std::vector<std::string>> part(nthr, std::vector<std::string>(11));
+    for (;;) {
+      Chunk* c;
+      { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return finished || !full.empty(); }); if (full.empty()) return; c = full.front(); full.pop_front(); }
+      std::vector<std::thread> th;
+      std::vector<long> bad(nthr, 0);
+      for (unsigned t = 0; t < nthr; t++) th.emplace_back([&, t] {
+        const int a = (int)((long)c->n * t / nthr), b = (int)((long)c->n * (t + 1) / nthr);
+        for (auto& r : part[t]) r.clear();
+        for (int e = a; e < b; e++) {
+          if (c->out[e].status != SMC_OK) { bad[t]++; continue; }
+          for (int o = lo; o <= hi; o++) part[t][o] += formatEccRow(c->out[e], o, deformed);
+          part[t][10] += formatEccRowAll(c->out[e], deformed);
+        }
+      });
+      for (auto& t : th) t.join();
+      for (long v : bad) failed += v;
+      for (int f = 0; f < 2; f++) {
+        if ((f == 0 && !use_sd) || (f == 1 && !use_ed)) continue;
+        char name[128];
+        for (int o = lo; o <= 10; o++) {
+          if (o > hi && o < 10) continue;
+          std::snprintf(name, sizeof name, base[f], o);
+          FILE* fp = std::fopen(path(name).c_str(), "ab");
+          if (!fp) { std::fprintf(stderr, "cannot open %s\n", path(name).c_str()); continue; }
+          for (unsigned t = 0; t < nthr; t++) std::fwrite(part[t][o].data(), 1, part[t][o].size(), fp);
+          std::fclose(fp);
+        }
+      }
+      if (binary) { FILE* fp = std::fopen(path("ecc_rows.bin").c_str(), "ab"); if (fp) { std::fwrite(c->out.data(), sizeof(smc_event_out), (size_t)c->n, fp); std::fclose(fp); } }
+      std::cout << "processed events: " << c->done << " / " << count << "\r" << std::flush;
+      { std::lock_guard<std::mutex> l(m); empty.push_back(c); } cv.notify_all();
+    }
+  });
+  int rc = 0;
+  for (int done = 0; done < count && !rc; done += chunk) {
     const int n = std::min(chunk, count - done);
-    if (smc_run_events(ctx, first + done, n, SMC_RUN_MOMENTS, out.data()) != SMC_OK) { err = smc_last_error(ctx); return 1; }
-    for (auto& r : rows) r.clear();
-    for (int e = 0; e < n; e++) {
-      if (out[e].status != SMC_OK) { std::cerr << "event " << first + done + e << ": status " << out[e].status << std::endl; continue; }
-      for (int o = std::max(from_order, 1); o <= std::min(to_order, 9); o++) rows[o] += formatEccRow(out[e], o, deformed);
-      rows[10] += formatEccRowAll(out[e], deformed);
-    }
-    for (int f = 0; f < 2; f++) {
-      if ((f == 0 && !use_sd) || (f == 1 && !use_ed)) continue;
-      char name[128];
-      for (int o = std::max(from_order, 1); o <= std::min(to_order, 9); o++) { std::snprintf(name, sizeof name, base[f], o); write_file(path(name), rows[o], true); }
-      std::snprintf(name, sizeof name, base[f], 10); write_file(path(name), rows[10], true);
-    }
-    std::cout << "processed events: " << done + n << " / " << count << "\r" << std::flush;
+    Chunk* c;
+    { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return !empty.empty(); }); c = empty.front(); empty.pop_front(); }
+    if (smc_run_events(ctx, first + done, n, SMC_RUN_MOMENTS, c->out.data()) != SMC_OK) { err = smc_last_error(ctx); rc = 1; n_failed_events = -1; { std::lock_guard<std::mutex> l(m); empty.push_back(c); } break; }
+    c->n = n; c->done = done + n;
+    { std::lock_guard<std::mutex> l(m); full.push_back(c); } cv.notify_all();
   }
+  { std::lock_guard<std::mutex> l(m); finished = true; } cv.notify_all();
+  writer.join();
   std::cout << std::endl;
+  if (failed) {      // an event whose collision list overflowed ncoll_cap has no row: say so loudly, the table is short
+    std::cerr << "superMC_b200: " << failed << " event(s) exceeded the per-event capacities (status != 0) and have no row; raise ncoll_cap" << std::endl;
+    n_failed_events = failed;
+  }
+  if (!rc && shard.world > 1) rc = merge_rank_outputs();
+  return rc;
+}
+
+// several ranks: every rank wrote its own directory (rank 0: data/, rank r: data_rank<r>/).  After a barrier rank 0 appends
+// the tables in rank order -- the result is byte-identical to a 1-GPU run because event k's row does not depend on which
+// GPU computed it -- and moves per-event files over.
+int MakeDensity::merge_rank_outputs() {
+  if (smc_comm_barrier(ctx) != SMC_OK) { err = smc_last_error(ctx); return 1; }
+  if (shard.rank == 0) {
+    const std::string root = root_data_dir;
+    for (int r = 1; r < shard.world; r++) {
+      const std::string rd = root + "_rank" + std::to_string(r);
+      DIR* d = opendir(rd.c_str());
+      if (!d) continue;
+      std::vector<std::string> names;
+      while (dirent* de = readdir(d)) { const std::string n = de->d_name; if (n != "." && n != "..") names.push_back(n); }
+      closedir(d);
+      std::sort(names.begin(), names.end());
+      for (const std::string& n : names) {
+        const std::string src = rd + "/" + n, dst = root + "/" + n;
+        const bool per_event = n.find("_event_") != std::string::npos;
+        const bool last_wins = (n == "wounded.data" || n == "nucl1.data" || n == "nucl2.data");      // rewritten per event: the last event is on the last rank
+        if (per_event || last_wins) { std::rename(src.c_str(), dst.c_str()); continue; }
+        if (n == "dNdyTable.dat") { std::remove(src.c_str()); continue; }                             // every rank builds the same table
+        FILE* in = std::fopen(src.c_str(), "rb"); FILE* out = std::fopen(dst.c_str(), "ab");
+        if (in && out) { char b[1 << 16]; size_t k; while ((k = std::fread(b, 1, sizeof b, in)) > 0) std::fwrite(b, 1, k, out); }
+        if (in) std::fclose(in);
+        if (out) std::fclose(out);
+        std::remove(src.c_str());
+      }
+      rmdir(rd.c_str());
+    }
+  }
+  if (smc_comm_barrier(ctx) != SMC_OK) { err = smc_last_error(ctx); return 1; }
   return 0;
 }
 
@@ -272,18 +380,24 @@ static int ebe_common(MakeDensity* self, smc_ctx* ctx, ParameterReader* paraRdr,
   if (o_rb) flags |= SMC_RUN_RHO_BINARY;
   if (o_sp) flags |= SMC_RUN_SPECTATORS;
   const size_t G = (size_t)Maxx * Maxy;
-  WriterPool pool(std::max(2u, std::min(16u, std::thread::hardware_concurrency())));
+  const bool binary = paraRdr->getVal("output_binary", 0) != 0;          // extension: raw float64 lattices (<stem>.bin) instead of text
+  WriterPool pool(std::max(2u, std::min(64u, std::thread::hardware_concurrency())));
   std::vector<smc_event_out> out(batch);
   auto P = [&](const char* fmt, long ev) { char b[160]; std::snprintf(b, sizeof b, fmt, ev); return data_dir + "/" + b; };
-  auto grid_job = [&](std::shared_ptr<std::vector<double>> g, const std::string& stem, double npart) {
-    if (use_4col) pool.submit([=] { std::string s; MakeDensity::formatDensity4Col(g->data(), Maxx, Maxy, Xmin, Ymin, dx, dy, rapMin, npart, s); write_file(stem + "_4col.dat", s, false); });
-    if (use_block) pool.submit([=] { std::string s; MakeDensity::formatDensityBlock(g->data(), Maxx, Maxy, s); write_file(stem + "_block.dat", s, false); });
+  // one page-locked block per (batch, grid kind), filled by ONE strided device->host copy and shared by the writer jobs
+  struct PinBuf { double* p; explicit PinBuf(size_t n) : p((double*)smc_pinned_alloc(n * sizeof(double))) {} ~PinBuf() { smc_pinned_free(p); } };
+  typedef std::shared_ptr<PinBuf> Buf;
+  auto grid_job = [&](Buf keep, const double* g, const std::string& stem, double npart) {
+    if (binary) { pool.submit([=] { (void)keep; write_file(stem + ".bin", std::string((const char*)g, G * sizeof(double)), false); }); return; }
+    if (use_4col) pool.submit([=] { (void)keep; std::string s; MakeDensity::formatDensity4Col(g, Maxx, Maxy, Xmin, Ymin, dx, dy, rapMin, npart, s); write_file(stem + "_4col.dat", s, false); });
+    if (use_block) pool.submit([=] { (void)keep; std::string s; MakeDensity::formatDensityBlock(g, Maxx, Maxy, s); write_file(stem + "_block.dat", s, false); });
   };
-  auto fetch = [&](int slot, int which, double scale) {
-    auto g = std::make_shared<std::vector<double>>(G);
-    if (smc_get_grid(ctx, slot, which, g->data()) != SMC_OK) { err = smc_last_error(ctx); g.reset(); return g; }
-    if (scale != 1.0) for (auto& v : *g) v *= scale;
-    return g;
+  auto fetch_all = [&](int n, int which, double scale) -> Buf {
+    Buf b = std::make_shared<PinBuf>((size_t)n * G);
+    if (!b->p) { err = "smc_pinned_alloc failed"; return Buf(); }
+    if (smc_get_grids(ctx, 0, n, which, b->p) != SMC_OK) { err = smc_last_error(ctx); return Buf(); }
+    if (scale != 1.0) for (size_t q = 0; q < (size_t)n * G; q++) b->p[q] *= scale;
+    return b;
   };
   const double ff = self->params.finalfactor;
   batch = std::max(1, std::min(batch, smc_max_batch(ctx)));               // the getters address one device batch
@@ -291,6 +405,14 @@ static int ebe_common(MakeDensity* self, smc_ctx* ctx, ParameterReader* paraRdr,
   for (int done = 0; done < count; done += batch) {
     const int n = std::min(batch, count - done);
     if (smc_run_events(ctx, first + done, n, flags, out.data()) != SMC_OK) { err = smc_last_error(ctx); return 1; }
+    Buf b_rho, b_rb, b_ta, b_tb, b_sum, b_sa, b_sb;
+    if ((use_sd || use_ed) && !(b_rho = fetch_all(n, SMC_GRID_RHO, ff))) return 1;
+    if (o_rb && !(b_rb = fetch_all(n, SMC_GRID_RHO_BINARY, 1.0))) return 1;
+    if (o_ta || o_rhob) {
+      if (!(b_ta = fetch_all(n, SMC_GRID_TA1, 1.0)) || !(b_tb = fetch_all(n, SMC_GRID_TA2, 1.0))) return 1;
+      if (o_rhob) { b_sum = std::make_shared<PinBuf>((size_t)n * G); if (!b_sum->p) { err = "smc_pinned_alloc failed"; return 1; } for (size_t q = 0; q < (size_t)n * G; q++) b_sum->p[q] = b_ta->p[q] + b_tb->p[q]; }
+    }
+    if (o_sp && (!(b_sa = fetch_all(n, SMC_GRID_SPEC_A, 1.0)) || !(b_sb = fetch_all(n, SMC_GRID_SPEC_B, 1.0)))) return 1;
     for (int e = 0; e < n; e++) {
       const long event = (long)(first + done + e) + 1;                   // the reference counts events from 1
       if (out[e].status != SMC_OK) { std::cerr << "event " << event << ": status " << out[e].status << std::endl; continue; }
@@ -324,20 +446,14 @@ static int ebe_common(MakeDensity* self, smc_ctx* ctx, ParameterReader* paraRdr,
         write_file(data_dir + "/" + nm, MakeDensity::formatEccRowAll(out[e], deformed), true);
       }
       if (use_sd || use_ed) {
-        auto g = fetch(e, SMC_GRID_RHO, ff); if (!g) return 1;
-        if (use_sd) grid_job(g, P("sd_event_%ld", event), npart);
-        if (use_ed) grid_job(g, P("ed_event_%ld", event), npart);       // identical numbers (quirk Q2)
+        const double* g = b_rho->p + (size_t)e * G;
+        if (use_sd) grid_job(b_rho, g, P("sd_event_%ld", event), npart);
+        if (use_ed) grid_job(b_rho, g, P("ed_event_%ld", event), npart);       // identical numbers (quirk Q2)
       }
-      if (o_rb) { auto g = fetch(e, SMC_GRID_RHO_BINARY, 1.0); if (!g) return 1; grid_job(g, P("rho_binary_event_%ld", event), npart); }
-      if (o_ta || o_rhob) {
-        auto a = fetch(e, SMC_GRID_TA1, 1.0), b2 = fetch(e, SMC_GRID_TA2, 1.0); if (!a || !b2) return 1;
-        if (o_ta) { grid_job(a, P("nuclear_thickness_TA_event_%ld", event), npart); grid_job(b2, P("nuclear_thickness_TB_event_%ld", event), npart); }
-        if (o_rhob) { auto s2 = std::make_shared<std::vector<double>>(G); for (size_t q = 0; q < G; q++) (*s2)[q] = (*a)[q] + (*b2)[q]; grid_job(s2, P("rhob_event_%ld", event), npart); }
-      }
-      if (o_sp) {
-        auto a = fetch(e, SMC_GRID_SPEC_A, 1.0), b2 = fetch(e, SMC_GRID_SPEC_B, 1.0); if (!a || !b2) return 1;
-        grid_job(a, P("spectator_density_A_event_%ld", event), npart); grid_job(b2, P("spectator_density_B_event_%ld", event), npart);
-      }
+      if (o_rb) grid_job(b_rb, b_rb->p + (size_t)e * G, P("rho_binary_event_%ld", event), npart);
+      if (o_ta) { grid_job(b_ta, b_ta->p + (size_t)e * G, P("nuclear_thickness_TA_event_%ld", event), npart); grid_job(b_tb, b_tb->p + (size_t)e * G, P("nuclear_thickness_TB_event_%ld", event), npart); }
+      if (o_rhob) grid_job(b_sum, b_sum->p + (size_t)e * G, P("rhob_event_%ld", event), npart);
+      if (o_sp) { grid_job(b_sa, b_sa->p + (size_t)e * G, P("spectator_density_A_event_%ld", event), npart); grid_job(b_sb, b_sb->p + (size_t)e * G, P("spectator_density_B_event_%ld", event), npart); }
     }
   }
   pool.wait();
@@ -346,11 +462,15 @@ static int ebe_common(MakeDensity* self, smc_ctx* ctx, ParameterReader* paraRdr,
 
 int MakeDensity::generate_profile_ebe(int nevent) {
   uint64_t first; int count; shard_range(nevent, &first, &count);
-  return ebe_common(this, ctx, paraRdr, false, nevent, first, count, data_dir, Maxx, Maxy, Xmin, Ymin, dx, dy, rapMin, deformed, 256, err);
+  int rc = ebe_common(this, ctx, paraRdr, false, nevent, first, count, data_dir, Maxx, Maxy, Xmin, Ymin, dx, dy, rapMin, deformed, 256, err);
+  if (!rc && shard.world > 1) rc = merge_rank_outputs();
+  return rc;
 }
 int MakeDensity::generate_profile_ebe_Jet(int nevent) {
   uint64_t first; int count; shard_range(nevent, &first, &count);
-  return ebe_common(this, ctx, paraRdr, true, nevent, first, count, data_dir, Maxx, Maxy, Xmin, Ymin, dx, dy, rapMin, deformed, 128, err);
+  int rc = ebe_common(this, ctx, paraRdr, true, nevent, first, count, data_dir, Maxx, Maxy, Xmin, Ymin, dx, dy, rapMin, deformed, 128, err);
+  if (!rc && shard.world > 1) rc = merge_rank_outputs();
+  return rc;
 }
 
 // ---- operation 3: averaged profiles (src/MakeDensity.cpp:736-2103) ----------------------------------
@@ -424,6 +544,16 @@ int MakeDensity::average_write() {
 
 int MakeDensity::generate_profile_average(int nevent) {
   if (average_accumulate(nevent)) return 1;
-  if (shard.world > 1) { err = "operation 3 on several GPUs: run through `python -m supermc_b200.launch` so the accumulators are all-reduced"; return 1; }
+  if (shard.world > 1) {
+    // the only exchange of the run: accumulator sums + accepted-event counts, one all-reduce (NCCL over NVLink, or the
+    // peer-memory kernel when ranks share a GPU); the header of the 4-column files carries the LAST event's Npart
+    if (smc_avg_allreduce(ctx) != SMC_OK) { err = smc_last_error(ctx); return 1; }
+    std::vector<double> all(shard.world, 0.0);
+    if (smc_comm_gather_doubles(ctx, &last_npart, 1, all.data(), shard.world, nullptr) != SMC_OK) { err = smc_last_error(ctx); return 1; }
+    int rc = 0;
+    if (shard.rank == 0) { for (int r = 0; r < shard.world; r++) if (all[r] > 0) last_npart = all[r]; rc = average_write(); }
+    if (smc_comm_barrier(ctx) != SMC_OK) { err = smc_last_error(ctx); return 1; }
+    return rc;
+  }
   return average_write();
 }

@@ -43,12 +43,13 @@ class MakeDensity {
 
  private:
   int load_tables();
+  int merge_rank_outputs();                    // several ranks: rank 0 appends / moves the other ranks' files in rank order
   void shard_range(int nevent, uint64_t* first, int* count) const;
   std::string path(const std::string& name) const { return data_dir + "/" + name; }
   ParameterReader* paraRdr;
   smc_ctx* ctx;
   bool ctx_ok;
-  std::string err, data_dir;
+  std::string err, data_dir, root_data_dir;
   smc_shard shard;
   smc_constants k;
   int Maxx, Maxy;
@@ -56,4 +57,6 @@ class MakeDensity {
   int binRapidity;
   bool deformed;
   double last_npart = 0;
+ public:
+  long n_failed_events = 0;                    // events without a row in the last operation-9 run (capacity overflow), -1 after an error
 };

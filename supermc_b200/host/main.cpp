@@ -1,7 +1,9 @@
 // superMC_b200.e -- drop-in for the reference executable (reference src/main.cpp:19-73): reads
 // parameters.dat, applies name=value overrides, runs the selected operation on the GPU.
-// Multi-GPU: one process per GPU; RANK / WORLD_SIZE / LOCAL_RANK (torchrun convention) select the shard
-// of global event ids and the device, and each rank writes into data/ (rank 0) or data_rank<r>/.
+// Multi-GPU: one process per GPU; RANK / WORLD_SIZE / LOCAL_RANK (torchrun convention, e.g.
+// `torchrun --no-python --nproc-per-node 8 ./superMC_b200.e ...` or a shell loop) select the shard of global event ids and
+// the device; MASTER_ADDR / MASTER_PORT (+1) or SMC_COMM_PORT is where rank 0 listens for the rendezvous.  Operation 3
+// all-reduces its accumulators (NCCL over NVLink); the tables and per-event files of the ranks are merged by rank 0.
 #include <chrono>
 #include <cstdlib>
 #include <iostream>
@@ -19,9 +21,7 @@ int main(int argc, char* argv[]) {
   const char* er = std::getenv("RANK"); const char* ew = std::getenv("WORLD_SIZE"); const char* el = std::getenv("LOCAL_RANK");
   smc_shard sh{er ? std::atoi(er) : 0, ew ? std::atoi(ew) : 1};
   const int device = el ? std::atoi(el) : 0;
-  std::string dd = "data";
-  if (sh.world > 1 && sh.rank > 0) dd = "data_rank" + std::to_string(sh.rank);
-  MakeDensity dens(&paraRdr, device, sh, dd);
+  MakeDensity dens(&paraRdr, device, sh, "data");      // rank r > 0 writes data_rank<r>/, merged into data/ by rank 0
   if (!dens.ok()) { std::cerr << "superMC_b200: " << dens.error() << std::endl; return 255; }
   if (timing) std::cerr << "# start-up (parameters, CUDA context, tables): " << std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() << " s" << std::endl;
   int nevent = 0, operation = 0;

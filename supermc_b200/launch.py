@@ -9,8 +9,8 @@ The reference's only parallel mode is "start 8 copies with different seeds"
 the number of GPUs.  Data path: no collective for operations 1, 2, 9 (per-event rows and files are
 independent; rank 0 concatenates the operation-9 tables in rank order, which reproduces the 1-GPU
 file byte for byte).  Operation 3: the accumulator sums that live in each GPU's memory are combined
-with one NCCL all-reduce over NVLink (torch.distributed on the raw device pointer), then rank 0 writes.
-torch is plumbing only: process group, barrier, all_reduce.
+with one all-reduce behind the C ABI (smc_avg_allreduce: ncclAllReduce over NVLink), then rank 0 writes.
+The helper functions below restate the host logic for the CPU tests (gloo, world size 2).
 """
 import ctypes as C
 import glob
@@ -70,58 +70,27 @@ def _host():
 
 
 def main(argv=None):
+    """One rank of a multi-GPU run (torchrun sets RANK / WORLD_SIZE / LOCAL_RANK / MASTER_*).  Everything, including the
+    rendezvous, the single seed of a randomSeed < 0 run, the operation-3 all-reduce (smc_avg_allreduce: NCCL over NVLink)
+    and the rank-ordered merge of the output files, happens in the C++ host layer (host/MakeDensity.cpp) behind the C ABI:
+    this module only forwards argv.  `torchrun --no-python supermc_b200/superMC_b200.e ...` is the same thing."""
     argv = list(sys.argv[1:] if argv is None else argv)
     pfile = "parameters.dat"
     if argv and "=" not in argv[0]:
         pfile = argv.pop(0)
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     L = _host()
     args = (C.c_char_p * max(len(argv), 1))(*[a.encode() for a in argv])
-    op_probe = C.c_double()
-    # operation 9 tables are merged in rank order; per-event files (operations 1, 2) carry global event ids
     h = L.smc_host_create(pfile.encode(), len(argv), args, local, rank, world, b"data")
-    rc = 1
     try:
-        if L.smc_host_get(h, b"operation", C.byref(op_probe)) != 0 or not L.smc_host_context(h):
+        if not L.smc_host_context(h):
             raise RuntimeError(L.smc_host_error(h).decode())
-        op = int(op_probe.value)
-        if op == 9 and world > 1 and rank > 0:       # private table directory for this rank
-            L.smc_host_destroy(h)
-            os.makedirs("data_rank%d" % rank, exist_ok=True)
-            h = L.smc_host_create(pfile.encode(), len(argv), args, local, rank, world, ("data_rank%d" % rank).encode())
-        if op == 3 and world > 1:
-            import torch
-            from . import capi
-            if L.smc_host_average_accumulate(h) != 0:
-                raise RuntimeError(L.smc_host_error(h).decode())
-            ctx = C.c_void_p(L.smc_host_context(h))
-            p = C.c_void_p(); n = C.c_int64(); cnt = C.c_int64()
-            lib = capi.lib()
-            lib.smc_avg_device_buffer(ctx, C.byref(p), C.byref(n)); lib.smc_avg_count(ctx, C.byref(cnt))
-            buf = torch.as_tensor(_DevBuf(p.value, n.value), device="cuda:%d" % local)
-            total = allreduce_sums(buf, cnt.value, dist)
-            torch.cuda.synchronize(local)
-            lib.smc_avg_set_count(ctx, C.c_int64(total))
-            rc = L.smc_host_average_write(h) if rank == 0 else 0
-        else:
-            rc = L.smc_host_run(h)
+        rc = L.smc_host_run(h)
         if rc != 0:
             raise RuntimeError(L.smc_host_error(h).decode())
-        if dist is not None:
-            dist.barrier()
-            if op == 9 and rank == 0:
-                merge_rank_tables("data", world)
     finally:
         L.smc_host_destroy(h)
-        if dist is not None:
-            dist.destroy_process_group()
     return rc
 
 

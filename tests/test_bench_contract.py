@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_reference_arm_prints_one_json_line():
     if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "superMC_ref.e")):
         pytest.skip("oracle/_ref is not built here")
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-events-per-process", "12"],
                          capture_output=True, text=True, timeout=600)
     lines = [l for l in out.stdout.splitlines() if l.strip()]
     assert out.returncode == 0 and len(lines) == 1, (out.stdout, out.stderr[-500:])
@@ -24,6 +24,10 @@ def test_reference_arm_prints_one_json_line():
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "Pb+Pb" in d["config"]["workload"] and d["gpu_launches"] == 0
+    # one process, the reference's own 8-process mode, one process per core
+    modes = d["cpu_baseline"]["modes"]
+    assert set(modes) == {"1_process", "8_process", "all_cores"} and modes["8_process"]["processes"] == 8
+    assert all(m["median"] > 0 and m["min"] <= m["median"] for m in modes.values()) and d["cpu_baseline"]["cpu_model"] != ""
 
 
 def test_algorithmic_work_follows_the_survey():

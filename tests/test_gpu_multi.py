@@ -1,5 +1,9 @@
-"""-m gpu, needs >= 2 GPUs (skipped otherwise): the torchrun launcher on 2 ranks reproduces the 1-GPU
-operation-9 table byte for byte, and the all-reduced operation-3 average equals the 1-GPU average."""
+"""-m gpu: several ranks of ONE run.
+* test_two_ranks_on_one_gpu: the drop-in executable superMC_b200.e as two processes (RANK 0/1, both on cuda:0 -- runs on
+  a 1-GPU box): the merged operation-9 tables are byte-identical to the 1-rank run, per-event files of operation 1 carry
+  global event ids, and the operation-3 average after smc_avg_allreduce (the peer-memory kernel over CUDA IPC, because
+  NCCL refuses two ranks on one device) equals the 1-rank average.
+* test_two_ranks_equal_one_rank: the same through torchrun on two GPUs (NCCL all-reduce); skipped on a 1-GPU box."""
 import os
 import shutil
 import subprocess
@@ -37,5 +41,41 @@ def test_two_ranks_equal_one_rank(tmp_path):
     a = _run(tmp_path / "avg", 1, ["operation=3", "nev=64", "bmin=6", "bmax=8", "average_to_order=2"], 29613)
     b = _run(tmp_path / "avg", 2, ["operation=3", "nev=64", "bmin=6", "bmax=8", "average_to_order=2"], 29614)
     for f in ("sdAvg_order_2_block.dat", "sdAvg_RP_order_2_block.dat", "TATB_fromSd_order_2_block.dat", "spectator_density_A_fromSd_order_2_block.dat"):
+        x, y = np.loadtxt(a / f), np.loadtxt(b / f)
+        assert np.allclose(x, y, rtol=1e-10, atol=1e-14), f
+
+
+def _exe_run(tmp, world, extra, port, ngpu=1):
+    d = tmp / ("x%d" % world); os.makedirs(d / "data")
+    shutil.copy(os.path.join(ROOT, "supermc_b200", "parameters.dat"), d)
+    exe = os.path.join(ROOT, "supermc_b200", "superMC_b200.e")
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r % ngpu), MASTER_ADDR="127.0.0.1", SMC_COMM_PORT=str(port))
+        procs.append(subprocess.Popen([exe] + ARGS + extra, cwd=d, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    return d / "data", outs
+
+
+def test_two_ranks_on_one_gpu(tmp_path):
+    a, _ = _exe_run(tmp_path / "t9", 1, ["operation=9", "nev=501"], 29711)
+    b, _ = _exe_run(tmp_path / "t9", 2, ["operation=9", "nev=501"], 29712)
+    assert sorted(os.listdir(a)) == sorted(os.listdir(b)) and not os.path.exists(str(b) + "_rank1")
+    for f in sorted(os.listdir(a)):
+        assert (a / f).read_bytes() == (b / f).read_bytes(), f
+    assert len((a / "sn_ecc_eccp_10.dat").read_bytes().splitlines()) == 501
+    # operation 1: per-event files with global ids, binary.dat appended in rank order
+    e1 = ["operation=1", "nev=7", "use_4col=0", "use_block=1"]
+    a, _ = _exe_run(tmp_path / "t1", 1, e1, 29713); b, _ = _exe_run(tmp_path / "t1", 2, e1, 29714)
+    assert sorted(os.listdir(a)) == sorted(os.listdir(b))
+    for f in sorted(os.listdir(a)):
+        assert (a / f).read_bytes() == (b / f).read_bytes(), f
+    # operation 3: accumulators summed across the two ranks
+    e3 = ["operation=3", "nev=64", "bmin=6", "bmax=8", "average_to_order=2", "output_TATB=1", "output_spectator_density=1", "use_4col=0"]
+    a, _ = _exe_run(tmp_path / "t3", 1, e3, 29715); b, outs = _exe_run(tmp_path / "t3", 2, e3, 29716)
+    files = sorted(os.listdir(a))
+    assert files == sorted(os.listdir(b)) and len(files) >= 6
+    for f in files:
         x, y = np.loadtxt(a / f), np.loadtxt(b / f)
         assert np.allclose(x, y, rtol=1e-10, atol=1e-14), f

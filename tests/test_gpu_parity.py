@@ -21,7 +21,7 @@ MOM_TOL = 1e-9
 
 def _ctx(g, **over):
     import supermc_b200 as smc
-    return smc.Context(g.smc_params(smc.capi, max_batch=64, **over))
+    return smc.Context(g.smc_params(smc.capi, max_batch=max(64, g.ntries), **over))      # the getters address one device batch
 
 
 @pytest.mark.parametrize("name", [s for s in SYSTEMS if s != "pbpb2760_rotate"])
