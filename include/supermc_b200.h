@@ -147,18 +147,22 @@ int  smc_load_quark_table(smc_ctx* ctx, const double* rows3, int n);
 int  smc_load_config_table(smc_ctx* ctx, int which, const double* xyz, int n_cfg, int a);
 
 /* MCnucl::makeTable (src/MCnucl.cpp:911-960): builds the tmax^2 dN/dy(TA,TB) table on the device with
- * a deterministic quadrature of KLNModel::func (src/KLNModel.cpp:219-277); host_out (tmax*tmax) optional */
+ * a deterministic quadrature of KLNModel::func (src/KLNModel.cpp:219-277), one table per rapidity slice at
+ * y = -ymax + 2 ymax / ny * iy; host_out (ny*tmax*tmax) optional */
 int  smc_build_kln_table(smc_ctx* ctx, double* host_out);
 /* rcBKfunc::rcBKfunc (src/rcBKfunc.cpp:15-210), sub_model 100 (59 files) / 101 (30 files): kt and N_A columns of the
  * javier/ft_rcbk_mv_qs02_*.dat files as [maxq0][maxy][maxkt]; needed before smc_build_kln_table for those sub-models */
 int  smc_load_rcbk_tables(smc_ctx* ctx, const double* kt, const double* na, int maxq0, int maxy, int maxkt);
-/* install a table computed elsewhere (e.g. the reference's data/dNdyTable.dat) */
+/* install a table computed elsewhere (e.g. the reference's data/dNdyTable.dat); ny tables of tmax*tmax, slice-major */
 int  smc_set_kln_table(smc_ctx* ctx, const double* table, int tmax, double dt);
 
 /* generateNuclei -> getBinaryCollision -> CentralityCut -> calculateThickness -> setDensity ->
  * dumpEccentricities for n accepted events with global ids first_event_id .. first_event_id+n-1
  * (src/MakeDensity.cpp:2143-2224).  Event k draws from Philox key=randomseed, counter=(k, try, ...),
- * so the result set does not depend on batch size or GPU count. */
+ * so the result set does not depend on batch size or GPU count.
+ * ny > 1: `out` receives n*ny rows, out[e*ny + iy] = event e at rapidity slice iy (the reference appends one table row
+ * per slice, MakeDensity.cpp:2170-2193); the grids left for the getters are those of the last slice, which is what the
+ * reference's files hold (every slice is written to the same file name). */
 int  smc_run_events(smc_ctx* ctx, uint64_t first_event_id, int n, unsigned flags, smc_event_out* out);
 /* same, nuclei supplied (parity entry; reference: the loop body after generateNuclei) */
 int  smc_run_from_positions(smc_ctx* ctx, int n, const smc_event_in* in, unsigned flags, smc_event_out* out);

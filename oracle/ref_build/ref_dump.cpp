@@ -34,7 +34,7 @@ struct McProbe : public MCnucl {
   using MCnucl::TA1; using MCnucl::TA2; using MCnucl::rho_binary; using MCnucl::spectator_1;
   using MCnucl::spectator_2; using MCnucl::rho; using MCnucl::Maxx; using MCnucl::Maxy;
   using MCnucl::dndy; using MCnucl::gaussCal; using MCnucl::siginNN; using MCnucl::dsq;
-  using MCnucl::dndyTable; using MCnucl::tmax; using MCnucl::dT;
+  using MCnucl::dndyTable; using MCnucl::tmax; using MCnucl::dT; using MCnucl::binRapidity;
 };
 struct GdProbe : public GlueDensity { using GlueDensity::density; };
 struct MdProbe : public MakeDensity {
@@ -114,6 +114,10 @@ int main(int argc, char* argv[]) {
     vector<double> t((size_t)mc->tmax * mc->tmax);
     for (int i = 0; i < mc->tmax; i++) for (int j = 0; j < mc->tmax; j++) t[(size_t)i * mc->tmax + j] = mc->dndyTable[0][i][j];
     wr2("kln_table", mc->tmax, mc->tmax, t);
+    for (int iy = 1; iy < mc->binRapidity; iy++) {      // one table per rapidity slice (ny > 1)
+      for (int i = 0; i < mc->tmax; i++) for (int j = 0; j < mc->tmax; j++) t[(size_t)i * mc->tmax + j] = mc->dndyTable[iy][i][j];
+      char nm[32]; snprintf(nm, sizeof nm, "kln_table_y%d", iy); wr2(nm, mc->tmax, mc->tmax, t);
+    }
     vector<double> c; c.push_back(mc->dT); c.push_back(mc->tmax); wr1("kln_consts", c);
   }
 
@@ -126,8 +130,9 @@ int main(int argc, char* argv[]) {
     }
     wr2("ugd_samples", (long)(v.size() / 5), 5, v);
   }
-  double*** d1 = new double**[1]; d1[0] = new double*[dens->Maxx];
-  for (int i = 0; i < dens->Maxx; i++) d1[0][i] = new double[dens->Maxy]();
+  const int nyb = mc->binRapidity;
+  double*** d1 = new double**[nyb];
+  for (int iy = 0; iy < nyb; iy++) { d1[iy] = new double*[dens->Maxx]; for (int i = 0; i < dens->Maxx; i++) d1[iy][i] = new double[dens->Maxy](); }
   char eccfile[] = "data/h_ecc_%d.dat";
 
   int event = 0, tryid = 0;
@@ -179,6 +184,13 @@ int main(int argc, char* argv[]) {
         wr1(P + "region", v); }
       dens->setSd(d1, 0);
       dens->dumpEccentricities(eccfile, d1, 0, from_order, to_order, mc->getNpart1() + mc->getNpart2(), mc->getNcoll(), b);
+      for (int iy = 1; iy < nyb; iy++) {      // the other rapidity slices (generateEccTable, MakeDensity.cpp:2170-2193): one more row each
+        mc->setDensity(iy, -1);
+        dens->setSd(d1, iy);
+        dens->dumpEccentricities(eccfile, d1, iy, from_order, to_order, mc->getNpart1() + mc->getNpart2(), mc->getNcoll(), b);
+        if (dgr) { char q[96]; snprintf(q, sizeof q, "%srho_y%d", pfx, iy); GdProbe* gd = static_cast<GdProbe*>(mc->rho); wrgrid(q, gd->density[iy], mc->Maxx, mc->Maxy); }
+      }
+      if (nyb > 1) mc->setDensity(0, -1);
       if (dtext) {      // the reference's own text writers on this event (format fixtures)
         char f1[] = "data/ref_block.dat", f2[] = "data/ref_4col.dat";
         dens->Npart = mc->getNpart1() + mc->getNpart2();

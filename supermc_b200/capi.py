@@ -162,18 +162,21 @@ class Context:
         self._ck(lib().smc_load_rcbk_tables(self.h, kt.ctypes.data_as(dp), na.ctypes.data_as(dp), q, y, k))
 
     def build_kln_table(self):
-        t = np.zeros((self.k.kln_tmax, self.k.kln_tmax))
+        """-> (tmax, tmax), or (ny, tmax, tmax) with several rapidity slices"""
+        ny = max(self.p.ny, 1)
+        t = np.zeros((ny, self.k.kln_tmax, self.k.kln_tmax))
         self._ck(lib().smc_build_kln_table(self.h, t.ctypes.data_as(dp)))
-        return t
+        return t[0] if ny == 1 else t
 
     def set_kln_table(self, table, dt):
-        t = np.ascontiguousarray(table, dtype=np.float64)
-        self._ck(lib().smc_set_kln_table(self.h, t.ctypes.data_as(dp), t.shape[0], C.c_double(dt)))
+        t = np.ascontiguousarray(table, dtype=np.float64)      # (tmax, tmax) or (ny, tmax, tmax)
+        assert t.ndim == 2 or t.shape[0] == max(self.p.ny, 1)
+        self._ck(lib().smc_set_kln_table(self.h, t.ctypes.data_as(dp), t.shape[-1], C.c_double(dt)))
 
     def run_events(self, first_event_id, n, flags=RUN_MOMENTS, out=None):
         """-> structured array (EVENT_OUT_DTYPE) of n accepted events.  `out` may be a preallocated array."""
         if out is None:
-            out = np.zeros(n, dtype=EVENT_OUT_DTYPE)
+            out = np.zeros(n * max(self.p.ny, 1), dtype=EVENT_OUT_DTYPE)      # ny > 1: row e*ny + iy
         self._ck(lib().smc_run_events(self.h, int(first_event_id), int(n), int(flags), out.ctypes.data))
         return out
 
@@ -204,7 +207,7 @@ class Context:
     def run_from_positions(self, events, flags=RUN_MOMENTS):
         """events: list of dicts(b, proj (A,8), targ (B,8), pair_uniform (A,B)|None, coll_weight (n,2)|None, given_w)"""
         arr, keep = self._event_in_array(events)
-        out = np.zeros(len(events), dtype=EVENT_OUT_DTYPE)
+        out = np.zeros(len(events) * max(self.p.ny, 1), dtype=EVENT_OUT_DTYPE)
         self._ck(lib().smc_run_from_positions(self.h, len(events), C.byref(arr), int(flags), out.ctypes.data))
         return out
 

@@ -54,7 +54,7 @@ extern "C" int smc_create(const smc_params* p, int device, smc_ctx** out) {
   ctx->d_grids = nullptr; ctx->grids_bytes = 0; ctx->d_srcrec = nullptr; ctx->srcrec_bytes = 0; ctx->d_cmpart = nullptr; ctx->d_pair_u = nullptr; ctx->pair_u_bytes = 0; ctx->d_coll_w = nullptr; ctx->coll_w_bytes = 0;
   ctx->d_rcbk = nullptr; ctx->rcbk_q = ctx->rcbk_y = ctx->rcbk_k = 0;
   ctx->d_quark = nullptr; ctx->d_cfgtab[0] = ctx->d_cfgtab[1] = nullptr; ctx->d_kln = nullptr; ctx->d_avg = nullptr; ctx->avg_doubles = 0; ctx->avg_count = 0;
-  ctx->stream = nullptr; ctx->ev0 = ctx->ev1 = nullptr; ctx->profile = 0; ctx->cur_slot = 0; ctx->comm = nullptr; ctx->epoch = 1; ctx->lists.epoch = 0; ctx->lists.n = 0;
+  ctx->stream = nullptr; ctx->ev0 = ctx->ev1 = nullptr; ctx->profile = 0; ctx->cur_slot = 0; ctx->comm = nullptr; ctx->epoch = 1; ctx->lists.epoch = 0; ctx->lists.n = 0; ctx->ny = p->ny; ctx->slice = 0;
   std::memset(ctx->slots, 0, sizeof ctx->slots);
   for (int i = 0; i < 8; i++) { ctx->stage_ms[i] = 0; ctx->pev[i] = nullptr; }
   *out = ctx;      // returned even on failure so the caller can read smc_last_error
@@ -76,7 +76,7 @@ extern "C" int smc_create(const smc_params* p, int device, smc_ctx** out) {
   if (p->which_mc_model == 1 && p->sub_model != 7 && p->sub_model != 100 && p->sub_model != 101) FAIL(SMC_ERR_PARAM, "MC-KLN sub_model must be 7 (KLN uGD), 100 or 101 (rcBK tables, src/ParamDefs.h)");
   if (p->collision_criterion == 3 || p->collision_criterion == 4)
     FAIL(SMC_ERR_PARAM, "collision_criterion 3 (quark overlap, GaussianNucleonsCal.cpp:70-97) and 4 (numeric overlap) are not built; the reference uses different hit tests for them (MCnucl.cpp:371-376)");
-  if (p->ny != 1) FAIL(SMC_ERR_PARAM, "ny != 1 (several rapidity slices) is not built");
+  if (p->ny < 1 || p->ny > 64) FAIL(SMC_ERR_PARAM, "ny (rapidity slices) must be 1..64");
   if (p->shape_of_nucleons < 1 || p->shape_of_nucleons > 4) FAIL(SMC_ERR_PARAM, "shape_of_nucleons must be 1, 2, 3 or 4");
   if (p->shape_of_nucleons == 3 && !(p->gaussian_lambda > 0)) FAIL(SMC_ERR_PARAM, "shape_of_nucleons 3 needs gaussian_lambda > 0");
   if (p->shape_of_entropy != 1 && p->shape_of_entropy != 2) FAIL(SMC_ERR_PARAM, "shape_of_entropy must be 1 or 2 (3 = quark substructure is out of scope)");
@@ -286,8 +286,9 @@ extern "C" int smc_set_kln_table(smc_ctx* ctx, const double* table, int tmax, do
   if (!ctx || !table || tmax < 3) return SMC_ERR_PARAM;
   CK(cudaSetDevice(ctx->device));
   if (ctx->d_kln) { cudaFree(ctx->d_kln); ctx->d_kln = nullptr; }
-  CK(cudaMalloc(&ctx->d_kln, (size_t)tmax * tmax * sizeof(double)));
-  CK(cudaMemcpy(ctx->d_kln, table, (size_t)tmax * tmax * sizeof(double), cudaMemcpyHostToDevice));
+  const size_t nt = (size_t)ctx->ny * tmax * tmax;            // one table per rapidity slice (dndyTable[iy], MCnucl.cpp:921-925)
+  CK(cudaMalloc(&ctx->d_kln, nt * sizeof(double)));
+  CK(cudaMemcpy(ctx->d_kln, table, nt * sizeof(double), cudaMemcpyHostToDevice));
   ctx->st.kln_table = ctx->d_kln; ctx->cfg.kln_tmax = tmax; ctx->cfg.kln_dT = dt;
   return SMC_OK;
 }
@@ -310,17 +311,22 @@ extern "C" int smc_build_kln_table(smc_ctx* ctx, double* host_out) {
   h.insert(h.end(), xk.begin(), xk.end()); h.insert(h.end(), wk.begin(), wk.end()); h.insert(h.end(), cp.begin(), cp.end());
   CK(cudaMemcpy(d, h.data(), nn * sizeof(double), cudaMemcpyHostToDevice));
   if (ctx->d_kln) { cudaFree(ctx->d_kln); ctx->d_kln = nullptr; }
-  CK(cudaMalloc(&ctx->d_kln, (size_t)tmax * tmax * sizeof(double)));
-  smc::KlnCfg kc; kc.ecm = ctx->p.ecm; kc.lambda = ctx->p.lambda; kc.y = -ctx->p.ymax;      /* rapMin, MakeDensity.cpp:54-56, MCnucl.cpp:932 */ kc.dT = ctx->k.kln_dt; kc.tmax = tmax; kc.pt_order = ctx->p.pt_order > 0 ? ctx->p.pt_order : 1;
+  const size_t nt = (size_t)ctx->ny * tmax * tmax;
+  CK(cudaMalloc(&ctx->d_kln, nt * sizeof(double)));
+  smc::KlnCfg kc; kc.ecm = ctx->p.ecm; kc.lambda = ctx->p.lambda; kc.dT = ctx->k.kln_dt; kc.tmax = tmax; kc.pt_order = ctx->p.pt_order > 0 ? ctx->p.pt_order : 1;
   kc.model = ctx->p.sub_model; kc.maxQ0 = ctx->rcbk_q; kc.maxY = ctx->rcbk_y; kc.maxKt = ctx->rcbk_k; kc.dQ0 = ctx->p.sub_model == 100 ? 0.1 : 0.168;
   kc.siginNN200 = ctx->k.siginnn200;
   { const size_t nn2 = (size_t)ctx->rcbk_q * ctx->rcbk_y * ctx->rcbk_k; kc.rkt = ctx->d_rcbk; kc.rna = ctx->d_rcbk ? ctx->d_rcbk + nn2 : nullptr; kc.ry2 = ctx->d_rcbk ? ctx->d_rcbk + 2 * nn2 : nullptr; }
   kc.npt = npt; kc.nkt = nkt; kc.nphi = nphi; kc.xp = d; kc.wp = d + npt; kc.xk = d + 2 * npt; kc.wk = d + 2 * npt + nkt; kc.cphi = d + 2 * npt + 2 * nkt;
-  CK(smc::launch_kln_table(kc, ctx->d_kln, ctx->stream)); ctx->launches++;
+  for (int iy = 0; iy < ctx->ny; iy++) {
+    // y = rapMin + (rapMax - rapMin) / binRapidity * iy with rapMin = -ymax, rapMax = ymax (MakeDensity.cpp:54-56, MCnucl.cpp:932)
+    kc.y = -ctx->p.ymax + (ctx->p.ymax - (-ctx->p.ymax)) / ctx->ny * iy;
+    CK(smc::launch_kln_table(kc, ctx->d_kln + (size_t)iy * tmax * tmax, ctx->stream)); ctx->launches++;
+  }
   CK(cudaStreamSynchronize(ctx->stream));
   cudaFree(d);
   ctx->st.kln_table = ctx->d_kln; ctx->cfg.kln_tmax = tmax; ctx->cfg.kln_dT = ctx->k.kln_dt;
-  if (host_out) CK(cudaMemcpy(host_out, ctx->d_kln, (size_t)tmax * tmax * sizeof(double), cudaMemcpyDeviceToHost));
+  if (host_out) CK(cudaMemcpy(host_out, ctx->d_kln, nt * sizeof(double), cudaMemcpyDeviceToHost));
   return SMC_OK;
 }
 
@@ -376,7 +382,8 @@ static int run_grid_stages(smc_ctx* ctx, int m, const int* kinds, int nd) { retu
 int smc_run_grid_stages(smc_ctx* ctx, int m, const int* kinds, int nd) {
   const smc::DevCfg& c = ctx->cfg;
   if (c.which_mc_model == 1 && !ctx->st.kln_table) FAIL(SMC_ERR_STATE, "MC-KLN density requires smc_build_kln_table / smc_set_kln_table first (MCnucl.cpp:636-640)");
-  ctx->st.nbd_pass = 0;            // the first density of an event; operation 3 counts its re-deposits from here
+  ctx->st.nbd_pass = ctx->slice;   // the first density of an event (one per rapidity slice); operation 3 counts its re-deposits from here
+  if (ctx->d_kln) ctx->st.kln_table = ctx->d_kln + (size_t)ctx->slice * c.kln_tmax * c.kln_tmax;
   if (ctx->profile) CK(cudaEventRecord(ctx->pev[1], ctx->stream));
   // deposit CTAs only cover each event's bounding rectangle: whoever reads whole grids needs zeros elsewhere
   if (ctx->need_zero) {
@@ -537,6 +544,25 @@ int smc_events_first_pass(smc_ctx* ctx, int m, const int* kinds, int nd) {
   return dsdy_cut_loop(ctx, m, kinds, nd);
 }
 
+// ny > 1 (MakeDensity.cpp:2170-2193): one more density + one more row per rapidity slice.  The event records and the
+// deposit inputs do not depend on the slice; MC-KLN looks its density up in the table of slice iy, the NBD fluctuation
+// draws afresh.  Rows go to out[(e * ny) + iy]; the grids left on the device are those of the last slice (the reference
+// writes every slice to the same file name, so the last one is what its files hold).
+static int run_slices(smc_ctx* ctx, int m, const int* kinds, int nd, smc_event_out* out) {
+  const int ny = ctx->ny; int rc;
+  std::vector<smc_event_out> tmp(m);
+  smc_fill_out(ctx, m, tmp.data());
+  for (int e = 0; e < m; e++) out[(size_t)e * ny] = tmp[e];
+  for (int iy = 1; iy < ny; iy++) {
+    ctx->slice = iy;
+    if ((rc = smc_run_grid_stages(ctx, m, kinds, nd)) || (rc = smc_fetch_results(ctx, m))) { ctx->slice = 0; return rc; }
+    smc_fill_out(ctx, m, tmp.data());
+    for (int e = 0; e < m; e++) out[(size_t)e * ny + iy] = tmp[e];
+  }
+  ctx->slice = 0;
+  return SMC_OK;
+}
+
 extern "C" int smc_run_events(smc_ctx* ctx, uint64_t first_event_id, int n, unsigned flags, smc_event_out* out) {
   if (!ctx || n < 0 || (!out && n > 0)) return SMC_ERR_PARAM;
   CK(cudaSetDevice(ctx->device));
@@ -547,7 +573,7 @@ extern "C" int smc_run_events(smc_ctx* ctx, uint64_t first_event_id, int n, unsi
   int kinds[8], nd = 0, rc;
   if ((rc = smc_plan_kinds(ctx, flags, kinds, &nd))) return rc;
   const int nb = (n + ctx->batch - 1) / ctx->batch;
-  if (nb >= 2 && ctx->p.cutdsdy != 1 && !ctx->profile && !getenv("SMC_NO_PIPELINE")) {
+  if (nb >= 2 && ctx->p.cutdsdy != 1 && !ctx->profile && ctx->ny == 1 && !getenv("SMC_NO_PIPELINE")) {
     // software pipeline over NS slots: batch i runs on the stream of slot i % NS; its rows are read back when the slot
     // comes round again, so K1/K2 of one batch overlap K3/K4 and the copies of the others
     static const int ns_env = getenv("SMC_SLOTS") ? atoi(getenv("SMC_SLOTS")) : 4;
@@ -588,7 +614,8 @@ extern "C" int smc_run_events(smc_ctx* ctx, uint64_t first_event_id, int n, unsi
     if ((rc = smc_fetch_results(ctx, m))) return rc;
     collect_stage_ms(ctx);
     if ((rc = dsdy_cut_loop(ctx, m, kinds, nd))) return rc;
-    smc_fill_out(ctx, m, out + off);
+    if (ctx->ny > 1) { if ((rc = run_slices(ctx, m, kinds, nd, out + (size_t)off * ctx->ny))) return rc; }
+    else smc_fill_out(ctx, m, out + off);
     ctx->last_n = m;
   }
   CK(cudaEventRecord(ctx->ev1, ctx->stream)); CK(cudaEventSynchronize(ctx->ev1));
@@ -681,7 +708,8 @@ extern "C" int smc_run_from_positions(smc_ctx* ctx, int n, const smc_event_in* i
     if ((rc = run_grid_stages(ctx, m, kinds, nd))) return rc;
     if ((rc = smc_fetch_results(ctx, m))) return rc;
     collect_stage_ms(ctx);
-    smc_fill_out(ctx, m, out + off);
+    if (ctx->ny > 1) { if ((rc = run_slices(ctx, m, kinds, nd, out + (size_t)off * ctx->ny))) return rc; }
+    else smc_fill_out(ctx, m, out + off);
     ctx->last_n = m;
   }
   CK(cudaEventRecord(ctx->ev1, ctx->stream)); CK(cudaEventSynchronize(ctx->ev1));

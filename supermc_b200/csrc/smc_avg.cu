@@ -196,19 +196,28 @@ static int avg_sequence(smc_ctx* ctx, int m) {
     return SMC_OK;
   };
   ctx->epoch++;                          // positions and boxes are about to move: host mirrors of the lists are stale
+  // order -> rapidity slice -> branch, as the reference nests them (MakeDensity.cpp:1268-1275): the moves are cumulative
+  // across slices too ("different rapidity slices are rotated separately, and this does not quite make sense").  Every
+  // slice is written to the same files at the end, so only the last slice's sums are kept.
+  const size_t tsz = (size_t)c.kln_tmax * c.kln_tmax;
   for (int order = ctx->avg_from; order <= ctx->avg_to; order++) {
     const int io = order - ctx->avg_from;
-    if ((rc = density())) return rc;                                                   // MakeDensity.cpp:1275
-    for (int branch = 0; branch < 2; branch++) {
-      if (!(ctx->avg_ed & (1 << branch))) continue;
-      double scale = branch == 1 ? c.finalFactor : 1.0;                                // ed branch: setRho(rho*finalFactor) first (:1391-1396)
-      if (ctx->avg_rp) {                                                               // :1289-1330 / :1397-1438
-        if ((rc = cm(order, scale)) || (rc = tf(0)) || (rc = density()) || (rc = acc(io, 1, branch))) return rc;
-        scale = 1.0;
+    for (int iy = 0; iy < ctx->ny; iy++) {
+      if (ctx->d_kln) st.kln_table = ctx->d_kln + (size_t)iy * tsz;
+      const bool keep = (iy == ctx->ny - 1);
+      if ((rc = density())) return rc;                                                   // MakeDensity.cpp:1275
+      for (int branch = 0; branch < 2; branch++) {
+        if (!(ctx->avg_ed & (1 << branch))) continue;
+        double scale = branch == 1 ? c.finalFactor : 1.0;                                // ed branch: setRho(rho*finalFactor) first (:1391-1396)
+        if (ctx->avg_rp) {                                                               // :1289-1330 / :1397-1438
+          if ((rc = cm(order, scale)) || (rc = tf(0)) || (rc = density()) || (keep && (rc = acc(io, 1, branch)))) return rc;
+          scale = 1.0;
+        }
+        if ((rc = cm(order, scale)) || (rc = tf(1)) || (rc = density()) || (keep && (rc = acc(io, 0, branch)))) return rc;   // :1331-1386 / :1439-1493
       }
-      if ((rc = cm(order, scale)) || (rc = tf(1)) || (rc = density()) || (rc = acc(io, 0, branch))) return rc;   // :1331-1386 / :1439-1493
     }
   }
+  if (ctx->d_kln) st.kln_table = ctx->d_kln;
   return SMC_OK;
 }
 

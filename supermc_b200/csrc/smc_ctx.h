@@ -53,6 +53,7 @@ struct smc_ctx {
   double* d_avg; int64_t avg_doubles; int64_t avg_count; int avg_from, avg_to, avg_rp, avg_ed;
   void* comm;                                      // multi-GPU state (smc_comm.cu)
   uint64_t epoch; smc_list_cache lists;            // epoch: bumped whenever the device records change
+  int ny, slice;                                   // rapidity slices (MCnucl.cpp:115): slice = the one the grid stages compute next
 };
 
 #define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(_e); return SMC_ERR_CUDA; } } while (0)

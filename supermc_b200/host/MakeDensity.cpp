@@ -136,7 +136,7 @@ MakeDensity::MakeDensity(ParameterReader* p, int device, smc_shard sh, const std
     p->setVal("rapMin", rapMin); p->setVal("rapMax", rapMax);
     finalFactor = params.finalfactor;
     deformed = (params.proj_deformed == 1 || params.targ_deformed == 1);
-    if (binRapidity != 1) { err = "ny != 1 (several rapidity slices) is not built: the B200 path computes the y = rapMin slice only"; return; }
+    if (binRapidity < 1) { err = "ny must be >= 1"; return; }
     if (ptflag < 0) { err = "PT_Flag < 0 (pT-differential tables) is unreachable in the reference (MCnucl.cpp:973 reads a misspelt key) and not built"; return; }
   } catch (std::exception& e) { err = e.what(); return; }
   const int rc = smc_create(&params, device, &ctx);
@@ -258,7 +258,8 @@ int MakeDensity::generateEccTable(int nevent) {
   const int lo = std::max(from_order, 1), hi = std::min(to_order, 9);
   const unsigned nthr = std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
   struct Chunk { std::vector<smc_event_out> out; int n = 0; long done = 0; };
-  Chunk buf[3]; for (auto& b : buf) b.out.resize(std::max(1, std::min(count, chunk)));
+  const int ny = binRapidity;            // one row per event and rapidity slice (MakeDensity.cpp:2170-2193)
+  Chunk buf[3]; for (auto& b : buf) b.out.resize((size_t)std::max(1, std::min(count, chunk)) * ny);
   std::mutex m; std::condition_variable cv; std::deque<Chunk*> full, empty; bool finished = false; long failed = 0;
   for (auto& b : buf) empty.push_back(&b);
   const char* base[2] = {"sn_ecc_eccp_%d.dat", "en_ecc_eccp_%d.dat"};     // en == sn numerically (quirk Q2)
@@ -270,7 +271,7 @@ int MakeDensity::generateEccTable(int nevent) {
       std::vector<std::thread> th;
       std::vector<long> bad(nthr, 0);
       for (unsigned t = 0; t < nthr; t++) th.emplace_back([&, t] {
-        const int a = (int)((long)c->n * t / nthr), b = (int)((long)c->n * (t + 1) / nthr);
+        const int a = (int)((long)c->n * ny * t / nthr), b = (int)((long)c->n * ny * (t + 1) / nthr);
         for (auto& r : part[t]) r.clear();
         for (int e = a; e < b; e++) {
           if (c->out[e].status != SMC_OK) { bad[t]++; continue; }
@@ -292,7 +293,7 @@ int MakeDensity::generateEccTable(int nevent) {
           std::fclose(fp);
         }
       }
-      if (binary) { FILE* fp = std::fopen(path("ecc_rows.bin").c_str(), "ab"); if (fp) { std::fwrite(c->out.data(), sizeof(smc_event_out), (size_t)c->n, fp); std::fclose(fp); } }
+      if (binary) { FILE* fp = std::fopen(path("ecc_rows.bin").c_str(), "ab"); if (fp) { std::fwrite(c->out.data(), sizeof(smc_event_out), (size_t)c->n * ny, fp); std::fclose(fp); } }
       std::cout << "processed events: " << c->done << " / " << count << "\r" << std::flush;
       { std::lock_guard<std::mutex> l(m); empty.push_back(c); } cv.notify_all();
     }
@@ -382,7 +383,11 @@ static int ebe_common(MakeDensity* self, smc_ctx* ctx, ParameterReader* paraRdr,
   const size_t G = (size_t)Maxx * Maxy;
   const bool binary = paraRdr->getVal("output_binary", 0) != 0;          // extension: raw float64 lattices (<stem>.bin) instead of text
   WriterPool pool(std::max(2u, std::min(64u, std::thread::hardware_concurrency())));
-  std::vector<smc_event_out> out(batch);
+  const int ny = std::max(1, self->params.ny);
+  std::vector<smc_event_out> out_all((size_t)batch * ny);
+  // the reference writes every rapidity slice to the same per-event file names (MakeDensity.cpp:311-445): the files hold
+  // the last slice, the eccentricity files one row per slice
+  rapMin = rapMin + (-rapMin - rapMin) / ny * (ny - 1);
   auto P = [&](const char* fmt, long ev) { char b[160]; std::snprintf(b, sizeof b, fmt, ev); return data_dir + "/" + b; };
   // one page-locked block per (batch, grid kind), filled by ONE strided device->host copy and shared by the writer jobs
   struct PinBuf { double* p; explicit PinBuf(size_t n) : p((double*)smc_pinned_alloc(n * sizeof(double))) {} ~PinBuf() { smc_pinned_free(p); } };
@@ -404,7 +409,7 @@ static int ebe_common(MakeDensity* self, smc_ctx* ctx, ParameterReader* paraRdr,
   auto ck = [&](int rc) { if (rc != SMC_OK && err.empty()) err = smc_last_error(ctx); return rc != SMC_OK; };
   for (int done = 0; done < count; done += batch) {
     const int n = std::min(batch, count - done);
-    if (smc_run_events(ctx, first + done, n, flags, out.data()) != SMC_OK) { err = smc_last_error(ctx); return 1; }
+    if (smc_run_events(ctx, first + done, n, flags, out_all.data()) != SMC_OK) { err = smc_last_error(ctx); return 1; }
     Buf b_rho, b_rb, b_ta, b_tb, b_sum, b_sa, b_sb;
     if ((use_sd || use_ed) && !(b_rho = fetch_all(n, SMC_GRID_RHO, ff))) return 1;
     if (o_rb && !(b_rb = fetch_all(n, SMC_GRID_RHO_BINARY, 1.0))) return 1;
@@ -415,6 +420,7 @@ static int ebe_common(MakeDensity* self, smc_ctx* ctx, ParameterReader* paraRdr,
     if (o_sp && (!(b_sa = fetch_all(n, SMC_GRID_SPEC_A, 1.0)) || !(b_sb = fetch_all(n, SMC_GRID_SPEC_B, 1.0)))) return 1;
     for (int e = 0; e < n; e++) {
       const long event = (long)(first + done + e) + 1;                   // the reference counts events from 1
+      const smc_event_out* out = out_all.data() + (size_t)e * ny - e;     // out[e] = slice 0 of event e
       if (out[e].status != SMC_OK) { std::cerr << "event " << event << ": status " << out[e].status << std::endl; continue; }
       const double npart = out[e].npart1 + out[e].npart2;
       int np = 0, nc = 0, ns = 0;
@@ -440,10 +446,11 @@ static int ebe_common(MakeDensity* self, smc_ctx* ctx, ParameterReader* paraRdr,
         char nm[160];
         for (int o = std::max(from_order, 1); o <= std::min(to_order, 9); o++) {
           std::snprintf(nm, sizeof nm, "%s_ecc_eccp_%d_event_%ld.dat", f == 0 ? "sn" : "en", o, event);
-          write_file(data_dir + "/" + nm, MakeDensity::formatEccRow(out[e], o, deformed), true);
+          std::string rows; for (int iy = 0; iy < ny; iy++) rows += MakeDensity::formatEccRow(out[e + iy], o, deformed);
+          write_file(data_dir + "/" + nm, rows, true);
         }
         std::snprintf(nm, sizeof nm, "%s_ecc_eccp_%d_event_%ld.dat", f == 0 ? "sn" : "en", 10, event);
-        write_file(data_dir + "/" + nm, MakeDensity::formatEccRowAll(out[e], deformed), true);
+        { std::string rows; for (int iy = 0; iy < ny; iy++) rows += MakeDensity::formatEccRowAll(out[e + iy], deformed); write_file(data_dir + "/" + nm, rows, true); }
       }
       if (use_sd || use_ed) {
         const double* g = b_rho->p + (size_t)e * G;
@@ -505,7 +512,8 @@ int MakeDensity::average_write() {
     if (smc_avg_get(ctx, order, variant, quantity, branch, g->data()) != SMC_OK) { err = smc_last_error(ctx); return 1; }
     char stem[200]; std::snprintf(stem, sizeof stem, fmt, order);
     const std::string st = path(stem); const double npart = last_npart;
-    const int mx = Maxx, my = Maxy; const double x0 = Xmin, y0 = Ymin, ddx = dx, ddy = dy, rap = rapMin;
+    const int mx = Maxx, my = Maxy; const double x0 = Xmin, y0 = Ymin, ddx = dx, ddy = dy;
+    const double rap = rapMin + (rapMax - rapMin) / binRapidity * (binRapidity - 1);      // the files hold the last slice (:1579-1900)
     if (use_4col) pool.submit([=] { std::string s; MakeDensity::formatDensity4Col(g->data(), mx, my, x0, y0, ddx, ddy, rap, npart, s); write_file(st + "_4col.dat", s, false); });
     if (use_block) pool.submit([=] { std::string s; MakeDensity::formatDensityBlock(g->data(), mx, my, s); write_file(st + "_block.dat", s, false); });
     return 0;

@@ -63,6 +63,9 @@ SYSTEMS = {
                                          cc_fluctuation_model=0, randomSeed=31, **{"lambda": 0.138})),
     "pbpb2760_kln_central": ("zero", 4, 1, dict(which_mc_model=1, sub_model=7, Aproj=208, Atarg=208, ecm=2760, tmax=71, tmax_subdivision=3,
                                                 cc_fluctuation_model=0, randomSeed=32, bmax=3.5, **{"lambda": 0.138})),
+    # three rapidity slices (ny = 3, ymax = 2: y = -2, -2/3, 2/3 -- MCnucl.cpp:932 divides by ny, not ny - 1): one table per slice
+    "auau200_kln_ny3": ("zero", 6, 1, dict(which_mc_model=1, sub_model=7, Aproj=197, Atarg=197, ecm=200, tmax=24, tmax_subdivision=3,
+                                           cc_fluctuation_model=0, randomSeed=27, bmin=8, ny=3, ymax=2)),
     # table-driven nuclei with synthetic configuration files in the reference's formats (tests/table_synth.py; the real files
     # are missing blobs upstream): O+O (Nucleus.cpp:462-478,555-574) and NN-correlated Au (Nucleus.cpp:481-522,623-666)
     "oo200_glb": ("rand", NEV, 1, dict(which_mc_model=5, sub_model=1, Aproj=16, Atarg=16, ecm=200, alpha=0.14,
@@ -101,7 +104,8 @@ def run_system(name):
     glob, tries = refio.group_tries(rec)
     ncol = 53 if (p.get("proj_deformed") or p.get("targ_deformed")) else 49   # deformed rows carry 4 uninitialised extras (quirk Q9)
     ecc = np.loadtxt(eccf).reshape(-1, ncol)[:, :49]
-    out = {k: glob[k] for k in ("kln_table", "kln_consts") if k in glob}
+    out = {k: glob[k] for k in glob if k.startswith("kln_")}
+    ny = int(p.get("ny", 1))
     if name == "pbpb2760_kln_central":         # same table as the minimum-bias run (deterministic BASES seed): keep one copy
         assert np.array_equal(np.load(os.path.join(ROOT, "tests", "golden", "pbpb2760_kln.npz"))["kln_table"], out.pop("kln_table"))
     out.update({"consts": glob["consts"], "params_keys": np.array(list(p.keys())), "params_vals": np.array([float(v) for v in p.values()]),
@@ -124,10 +128,13 @@ def run_system(name):
             out[pre + "proj_x"] = t["proj_x"]; out[pre + "targ_x"] = t["targ_x"]
         if acc:
             out[pre + "dndy"] = t["dndy"]; out[pre + "region"] = t["region"]; out[pre + "spectators"] = t["spectators"]
-            out[pre + "ecc_index"] = np.array(ia)
+            out[pre + "ecc_index"] = np.array(ia * ny)          # ny rows per event, slice-major
             if ia < ngrid:
                 for k in ("TA1", "TA2", "rho", "rho_binary", "spec1", "spec2"):
                     out[pre + k] = t[k]
+                for k in t:
+                    if k.startswith("rho_y"):
+                        out[pre + k] = t[k]
                 for k in t:
                     if k.startswith("rp") or k.startswith("rot"):
                         if k.endswith("/TA1") or k.endswith("/TA2") or k.endswith("spec1") or k.endswith("spec2") or k.endswith("rho_binary") or k.endswith("_x"):

@@ -50,6 +50,8 @@ class Golden:
             kw["gaussian_lambda"] = p["gaussian_lambda"]
         if "lambda" in p:
             kw.update({"lambda": p["lambda"], "tmax": int(p["tmax"]), "tmax_subdivision": int(p["tmax_subdivision"])})
+        if "ny" in p:
+            kw.update(ny=int(p["ny"]), ymax=p["ymax"])
         kw.update(over)
         return capi.default_params(**kw)
 

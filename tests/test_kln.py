@@ -147,3 +147,72 @@ def test_gpu_rcbk_table_equals_oracle(oracle_lib, tmp_path, monkeypatch):
         v = port.rcbk_dndy(k, t, 0.0, dT * i, dT * j, 100, 50, 16)
         assert abs(T[i, j] / v - 1) < 1e-9, (i, j, T[i, j], v)
     ctx.close()
+
+
+# ---- several rapidity slices (ny = 3, ymax = 2): one table per slice at y = rapMin + (rapMax - rapMin) / ny * iy ----
+def _ny3():
+    g = Golden("auau200_kln_ny3")
+    tables = np.stack([g.z["kln_table"], g.z["kln_table_y1"], g.z["kln_table_y2"]])
+    ys = [-2.0 + 4.0 / 3 * iy for iy in range(3)]              # MCnucl.cpp:932 (divides by ny, not ny - 1)
+    return g, tables, ys
+
+
+def test_oracle_rapidity_slices_vs_reference(oracle_lib):
+    port = oracle_lib
+    g, tables, ys = _ny3()
+    dT = float(g.z["kln_consts"][0])
+    k = port.kln(g.par["ecm"], g.par["lambda"])
+    for iy, y in enumerate(ys):
+        for i, j in [(2, 3), (10, 31), (40, 8), (69, 69)]:
+            v = port.kln_dndy(k, y, dT * i, dT * j, 400, 200, 64)
+            assert abs(v / tables[iy][i, j] - 1) < 5e-3, (iy, i, j, v, tables[iy][i, j])
+    assert np.abs(tables[0] / np.maximum(tables[2], 1e-300) - 1)[1:, 1:].max() > 0.05       # the slices really differ
+    cfg = g.oracle_cfg(port)
+    t = [t for t in g.tries() if "rho_y1" in t][0]
+    for iy, key in enumerate(("rho", "rho_y1", "rho_y2")):
+        rho, _ = port.density_kln(cfg, t["TA1"], t["TA2"], tables[iy], dT)
+        assert np.array_equal(rho, t[key])
+        boxes = np.concatenate([t["proj"][t["proj_part"].astype(int), 3:7], t["targ"][t["targ_part"].astype(int), 3:7], np.zeros((1, 4))])
+        e = port.eccentricities(cfg, rho * g.par["finalfactor"], boxes)
+        assert np.array_equal(e["mom"], g.ecc_rows[int(t["ecc_index"]) + iy][:45].reshape(9, 5))
+
+
+@pytest.mark.gpu
+def test_gpu_rapidity_slices_match_reference(oracle_lib, monkeypatch):
+    import supermc_b200 as smc
+    port = oracle_lib
+    g, tables, ys = _ny3(); cfg = g.oracle_cfg(port)
+    dT = float(g.z["kln_consts"][0])
+    ctx = smc.Context(g.smc_params(smc.capi, max_batch=32))
+    assert ctx.p.ny == 3
+    # (1) the device builds one table per slice, each within BASES' error of the reference's
+    monkeypatch.setenv("SMC_KLN_QUAD", "200,100,32")
+    T = ctx.build_kln_table()
+    assert T.shape == tables.shape
+    for iy in range(3):
+        assert np.abs(T[iy][1:, 1:] / tables[iy][1:, 1:] - 1).max() < 5e-3, iy
+    k = port.kln(g.par["ecm"], g.par["lambda"])
+    assert abs(T[1][7, 22] / port.kln_dndy(k, ys[1], dT * 7, dT * 22, 200, 100, 32) - 1) < 1e-10
+    # (2) with the reference's tables installed: one row per event and slice, equal to the reference's rows
+    ctx.set_kln_table(tables, dT)
+    tries = g.tries()
+    out = ctx.run_from_positions([event_in_from(t, port, cfg) for t in tries], smc.RUN_MOMENTS | smc.RUN_THICKNESS)
+    assert len(out) == 3 * len(tries)
+    for it, t in enumerate(tries):
+        if not int(t["hdr"][4]):
+            continue
+        for iy in range(3):
+            o = out[3 * it + iy]; row = g.ecc_rows[int(t["ecc_index"]) + iy]
+            assert (o["ncoll"], o["npart1"]) == (int(t["hdr"][1]), int(t["hdr"][2]))
+            assert np.abs(o["mom"][:, :4] - row[:45].reshape(9, 5)[:, :4]).max() < 1e-9, (it, iy)
+            assert abs(o["total"] / row[47] - 1) < 1e-10
+        if "rho_y2" in t:      # the grid left on the device is the last slice's
+            assert rel_err(ctx.grid(it, smc.GRID_RHO), t["rho_y2"]).max() < 1e-9
+    # (3) sampled events: ny rows each, slices differ, event content independent of ny
+    ev = ctx.run_events(0, 8)
+    one = smc.Context(g.smc_params(smc.capi, max_batch=32, ny=1, ymax=2.0))
+    one.set_kln_table(tables[0], dT)
+    ev1 = one.run_events(0, 8)
+    assert len(ev) == 24 and np.array_equal(ev["b"][0::3], ev1["b"]) and np.array_equal(ev["ncoll"][1::3], ev1["ncoll"])
+    assert np.allclose(ev["total"][0::3], ev1["total"], rtol=1e-13) and (np.abs(ev["total"][2::3] / ev["total"][0::3] - 1) > 1e-3).all()
+    ctx.close(); one.close()
