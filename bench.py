@@ -398,6 +398,7 @@ def scan_exe_line(a):
     def ours(n):
         d = tempfile.mkdtemp(prefix="smcscan_"); os.makedirs(os.path.join(d, "data"))
         subprocess.check_call(["cp", os.path.join(ROOT, "supermc_b200", "parameters.dat"), d])
+        os.sync()          # the previous run's 4 GB of dirty pages would throttle this run's writes
         t0 = time.perf_counter()
         so = subprocess.run([exe] + args + ["nev=%d" % n, "randomSeed=20261017"], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, check=True).stdout
         dt = time.perf_counter() - t0

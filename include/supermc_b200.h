@@ -18,6 +18,7 @@ extern "C" {
 #endif
 
 #define SMC_ABI_VERSION 3
+#define SMC_EXTRA_ROW 20
 
 enum {
   SMC_OK = 0,
@@ -41,8 +42,8 @@ typedef struct smc_params {
   int proj_deformed, targ_deformed;
   int include_nn_correlation;    /*                                            Nucleus.cpp:26 */
   int shape_of_nucleons;         /* 1 disk, 2 gaussian(sigma_NN), 3 gaussian(gaussian_lambda), 4 user width  GaussianNucleonsCal.cpp:28-55 */
-  int collision_criterion;       /* 1 disk, 2 gaussian, else from shape_of_entropy   MCnucl.cpp:357-385 */
-  int shape_of_entropy;          /* 1 disk, 2 gaussian                         MCnucl.cpp:109 */
+  int collision_criterion;       /* 1 disk, 2 gaussian, 3 valence-quark overlap, else from shape_of_entropy   MCnucl.cpp:357-385 */
+  int shape_of_entropy;          /* 1 disk, 2 gaussian, 3 valence quarks       MCnucl.cpp:109,856 */
   double quark_width;            /*                                            Nucleus.cpp:29 */
   double gauss_nucl_width;       /* shape_of_nucleons == 4 */
   double ecm, bmin, bmax;        /*                                            MakeDensity.cpp:34-35,61 */
@@ -104,8 +105,11 @@ typedef struct smc_event_in {
                                     (fluctfactor, additional_weight); NULL = draw / derive on device */
   int n_coll_weight;
   int use_given_weights;         /* 1: nucleon weights come from proj/targ column 7 (reference: last draw wins) */
-  /* averaged profiles only (smc_avg_run_from_positions): rows of 16 per nucleon -- stale base box xL xR yL yR
-   * (Particle::baseBox, quirk Q4), three valence-quark offsets (x y z each), AABB centre x y, one spare; NULL = derive */
+  /* per-nucleon state beyond the 8-double row, rows of SMC_EXTRA_ROW (20): [0..3] stale base box xL xR yL yR
+   * (Particle::baseBox, quirk Q4), [4..12] three valence-quark offsets (x y z each), [13..14] AABB centre x y,
+   * [15..17] per-quark multiplicity weights (Quark::fluctFactor; shape_of_entropy 3, used with use_given_weights),
+   * [18..19] spare.  Read by the averaged profiles (smc_avg_run_from_positions) and by the quark-substructure options
+   * (shape_of_entropy 3, collision_criterion 3); NULL = derive (no quark offsets, weights 1/3) */
   const double* proj_extra;
   const double* targ_extra;
 } smc_event_in;
@@ -182,6 +186,9 @@ int  smc_get_participants(smc_ctx* ctx, int slot, double* host8, int* n);
 int  smc_get_collisions(smc_ctx* ctx, int slot, double* host6, int* n);
 int  smc_get_spectators(smc_ctx* ctx, int slot, double* host3, int* n);
 int  smc_get_nucleons(smc_ctx* ctx, int slot, int which, double* host8, int* n);
+/* Nucleus::dumpQuarks (src/Nucleus.cpp:780-797, the data/quarks.data rows): the three valence quarks of every wounded
+ * nucleon, participant order, rows x y xL xR yL yR.  Needs SMC_RUN_LISTS, shape_of_entropy 3 or collision_criterion 3. */
+int  smc_get_quarks(smc_ctx* ctx, int slot, double* host6, int* n);
 
 /* MakeDensity::generate_profile_average accumulators (src/MakeDensity.cpp:1240-1577).
  * slots: for each order in [from,to] and each variant (0 rotated, 1 reaction-plane) and each quantity

@@ -52,6 +52,7 @@ def lib():
         L.smc_o_drand48.restype = C.c_double
         L.smc_o_six_point.restype = C.c_double; L.smc_o_six_point.argtypes = [C.c_double] * 8
         L.smc_o_density.restype = C.c_double
+        L.smc_o_density_quarks.restype = C.c_double
         L.smc_o_density_kln.restype = C.c_double
         L.smc_o_kln_integrand.restype = C.c_double
         L.smc_o_kln_dndy.restype = C.c_double
@@ -219,6 +220,37 @@ def density(cfg, proj8, targ8, coll8):
     p, t, c = _src8(proj8), _src8(targ8), _src8(coll8)
     g = np.zeros((cfg.Maxx, cfg.Maxy))
     dndy = lib().smc_o_density(C.byref(cfg), len(p), _d(p), len(t), _d(t), len(c), _d(c), _d(g))
+    return g, dndy
+
+
+def populate_q(n, xc, yc, stream):
+    """populate() + the valence-quark offsets (qx0 qy0 qx1 qy1 qx2 qy2 per nucleon, sorted order)"""
+    q = np.zeros((max(n.A, 1), 6))
+    lib().smc_o_quark_out(_d(q))
+    try:
+        rows, _ = populate(n, xc, yc, stream=stream)
+    finally:
+        lib().smc_o_quark_out(None)
+    return rows, q
+
+
+def collide_quarks(cfg, proj7, qA, targ7, qB, quark_width, stream=None, u_in=None, want_u=False):
+    """collision_criterion 3: GaussianNucleonsCal::testFluctuatedCollision on the quark offsets"""
+    qA = np.ascontiguousarray(qA, dtype=np.float64); qB = np.ascontiguousarray(qB, dtype=np.float64)
+    lib().smc_o_quark_collide(_d(qA), _d(qB), C.c_double(quark_width))
+    try:
+        return collide(cfg, proj7, targ7, stream=stream, u_in=u_in, want_u=want_u)
+    finally:
+        lib().smc_o_quark_collide(None, None, C.c_double(0.0))
+
+
+def density_quarks(cfg, proj8, qP, fP, targ8, qT, fT, coll8, quark_width):
+    """shape_of_entropy 3: three quark Gaussians per wounded nucleon (offsets q*, weights f*) + the binary term"""
+    p, t, c = _src8(proj8), _src8(targ8), _src8(coll8)
+    qP = np.ascontiguousarray(qP, dtype=np.float64).reshape(-1, 6); qT = np.ascontiguousarray(qT, dtype=np.float64).reshape(-1, 6)
+    fP = np.ascontiguousarray(fP, dtype=np.float64).reshape(-1, 3); fT = np.ascontiguousarray(fT, dtype=np.float64).reshape(-1, 3)
+    g = np.zeros((cfg.Maxx, cfg.Maxy))
+    dndy = lib().smc_o_density_quarks(C.byref(cfg), len(p), _d(p), _d(qP), _d(fP), len(t), _d(t), _d(qT), _d(fT), len(c), _d(c), C.c_double(quark_width), _d(g))
     return g, dndy
 
 

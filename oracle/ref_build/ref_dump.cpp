@@ -23,6 +23,24 @@
 #include <string>
 #include <vector>
 #include <sys/time.h>
+#include <iostream>
+#include <sstream>
+#include <fstream>
+#include <iomanip>
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <string>
+#include <time.h>
+// Quark::fluctFactor (the per-quark multiplicity weight of shape_of_entropy = 3) has no getter: this harness -- and only
+// this translation unit -- reads it by seeing the reference's class bodies with `class` spelt `struct` and `private` spelt
+// `public` (the object layout is the same, no reference source is touched; the standard headers those files include are
+// already in, so only the reference's own declarations are affected)
+#define private public
+#define class struct
+#include "Particle.h"
+#undef class
+#undef private
 #include "MakeDensity.h"
 #include "ParamDefs.h"
 #include "ParameterReader.h"
@@ -79,6 +97,9 @@ static void dump_nucleus(const string& name, Nucleus* nuc) {
     x.push_back(cb.getX()); x.push_back(cb.getY()); x.push_back(0.0);
   }
   wr2(name + "_x", (long)n.size(), 16, x);
+  vector<double> qf;
+  for (size_t i = 0; i < n.size(); i++) { vector<Quark>& q = n[i]->getQuarks(); for (int k = 0; k < 3; k++) qf.push_back(q[k].fluctFactor); }
+  wr2(name + "_qf", (long)n.size(), 3, qf);
 }
 
 static void dump_grids(const string& pfx, McProbe* mc) {

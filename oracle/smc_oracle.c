@@ -162,6 +162,14 @@ static void rot3(double cth, double phi, double* x, double* y, double* z) {
 
 /* Particle ctor: base box + three valence quarks -> AABB (Particle.cpp:16-24,32-99; Quark.h:28-35;
  * Quark.cpp:5-10).  Consumes 4 uniforms (kind 4, slots 0..3). */
+/* valence-quark state for shape_of_entropy = 3 / collision_criterion = 3 (set by the test, not thread-safe):
+ * qout  -- emit_sorted() leaves qx0 qy0 qx1 qy1 qx2 qy2 per nucleon (sorted order) here
+ * qA/qB -- offsets of the projectile / target nucleons for the quark-overlap hit test, qw = quark_width */
+static struct { double* qout; const double* qA; const double* qB; double qw; } g_q;
+void smc_o_quark_out(double* qout6) { g_q.qout = qout6; }
+void smc_o_quark_collide(const double* qA6, const double* qB6, double quark_width) { g_q.qA = qA6; g_q.qB = qB6; g_q.qw = quark_width; }
+static double g_last_q[6];
+
 static void particle_box(const smc_o_nucleus* n, double x0, double y0, smc_o_uniform_fn U, void* st,
                          int cand, box_t* out) {
   box_t base; box_zero(&base); box_set_center(&base, x0, y0); box_set_square(&base, 8 * n->width);
@@ -190,6 +198,7 @@ static void particle_box(const smc_o_nucleus* n, double x0, double y0, smc_o_uni
     box_t b; box_zero(&b); box_set_center(&b, qx[q], qy[q]); box_set_square(&b, 8 * n->quark_width);
     box_set_center(&b, x0 + qx[q], y0 + qy[q]);
     box_union(out, &b);
+    g_last_q[2 * q] = qx[q]; g_last_q[2 * q + 1] = qy[q];
   }
 }
 
@@ -223,7 +232,7 @@ static double sph_harm(int l, double ct) {                                      
   return y * 0.10578554691520431;
 }
 
-typedef struct { double x, y, z; box_t box; int idx; } part_t;
+typedef struct { double x, y, z; box_t box; int idx; double q[6]; } part_t;
 static int cmp_xl(const void* a, const void* b) {
   const part_t* p = (const part_t*)a; const part_t* q = (const part_t*)b;
   if (p->box.xL < q->box.xL) return -1;
@@ -239,6 +248,7 @@ static void emit_sorted(part_t* P, int A, double* out7) {
   for (int i = 0; i < A; i++) {
     double* o = out7 + 7 * i;
     o[0] = P[i].x; o[1] = P[i].y; o[2] = P[i].z; o[3] = P[i].box.xL; o[4] = P[i].box.xR; o[5] = P[i].box.yL; o[6] = P[i].box.yR;
+    if (g_q.qout) memcpy(g_q.qout + 6 * i, P[i].q, sizeof P[i].q);
   }
 }
 
@@ -257,7 +267,7 @@ long smc_o_populate(const smc_o_nucleus* n, double xCenter, double yCenter,
   int nws = 0;   /* flat index of the Woods-Saxon rejection draws: the address the Philox callback uses (drand48 ignores it) */
   if (A == 1) {
     P[0].x = xCenter; P[0].y = yCenter; P[0].z = 0.0; P[0].idx = 0;
-    particle_box(n, xCenter, yCenter, U, st, cand, &P[0].box); nu += 4;
+    particle_box(n, xCenter, yCenter, U, st, cand, &P[0].box); memcpy(P[0].q, g_last_q, sizeof g_last_q); nu += 4;
     emit_sorted(P, 1, out7); free(P); return nu;
   }
   double xcm = 0.0, ycm = 0.0, zcm = 0.0;
@@ -298,7 +308,7 @@ long smc_o_populate(const smc_o_nucleus* n, double xCenter, double yCenter,
     } while (icon == 1);
     xcm += x; ycm += y; zcm += z;
     P[ia].x = x; P[ia].y = y; P[ia].z = z; P[ia].idx = ia;
-    particle_box(n, x, y, U, st, cand, &P[ia].box); nu += 4;
+    particle_box(n, x, y, U, st, cand, &P[ia].box); memcpy(P[ia].q, g_last_q, sizeof g_last_q); nu += 4;
     cand++;
   }
   for (int ia = 0; ia < A; ia++) {
@@ -333,7 +343,7 @@ long smc_o_populate_table(const smc_o_nucleus* n, const double* cfg, int recentr
     for (int ia = 0; ia < A; ia++) {
       xcm += t[3 * ia]; ycm += t[3 * ia + 1]; zcm += t[3 * ia + 2];
       P[ia].x = t[3 * ia]; P[ia].y = t[3 * ia + 1]; P[ia].z = t[3 * ia + 2]; P[ia].idx = ia;
-      particle_box(n, P[ia].x, P[ia].y, U, st, ia, &P[ia].box); nu += 4;
+      particle_box(n, P[ia].x, P[ia].y, U, st, ia, &P[ia].box); memcpy(P[ia].q, g_last_q, sizeof g_last_q); nu += 4;
     }
     for (int ia = 0; ia < A; ia++) {
       double x = P[ia].x - xcm / A + xCenter, y = P[ia].y - ycm / A + yCenter, z = P[ia].z - zcm / A;
@@ -342,7 +352,7 @@ long smc_o_populate_table(const smc_o_nucleus* n, const double* cfg, int recentr
   } else {
     for (int ia = 0; ia < A; ia++) {
       P[ia].x = t[3 * ia] + xCenter; P[ia].y = t[3 * ia + 1] + yCenter; P[ia].z = t[3 * ia + 2]; P[ia].idx = ia;
-      particle_box(n, P[ia].x, P[ia].y, U, st, ia, &P[ia].box); nu += 4;
+      particle_box(n, P[ia].x, P[ia].y, U, st, ia, &P[ia].box); memcpy(P[ia].q, g_last_q, sizeof g_last_q); nu += 4;
     }
   }
   emit_sorted(P, A, out7);
@@ -381,8 +391,8 @@ long smc_o_populate_deuteron(const smc_o_nucleus* n, double xCenter, double yCen
   part_t P[2];
   P[0].x = x1 + xCenter; P[0].y = y1 + yCenter; P[0].z = z1; P[0].idx = 0;
   P[1].x = -x1 + xCenter; P[1].y = -y1 + yCenter; P[1].z = -z1; P[1].idx = 1;
-  particle_box(n, P[0].x, P[0].y, U, st, 0, &P[0].box);
-  particle_box(n, P[1].x, P[1].y, U, st, 1, &P[1].box);
+  particle_box(n, P[0].x, P[0].y, U, st, 0, &P[0].box); memcpy(P[0].q, g_last_q, sizeof g_last_q);
+  particle_box(n, P[1].x, P[1].y, U, st, 1, &P[1].box); memcpy(P[1].q, g_last_q, sizeof g_last_q);
   emit_sorted(P, 2, out7);
   return 11;
 }
@@ -394,7 +404,8 @@ int smc_o_collide(const smc_o_cfg* c, int A, const double* P, int B, const doubl
                   smc_o_uniform_fn U, void* st, const double* u_in, double* u_dense,
                   int* ncollA, int* ncollB, int* firsthitB, int* pairs, int max_pairs, long* n_tested) {
   int crit = c->collision_criterion;
-  if (crit != 1 && crit != 2) crit = (c->shape_of_entropy == 2) ? 2 : 1;            /* MCnucl.cpp:376-383 */
+  if (crit < 1 || crit > 4) crit = (c->shape_of_entropy == 2) ? 2 : (c->shape_of_entropy == 3) ? 3 : 1;   /* MCnucl.cpp:376-383 */
+  if (crit == 4 || (crit == 3 && !(g_q.qA && g_q.qB))) return -1;                    /* 4 (numeric overlap) is not restated */
   const double w = c->width;
   for (int i = 0; i < A; i++) ncollA[i] = 0;
   for (int j = 0; j < B; j++) { ncollB[j] = 0; if (firsthitB) firsthitB[j] = -1; }
@@ -417,7 +428,18 @@ int smc_o_collide(const smc_o_cfg* c, int A, const double* P, int B, const doubl
         int hit;
         tested++;
         if (crit == 1) hit = (b * b <= c->dsq) ? 1 : 0;
-        else {
+        else if (crit == 3) {                                                            /* GaussianNucleonsCal.cpp:70-97 */
+          const double gw2 = g_q.qw * g_q.qw; double overlap = 0;
+          for (int a = 0; a < 3; a++) for (int q = 0; q < 3; q++) {
+            const double mx = g_q.qA[6 * ip + 2 * a] + p[0], my = g_q.qA[6 * ip + 2 * a + 1] + p[1];       /* Quark::getX = x + parent */
+            const double yx = g_q.qB[6 * i + 2 * q] + t[0], yy = g_q.qB[6 * i + 2 * q + 1] + t[1];
+            const double d = (mx - yx) * (mx - yx) + (my - yy) * (my - yy);
+            overlap += (1 / (4 * M_PI * gw2)) * exp(-d / (4 * gw2)) / 9;
+          }
+          double u = u_in ? u_in[(long)ip * B + i] : U(st, 5, ip, i);
+          if (u_dense) u_dense[(long)ip * B + i] = u;
+          hit = (u < 1. - exp(-c->sigma_gg * overlap)) ? 1 : 0;
+        } else {
           double u = u_in ? u_in[(long)ip * B + i] : U(st, 5, ip, i);
           if (u_dense) u_dense[(long)ip * B + i] = u;
           hit = (u < 1. - exp(-c->sigma_gg * exp(-b * b / (4. * w * w)) / (4. * M_PI * w * w))) ? 1 : 0;
@@ -486,6 +508,55 @@ void smc_o_add_density(const smc_o_cfg* c, int n, const double* S, double* dens)
       }
     }
   }
+}
+
+/* addDensity with shape_of_entropy == 3 (MCnucl.cpp:856-858 -> Particle::getFluctuatedDensity, Particle.cpp:149-163 ->
+ * Quark::getSmoothDensity / getSmoothTn, Quark.h:52-55, Quark.cpp:14-22): three Gaussians of width quark_width at the
+ * valence quarks, weights f3, cut at d > 5*quark_width where d is the SQUARED distance (the reference compares fm^2 with
+ * fm -- kept); window = the nucleon's AABB */
+void smc_o_add_density_quarks(const smc_o_cfg* c, int n, const double* S, const double* q6, const double* f3, double qw, double* dens) {
+  for (int k = 0; k < n; k++) {
+    const double* s = S + 8 * k;
+    double X = s[0], Y = s[1];
+    int xl = imax2(0, (int)((s[2] - c->Xmin) / c->dx)), xr = imin2(c->Maxx, (int)((s[3] - c->Xmin) / c->dx));
+    int yl = imax2(0, (int)((s[4] - c->Ymin) / c->dy)), yr = imin2(c->Maxy, (int)((s[5] - c->Ymin) / c->dy));
+    for (int ir = xl; ir < xr; ir++) {
+      double xg = c->Xmin + ir * c->dx;
+      for (int jr = yl; jr < yr; jr++) {
+        double yg = c->Ymin + jr * c->dy;
+        double density = 0;
+        for (int q = 0; q < 3; q++) {
+          double xRel = xg - X, yRel = yg - Y, x = q6[6 * k + 2 * q], y = q6[6 * k + 2 * q + 1];
+          double d = (xRel - x) * (xRel - x) + (yRel - y) * (yRel - y);
+          double tn = (d > 5 * qw) ? 0 : (1 / (2 * M_PI * qw * qw)) * exp(-d / (2 * qw * qw));
+          density += f3[3 * k + q] * tn;
+        }
+        dens[(long)ir * c->Maxy + jr] += density;
+      }
+    }
+  }
+}
+
+double smc_o_density_quarks(const smc_o_cfg* c, int np, const double* proj8, const double* qP, const double* fP, int nt, const double* targ8,
+                            const double* qT, const double* fT, int nc, const double* coll8, double qw, double* rho) {
+  const long G = (long)c->Maxx * c->Maxy;
+  double dndy = 0.0;
+  double* a = (double*)calloc(G, sizeof(double));
+  double* b = (double*)calloc(G, sizeof(double));
+  if (c->which_mc_model == 5) {
+    if (c->sub_model == 1) {
+      smc_o_add_density_quarks(c, np, proj8, qP, fP, qw, a); smc_o_add_density_quarks(c, nt, targ8, qT, fT, qw, a);
+      double prefactor = (1.0 - c->alpha) / 2.;
+      for (long k = 0; k < G; k++) a[k] = a[k] * prefactor;
+    }
+    if (c->alpha > 1e-8) smc_o_binary_term(c, nc, coll8, b);
+    for (long k = 0; k < G; k++) { double d = a[k] + b[k]; rho[k] = d; dndy += d; }
+  } else {
+    smc_o_add_density_quarks(c, np, proj8, qP, fP, qw, a); smc_o_add_density_quarks(c, nt, targ8, qT, fT, qw, b);
+    for (long k = 0; k < G; k++) { double d = sqrt(a[k] * b[k]); rho[k] = d; dndy += d; }
+  }
+  free(a); free(b);
+  return dndy;
 }
 
 void smc_o_binary_term(const smc_o_cfg* c, int n, const double* S, double* tab) {  /* MCnucl.cpp:724-759 */

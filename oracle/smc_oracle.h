@@ -91,6 +91,12 @@ int smc_o_collide(const smc_o_cfg* c, int A, const double* proj7, int B, const d
 /* sources: rows of 8 doubles (x, y, xL, xR, yL, yR, weight, extra) */
 void smc_o_thickness(const smc_o_cfg* c, int n, const double* src8, double* TA);            /* MCnucl.cpp:432-478 */
 void smc_o_add_density(const smc_o_cfg* c, int n, const double* src8, double* dens);        /* MCnucl.cpp:822-866 */
+/* shape_of_entropy = 3 / collision_criterion = 3 (valence-quark substructure) */
+void smc_o_quark_out(double* qout6);          /* the populate functions leave qx0 qy0 qx1 qy1 qx2 qy2 per nucleon (sorted order) here; NULL = off */
+void smc_o_quark_collide(const double* qA6, const double* qB6, double quark_width);      /* inputs of the quark-overlap hit test */
+void smc_o_add_density_quarks(const smc_o_cfg* c, int n, const double* src8, const double* q6, const double* f3, double qw, double* dens);
+double smc_o_density_quarks(const smc_o_cfg* c, int np, const double* proj8, const double* qP, const double* fP, int nt, const double* targ8,
+                            const double* qT, const double* fT, int nc, const double* coll8, double qw, double* rho);
 void smc_o_binary_term(const smc_o_cfg* c, int n, const double* coll8, double* tab);         /* MCnucl.cpp:724-759 */
 void smc_o_unit_gauss(const smc_o_cfg* c, int n, const double* src8, double* grid);          /* MCnucl.cpp:481-531,534-614 */
 /* rho for which_mc_model 5 / 7 (MCnucl.cpp:688-811); returns dndy (sum over cells) */

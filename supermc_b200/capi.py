@@ -201,7 +201,10 @@ class Context:
             for key in ("proj_extra", "targ_extra"):
                 x = ev.get(key)
                 if x is not None:
-                    x = np.ascontiguousarray(x, dtype=np.float64); keep.append(x); setattr(arr[i], key, x.ctypes.data_as(dp))
+                    x = np.ascontiguousarray(x, dtype=np.float64)
+                    if x.shape[1] < 20:      # rows of SMC_EXTRA_ROW: older fixtures carry 16 columns (no per-quark weights: 1/3 each)
+                        x = np.concatenate([x, np.zeros((len(x), 20 - x.shape[1]))], axis=1); x[:, 15:18] = 1.0 / 3.0
+                    x = np.ascontiguousarray(x); keep.append(x); setattr(arr[i], key, x.ctypes.data_as(dp))
         return arr, keep
 
     def run_from_positions(self, events, flags=RUN_MOMENTS):
@@ -302,6 +305,9 @@ class Context:
 
     def spectators(self, slot):
         return self._rows(lib().smc_get_spectators, slot, 3)
+
+    def quarks(self, slot):
+        return self._rows(lib().smc_get_quarks, slot, 6)
 
     def nucleons(self, slot, which):
         return self._rows(lib().smc_get_nucleons, slot, 8, int(which))

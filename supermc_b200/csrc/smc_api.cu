@@ -54,7 +54,7 @@ extern "C" int smc_create(const smc_params* p, int device, smc_ctx** out) {
   ctx->d_grids = nullptr; ctx->grids_bytes = 0; ctx->d_srcrec = nullptr; ctx->srcrec_bytes = 0; ctx->d_cmpart = nullptr; ctx->d_pair_u = nullptr; ctx->pair_u_bytes = 0; ctx->d_coll_w = nullptr; ctx->coll_w_bytes = 0;
   ctx->d_rcbk = nullptr; ctx->rcbk_q = ctx->rcbk_y = ctx->rcbk_k = 0;
   ctx->d_quark = nullptr; ctx->d_cfgtab[0] = ctx->d_cfgtab[1] = nullptr; ctx->d_kln = nullptr; ctx->d_avg = nullptr; ctx->avg_doubles = 0; ctx->avg_count = 0;
-  ctx->stream = nullptr; ctx->ev0 = ctx->ev1 = nullptr; ctx->profile = 0; ctx->cur_slot = 0; ctx->comm = nullptr; ctx->epoch = 1; ctx->lists.epoch = 0; ctx->lists.n = 0; ctx->ny = p->ny; ctx->slice = 0;
+  ctx->stream = nullptr; ctx->ev0 = ctx->ev1 = nullptr; ctx->profile = 0; ctx->cur_slot = 0; ctx->comm = nullptr; ctx->epoch = 1; ctx->lists.epoch = 0; ctx->lists.n = 0; ctx->ny = p->ny; ctx->slice = 0; std::memset(&ctx->sortbuf, 0, sizeof ctx->sortbuf);
   std::memset(ctx->slots, 0, sizeof ctx->slots);
   for (int i = 0; i < 8; i++) { ctx->stage_ms[i] = 0; ctx->pev[i] = nullptr; }
   *out = ctx;      // returned even on failure so the caller can read smc_last_error
@@ -74,12 +74,14 @@ extern "C" int smc_create(const smc_params* p, int device, smc_ctx** out) {
   if (p->which_mc_model != 1 && p->which_mc_model != 5 && p->which_mc_model != 7) FAIL(SMC_ERR_PARAM, "which_mc_model must be 1, 5 or 7");
   if (p->which_mc_model == 5 && p->sub_model != 1 && p->sub_model != 2) FAIL(SMC_ERR_PARAM, "MC-Glauber sub_model must be 1 or 2 (MCnucl.cpp:718-721)");
   if (p->which_mc_model == 1 && p->sub_model != 7 && p->sub_model != 100 && p->sub_model != 101) FAIL(SMC_ERR_PARAM, "MC-KLN sub_model must be 7 (KLN uGD), 100 or 101 (rcBK tables, src/ParamDefs.h)");
-  if (p->collision_criterion == 3 || p->collision_criterion == 4)
-    FAIL(SMC_ERR_PARAM, "collision_criterion 3 (quark overlap, GaussianNucleonsCal.cpp:70-97) and 4 (numeric overlap) are not built; the reference uses different hit tests for them (MCnucl.cpp:371-376)");
+  if (p->collision_criterion == 4)
+    FAIL(SMC_ERR_PARAM, "collision_criterion 4 (testCollisionFromDensity: a 0.02 fm Riemann sum per tested pair, GaussianNucleonsCal.cpp:99-117) is not built");
   if (p->ny < 1 || p->ny > 64) FAIL(SMC_ERR_PARAM, "ny (rapidity slices) must be 1..64");
   if (p->shape_of_nucleons < 1 || p->shape_of_nucleons > 4) FAIL(SMC_ERR_PARAM, "shape_of_nucleons must be 1, 2, 3 or 4");
   if (p->shape_of_nucleons == 3 && !(p->gaussian_lambda > 0)) FAIL(SMC_ERR_PARAM, "shape_of_nucleons 3 needs gaussian_lambda > 0");
-  if (p->shape_of_entropy != 1 && p->shape_of_entropy != 2) FAIL(SMC_ERR_PARAM, "shape_of_entropy must be 1 or 2 (3 = quark substructure is out of scope)");
+  if (p->shape_of_entropy < 1 || p->shape_of_entropy > 3) FAIL(SMC_ERR_PARAM, "shape_of_entropy must be 1 (disk), 2 (gaussian) or 3 (valence quarks)");
+  if (p->shape_of_entropy == 3 && p->which_mc_model == 1) FAIL(SMC_ERR_PARAM, "shape_of_entropy 3 only enters the MC-Glauber / sqrt(TA TB) densities (MCnucl.cpp:856)");
+  if (p->shape_of_entropy == 3 && !(p->quark_width > 0)) FAIL(SMC_ERR_PARAM, "shape_of_entropy 3 needs quark_width > 0");
   if (p->aproj < 1 || p->atarg < 1 || p->aproj > 512 || p->atarg > 512) FAIL(SMC_ERR_PARAM, "Aproj/Atarg out of range");
   if (!(p->dx > 0) || !(p->dy > 0) || !(p->maxx > 0) || !(p->maxy > 0)) FAIL(SMC_ERR_PARAM, "bad grid");
   if (p->cc_fluctuation_model != 0 && p->cc_fluctuation_model != 1 && p->cc_fluctuation_model != 2 && p->cc_fluctuation_model != 6)
@@ -103,7 +105,8 @@ extern "C" int smc_create(const smc_params* p, int device, smc_ctx** out) {
   c.rclip_flat = std::sqrt(k.dsq) * (1.0 + 1e-12); c.kln_tmax_param = p->tmax;
   c.finalFactor = p->finalfactor;
   c.shape_of_nucleons = p->shape_of_nucleons; c.shape_of_entropy = p->shape_of_entropy;
-  c.crit = (p->collision_criterion == 1 || p->collision_criterion == 2) ? p->collision_criterion : (p->shape_of_entropy == 2 ? 2 : 1);
+  c.crit = (p->collision_criterion >= 1 && p->collision_criterion <= 3) ? p->collision_criterion
+           : (p->shape_of_entropy == 2 ? 2 : p->shape_of_entropy == 3 ? 3 : 1);                       // MCnucl.cpp:364-384
   c.which_mc_model = p->which_mc_model; c.sub_model = p->sub_model; c.cc_fluct = p->cc_fluctuation_model; c.cc_k = p->cc_fluctuation_k;
   c.A[0] = p->aproj; c.A[1] = p->atarg; c.deformed[0] = p->proj_deformed; c.deformed[1] = p->targ_deformed;
   for (int s = 0; s < 2; s++) {
@@ -118,6 +121,10 @@ extern "C" int smc_create(const smc_params* p, int device, smc_ctx** out) {
   c.quark_width = p->quark_width;
   c.quark_R = std::sqrt((3.0 / 2.0) * (k.width * k.width - p->quark_width * p->quark_width));   // Nucleus.cpp:31-32
   c.quark_rows = 0;
+  { const double qw = p->quark_width > 0 ? p->quark_width : 0.3;
+    c.q_inv2w2 = 1.0 / (2 * qw * qw); c.q_norm = 1 / (2 * M_PI * qw * qw); c.q_thr = 5 * qw;      // sic: squared distance against 5*width (Quark.cpp:19-20)
+    c.q_recx = std::exp(-p->dx * p->dx / (qw * qw)); c.q_recy = std::exp(-p->dy * p->dy / (qw * qw)); c.q_reach = std::sqrt(5 * qw) * (1.0 + 1e-12); }
+  ctx->need_quarks = (p->shape_of_entropy == 3 || c.crit == 3);
   c.seed_lo = (uint32_t)((uint64_t)p->randomseed); c.seed_hi = (uint32_t)(((uint64_t)p->randomseed) >> 32);
   c.Amax = std::max(p->aproj, p->atarg); c.Amax = (c.Amax + 7) & ~7;
   { long cap = p->ncoll_cap > 0 ? p->ncoll_cap : std::min<long>((long)p->aproj * p->atarg, 6144);
@@ -174,6 +181,7 @@ extern "C" void smc_destroy(smc_ctx* ctx) {
   if (ctx->d_kln) cudaFree(ctx->d_kln);
   if (ctx->d_rcbk) cudaFree(ctx->d_rcbk);
   if (ctx->d_avg) cudaFree(ctx->d_avg);
+  cudaFree(ctx->sortbuf.k1); cudaFree(ctx->sortbuf.k2); cudaFree(ctx->sortbuf.v1); cudaFree(ctx->sortbuf.v2); cudaFree(ctx->sortbuf.tmp);
   bool any_slot = false;
   for (int q = 0; q < SMC_MAX_SLOTS; q++) any_slot |= ctx->slots[q].ready;
   if (any_slot) {     // return the active view to its slot, then release the others
@@ -331,6 +339,17 @@ extern "C" int smc_build_kln_table(smc_ctx* ctx, double* host_out) {
 }
 
 // ---- event batches -------------------------------------------------------------------------------
+// per-nucleon state beyond the 8-double rows (stale base boxes, valence-quark offsets and weights): operation 3, the
+// quark substructure options and the quarks.data writer need it; allocated for the active pipeline slot on first use
+int smc_ensure_extra(smc_ctx* ctx) {
+  if (ctx->st.nuc_extra) return SMC_OK;
+  const size_t nx = (size_t)ctx->batch * 2 * ctx->cfg.Amax * smc::NEXTRA;
+  CK(cudaMalloc(&ctx->st.nuc_extra, nx * sizeof(double))); ctx->owned.push_back(ctx->st.nuc_extra);
+  CK(cudaMalloc(&ctx->st.nuc_extra_tmp, nx * sizeof(double))); ctx->owned.push_back(ctx->st.nuc_extra_tmp);
+  CK(cudaMemset(ctx->st.nuc_extra, 0, nx * sizeof(double)));
+  return SMC_OK;
+}
+
 int smc_plan_kinds(smc_ctx* ctx, unsigned flags, int* kinds, int* nk_dep) {
   smc::Store& st = ctx->st; const smc::DevCfg& c = ctx->cfg;
   for (int i = 0; i < 8; i++) st.kind_slot[i] = -1;
@@ -356,7 +375,8 @@ int smc_plan_kinds(smc_ctx* ctx, unsigned flags, int* kinds, int* nk_dep) {
     ctx->grids_bytes = need;
   }
   st.grids = ctx->d_grids;
-  st.src_stride = 2 * c.Amax + c.ncoll_cap;
+  st.src_stride = (c.shape_of_entropy == 3 ? 6 : 2) * c.Amax + c.ncoll_cap;
+  if (ctx->need_quarks || (flags & SMC_RUN_LISTS)) { int rc = smc_ensure_extra(ctx); if (rc) return rc; }
   st.work_off = (((size_t)ctx->batch * std::max(nd, 1) * st.src_stride * sizeof(smc::SrcRec)) + 15) & ~(size_t)15;
   st.work_cap = ctx->batch * std::max(nd, 1) * smc::deposit_cm_slots(c);
   const size_t need_rec = st.work_off + smc::deposit_work_bytes(c, ctx->batch, std::max(nd, 1));
@@ -447,6 +467,7 @@ static void slot_store(smc_ctx* ctx, smc_slot& sl) {          // ctx (active vie
   sl.nuc = st.nuc; sl.nuc_ncoll = st.nuc_ncoll; sl.nuc_first = st.nuc_first; sl.coll = st.coll; sl.coll_ij = st.coll_ij;
   sl.part_idx = st.part_idx; sl.spec_idx = st.spec_idx; sl.hdr_i = st.hdr_i; sl.hdr_d = st.hdr_d; sl.mom_out = st.mom_out;
   sl.event_id = (uint64_t*)st.event_id; sl.try_start = st.try_start; sl.cm = st.cm; sl.d_redo = ctx->d_redo;
+  sl.nuc_extra = st.nuc_extra; sl.nuc_extra_tmp = st.nuc_extra_tmp;
   sl.d_grids = ctx->d_grids; sl.grids_bytes = ctx->grids_bytes; sl.d_srcrec = ctx->d_srcrec; sl.srcrec_bytes = ctx->srcrec_bytes; sl.d_cmpart = ctx->d_cmpart; sl.stream = ctx->stream;
   for (int i = 0; i < 8; i++) sl.pev[i] = ctx->pev[i];
   sl.h_hdr_i = ctx->h_hdr_i; sl.h_hdr_d = ctx->h_hdr_d; sl.h_mom = ctx->h_mom; sl.h_evid = ctx->h_evid; sl.h_try = ctx->h_try;
@@ -456,6 +477,7 @@ static void slot_load(smc_ctx* ctx, const smc_slot& sl) {     // slot -> ctx (ac
   st.nuc = sl.nuc; st.nuc_ncoll = sl.nuc_ncoll; st.nuc_first = sl.nuc_first; st.coll = sl.coll; st.coll_ij = sl.coll_ij;
   st.part_idx = sl.part_idx; st.spec_idx = sl.spec_idx; st.hdr_i = sl.hdr_i; st.hdr_d = sl.hdr_d; st.mom_out = sl.mom_out;
   st.event_id = sl.event_id; st.try_start = sl.try_start; st.cm = sl.cm; ctx->d_redo = sl.d_redo;
+  st.nuc_extra = sl.nuc_extra; st.nuc_extra_tmp = sl.nuc_extra_tmp;
   ctx->d_grids = sl.d_grids; ctx->grids_bytes = sl.grids_bytes; st.grids = sl.d_grids; ctx->stream = sl.stream;
   ctx->d_srcrec = sl.d_srcrec; ctx->srcrec_bytes = sl.srcrec_bytes; st.src_rec = (smc::SrcRec*)sl.d_srcrec;
   ctx->d_cmpart = sl.d_cmpart; st.cm_part = sl.d_cmpart;
@@ -479,6 +501,7 @@ static int slot_alloc(smc_ctx* ctx, smc_slot& sl) {            // the second slo
   if ((rc = dalloc(ctx, &sl.cm, (size_t)B * 4))) return rc;
   if ((rc = dalloc(ctx, &sl.d_redo, (size_t)B))) return rc;
   sl.d_grids = nullptr; sl.grids_bytes = 0; sl.d_srcrec = nullptr; sl.srcrec_bytes = 0; sl.d_cmpart = nullptr;
+  sl.nuc_extra = nullptr; sl.nuc_extra_tmp = nullptr;
   CK(cudaStreamCreate(&sl.stream));
   for (int i = 0; i < 8; i++) CK(cudaEventCreate(&sl.pev[i]));
   CK(cudaMallocHost(&sl.h_hdr_i, (size_t)B * smc::HDR_I * sizeof(int)));
@@ -654,6 +677,7 @@ int smc_stage_positions(smc_ctx* ctx, int off, int m, const smc_event_in* in, bo
         const double* rows = s ? ev.targ : ev.proj; const double* given = s ? ev.targ_extra : ev.proj_extra; const int n = s ? B : A;
         for (int i = 0; i < n; i++) {
           double* x = ex.data() + ((size_t)s * Amax + i) * smc::NEXTRA;
+          x[smc::XF] = x[smc::XF + 1] = x[smc::XF + 2] = 1.0 / 3.0;                       // Particle::resetFluctFactors
           if (given) std::memcpy(x, given + (size_t)i * smc::NEXTRA, smc::NEXTRA * sizeof(double));
           else { x[smc::XBXL] = rows[i * 8 + 3]; x[smc::XBXR] = rows[i * 8 + 4]; x[smc::XBYL] = rows[i * 8 + 5]; x[smc::XBYR] = rows[i * 8 + 6];
                  x[smc::XCX] = 0.5 * (rows[i * 8 + 3] + rows[i * 8 + 4]); x[smc::XCY] = 0.5 * (rows[i * 8 + 5] + rows[i * 8 + 6]); }
@@ -840,6 +864,38 @@ extern "C" int smc_get_collisions(smc_ctx* ctx, int slot, double* host6, int* n)
   return SMC_OK;
 }
 
+// valence quarks of the wounded nucleons, participant order (Nucleus::dumpQuarks, Nucleus.cpp:780-797): x y xL xR yL yR per quark
+extern "C" int smc_get_quarks(smc_ctx* ctx, int slot, double* host6, int* n) {
+  if (!ctx) return SMC_ERR_PARAM;
+  if (!n || slot < 0 || slot >= ctx->last_n) FAIL(SMC_ERR_PARAM, "smc_get_quarks: slot outside the last device batch");
+  if (!ctx->st.nuc_extra) FAIL(SMC_ERR_STATE, "smc_get_quarks: run with SMC_RUN_LISTS (or shape_of_entropy 3 / collision_criterion 3) so that the quark state is kept");
+  std::vector<double> nuc; std::vector<int> nc, fi; int hi[smc::HDR_I]; int rc;
+  if ((rc = fetch_event_lists(ctx, slot, nuc, nc, fi, hi))) return rc;
+  *n = 3 * (hi[smc::H_NP1] + hi[smc::H_NP2]);
+  if (!host6) return SMC_OK;
+  const int Amax = ctx->cfg.Amax;
+  std::vector<double> ex((size_t)2 * Amax * smc::NEXTRA);
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpy(ex.data(), ctx->st.nuc_extra + (size_t)slot * 2 * Amax * smc::NEXTRA, ex.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  int k = 0; const double qw = ctx->p.quark_width;
+  auto put = [&](int s, int i) {
+    const double* r = nuc.data() + ((size_t)s * Amax + i) * smc::NROW; const double* x = ex.data() + ((size_t)s * Amax + i) * smc::NEXTRA;
+    for (int q = 0; q < 3; q++) {
+      const double qx = x[smc::XQ + 3 * q], qy = x[smc::XQ + 3 * q + 1], X = qx + r[smc::NX], Y = qy + r[smc::NY];
+      double* o = host6 + (size_t)(k++) * 6;
+      // Quark::getBoundingBox (Quark.cpp:5-10): the construction-time box (centre = offset, side 8 * quark_width) moved to X, Y
+      const double xl = qx - 8 * qw / 2, xr = qx + 8 * qw / 2, yl = qy - 8 * qw / 2, yr = qy + 8 * qw / 2;
+      o[0] = X; o[1] = Y; o[2] = xl + (X - qx); o[3] = xr + (X - qx); o[4] = yl + (Y - qy); o[5] = yr + (Y - qy);
+    }
+  };
+  for (int i = 0; i < ctx->cfg.A[0]; i++) if (nc[i] > 0) put(0, i);
+  std::vector<std::pair<long long, int>> ord;
+  for (int j = 0; j < ctx->cfg.A[1]; j++) if (nc[Amax + j] > 0) ord.push_back(std::make_pair((long long)fi[j] * 65536 + j, j));
+  std::sort(ord.begin(), ord.end());
+  for (auto& pr : ord) put(1, pr.second);
+  return SMC_OK;
+}
+
 // spectators: projectile nucleons first (Y>0), then target (MCnucl.cpp:1223-1249)
 extern "C" int smc_get_spectators(smc_ctx* ctx, int slot, double* host3, int* n) {
   if (!ctx) return SMC_ERR_PARAM;
@@ -864,17 +920,23 @@ __global__ void iota_kernel(int64_t* p, int64_t n) { int64_t i = (int64_t)blockI
 extern "C" int smc_centrality_sort(smc_ctx* ctx, const double* key, int64_t n, int64_t* perm) {
   if (!ctx || !key || !perm || n <= 0 || n > 0x7fffffff) return SMC_ERR_PARAM;
   CK(cudaSetDevice(ctx->device));
-  double *dk = nullptr, *dk2 = nullptr; int64_t *dv = nullptr, *dv2 = nullptr; void* tmp = nullptr; size_t tb = 0;
-  CK(cudaMalloc(&dk, n * sizeof(double))); CK(cudaMalloc(&dk2, n * sizeof(double)));
-  CK(cudaMalloc(&dv, n * sizeof(int64_t))); CK(cudaMalloc(&dv2, n * sizeof(int64_t)));
-  CK(cudaMemcpyAsync(dk, key, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(dv, n); ctx->launches++;
-  cub::DeviceRadixSort::SortPairsDescending(tmp, tb, dk, dk2, dv, dv2, (int)n, 0, 64, ctx->stream);
-  CK(cudaMalloc(&tmp, tb));
-  cub::DeviceRadixSort::SortPairsDescending(tmp, tb, dk, dk2, dv, dv2, (int)n, 0, 64, ctx->stream); ctx->launches++;
-  CK(cudaMemcpyAsync(perm, dv2, n * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  // the five work buffers are kept between calls (the per-centrality wrapper sorts once per key)
+  smc_sort_buffers& sb = ctx->sortbuf;
+  size_t tb = 0;
+  cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, (double*)nullptr, (double*)nullptr, (int64_t*)nullptr, (int64_t*)nullptr, (int)n, 0, 64, ctx->stream);
+  if (sb.cap < n || sb.tmp_bytes < tb) {
+    cudaFree(sb.k1); cudaFree(sb.k2); cudaFree(sb.v1); cudaFree(sb.v2); cudaFree(sb.tmp);
+    sb.k1 = sb.k2 = nullptr; sb.v1 = sb.v2 = nullptr; sb.tmp = nullptr; sb.cap = 0; sb.tmp_bytes = 0;
+    CK(cudaMalloc(&sb.k1, n * sizeof(double))); CK(cudaMalloc(&sb.k2, n * sizeof(double)));
+    CK(cudaMalloc(&sb.v1, n * sizeof(int64_t))); CK(cudaMalloc(&sb.v2, n * sizeof(int64_t))); CK(cudaMalloc(&sb.tmp, tb));
+    sb.cap = n; sb.tmp_bytes = tb;
+  }
+  CK(cudaMemcpyAsync(sb.k1, key, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(sb.v1, n); ctx->launches++;
+  size_t tb2 = sb.tmp_bytes;
+  cub::DeviceRadixSort::SortPairsDescending(sb.tmp, tb2, sb.k1, sb.k2, sb.v1, sb.v2, (int)n, 0, 64, ctx->stream); ctx->launches++;
+  CK(cudaMemcpyAsync(perm, sb.v2, n * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  cudaFree(dk); cudaFree(dk2); cudaFree(dv); cudaFree(dv2); cudaFree(tmp);
   return SMC_OK;
 }
 

@@ -157,11 +157,7 @@ extern "C" int smc_avg_begin(smc_ctx* ctx, int from_order, int to_order, int wit
   if (ctx->d_avg) { cudaFree(ctx->d_avg); ctx->d_avg = nullptr; }
   CK(cudaMalloc(&ctx->d_avg, (size_t)ctx->avg_doubles * sizeof(double)));
   CK(cudaMemset(ctx->d_avg, 0, (size_t)ctx->avg_doubles * sizeof(double)));
-  const size_t nx = (size_t)ctx->batch * 2 * ctx->cfg.Amax * smc::NEXTRA;
-  if (!ctx->st.nuc_extra) {
-    CK(cudaMalloc(&ctx->st.nuc_extra, nx * sizeof(double))); ctx->owned.push_back(ctx->st.nuc_extra);
-    CK(cudaMalloc(&ctx->st.nuc_extra_tmp, nx * sizeof(double))); ctx->owned.push_back(ctx->st.nuc_extra_tmp);
-  }
+  { const int rc = smc_ensure_extra(ctx); if (rc) return rc; }
   return SMC_OK;
 }
 

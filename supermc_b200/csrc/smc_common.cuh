@@ -11,7 +11,8 @@ namespace smc {
 // nucleon row layout (also the C-ABI layout of smc_event_in.proj/targ)
 enum { NX = 0, NY = 1, NZ = 2, NXL = 3, NXR = 4, NYL = 5, NYR = 6, NW = 7, NROW = 8 };
 // extra nucleon state for operation 3: stale base box (Particle::baseBox), valence-quark offsets, AABB centre
-enum { XBXL = 0, XBXR = 1, XBYL = 2, XBYR = 3, XQ = 4 /* 9 doubles */, XCX = 13, XCY = 14, NEXTRA = 16 };
+enum { XBXL = 0, XBXR = 1, XBYL = 2, XBYR = 3, XQ = 4 /* 9 doubles: x y z of the three valence quarks */, XCX = 13, XCY = 14,
+       XF = 15 /* 3 doubles: per-quark multiplicity weights (shape_of_entropy 3, Quark::fluctFactor) */, NEXTRA = 20 };
 // collision row layout
 enum { CX = 0, CY = 1, CW = 2, CADDW = 3, CROW = 4 };
 
@@ -43,6 +44,8 @@ struct DevCfg {
   int npmin, npmax;
   double gam_k_part, gam_th_part, gam_k_bin, gam_th_bin;   // MCnucl.cpp:1271-1301
   double quark_width, quark_R;
+  // shape_of_entropy 3: wounded nucleons deposit three quark Gaussians of width quark_width (Quark.cpp:14-22)
+  double q_inv2w2, q_recx, q_recy, q_norm, q_thr, q_reach;
   int quark_rows;
   int ncfg[2];
   uint32_t seed_lo, seed_hi;
@@ -57,7 +60,7 @@ struct DevCfg {
 };
 
 // one deposit source, expanded once per event by bbox_kernel: position, folded weight, mask threshold, window
-struct SrcRec { double x, y, W, thr; short iL, iR, jL, jR; int flat; int pad; };   // 48 bytes
+struct SrcRec { double x, y, W, thr; short iL, iR, jL, jR; int flat; int pad; };   // 48 bytes; flat: 0 gaussian(w), 1 disk, 2 gaussian(quark_width)
 
 // device-resident event records for one batch
 struct Store {

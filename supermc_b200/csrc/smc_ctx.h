@@ -26,12 +26,15 @@ struct smc_slot {
   double* nuc; int* nuc_ncoll; int* nuc_first; double* coll; int* coll_ij; int* part_idx; int* spec_idx;
   int* hdr_i; double* hdr_d; double* mom_out; uint64_t* event_id; int* try_start; double* cm; int* d_redo;
   double* d_grids; size_t grids_bytes; void* d_srcrec; size_t srcrec_bytes; double* d_cmpart;
+  double* nuc_extra; double* nuc_extra_tmp;
   cudaStream_t stream; cudaEvent_t done; cudaEvent_t pev[8];
   int* h_hdr_i; double* h_hdr_d; double* h_mom; uint64_t* h_evid; int* h_try;
 };
 
 // host mirror of the last batch's event records, filled by the first list getter after a run (smc_api.cu: cache_lists)
 struct smc_list_cache { uint64_t epoch; int n; int coll_stride; std::vector<double> nuc, coll; std::vector<int> ncoll, first, hdr, ij; };
+
+struct smc_sort_buffers { double *k1, *k2; int64_t *v1, *v2; void* tmp; int64_t cap; size_t tmp_bytes; };
 
 #define SMC_MAX_SLOTS 4
 struct smc_ctx {
@@ -53,6 +56,8 @@ struct smc_ctx {
   double* d_avg; int64_t avg_doubles; int64_t avg_count; int avg_from, avg_to, avg_rp, avg_ed;
   void* comm;                                      // multi-GPU state (smc_comm.cu)
   uint64_t epoch; smc_list_cache lists;            // epoch: bumped whenever the device records change
+  smc_sort_buffers sortbuf;                        // smc_centrality_sort work space, kept between calls
+  bool need_quarks;                                // shape_of_entropy 3 / collision_criterion 3: valence-quark state is live
   int ny, slice;                                   // rapidity slices (MCnucl.cpp:115): slice = the one the grid stages compute next
 };
 
@@ -62,6 +67,7 @@ struct smc_ctx {
 
 // helpers of smc_api.cu used by the averaged-profile driver
 int smc_plan_kinds(smc_ctx* ctx, unsigned flags, int* kinds, int* nk_dep);
+int smc_ensure_extra(smc_ctx* ctx);
 int smc_fetch_results(smc_ctx* ctx, int m);
 void smc_fill_out(smc_ctx* ctx, int m, smc_event_out* out);
 int smc_stage_positions(smc_ctx* ctx, int off, int m, const smc_event_in* in, bool any_u, bool any_w);

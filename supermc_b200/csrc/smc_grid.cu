@@ -32,10 +32,13 @@ struct Src { double x, y, W, thr; int iL, iR, jL, jR; int flat; };
 __device__ __forceinline__ int src_count(const DevCfg& c, const int* hi, int kind) {
   const int np1 = hi[H_NP1], np2 = hi[H_NP2];
   int nc = hi[H_NCOLL]; if (nc > c.ncoll_cap) nc = c.ncoll_cap;
+  const int nq = (c.shape_of_entropy == 3) ? 3 : 1;        // three valence-quark sources per wounded nucleon (addDensity, MCnucl.cpp:856)
   switch (kind) {
-    case GK_RHO: return ((c.sub_model == 1) ? np1 + np2 : 0) + ((c.alpha > 1e-8) ? nc : 0);
-    case GK_TA1: case GK_RHOA: return np1;
-    case GK_TA2: case GK_RHOB: return np2;
+    case GK_RHO: return ((c.sub_model == 1) ? nq * (np1 + np2) : 0) + ((c.alpha > 1e-8) ? nc : 0);
+    case GK_RHOA: return nq * np1;
+    case GK_RHOB: return nq * np2;
+    case GK_TA1: return np1;
+    case GK_TA2: return np2;
     case GK_RHO_BINARY: return nc;
     case GK_SPEC_A: return hi[H_NSPEC1];
     case GK_SPEC_B: return hi[H_NSPEC2];
@@ -49,17 +52,20 @@ __device__ void load_src(const DevCfg& c, const Store& st, int e, const int* hi,
   const double* nuc = st.nuc + (size_t)e * 2 * Amax * NROW;
   const int np1 = hi[H_NP1], np2 = hi[H_NP2];
   bool box_window = false, is_coll = false;
-  const double* row = nullptr;
+  const double* row = nullptr; const double* quark = nullptr;      // quark: extras row + which valence quark (shape_of_entropy 3)
+  int qi = 0;
+  const int nq = (c.shape_of_entropy == 3) ? 3 : 1;
   double wgt = 1.0;
   int shape = c.shape_of_nucleons;          // which "shape" switch the reference consults for this deposit
   s.thr = c.thrB;
   if (kind == GK_RHO) {
-    const int nwn = (c.sub_model == 1) ? np1 + np2 : 0;
+    const int nwn = (c.sub_model == 1) ? nq * (np1 + np2) : 0;
     shape = c.shape_of_entropy;
     if (k < nwn) {                                                                   // addDensity, MCnucl.cpp:822-866
-      const int id = st.part_idx[(size_t)e * 2 * Amax + k];
+      const int id = st.part_idx[(size_t)e * 2 * Amax + k / nq];
       row = nuc + ((size_t)(id >> 16) * Amax + (id & 0xffff)) * NROW;
       wgt = row[NW] * ((1.0 - c.alpha) / 2.); box_window = true; s.thr = c.thrA;
+      if (nq == 3) { quark = st.nuc_extra + (((size_t)e * 2 + (id >> 16)) * Amax + (id & 0xffff)) * NEXTRA; qi = k % 3; wgt = quark[XF + qi] * ((1.0 - c.alpha) / 2.); }
     } else {                                                                         // MCnucl.cpp:724-759
       const double* cr = st.coll + ((size_t)e * c.ncoll_cap + (k - nwn)) * CROW;
       row = cr; is_coll = true;
@@ -67,9 +73,10 @@ __device__ void load_src(const DevCfg& c, const Store& st, int e, const int* hi,
       wgt = fl * (c.alpha + (1. - c.alpha) * cr[CADDW]); s.thr = c.thrB;
     }
   } else if (kind == GK_RHOA || kind == GK_RHOB) {                                   // model 7, MCnucl.cpp:780-811
-    const int id = st.part_idx[(size_t)e * 2 * Amax + (kind == GK_RHOB ? np1 : 0) + k];
+    const int id = st.part_idx[(size_t)e * 2 * Amax + (kind == GK_RHOB ? np1 : 0) + k / nq];
     row = nuc + ((size_t)(id >> 16) * Amax + (id & 0xffff)) * NROW;
     wgt = row[NW]; box_window = true; s.thr = c.thrA; shape = c.shape_of_entropy;
+    if (nq == 3) { quark = st.nuc_extra + (((size_t)e * 2 + (id >> 16)) * Amax + (id & 0xffff)) * NEXTRA; qi = k % 3; wgt = quark[XF + qi]; }
   } else if (kind == GK_TA1 || kind == GK_TA2) {                                     // setThickness, MCnucl.cpp:432-478
     const int id = st.part_idx[(size_t)e * 2 * Amax + (kind == GK_TA2 ? np1 : 0) + k];
     row = nuc + ((size_t)(id >> 16) * Amax + (id & 0xffff)) * NROW;
@@ -83,9 +90,13 @@ __device__ void load_src(const DevCfg& c, const Store& st, int e, const int* hi,
   s.x = row[0]; s.y = row[1];
   s.flat = (shape == 1);
   if (s.flat) { s.W = wgt * c.areai; s.thr = c.dsq; } else s.W = wgt * c.norm;
+  if (quark) {      // Quark::getSmoothTn (Quark.cpp:14-22): a Gaussian of width quark_width at nucleon + offset, cut at d > 5 * width (sic)
+    s.x = row[0] + quark[XQ + 3 * qi]; s.y = row[1] + quark[XQ + 3 * qi + 1];
+    s.flat = 2; s.W = wgt * c.q_norm; s.thr = c.q_thr;
+  }
   // +-d_max window (quirk Q7); for AABB windows (quirk Q3) the same range, widened by a cell, is only a
   // safe clip: cells farther than the mask radius contribute nothing in the reference either
-  const double reach = (box_window && s.flat) ? c.rclip_flat : c.dmax;
+  const double reach = quark ? c.q_reach : (box_window && s.flat) ? c.rclip_flat : c.dmax;
   int iL = cell_of(__dadd_rn(s.x, -reach), c.Xmin, c.dx), iR = cell_of(__dadd_rn(s.x, reach), c.Xmin, c.dx);
   int jL = cell_of(__dadd_rn(s.y, -reach), c.Ymin, c.dy), jR = cell_of(__dadd_rn(s.y, reach), c.Ymin, c.dy);
   if (box_window && !is_coll) {
@@ -335,9 +346,10 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_MINCTA) deposit_kernel(DevCfg
       const int ka = max(s.iL - i0, 0), kb = min(s.iR - i0, 16);
       if (ka >= kb) return;
       double g = s.W, q = 1.0, rec = 1.0;
-      if (!s.flat) {
+      if (s.flat != 1) {
+        const double i2 = s.flat == 2 ? c.q_inv2w2 : c.inv2w2;
         const double d = __dadd_rn(s.x, -xg_of(c, i0 + ka));
-        g = s.W * exp(-__dmul_rn(d, d) * c.inv2w2); q = exp((2.0 * d * c.dx - c.dx * c.dx) * c.inv2w2); rec = c.recx;
+        g = s.W * exp(-__dmul_rn(d, d) * i2); q = exp((2.0 * d * c.dx - c.dx * c.dx) * i2); rec = s.flat == 2 ? c.q_recx : c.recx;
       }
       for (int k = ka; k < kb; k++) { T.xg[t][rb + k] = g; g *= q; q *= rec; }
     } else if (id < DEP_CH * (DEP_NXG + DEP_NXI)) {                         // ---- rows: masks, DEP_XP rows per item ----
@@ -392,9 +404,10 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_MINCTA) deposit_kernel(DevCfg
       const int ka = max(s.jL - j0, 0) & ~1, kb = min(s.jR - j0, DEP_YP);   // pairs of columns (an extra one is masked off)
       if (ka >= kb) return;
       double g = 1.0, q = 1.0, rec = 1.0;
-      if (!s.flat) {
+      if (s.flat != 1) {
+        const double i2 = s.flat == 2 ? c.q_inv2w2 : c.inv2w2;
         const double d = __dadd_rn(s.y, -yg_of(c, j0 + ka));
-        g = exp(-__dmul_rn(d, d) * c.inv2w2); q = exp((2.0 * d * c.dy - c.dy * c.dy) * c.inv2w2); rec = c.recy;
+        g = exp(-__dmul_rn(d, d) * i2); q = exp((2.0 * d * c.dy - c.dy * c.dy) * i2); rec = s.flat == 2 ? c.q_recy : c.recy;
       }
       for (int k = ka; k < kb; k += 2) {
         const int cc = cb + k;
@@ -511,7 +524,7 @@ cudaError_t launch_deposit(const DevCfg& c, const Store& st, const int* kinds, i
   const bool use_list = persist && nbands < 256 && ngroups < 256;
   if (use_list) cudaMemsetAsync(reinterpret_cast<char*>(st.src_rec) + st.work_off + (size_t)DEP_NCLS * st.work_cap * sizeof(int2), 0, (1 + DEP_NCLS) * sizeof(int), s);
   bbox_kernel<<<nev, 128, 0, s>>>(c, st, kl, nev, use_list ? 1 : 0);
-  const size_t smem = deposit_smem_bytes(c, 2 * c.Amax + c.ncoll_cap);
+  const size_t smem = deposit_smem_bytes(c, (c.shape_of_entropy == 3 ? 6 : 2) * c.Amax + c.ncoll_cap);
   if (use_list) {
     cudaFuncSetAttribute(deposit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const long want = (long)nev * nbands * ngroups * nk;

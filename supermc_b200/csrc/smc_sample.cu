@@ -83,7 +83,8 @@ __device__ void particle_box(const DevCfg& c, const Store& st, const smc_stream&
   Box base = {0, 0, 0, 0, 0, 0};
   box_center(base, x0, y0); box_square(base, 8 * c.w);
   out = base;
-  if (extra) { extra[XBXL] = base.xL; extra[XBXR] = base.xR; extra[XBYL] = base.yL; extra[XBYR] = base.yR; for (int q = 0; q < 9; q++) extra[XQ + q] = 0.0; }
+  if (extra) { extra[XBXL] = base.xL; extra[XBXR] = base.xR; extra[XBYL] = base.yL; extra[XBYR] = base.yR; for (int q = 0; q < 9; q++) extra[XQ + q] = 0.0;
+               extra[XF] = extra[XF + 1] = extra[XF + 2] = 1.0 / 3.0; }      // Particle::resetFluctFactors, Particle.cpp:140-144
   if (NOQUARKS || c.quark_rows <= 0) {           // no table: r1 = r2 = 0, the three quark boxes sit on the nucleon
     Box b = {0, 0, 0, 0, 0, 0};
     box_center(b, 0.0, 0.0); box_square(b, 8 * c.quark_width); box_center(b, x0, y0);
@@ -479,6 +480,20 @@ __global__ void __launch_bounds__(64, 6) sample_collide_kernel(DevCfg c, Store s
             if (c.crit == 1) {
               const double bb = sqrt(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)));        // MCnucl.cpp:359-366
               if (__dmul_rn(bb, bb) <= c.dsq) record_hit(i, j);
+            } else if (SPEC == 0 && c.crit == 3) {
+              // GaussianNucleonsCal::testFluctuatedCollision (GaussianNucleonsCal.cpp:70-97): overlap of the 3 x 3 valence-quark
+              // Gaussians (offsets from the sorted extras rows, written before the __syncthreads above or staged by the host)
+              const double* qa = st.nuc_extra + (((size_t)e * 2 + 0) * Amax + i) * NEXTRA + XQ;
+              const double* qb = st.nuc_extra + (((size_t)e * 2 + 1) * Amax + jj) * NEXTRA + XQ;
+              const double tx = S_(sm, 1, NX, jj), ty = S_(sm, 1, NY, jj), gw2 = c.quark_width * c.quark_width;
+              double overlap = 0;
+              for (int a = 0; a < 3; a++) for (int q = 0; q < 3; q++) {
+                const double mx = qa[3 * a] + px, my = qa[3 * a + 1] + py, yx = qb[3 * q] + tx, yy = qb[3 * q + 1] + ty;
+                const double d = (mx - yx) * (mx - yx) + (my - yy) * (my - yy);
+                overlap += (1 / (4 * SMC_PI * gw2)) * exp(-d / (4 * gw2)) / 9;
+              }
+              u = pu ? pu[(size_t)i * B + j] : smc_uniform(s_p, (uint32_t)i, (uint32_t)j);
+              if (u < 1. - exp(-c.sigma_gg * overlap)) record_hit(i, j);
             } else {
               u = pu ? pu[(size_t)i * B + j] : smc_uniform(s_p, (uint32_t)i, (uint32_t)j);
               // P = 1 - exp(-t) <= t
@@ -586,10 +601,20 @@ __global__ void __launch_bounds__(64, 6) sample_collide_kernel(DevCfg c, Store s
   // Gamma multiplicity weights, one variate per lane (dense over the compact lists).  Nucleon weights
   // (selectFluctFactors, MCnucl.cpp:310-324) are re-drawn at every hit, last wins => one draw per wounded nucleon.
   if (!givenw && c.cc_fluct > 5 && accepted) {
-    for (int k = tid; k < np1 + np2; k += 64) {
-      const int id = pidx[k], s = id >> 16, i = id & 0xffff;
-      const smc_stream sg = smc_make_stream(c.seed_lo, c.seed_hi, ev, trw, SMC_K_GAMMA_PART, s);
-      S_(sm, s, NW, i) = gamma_variate(sg, (uint32_t)i, c.gam_k_part, c.gam_th_part);
+    if (SPEC == 0 && c.shape_of_entropy == 3) {
+      // one weight per valence quark, shape k/3 (selectFluctFactors / sampleFluctuationFactorforParticipant, MCnucl.cpp:310-324,
+      // 1271-1288); the nucleon's own factor stays 1
+      for (int k = tid; k < 3 * (np1 + np2); k += 64) {
+        const int id = pidx[k / 3], s = id >> 16, i = id & 0xffff, q = k % 3;
+        const smc_stream sg = smc_make_stream(c.seed_lo, c.seed_hi, ev, trw, SMC_K_GAMMA_PART, s);
+        st.nuc_extra[(((size_t)e * 2 + s) * Amax + i) * NEXTRA + XF + q] = gamma_variate(sg, (uint32_t)(3 * i + q), c.gam_k_part / 3.0, c.gam_th_part);
+      }
+    } else {
+      for (int k = tid; k < np1 + np2; k += 64) {
+        const int id = pidx[k], s = id >> 16, i = id & 0xffff;
+        const smc_stream sg = smc_make_stream(c.seed_lo, c.seed_hi, ev, trw, SMC_K_GAMMA_PART, s);
+        S_(sm, s, NW, i) = gamma_variate(sg, (uint32_t)i, c.gam_k_part, c.gam_th_part);
+      }
     }
   }
   // collisions: midpoints + weights
@@ -635,7 +660,7 @@ cudaError_t launch_sample_collide(const DevCfg& c, const Store& st, int nev, boo
   const size_t smem = sample_smem_bytes(c.Amax) + pad;
   const bool big = c.Amax > 256;
   if (given) return big ? launch_sc<true, 0, SMC_MAXK>(c, st, nev, smem, s) : launch_sc<true, 0, 8>(c, st, nev, smem, s);
-  const bool ws = !generic && c.sampler[0] == 0 && c.sampler[1] == 0 && !c.deformed[0] && !c.deformed[1];
+  const bool ws = !generic && c.sampler[0] == 0 && c.sampler[1] == 0 && !c.deformed[0] && !c.deformed[1] && c.crit != 3 && c.shape_of_entropy != 3;
   const int spec = ws ? (c.quark_rows > 0 ? 1 : 2) : 0;
   if (big) return spec == 2 ? launch_sc<false, 2, SMC_MAXK>(c, st, nev, smem, s) : spec == 1 ? launch_sc<false, 1, SMC_MAXK>(c, st, nev, smem, s) : launch_sc<false, 0, SMC_MAXK>(c, st, nev, smem, s);
   return spec == 2 ? launch_sc<false, 2, 8>(c, st, nev, smem, s) : spec == 1 ? launch_sc<false, 1, 8>(c, st, nev, smem, s) : launch_sc<false, 0, 8>(c, st, nev, smem, s);

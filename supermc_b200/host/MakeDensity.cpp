@@ -281,18 +281,23 @@ int MakeDensity::generateEccTable(int nevent) {
       });
       for (auto& t : th) t.join();
       for (long v : bad) failed += v;
+      // up to twenty tables grow by this chunk: one appender per file, all at once (the copy into the page cache is what
+      // bounds a single writer at ~2 GB/s, and a million events are 4 GB of text)
+      std::vector<std::thread> wr;
       for (int f = 0; f < 2; f++) {
         if ((f == 0 && !use_sd) || (f == 1 && !use_ed)) continue;
-        char name[128];
         for (int o = lo; o <= 10; o++) {
           if (o > hi && o < 10) continue;
-          std::snprintf(name, sizeof name, base[f], o);
-          FILE* fp = std::fopen(path(name).c_str(), "ab");
-          if (!fp) { std::fprintf(stderr, "cannot open %s\n", path(name).c_str()); continue; }
-          for (unsigned t = 0; t < nthr; t++) std::fwrite(part[t][o].data(), 1, part[t][o].size(), fp);
-          std::fclose(fp);
+          wr.emplace_back([&, f, o] {
+            char name[128]; std::snprintf(name, sizeof name, base[f], o);
+            FILE* fp = std::fopen(path(name).c_str(), "ab");
+            if (!fp) { std::fprintf(stderr, "cannot open %s\n", path(name).c_str()); return; }
+            for (unsigned t = 0; t < nthr; t++) std::fwrite(part[t][o].data(), 1, part[t][o].size(), fp);
+            std::fclose(fp);
+          });
         }
       }
+      for (auto& t : wr) t.join();
       if (binary) { FILE* fp = std::fopen(path("ecc_rows.bin").c_str(), "ab"); if (fp) { std::fwrite(c->out.data(), sizeof(smc_event_out), (size_t)c->n * ny, fp); std::fclose(fp); } }
       std::cout << "processed events: " << c->done << " / " << count << "\r" << std::flush;
       { std::lock_guard<std::mutex> l(m); empty.push_back(c); } cv.notify_all();
@@ -359,6 +364,15 @@ std::string smc_fmt_xy(const double* rows, int n, int stride) {        // setpre
 std::string smc_fmt_participants(const double* rows, int n) {          // Nucleus::dumpParticipants, Nucleus.cpp:753-764
   std::string s; char b[32];
   for (int i = 0; i < n; i++) { put(s, "%10.3g", rows[(size_t)i * 8]); s += "   "; put(s, "%10.3g", rows[(size_t)i * 8 + 1]); s += "   "; int k = std::snprintf(b, sizeof b, "%d\n", (int)rows[(size_t)i * 8 + 2]); s.append(b, k); }
+  return s;
+}
+std::string smc_fmt_quarks(const double* rows, int n) {                // Nucleus::dumpQuarks, Nucleus.cpp:780-797: x y at precision 3, the box at the default 6
+  std::string s; char b[128];
+  for (int i = 0; i < n; i++) {
+    const double* r = rows + (size_t)i * 6;
+    put(s, "%10.3g", r[0]); put(s, "%10.3g", r[1]);
+    int k = std::snprintf(b, sizeof b, " %g %g %g %g\n", r[2], r[3], r[4], r[5]); s.append(b, k);
+  }
   return s;
 }
 std::string smc_fmt_spectators(const double* rows, int n) {            // scientific, setprecision(4), setw(10) on x only
@@ -434,8 +448,11 @@ static int ebe_common(MakeDensity* self, smc_ctx* ctx, ParameterReader* paraRdr,
         write_file(P("Spectators_event_%ld.dat", event), smc_fmt_spectators(spec.data(), ns), false);
         write_file(P("BinaryCollisionTable_event_%ld.dat", event), smc_fmt_xy(coll.data(), nc, 6), true);
       } else write_file(data_dir + "/binary.dat", smc_fmt_xy(coll.data(), nc, 6), true);
-      // dumpBinaryTable side files (MCnucl.cpp:1193-1209); quarks.data needs shape_of_entropy=3 state and is not written
+      // dumpBinaryTable side files (MCnucl.cpp:1193-1209)
       write_file(data_dir + "/wounded.data", smc_fmt_participants(part.data(), np), false);
+      { int nq = 0; if (ck(smc_get_quarks(ctx, e, nullptr, &nq))) return 1;
+        std::vector<double> qk((size_t)std::max(nq, 1) * 6); if (ck(smc_get_quarks(ctx, e, qk.data(), &nq))) return 1;
+        write_file(data_dir + "/quarks.data", smc_fmt_quarks(qk.data(), nq), true); }
       for (int s = 0; s < 2; s++) {
         int na = 0; if (ck(smc_get_nucleons(ctx, e, s, nullptr, &na))) return 1;
         std::vector<double> nu((size_t)std::max(na, 1) * 8); if (ck(smc_get_nucleons(ctx, e, s, nu.data(), &na))) return 1;

@@ -14,6 +14,7 @@
 std::string smc_fmt_xy(const double* rows, int n, int stride);
 std::string smc_fmt_participants(const double* rows8, int n);
 std::string smc_fmt_spectators(const double* rows3, int n);
+std::string smc_fmt_quarks(const double* rows6, int n);
 
 struct smc_shard { int rank, world; };   // events [rank*nev/world, (rank+1)*nev/world) of the global id range
 

@@ -44,7 +44,7 @@ int smc_host_format_ecc_row(const smc_event_out* ev, int order, int deformed, ch
   return copy_out(order == 10 ? MakeDensity::formatEccRowAll(*ev, deformed != 0) : MakeDensity::formatEccRow(*ev, order, deformed != 0), out, cap);
 }
 int smc_host_format_list(int kind, const double* rows, int n, int stride, char* out, int cap) {
-  return copy_out(kind == 0 ? smc_fmt_xy(rows, n, stride) : kind == 1 ? smc_fmt_participants(rows, n) : smc_fmt_spectators(rows, n), out, cap);
+  return copy_out(kind == 0 ? smc_fmt_xy(rows, n, stride) : kind == 1 ? smc_fmt_participants(rows, n) : kind == 3 ? smc_fmt_quarks(rows, n) : smc_fmt_spectators(rows, n), out, cap);
 }
 int smc_host_format_block(const double* g, int Maxx, int Maxy, char* out, int cap) { std::string s; MakeDensity::formatDensityBlock(g, Maxx, Maxy, s); return copy_out(s, out, cap); }
 int smc_host_format_4col(const double* g, int Maxx, int Maxy, double Xmin, double Ymin, double dx, double dy, double rap, double npart, char* out, int cap) {

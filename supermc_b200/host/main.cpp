@@ -7,6 +7,7 @@
 #include <chrono>
 #include <cstdlib>
 #include <iostream>
+#include <unistd.h>
 #include "MakeDensity.h"
 
 int main(int argc, char* argv[]) {
@@ -33,5 +34,9 @@ int main(int argc, char* argv[]) {
   if (rc) std::cerr << "superMC_b200: " << dens.error() << std::endl;
   std::cout << "Time elapsed (in seconds): " << dt << std::endl;
   if (timing) std::cerr << "# event loop: " << dt << " s; since process start: " << std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() << " s (context teardown follows)" << std::endl;
+  // every file is closed and every rank has passed its last barrier: returning through the destructors would only hand
+  // several GB of device memory back piece by piece (0.3-0.6 s); the driver reclaims it with the process
+  const char* fe = std::getenv("SMC_FAST_EXIT");
+  if (!(fe && fe[0] == '0')) { std::cout.flush(); std::cerr.flush(); std::fflush(nullptr); _exit(rc); }
   return rc;
 }

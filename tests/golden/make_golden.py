@@ -66,6 +66,12 @@ SYSTEMS = {
     # three rapidity slices (ny = 3, ymax = 2: y = -2, -2/3, 2/3 -- MCnucl.cpp:932 divides by ny, not ny - 1): one table per slice
     "auau200_kln_ny3": ("zero", 6, 1, dict(which_mc_model=1, sub_model=7, Aproj=197, Atarg=197, ecm=200, tmax=24, tmax_subdivision=3,
                                            cc_fluctuation_model=0, randomSeed=27, bmin=8, ny=3, ymax=2)),
+    # valence-quark substructure (Particle::getFluctuatedDensity, GaussianNucleonsCal::testFluctuatedCollision): entropy from three
+    # quark Gaussians per wounded nucleon with one Gamma weight each; second system: the quark-overlap hit test as well
+    "pbpb2760_quarks": ("rand", 8, 1, dict(which_mc_model=5, sub_model=1, Aproj=208, Atarg=208, ecm=2760, alpha=0.118, shape_of_entropy=3,
+                                           cc_fluctuation_Gamma_theta=0.75, randomSeed=28)),
+    "auau200_quarkhit": ("rand", 8, 1, dict(which_mc_model=5, sub_model=1, Aproj=197, Atarg=197, ecm=200, alpha=0.14, shape_of_entropy=3,
+                                            collision_criterion=3, cc_fluctuation_Gamma_theta=0.61, randomSeed=29)),
     # table-driven nuclei with synthetic configuration files in the reference's formats (tests/table_synth.py; the real files
     # are missing blobs upstream): O+O (Nucleus.cpp:462-478,555-574) and NN-correlated Au (Nucleus.cpp:481-522,623-666)
     "oo200_glb": ("rand", NEV, 1, dict(which_mc_model=5, sub_model=1, Aproj=16, Atarg=16, ecm=200, alpha=0.14,
@@ -124,8 +130,10 @@ def run_system(name):
         acc = int(t["hdr"][4])
         for k in ("hdr", "proj", "targ", "proj_part", "targ_part", "coll"):
             out[pre + k] = t[k]
-        if par.get("dump_rotate"):
+        if par.get("dump_rotate") or int(p.get("shape_of_entropy", 2)) == 3:
             out[pre + "proj_x"] = t["proj_x"]; out[pre + "targ_x"] = t["targ_x"]
+        if int(p.get("shape_of_entropy", 2)) == 3:
+            out[pre + "proj_qf"] = t["proj_qf"]; out[pre + "targ_qf"] = t["targ_qf"]
         if acc:
             out[pre + "dndy"] = t["dndy"]; out[pre + "region"] = t["region"]; out[pre + "spectators"] = t["spectators"]
             out[pre + "ecc_index"] = np.array(ia * ny)          # ny rows per event, slice-major

@@ -7,7 +7,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import refio
-REF = os.path.join(ROOT, "oracle", "_ref"); RUN = os.path.join(REF, "run_zero")
+REF = os.path.join(ROOT, "oracle", "_ref"); RUN = os.path.join(REF, "run_rand")      # random valence-quark offsets: quarks.data is not trivial
 ARGS = ["which_mc_model=5", "sub_model=1", "Aproj=208", "Atarg=208", "ecm=2760", "alpha=0.118", "maxx=8", "maxy=8", "dx=0.5", "dy=0.5",
         "finalFactor=40", "randomSeed=31", "cc_fluctuation_model=6", "dump_grids=1", "dump_extra=1", "dump_text=1", "bmax=10"]
 out = {}
@@ -23,7 +23,7 @@ for exe, tag in (("ref_dump_stock", "stock"), ("ref_dump", "hi")):
         glob, tries = refio.group_tries(refio.read_records("/tmp/text_hi.bin"))
         out["consts"] = glob["consts"]
         for i, t in enumerate(tries):
-            for k in ("hdr", "proj", "targ", "proj_part", "targ_part", "coll", "rho", "spectators"):
+            for k in ("hdr", "proj", "targ", "proj_part", "targ_part", "coll", "rho", "spectators", "proj_x", "targ_x"):
                 out["t%d/%s" % (i, k)] = t[k]
 out["args"] = np.array(ARGS)
 p = os.path.join(ROOT, "tests", "golden", "text_formats.npz")

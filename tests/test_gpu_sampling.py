@@ -4,10 +4,10 @@
    tests/test_oracle_vs_ref.py) is driven with the *same Philox event streams* the CUDA path uses; the
    two must then produce the same tries, the same accepted events, the same integers, and positions
    equal up to libm rounding (cbrt vs pow(.,1/3), sincos).
-2. Statistics (north_star level L3): Npart, Ncoll, dS/dy, |eps2|, |eps3| of 10^5 GPU events against
-   10^5 events of the unmodified reference (tests/golden/ks_pbpb2760_ref.npz, generated by
-   tests/golden/make_ks_reference.py), two-sample KS p > 0.001 each, plus the reference's own shipped
-   centrality-cut table for Pb+Pb 2.76 TeV (Npart thresholds).
+2. Statistics (north_star level L3): Npart, Ncoll, dS/dy, b, |eps2|, |eps3|, |eps2'|, <r^2> of 10^5 GPU events against
+   10^5 events of the unmodified reference for Pb+Pb 2.76 TeV, Au+Au 200 GeV, p+Pb 5.02 TeV (MC-Glauber) and MC-KLN
+   Au+Au 200 GeV (tests/golden/ks_*_ref.npz), two-sample KS p > 0.01 each, plus the reference's own shipped
+   centrality-cut tables (Npart and dS/dy thresholds at 5 ... 80 %).
 3. Result set independent of batch size / first_event_id split (what makes multi-GPU sharding safe).
 """
 import os
@@ -85,29 +85,66 @@ def _ks_p(x, y):
     return stats.ks_2samp(x, y).pvalue
 
 
-def test_distributions_match_reference_ks():
+KS_SYSTEMS = {  # name: (golden system for the parameters, shipped-table stem or None, KLN)
+    "pbpb2760": ("pbpb2760_glb", "MCGlbPbPb2760_withMultFluct", False),
+    "auau200": ("auau200_glb_quarks", "MCGlbAuAu200_withMultFluct", False),
+    "ppb5020": ("ppb5020_glb_quarks", None, False),
+    "auau200_kln": ("auau200_kln", "MCKLNAuAu200_noMultFluct", True),
+}
+
+
+def _ks_sample(name, seed, n):
     import supermc_b200 as smc
-    path = os.path.join(GOLDEN, "ks_pbpb2760_ref.npz")
-    if not os.path.exists(path):
-        pytest.skip("KS reference sample not generated yet")
-    ref = np.load(path)
-    g = Golden("pbpb2760_glb")
-    n = int(os.environ.get("SMC_KS_EVENTS", "100000"))
-    ctx = smc.Context(g.smc_params(smc.capi, max_batch=2048, randomseed=20261017))
+    gname, _, kln = KS_SYSTEMS[name]
+    g = Golden(gname)
+    over = dict(max_batch=2048, randomseed=seed, bmin=0.0, bmax=20.0)
+    if kln:
+        over.update(tmax=71, tmax_subdivision=3)
+    ctx = smc.Context(g.smc_params(smc.capi, **over))
+    if kln:
+        ctx.build_kln_table()                    # the device quadrature (each entry within 0.5 % of the reference's BASES table)
     out = ctx.run_events(0, n, smc.RUN_MOMENTS)
     assert (out["status"] == 0).all()
-    got = dict(npart=(out["npart1"] + out["npart2"]).astype(float), ncoll=out["ncoll"].astype(float), dsdy=out["total"],
-               b=out["b"], e2=np.hypot(out["mom"][:, 1, 0], out["mom"][:, 1, 1]), e3=np.hypot(out["mom"][:, 2, 0], out["mom"][:, 2, 1]),
-               e2p=np.hypot(out["mom"][:, 1, 2], out["mom"][:, 1, 3]), r2=out["mom"][:, 1, 4])
-    ps = {k: _ks_p(got[k], ref[k]) for k in got}
-    print("KS p-values:", {k: round(v, 4) for k, v in ps.items()}, "n_gpu=%d n_ref=%d" % (n, len(ref["npart"])))
-    for k, v in ps.items():
-        assert v > 1e-3, (k, v)
-    # acceptance of the rejection loop: <tries> must match too
-    assert abs(out["tries"].mean() - float(ref["mean_tries"])) < 0.03
-    # the reference's shipped table (scripts/centrality_cut_tables/..MCGlbPbPb2760..): Npart cuts at 5/10/20/30/50 %
-    srt = np.sort(got["npart"])[::-1]
-    for cen, cut in ((5, 358), (10, 307), (50, 72)):
-        val = srt[int(n * cen / 100)]
-        assert abs(val - cut) <= 4, (cen, val, cut)
     ctx.close()
+    return out, dict(npart=(out["npart1"] + out["npart2"]).astype(float), ncoll=out["ncoll"].astype(float), dsdy=out["total"],
+                     b=out["b"], e2=np.hypot(out["mom"][:, 1, 0], out["mom"][:, 1, 1]), e3=np.hypot(out["mom"][:, 2, 0], out["mom"][:, 2, 1]),
+                     e2p=np.hypot(out["mom"][:, 1, 2], out["mom"][:, 1, 3]), r2=out["mom"][:, 1, 4])
+
+
+@pytest.mark.parametrize("name", list(KS_SYSTEMS))
+def test_distributions_match_reference_ks(name):
+    """north_star level L3: two-sample KS of eight observables of 10^5 sampled events against 10^5 events of the
+    unmodified reference (its own 8-process mode; tests/golden/run_ks_reference.sh + make_ks_reference.py), gate
+    p > 0.01 as SURVEY.md 8(c) states.  Eight observables x four systems at a 1 % gate would fail a perfect
+    implementation one time in four, so an observable below the gate is re-tested on a second, independent 10^5-event
+    sample and must pass there (false-alarm rate 1e-4 per observable)."""
+    path = os.path.join(GOLDEN, "ks_%s_ref.npz" % name)
+    if not os.path.exists(path):
+        pytest.skip("KS reference sample for %s not generated" % name)
+    ref = np.load(path)
+    n = int(os.environ.get("SMC_KS_EVENTS", "100000"))
+    out, got = _ks_sample(name, 20261017, n)
+    ps = {k: _ks_p(got[k], ref[k]) for k in got}
+    print("KS p-values %s:" % name, {k: round(v, 4) for k, v in ps.items()}, "n_gpu=%d n_ref=%d" % (n, len(ref["npart"])))
+    low = [k for k, v in ps.items() if v <= 0.01]
+    if low:
+        _, got2 = _ks_sample(name, 77, n)
+        ps2 = {k: _ks_p(got2[k], ref[k]) for k in low}
+        print("second sample:", ps2)
+        for k, v in ps2.items():
+            assert v > 0.01, (name, k, ps[k], v)
+    # acceptance of the rejection loop: <tries> must match too
+    assert abs(out["tries"].mean() / float(ref["mean_tries"]) - 1) < 0.02
+    # the reference's own shipped centrality tables (scripts/centrality_cut_tables/, rows at 5 ... 80 % copied into
+    # tests/golden/shipped_centrality_rows.npz): Npart thresholds within +-4, dS/dy thresholds within 2 %
+    stem = KS_SYSTEMS[name][1]
+    if stem:
+        rows = np.load(os.path.join(GOLDEN, "shipped_centrality_rows.npz"))
+        srt = np.sort(got["dsdy"])[::-1]
+        for r in rows["total_entropy_" + stem]:
+            val = srt[int(n * r[0] / 100)]
+            assert abs(val / r[1] - 1) < 0.02, (name, r[0], val, r[1])
+        if "Npart_" + stem in rows.files:
+            srt = np.sort(got["npart"])[::-1]
+            for r in rows["Npart_" + stem]:
+                assert abs(srt[int(n * r[0] / 100)] - r[1]) <= 4, (name, r[0], srt[int(n * r[0] / 100)], r[1])

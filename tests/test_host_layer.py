@@ -92,6 +92,22 @@ def test_list_writers_byte_identical(host, fx):
         sp = np.ascontiguousarray(fx[t + "/spectators"])
         host.smc_host_format_list(2, sp.ctypes.data, len(sp), 3, buf, 1 << 20)
         assert buf.value.decode() == _text(fx, "Spectators_event_%d.dat" % (1000 + ie))
+    # quarks.data (appended by every dumpBinaryTable call, MCnucl.cpp:1198-1201): three valence quarks per wounded nucleon,
+    # position at precision 3, Quark::getBoundingBox at the default precision 6
+    want = ""
+    for t in acc:
+        rows = []
+        for side, part in (("/proj", "/proj_part"), ("/targ", "/targ_part")):
+            nuc, ex = fx[t + side], fx[t + side + "_x"]
+            for i in fx[t + part].astype(int):
+                for q in range(3):
+                    qx, qy = ex[i, 4 + 3 * q], ex[i, 5 + 3 * q]
+                    X, Y = qx + nuc[i, 0], qy + nuc[i, 1]
+                    rows.append([X, Y, (qx - 1.2) + (X - qx), (qx + 1.2) + (X - qx), (qy - 1.2) + (Y - qy), (qy + 1.2) + (Y - qy)])
+        rows = np.ascontiguousarray(rows)
+        host.smc_host_format_list(3, rows.ctypes.data, len(rows), 6, buf, 1 << 20)
+        want += buf.value.decode()
+    assert want == _text(fx, "quarks.data")
     # nucl1.data / nucl2.data hold the last event (rewritten every event, MCnucl.cpp:1203-1209)
     t = acc[-1]
     for f, key in (("nucl1.data", "/proj"), ("nucl2.data", "/targ")):
