@@ -228,6 +228,15 @@ double smc_comm_last_allreduce_ms(const smc_ctx* ctx);    /* device time of the 
 /* scripts/centrality_cut_h5.py:36-110: sort n events descending by key; perm receives the order */
 int  smc_centrality_sort(smc_ctx* ctx, const double* key, int64_t n, int64_t* perm);
 
+/* ---- the reference's 3-D extension (scripts/generate_3d_profiles/profile_3d.cpp, main.cpp) -----------------------
+ * n sources (x, y, id: 1 projectile / 2 target, as in ParticipantTable_event_<k>.dat) become Gaussians in (eta_s, x, y):
+ * rho_out[neta][nx][ny].  random_flag as profile_3d::set_variables (0: eta = +-2; 1: eta drawn from the tabulated
+ * distribution; 2, 3: widths fluctuate too).  eta_in / sigma3_in (n and 3n doubles: sigma_x sigma_y sigma_eta) override the
+ * draws (parity entry; the reference seeds with time()); eta_used / sigma3_used report what was used.  No context needed. */
+typedef struct smc_profile3d_params { int nx, ny, neta; double dx, dy, deta; double ecm; int random_flag; int64_t seed; } smc_profile3d_params;
+int  smc_profile3d(int device, const smc_profile3d_params* p, int n, const double* x, const double* y, const int* id,
+                   const double* eta_in, const double* sigma3_in, double* rho_out, double* eta_used, double* sigma3_used);
+
 /* diagnostics: kernels launched by this context so far, device time of the last run [ms];
  * with profiling on, CUDA-event time per stage {sample+collide, deposit, combine, moments} accumulates */
 int     smc_set_profiling(smc_ctx* ctx, int on);

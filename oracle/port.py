@@ -254,6 +254,14 @@ def density_quarks(cfg, proj8, qP, fP, targ8, qT, fT, coll8, quark_width):
     return g, dndy
 
 
+def profile3d(nx, ny, neta, dx, dy, deta, src7):
+    """profile_3d::generate_3d_profile with the rapidities and widths given (rows x y id eta sx sy se)"""
+    s = np.ascontiguousarray(src7, dtype=np.float64).reshape(-1, 7)
+    rho = np.zeros((neta, nx, ny))
+    lib().smc_o_profile3d(int(nx), int(ny), int(neta), C.c_double(dx), C.c_double(dy), C.c_double(deta), len(s), _d(s), _d(rho))
+    return rho
+
+
 def density_kln(cfg, TA1, TA2, table, dT):
     table = np.ascontiguousarray(table, dtype=np.float64)
     TA1 = np.ascontiguousarray(TA1); TA2 = np.ascontiguousarray(TA2)

@@ -1005,3 +1005,34 @@ void smc_o_fluctuate_density(const smc_o_cfg* c, int model, double cc_k, const d
       rho[q] = n / (c->dx * c->dy);
     }
 }
+
+
+/* ======================================================================================
+ * 3-D extension: profile_3d::generate_3d_profile (scripts/generate_3d_profiles/profile_3d.cpp:274-325) with the
+ * rapidities and widths given: src7 rows x y id eta sigma_x sigma_y sigma_eta; rho[neta][nx][ny]
+ * ====================================================================================== */
+void smc_o_profile3d(int nx, int ny, int neta, double dx, double dy, double deta, int n, const double* src7, double* rho) {
+  for (long q = 0; q < (long)neta * nx * ny; q++) rho[q] = 0.0;
+  for (int i = 0; i < n; i++) {
+    const double* s = src7 + 7 * i;
+    double part_x = s[0], part_y = s[1], part_eta = s[3];
+    int idx_x0 = (int)(part_x / dx + (nx - 1) / 2), idx_y0 = (int)(part_y / dy + (ny - 1) / 2), idx_eta0 = (int)(part_eta / deta + (neta - 1) / 2);
+    double sx = s[4], sy = s[5], se = s[6];
+    int rx = (int)(6 * sx / dx), ry = (int)(6 * sy / dy), re = (int)(6 * se / deta);
+    int xl = imax2(idx_x0 - rx, 0), xr = imin2(idx_x0 + rx, nx), yl = imax2(idx_y0 - ry, 0), yr = imin2(idx_y0 + ry, ny);
+    int el = imax2(idx_eta0 - re, 0), er = imin2(idx_eta0 + re, neta);
+    for (int j = el; j < er; j++) {
+      double eg = (j - (neta - 1) / 2.) * deta;
+      double dis_eta = (eg - part_eta) * (eg - part_eta) / (2. * se * se), norm_eta = 1. / sqrt(2. * M_PI * se * se);
+      for (int k = xl; k < xr; k++) {
+        double xg = (k - (nx - 1) / 2.) * dx;
+        double dis_x = (xg - part_x) * (xg - part_x) / (2. * sx * sx), norm_x = 1. / sqrt(2. * M_PI * sx * sx);
+        for (int l = yl; l < yr; l++) {
+          double yg = (l - (ny - 1) / 2.) * dy;
+          double dis_y = (yg - part_y) * (yg - part_y) / (2. * sy * sy), norm_y = 1. / sqrt(2. * M_PI * sy * sy);
+          rho[((long)j * nx + k) * ny + l] += exp(-dis_eta - dis_x - dis_y) * norm_eta * norm_x * norm_y;
+        }
+      }
+    }
+  }
+}

@@ -135,6 +135,9 @@ long smc_o_nbd_quantile(double p, double r, double u);
 void smc_o_fluctuate_density(const smc_o_cfg* c, int model, double cc_k, const double* TA1, const double* TA2,
                              const double* u, double* rho);
 
+/* 3-D extension (scripts/generate_3d_profiles/profile_3d.cpp:274-325); src7 rows x y id eta sigma_x sigma_y sigma_eta */
+void smc_o_profile3d(int nx, int ny, int neta, double dx, double dy, double deta, int n, const double* src7, double* rho);
+
 #ifdef __cplusplus
 }
 #endif

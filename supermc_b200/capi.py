@@ -53,6 +53,28 @@ EVENT_OUT_DTYPE = np.dtype([("b", "f8"), ("npart1", "i4"), ("npart2", "i4"), ("n
                             ("yc", "f8"), ("mom", "f8", (9, 5)), ("rn0", "f8"), ("nonzero_cells", "i4"), ("reserved", "i4")], align=True)
 
 
+class Profile3dParams(C.Structure):
+    _fields_ = [("nx", C.c_int), ("ny", C.c_int), ("neta", C.c_int), ("dx", C.c_double), ("dy", C.c_double), ("deta", C.c_double),
+                ("ecm", C.c_double), ("random_flag", C.c_int), ("seed", C.c_int64)]
+
+
+def profile3d(x, y, ids, nx=261, ny=261, neta=101, dx=0.1, dy=0.1, deta=0.1, ecm=19.6, random_flag=1, seed=1, eta=None, sigma3=None, device=0):
+    """scripts/generate_3d_profiles: participants -> rho[neta][nx][ny]; returns (rho, eta_used, sigma3_used)"""
+    x = np.ascontiguousarray(x, dtype=np.float64); y = np.ascontiguousarray(y, dtype=np.float64); ids = np.ascontiguousarray(ids, dtype=np.int32)
+    n = len(x)
+    p = Profile3dParams(nx, ny, neta, dx, dy, deta, ecm, random_flag, seed)
+    rho = np.zeros((neta, nx, ny)); eu = np.zeros(n); su = np.zeros((n, 3))
+    e_in = None if eta is None else np.ascontiguousarray(eta, dtype=np.float64)
+    s_in = None if sigma3 is None else np.ascontiguousarray(sigma3, dtype=np.float64)
+    L = lib()
+    L.smc_profile3d.argtypes = [C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 8
+    rc = L.smc_profile3d(int(device), C.byref(p), n, x.ctypes.data, y.ctypes.data, ids.ctypes.data, e_in.ctypes.data if e_in is not None else None,
+                         s_in.ctypes.data if s_in is not None else None, rho.ctypes.data, eu.ctypes.data, su.ctypes.data)
+    if rc != 0:
+        raise SmcError("smc_profile3d: rc=%d" % rc)
+    return rho, eu, su
+
+
 class SmcError(RuntimeError):
     pass
 
