@@ -103,6 +103,16 @@ def algorithmic_flops(ev, width, dx, kln=False):
     return float(f_dep.sum()), float(f_mom.sum()), float(f_smp.sum())
 
 
+def measured_peaks():
+    """MEASURED_PEAKS.json (driver-written); fallback: the HBM figure B200_PROFILING.md states for this pool"""
+    peaks = {"hbm_gbs": 6650.0, "source": "fallback of B200_PROFILING.md"}
+    try:
+        peaks.update(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))); peaks["source"] = "MEASURED_PEAKS.json"
+    except Exception:
+        pass
+    return peaks
+
+
 def ref_paths():
     exe = os.path.join(ROOT, "oracle", "_ref", "superMC_ref.e")
     run = os.path.join(ROOT, "oracle", "_ref", "run_zero")
@@ -556,47 +566,72 @@ EBE_ARGS = ["which_mc_model=5", "sub_model=1", "Aproj=197", "Atarg=197", "ecm=20
 def ebe_line(a):
     """BASELINE.json configs[0]: MC-Glauber Au+Au 200 GeV, event-by-event entropy density (one 261^2 text block per event)
     + eccentricities, through supermc_b200/superMC_b200.e -- wall clock of the whole process, start-up, CUDA
-    initialisation and text formatting included; next to it the unmodified reference binary (start-up run subtracted)."""
+    initialisation and text formatting included; the same run with output_binary=1 (raw float64 lattices instead of text)
+    shows what the text path costs; next to it the unmodified reference binary, one process and one process per host core
+    (start-up runs subtracted)."""
     exe = os.path.join(ROOT, "supermc_b200", "superMC_b200.e")
     nev = 1000
 
-    def ours(n):
+    def ours(n, extra=()):
         d = tempfile.mkdtemp(prefix="smcebe_"); os.makedirs(os.path.join(d, "data"))
         subprocess.check_call(["cp", os.path.join(ROOT, "supermc_b200", "parameters.dat"), d])
+        os.sync()          # the previous run's GBs of dirty pages would throttle this run's writes
         t0 = time.perf_counter()
-        so = subprocess.run([exe] + EBE_ARGS + ["nev=%d" % n], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, check=True).stdout
+        so = subprocess.run([exe] + EBE_ARGS + list(extra) + ["nev=%d" % n], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, check=True).stdout
         dt = time.perf_counter() - t0
         loop = [float(l.split(":")[1]) for l in so.splitlines() if l.startswith("Time elapsed (in seconds)")]      # main.cpp:65-68
-        nfiles = len([f for f in os.listdir(os.path.join(d, "data")) if f.startswith("sd_event_")])
+        names = os.listdir(os.path.join(d, "data"))
+        nfiles = len([f for f in names if f.startswith("sd_event_")])
+        nbytes = sum(os.path.getsize(os.path.join(d, "data", f)) for f in names)
         subprocess.call(["rm", "-rf", d])
-        return dt, nfiles, (loop[0] if loop else None)
+        return dt, nfiles, (loop[0] if loop else None), nbytes
     for _ in range(max(a.warmup, 1)):
-        t_start, _, _ = ours(8)
-    tot, files, loops = 0.0, 0, []
+        t_start, _, _, _ = ours(8)
+    tot, files, loops, nbytes = 0.0, 0, [], 0
     for _ in range(a.steps):
-        dt, nf, lp = ours(nev); tot += dt; files += nf; loops.append(lp)
+        dt, nf, lp, nb = ours(nev); tot += dt; files += nf; loops.append(lp); nbytes += nb
+    _, _, loop_bin, bytes_bin = ours(nev, ["output_binary=1"])
     v = nev * a.steps / tot
+    loop_rate = nev * len(loops) / sum(loops) if all(loops) else None
+    G8 = 8 * 261 * 261
+    peaks = measured_peaks()
     line = {"metric": "events/sec", "value": v, "unit": "events/s", "n_gpus": 1, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * tot / a.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "MC-Glauber Au+Au 200 GeV event-by-event profiles (operation 1), 261x261 grid, one text block file per event, "
                                    "whole-process wall clock incl. start-up (an 8-event run of the same binary takes %.2f s)" % t_start,
-                       "events_per_step": nev, "files_written": files, "event_loop_s_reported_by_the_program": loops},
-            "e2e": {"value": v, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8 * 261 * 261 * nev},
-            "roofline": None}
+                       "events_per_step": nev, "files_written": files, "event_loop_s_reported_by_the_program": loops,
+                       "event_loop_events_per_s": loop_rate, "text_bytes_per_step": nbytes // max(a.steps, 1),
+                       "host_text_gb_per_s_in_the_loop": (nbytes / max(a.steps, 1)) / (sum(loops) / len(loops)) / 1e9 if all(loops) else None,
+                       "binary_output": {"event_loop_events_per_s": nev / loop_bin if loop_bin else None, "bytes_per_step": bytes_bin,
+                                         "note": "same run with output_binary=1: raw float64 lattices instead of %22.12g text"}},
+            "e2e": {"value": v, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": G8 * nev},
+            "roofline": {"bound": "hbm", "kernel": "deposit_kernel (lattice writes) + device->host copy of every lattice", "achieved": (loop_rate or v) * 2 * G8 / 1e9,
+                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": (loop_rate or v) * 2 * G8 / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                         "note": "algorithmic bytes = one write + one read of the 8 G-byte lattice per event; this mode is bound by the host side "
+                                 "(text formatting and the copy of ~3 MB of text per event into the page cache), not by the GPU"}}
     rexe, run = ref_paths()
     if not a.no_cpu_baseline and os.path.exists(rexe):
-        def ref(n):
-            d = tempfile.mkdtemp(prefix="smcref_"); os.makedirs(os.path.join(d, "data"))
-            for f in ("parameters.dat", "EOS", "tables"):
-                os.symlink(os.path.join(run, f), os.path.join(d, f))
+        def ref(n, procs):
+            ds = []
+            for _ in range(procs):
+                d = tempfile.mkdtemp(prefix="smcref_"); os.makedirs(os.path.join(d, "data")); ds.append(d)
+                for f in ("parameters.dat", "EOS", "tables"):
+                    os.symlink(os.path.join(run, f), os.path.join(d, f))
             t0 = time.perf_counter()
-            subprocess.call([rexe] + EBE_ARGS + ["nev=%d" % n], cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            ps = [subprocess.Popen([rexe] + EBE_ARGS + ["nev=%d" % n, "randomSeed=%d" % (7 + i)], cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for i, d in enumerate(ds)]
+            for q in ps:
+                q.wait()
             dt = time.perf_counter() - t0
-            subprocess.call(["rm", "-rf", d])
+            for d in ds:
+                subprocess.call(["rm", "-rf", d])
             return dt
-        t1 = ref(1); t = ref(41)
+        t1 = ref(1, 1); t = ref(41, 1)
         line["cpu_baseline"] = dict(value=40 / max(t - t1, 1e-3), unit="events/s", cores=1, kind="reference",
                                     sample="41 events of the same workload, oracle/_ref/superMC_ref.e, 1-event start-up run subtracted")
+        P = os.cpu_count() or 1
+        tp1 = ref(1, P); tp = ref(41, P)
+        line["cpu_baseline_all_cores"] = dict(value=P * 40 / max(tp - tp1, 1e-3), unit="events/s", cores=P, kind="reference",
+                                              sample="%d concurrent processes x 41 events (its own multi-process mode), start-up runs subtracted" % P)
     return line
 
 

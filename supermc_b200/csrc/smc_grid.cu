@@ -528,7 +528,9 @@ cudaError_t launch_deposit(const DevCfg& c, const Store& st, const int* kinds, i
   if (use_list) {
     cudaFuncSetAttribute(deposit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const long want = (long)nev * nbands * ngroups * nk;
-    const int grid = (int)std::min<long>(want, (long)n_sm * DEP_MINCTA * persist);
+    // SMC_DEP_CTAS < DEP_MINCTA leaves room on every SM for CTAs of the other pipeline slots' kernels (sampler, moments)
+    static const int per_sm = getenv("SMC_DEP_CTAS") ? std::max(1, std::min(atoi(getenv("SMC_DEP_CTAS")), DEP_MINCTA)) : DEP_MINCTA;
+    const int grid = (int)std::min<long>(want, (long)n_sm * per_sm * persist);
     deposit_kernel<true><<<grid, DEP_THREADS, smem, s>>>(c, st, kl, nev, nbands);
   } else {
     cudaFuncSetAttribute(deposit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

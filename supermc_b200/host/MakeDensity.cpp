@@ -62,29 +62,52 @@ int ival(ParameterReader* p, const char* n) { return (int)p->getVal(n); }
 }  // namespace
 
 // ---- formatting (printf %g == iostream default floatfield with the same precision) -----------------
+namespace {
+// one "%<width>.<prec>g" cell, right-aligned; returns its length (>= width)
+inline int fmt_cell(char* dst, double v, int width, int prec) {
+  char b[40];
+  const auto r = std::to_chars(b, b + sizeof b, v, std::chars_format::general, prec);
+  const int n = (int)(r.ptr - b), pad = n < width ? width - n : 0;
+  std::memset(dst, ' ', (size_t)pad); std::memcpy(dst + pad, b, (size_t)n);
+  return pad + n;
+}
+struct RowCells { char mom[45][24]; int mlen[45]; char tail[4 * 24 + 8 * 24 + 2]; int tlen; };
+// the 49 (+4 for deformed nuclei) cells of one event: 45 moments, then Npart Ncoll total b [0 0 0 0] "\n" as one tail
+inline void format_cells(const smc_event_out& ev, bool deformed, RowCells& rc) {
+  for (int n = 0; n < 9; n++) for (int k = 0; k < 5; k++) rc.mlen[n * 5 + k] = fmt_cell(rc.mom[n * 5 + k], ev.mom[n][k], 16, 8);
+  int t = 0;
+  t += fmt_cell(rc.tail + t, (double)(ev.npart1 + ev.npart2), 10, 5); t += fmt_cell(rc.tail + t, (double)ev.ncoll, 10, 5);
+  t += fmt_cell(rc.tail + t, ev.total, 16, 8); t += fmt_cell(rc.tail + t, ev.b, 16, 8);
+  if (deformed) for (int k = 0; k < 4; k++) t += fmt_cell(rc.tail + t, 0.0, 16, 8);   // mc->lastCx1.. are never assigned upstream (quirk Q9)
+  rc.tail[t++] = '\n'; rc.tlen = t;
+}
+}  // namespace
 std::string MakeDensity::formatEccRow(const smc_event_out& ev, int order, bool deformed) {
-  std::string s; const double* m = ev.mom[order - 1];
-  for (int k = 0; k < 5; k++) put_g(s, m[k], 16, 8);
-  put_g(s, (double)(ev.npart1 + ev.npart2), 10, 5); put_g(s, (double)ev.ncoll, 10, 5);
-  put_g(s, ev.total, 16, 8); put_g(s, ev.b, 16, 8);
-  if (deformed) for (int k = 0; k < 4; k++) put_g(s, 0.0, 16, 8);   // mc->lastCx1.. are never assigned upstream (quirk Q9)
-  s += "\n"; return s;
+  RowCells rc; format_cells(ev, deformed, rc);
+  std::string s;
+  for (int k = 0; k < 5; k++) s.append(rc.mom[(order - 1) * 5 + k], (size_t)rc.mlen[(order - 1) * 5 + k]);
+  s.append(rc.tail, (size_t)rc.tlen); return s;
 }
 std::string MakeDensity::formatEccRowAll(const smc_event_out& ev, bool deformed) {
-  std::string s;
-  s.reserve(49 * 16 + 8);
-  for (int n = 1; n < 10; n++) for (int k = 0; k < 5; k++) put_g(s, ev.mom[n - 1][k], 16, 8);
-  put_g(s, (double)(ev.npart1 + ev.npart2), 10, 5); put_g(s, (double)ev.ncoll, 10, 5);
-  put_g(s, ev.total, 16, 8); put_g(s, ev.b, 16, 8);
-  if (deformed) for (int k = 0; k < 4; k++) put_g(s, 0.0, 16, 8);
-  s += "\n"; return s;
+  RowCells rc; format_cells(ev, deformed, rc);
+  std::string s; s.reserve(49 * 16 + 8);
+  for (int q = 0; q < 45; q++) s.append(rc.mom[q], (size_t)rc.mlen[q]);
+  s.append(rc.tail, (size_t)rc.tlen); return s;
 }
 void MakeDensity::formatDensityBlock(const double* g, int Maxx, int Maxy, std::string& out) {
-  out.clear(); out.reserve((size_t)Maxx * (Maxy * 22 + 1));
+  // "%22.12g" cells written straight into the final buffer; most of a lattice is exact zeros (outside the event's
+  // rectangle), which print as "0" without a conversion
+  out.resize((size_t)Maxx * ((size_t)Maxy * 26 + 1));
+  char* p = &out[0];
   for (int i = 0; i < Maxx; i++) {
-    for (int j = 0; j < Maxy; j++) put_g(out, g[(size_t)i * Maxy + j], 22, 12);
-    out += "\n";
+    for (int j = 0; j < Maxy; j++) {
+      const double v = g[(size_t)i * Maxy + j];
+      if (v == 0.0 && !std::signbit(v)) { std::memset(p, ' ', 21); p[21] = '0'; p += 22; }
+      else p += fmt_cell(p, v, 22, 12);
+    }
+    *p++ = '\n';
   }
+  out.resize((size_t)(p - &out[0]));
 }
 void MakeDensity::formatDensity4Col(const double* g, int Maxx, int Maxy, double Xmin, double Ymin, double dx, double dy,
                                     double rap, double npart, std::string& out) {
@@ -246,43 +269,35 @@ int MakeDensity::run(int operation, int nevent) {
 }
 
 // ---- operation 9: minimum-bias eccentricity table ---------------------------------------------------
-// The GPU produces ~0.75 M rows/s; one thread formats ~50 k rows/s.  So the loop is a pipeline: the main thread keeps the
-// GPU busy (smc_run_events on chunk k+1) while a writer thread takes chunk k, formats its rows on all host cores
-// (contiguous slices, so the files keep event order) and appends them to the ten/twenty tables.
+// The GPU produces ~0.75 M events/s and every event is 2 x 1970 bytes of text (ten tables per branch), so the loop is a
+// three-stage pipeline over chunks of events: the main thread keeps the GPU busy (smc_run_events on chunk k+1), a formatter
+// stage turns chunk k into text on all host cores (contiguous slices, so the files keep event order), and a writer stage
+// appends chunk k-1 to the ten / twenty tables, one appender per file.  Every number of an event is formatted once: the
+// nine per-order rows and the all-orders row are assembled from the same 49 right-aligned cells.
 int MakeDensity::generateEccTable(int nevent) {
   const int from_order = ival(paraRdr, "ecc_from_order"), to_order = ival(paraRdr, "ecc_to_order");
   const bool use_sd = paraRdr->getVal("use_sd") != 0, use_ed = paraRdr->getVal("use_ed") != 0;
   const bool binary = paraRdr->getVal("output_binary", 0) != 0;          // extension: raw smc_event_out rows next to the text tables
   uint64_t first; int count; shard_range(nevent, &first, &count);
-  const int chunk = std::max(1, (int)paraRdr->getVal("host_chunk", 32768));
+  const int chunk = std::max(1, (int)paraRdr->getVal("host_chunk", 65536));
   const int lo = std::max(from_order, 1), hi = std::min(to_order, 9);
   const unsigned nthr = std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
-  struct Chunk { std::vector<smc_event_out> out; int n = 0; long done = 0; };
   const int ny = binRapidity;            // one row per event and rapidity slice (MakeDensity.cpp:2170-2193)
+  struct Chunk { std::vector<smc_event_out> out; int n = 0; long done = 0; };
+  struct Text { std::vector<std::vector<std::string>> part; const Chunk* src = nullptr; long done = 0; };   // part[thread][table 1..10]
   Chunk buf[3]; for (auto& b : buf) b.out.resize((size_t)std::max(1, std::min(count, chunk)) * ny);
-  std::mutex m; std::condition_variable cv; std::deque<Chunk*> full, empty; bool finished = false; long failed = 0;
+  Text txt[2]; for (auto& t : txt) t.part.assign(nthr, std::vector<std::string>(11));
+  std::mutex m; std::condition_variable cv;
+  std::deque<Chunk*> full, empty; std::deque<Text*> tfull, tempty; bool finished = false, formatted = false; long failed = 0;
   for (auto& b : buf) empty.push_back(&b);
+  for (auto& t : txt) tempty.push_back(&t);
   const char* base[2] = {"sn_ecc_eccp_%d.dat", "en_ecc_eccp_%d.dat"};     // en == sn numerically (quirk Q2)
+  // stage 3: append a formatted chunk to the tables, one appender per file, all at once (the copy into the page cache is
+  // what bounds a single writer at ~2 GB/s, and a million events are 4 GB of text)
   std::thread writer([&] {
-    std::vector<std::vector<std::string>> part(nthr, std::vector<std::string>(11));
     for (;;) {
-      Chunk* c;
-      { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return finished || !full.empty(); }); if (full.empty()) return; c = full.front(); full.pop_front(); }
-      std::vector<std::thread> th;
-      std::vector<long> bad(nthr, 0);
-      for (unsigned t = 0; t < nthr; t++) th.emplace_back([&, t] {
-        const int a = (int)((long)c->n * ny * t / nthr), b = (int)((long)c->n * ny * (t + 1) / nthr);
-        for (auto& r : part[t]) r.clear();
-        for (int e = a; e < b; e++) {
-          if (c->out[e].status != SMC_OK) { bad[t]++; continue; }
-          for (int o = lo; o <= hi; o++) part[t][o] += formatEccRow(c->out[e], o, deformed);
-          part[t][10] += formatEccRowAll(c->out[e], deformed);
-        }
-      });
-      for (auto& t : th) t.join();
-      for (long v : bad) failed += v;
-      // up to twenty tables grow by this chunk: one appender per file, all at once (the copy into the page cache is what
-      // bounds a single writer at ~2 GB/s, and a million events are 4 GB of text)
+      Text* t;
+      { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return formatted || !tfull.empty(); }); if (tfull.empty()) return; t = tfull.front(); tfull.pop_front(); }
       std::vector<std::thread> wr;
       for (int f = 0; f < 2; f++) {
         if ((f == 0 && !use_sd) || (f == 1 && !use_ed)) continue;
@@ -292,16 +307,53 @@ int MakeDensity::generateEccTable(int nevent) {
             char name[128]; std::snprintf(name, sizeof name, base[f], o);
             FILE* fp = std::fopen(path(name).c_str(), "ab");
             if (!fp) { std::fprintf(stderr, "cannot open %s\n", path(name).c_str()); return; }
-            for (unsigned t = 0; t < nthr; t++) std::fwrite(part[t][o].data(), 1, part[t][o].size(), fp);
+            for (unsigned q = 0; q < nthr; q++) std::fwrite(t->part[q][o].data(), 1, t->part[q][o].size(), fp);
             std::fclose(fp);
           });
         }
       }
-      for (auto& t : wr) t.join();
-      if (binary) { FILE* fp = std::fopen(path("ecc_rows.bin").c_str(), "ab"); if (fp) { std::fwrite(c->out.data(), sizeof(smc_event_out), (size_t)c->n * ny, fp); std::fclose(fp); } }
-      std::cout << "processed events: " << c->done << " / " << count << "\r" << std::flush;
-      { std::lock_guard<std::mutex> l(m); empty.push_back(c); } cv.notify_all();
+      for (auto& w : wr) w.join();
+      std::cout << "processed events: " << t->done << " / " << count << "\r" << std::flush;
+      { std::lock_guard<std::mutex> l(m); tempty.push_back(t); } cv.notify_all();
     }
+  });
+  // stage 2: rows -> text
+  std::thread formatter([&] {
+    for (;;) {
+      Chunk* c; Text* t;
+      { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return finished || !full.empty(); }); if (full.empty()) break; c = full.front(); full.pop_front(); }
+      { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return !tempty.empty(); }); t = tempty.front(); tempty.pop_front(); }
+      std::vector<std::thread> th;
+      std::vector<long> bad(nthr, 0);
+      for (unsigned q = 0; q < nthr; q++) th.emplace_back([&, q] {
+        const int a = (int)((long)c->n * ny * q / nthr), b = (int)((long)c->n * ny * (q + 1) / nthr);
+        auto& P = t->part[q];
+        for (auto& r : P) r.clear();
+        for (int o = lo; o <= hi; o++) P[o].reserve((size_t)(b - a) * 200);
+        P[10].reserve((size_t)(b - a) * 860);
+        RowCells rc;
+        for (int e = a; e < b; e++) {
+          if (c->out[e].status != SMC_OK) { bad[q]++; continue; }
+          format_cells(c->out[e], deformed, rc);
+          for (int n = 1; n <= 9; n++) {
+            const bool own = n >= lo && n <= hi;
+            for (int k = 0; k < 5; k++) {
+              const char* s = rc.mom[(n - 1) * 5 + k]; const size_t L = (size_t)rc.mlen[(n - 1) * 5 + k];
+              if (own) P[n].append(s, L);
+              P[10].append(s, L);
+            }
+            if (own) P[n].append(rc.tail, (size_t)rc.tlen);
+          }
+          P[10].append(rc.tail, (size_t)rc.tlen);
+        }
+      });
+      for (auto& x : th) x.join();
+      for (long v : bad) failed += v;
+      if (binary) { FILE* fp = std::fopen(path("ecc_rows.bin").c_str(), "ab"); if (fp) { std::fwrite(c->out.data(), sizeof(smc_event_out), (size_t)c->n * ny, fp); std::fclose(fp); } }
+      t->done = c->done;
+      { std::lock_guard<std::mutex> l(m); empty.push_back(c); tfull.push_back(t); } cv.notify_all();
+    }
+    { std::lock_guard<std::mutex> l(m); formatted = true; } cv.notify_all();
   });
   int rc = 0;
   for (int done = 0; done < count && !rc; done += chunk) {
@@ -313,7 +365,7 @@ int MakeDensity::generateEccTable(int nevent) {
     { std::lock_guard<std::mutex> l(m); full.push_back(c); } cv.notify_all();
   }
   { std::lock_guard<std::mutex> l(m); finished = true; } cv.notify_all();
-  writer.join();
+  formatter.join(); writer.join();
   std::cout << std::endl;
   if (failed) {      // an event whose collision list overflowed ncoll_cap has no row: say so loudly, the table is short
     std::cerr << "superMC_b200: " << failed << " event(s) exceeded the per-event capacities (status != 0) and have no row; raise ncoll_cap" << std::endl;
@@ -406,10 +458,12 @@ static int ebe_common(MakeDensity* self, smc_ctx* ctx, ParameterReader* paraRdr,
   // one page-locked block per (batch, grid kind), filled by ONE strided device->host copy and shared by the writer jobs
   struct PinBuf { double* p; explicit PinBuf(size_t n) : p((double*)smc_pinned_alloc(n * sizeof(double))) {} ~PinBuf() { smc_pinned_free(p); } };
   typedef std::shared_ptr<PinBuf> Buf;
-  auto grid_job = [&](Buf keep, const double* g, const std::string& stem, double npart) {
-    if (binary) { pool.submit([=] { (void)keep; write_file(stem + ".bin", std::string((const char*)g, G * sizeof(double)), false); }); return; }
-    if (use_4col) pool.submit([=] { (void)keep; std::string s; MakeDensity::formatDensity4Col(g, Maxx, Maxy, Xmin, Ymin, dx, dy, rapMin, npart, s); write_file(stem + "_4col.dat", s, false); });
-    if (use_block) pool.submit([=] { (void)keep; std::string s; MakeDensity::formatDensityBlock(g, Maxx, Maxy, s); write_file(stem + "_block.dat", s, false); });
+  // stem2 (optional): a second file set with the same numbers (sd and ed are identical, quirk Q2): formatted once, written twice
+  auto grid_job = [&](Buf keep, const double* g, const std::string& stem, double npart, const std::string& stem2 = std::string()) {
+    auto both = [=](const char* ext, const std::string& text) { write_file(stem + ext, text, false); if (!stem2.empty()) write_file(stem2 + ext, text, false); };
+    if (binary) { pool.submit([=] { (void)keep; both(".bin", std::string((const char*)g, G * sizeof(double))); }); return; }
+    if (use_4col) pool.submit([=] { (void)keep; std::string s; MakeDensity::formatDensity4Col(g, Maxx, Maxy, Xmin, Ymin, dx, dy, rapMin, npart, s); both("_4col.dat", s); });
+    if (use_block) pool.submit([=] { (void)keep; std::string s; MakeDensity::formatDensityBlock(g, Maxx, Maxy, s); both("_block.dat", s); });
   };
   auto fetch_all = [&](int n, int which, double scale) -> Buf {
     Buf b = std::make_shared<PinBuf>((size_t)n * G);
@@ -471,8 +525,9 @@ static int ebe_common(MakeDensity* self, smc_ctx* ctx, ParameterReader* paraRdr,
       }
       if (use_sd || use_ed) {
         const double* g = b_rho->p + (size_t)e * G;
-        if (use_sd) grid_job(b_rho, g, P("sd_event_%ld", event), npart);
-        if (use_ed) grid_job(b_rho, g, P("ed_event_%ld", event), npart);       // identical numbers (quirk Q2)
+        if (use_sd && use_ed) grid_job(b_rho, g, P("sd_event_%ld", event), npart, P("ed_event_%ld", event));   // identical numbers (quirk Q2)
+        else if (use_sd) grid_job(b_rho, g, P("sd_event_%ld", event), npart);
+        else grid_job(b_rho, g, P("ed_event_%ld", event), npart);
       }
       if (o_rb) grid_job(b_rb, b_rb->p + (size_t)e * G, P("rho_binary_event_%ld", event), npart);
       if (o_ta) { grid_job(b_ta, b_ta->p + (size_t)e * G, P("nuclear_thickness_TA_event_%ld", event), npart); grid_job(b_tb, b_tb->p + (size_t)e * G, P("nuclear_thickness_TB_event_%ld", event), npart); }

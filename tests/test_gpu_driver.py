@@ -34,6 +34,19 @@ def test_operation9_table(tmp_path):
     assert np.array_equal(t10[:, 45], ev["npart1"] + ev["npart2"]) and np.array_equal(t10[:, 46], ev["ncoll"])
     assert np.allclose(t10[:, :45], ev["mom"].reshape(300, 45), rtol=2e-7, atol=1e-12)      # 8 printed digits
     assert np.allclose(t10[:, 48], ev["b"], rtol=2e-7)
+    # the tables of the executable's pipeline (every number formatted once, rows assembled from cells) are, byte for byte,
+    # the rows of the formatter that tests/test_host_layer.py pins to reference-written files
+    import ctypes as C
+    host = C.CDLL(os.path.join(ROOT, "supermc_b200", "libsupermc_host.so"))
+    buf = C.create_string_buffer(4096)
+    for order in (1, 2, 9, 10):
+        want = b""
+        for e in range(300):
+            eo = smc.EventOut.from_buffer_copy(ev[e].tobytes())
+            n = host.smc_host_format_ecc_row(C.byref(eo), order, 0, buf, 4096)
+            assert n > 0
+            want += buf.value
+        assert (d / "data" / ("sn_ecc_eccp_%d.dat" % order)).read_bytes() == want, order
 
 
 def test_operation2_files(tmp_path):
