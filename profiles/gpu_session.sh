@@ -17,6 +17,10 @@ for p in $parts; do
     ncu)   timeout 900 ncu --set full --clock-control none --import-source on -k regex:"deposit_kernel|sample_collide|moments_kernel" -s 3 -c 3 -f -o ${O}_prof python profiles/prof_run.py 2048 2048 > ${O}_prof.log 2>&1 ;;
     ncukln) timeout 900 ncu --set full --clock-control none --import-source on -k regex:"deposit_kernel|combine_kernel|moments_kernel" -s 3 -c 3 -f -o ${O}_prof_kln python profiles/prof_run.py 2048 2048 kln > ${O}_prof_kln.log 2>&1 ;;
     smoke) timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > ${O}_smoke.txt 2>&1 ;;
+    scanexe) timeout 400 python bench.py --workload scan-exe --steps 2 --warmup 1 > ${O}_bench_scanexe.json 2> ${O}_bench_scanexe.err ;;
+    ebe)   timeout 400 python bench.py --workload ebe --steps 2 --warmup 1 > ${O}_bench_ebe.json 2> ${O}_bench_ebe.err ;;
+    avg)   timeout 600 python bench.py --workload avg --steps 2 --warmup 1 > ${O}_bench_avg.json 2> ${O}_bench_avg.err ;;
+    sass)  cuobjdump -sass supermc_b200/libsupermc_b200.so > ${O}_sass.txt 2>&1 ;;
   esac
 done
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > ${O}_smi.txt 2>&1

@@ -799,6 +799,11 @@ static int cache_lists(smc_ctx* ctx) {
     CK(cudaMemcpy2D(lc.coll.data(), (size_t)mx * smc::CROW * sizeof(double), ctx->st.coll, (size_t)ctx->cfg.ncoll_cap * smc::CROW * sizeof(double), (size_t)mx * smc::CROW * sizeof(double), n, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy2D(lc.ij.data(), (size_t)mx * sizeof(int), ctx->st.coll_ij, (size_t)ctx->cfg.ncoll_cap * sizeof(int), (size_t)mx * sizeof(int), n, cudaMemcpyDeviceToHost));
   }
+  lc.extra.clear();
+  if (ctx->st.nuc_extra) {      // valence-quark state (smc_get_quarks)
+    lc.extra.resize((size_t)n * 2 * Amax * smc::NEXTRA);
+    CK(cudaMemcpy(lc.extra.data(), ctx->st.nuc_extra, lc.extra.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  }
   lc.epoch = ctx->epoch; lc.n = n;
   return SMC_OK;
 }
@@ -874,12 +879,11 @@ extern "C" int smc_get_quarks(smc_ctx* ctx, int slot, double* host6, int* n) {
   *n = 3 * (hi[smc::H_NP1] + hi[smc::H_NP2]);
   if (!host6) return SMC_OK;
   const int Amax = ctx->cfg.Amax;
-  std::vector<double> ex((size_t)2 * Amax * smc::NEXTRA);
-  CK(cudaSetDevice(ctx->device));
-  CK(cudaMemcpy(ex.data(), ctx->st.nuc_extra + (size_t)slot * 2 * Amax * smc::NEXTRA, ex.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  if (ctx->lists.extra.size() < (size_t)(slot + 1) * 2 * Amax * smc::NEXTRA) FAIL(SMC_ERR_STATE, "smc_get_quarks: the quark state of this batch was not kept");
+  const double* ex = ctx->lists.extra.data() + (size_t)slot * 2 * Amax * smc::NEXTRA;
   int k = 0; const double qw = ctx->p.quark_width;
   auto put = [&](int s, int i) {
-    const double* r = nuc.data() + ((size_t)s * Amax + i) * smc::NROW; const double* x = ex.data() + ((size_t)s * Amax + i) * smc::NEXTRA;
+    const double* r = nuc.data() + ((size_t)s * Amax + i) * smc::NROW; const double* x = ex + ((size_t)s * Amax + i) * smc::NEXTRA;
     for (int q = 0; q < 3; q++) {
       const double qx = x[smc::XQ + 3 * q], qy = x[smc::XQ + 3 * q + 1], X = qx + r[smc::NX], Y = qy + r[smc::NY];
       double* o = host6 + (size_t)(k++) * 6;

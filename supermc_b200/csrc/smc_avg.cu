@@ -168,10 +168,20 @@ static int avg_sequence(smc_ctx* ctx, int m) {
   if ((rc = smc_plan_kinds(ctx, SMC_RUN_THICKNESS | SMC_RUN_RHO_BINARY | SMC_RUN_SPECTATORS, kinds, &nd))) return rc;
   ctx->need_zero = false;
   if (c.which_mc_model == 1 && !st.kln_table) FAIL(SMC_ERR_STATE, "MC-KLN needs its table first");
-  auto density = [&]() -> int {          // calculateThickness + setDensity + calculate_rho_binary + calculate_spectator_density
+  // The reference recomputes every lattice at each of the five density steps of an order; only some are read before the
+  // next move of the event: the order's first density feeds calcCMAngle alone (rho), the reaction-plane pass accumulates
+  // everything but the spectator lattices (MakeDensity.cpp:1289-1330), the rotated pass everything.  Deposit what is read.
+  int k_rho[8], n_rho = 0, k_rp[8], n_rp = 0;
+  for (int i = 0; i < nd; i++) {
+    const int k = kinds[i];
+    const bool for_rho = (c.which_mc_model == 5) ? k == smc::GK_RHO : (c.which_mc_model == 7) ? (k == smc::GK_RHOA || k == smc::GK_RHOB) : (k == smc::GK_TA1 || k == smc::GK_TA2);
+    if (for_rho || (c.cc_fluct == 2 && (k == smc::GK_TA1 || k == smc::GK_TA2))) k_rho[n_rho++] = k;
+    if (k != smc::GK_SPEC_A && k != smc::GK_SPEC_B) k_rp[n_rp++] = k;
+  }
+  auto density = [&](const int* ks, int nk) -> int {          // calculateThickness + setDensity + calculate_rho_binary + calculate_spectator_density
     // no zero fill: deposit, combine, cm_angle and accumulate all work on the event's bounding rectangle (spectator
     // lattices are written whole)
-    CK(smc::launch_deposit(c, st, kinds, nd, m, ctx->stream)); ctx->launches += 2;
+    CK(smc::launch_deposit(c, st, ks, nk, m, ctx->stream)); ctx->launches += 2;
     if (c.which_mc_model != 5) { CK(smc::launch_combine(c, st, m, ctx->stream)); ctx->launches++; }
     if (c.cc_fluct == 1 || c.cc_fluct == 2) { st.nbd_pass++; CK(smc::launch_fluctuate(c, st, m, ctx->stream)); ctx->launches++; }   // fresh draws per setDensity
     return SMC_OK;
@@ -201,15 +211,15 @@ static int avg_sequence(smc_ctx* ctx, int m) {
     for (int iy = 0; iy < ctx->ny; iy++) {
       if (ctx->d_kln) st.kln_table = ctx->d_kln + (size_t)iy * tsz;
       const bool keep = (iy == ctx->ny - 1);
-      if ((rc = density())) return rc;                                                   // MakeDensity.cpp:1275
+      if ((rc = density(k_rho, n_rho))) return rc;                                       // MakeDensity.cpp:1275
       for (int branch = 0; branch < 2; branch++) {
         if (!(ctx->avg_ed & (1 << branch))) continue;
         double scale = branch == 1 ? c.finalFactor : 1.0;                                // ed branch: setRho(rho*finalFactor) first (:1391-1396)
         if (ctx->avg_rp) {                                                               // :1289-1330 / :1397-1438
-          if ((rc = cm(order, scale)) || (rc = tf(0)) || (rc = density()) || (keep && (rc = acc(io, 1, branch)))) return rc;
+          if ((rc = cm(order, scale)) || (rc = tf(0)) || (rc = density(k_rp, n_rp)) || (keep && (rc = acc(io, 1, branch)))) return rc;
           scale = 1.0;
         }
-        if ((rc = cm(order, scale)) || (rc = tf(1)) || (rc = density()) || (keep && (rc = acc(io, 0, branch)))) return rc;   // :1331-1386 / :1439-1493
+        if ((rc = cm(order, scale)) || (rc = tf(1)) || (rc = density(kinds, nd)) || (keep && (rc = acc(io, 0, branch)))) return rc;   // :1331-1386 / :1439-1493
       }
     }
   }

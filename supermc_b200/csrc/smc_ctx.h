@@ -32,7 +32,7 @@ struct smc_slot {
 };
 
 // host mirror of the last batch's event records, filled by the first list getter after a run (smc_api.cu: cache_lists)
-struct smc_list_cache { uint64_t epoch; int n; int coll_stride; std::vector<double> nuc, coll; std::vector<int> ncoll, first, hdr, ij; };
+struct smc_list_cache { uint64_t epoch; int n; int coll_stride; std::vector<double> nuc, coll, extra; std::vector<int> ncoll, first, hdr, ij; };
 
 struct smc_sort_buffers { double *k1, *k2; int64_t *v1, *v2; void* tmp; int64_t cap; size_t tmp_bytes; };
 

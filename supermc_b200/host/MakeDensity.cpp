@@ -6,6 +6,7 @@
 #include <condition_variable>
 #include <memory>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <dirent.h>
@@ -411,25 +412,28 @@ int MakeDensity::merge_rank_outputs() {
 
 // ---- list dumps (MCnucl::dumpBinaryTable / dumpparticipantTable / dumpSpectatorsTable, MCnucl.cpp:1177-1269) ----
 std::string smc_fmt_xy(const double* rows, int n, int stride) {        // setprecision(3) setw(10) x2
-  std::string s; for (int i = 0; i < n; i++) { put(s, "%10.3g", rows[(size_t)i * stride]); put(s, "%10.3g", rows[(size_t)i * stride + 1]); s += "\n"; } return s;
+  std::string s; s.reserve((size_t)n * 21);
+  for (int i = 0; i < n; i++) { put_g(s, rows[(size_t)i * stride], 10, 3); put_g(s, rows[(size_t)i * stride + 1], 10, 3); s += "\n"; } return s;
 }
 std::string smc_fmt_participants(const double* rows, int n) {          // Nucleus::dumpParticipants, Nucleus.cpp:753-764
-  std::string s; char b[32];
-  for (int i = 0; i < n; i++) { put(s, "%10.3g", rows[(size_t)i * 8]); s += "   "; put(s, "%10.3g", rows[(size_t)i * 8 + 1]); s += "   "; int k = std::snprintf(b, sizeof b, "%d\n", (int)rows[(size_t)i * 8 + 2]); s.append(b, k); }
+  std::string s; s.reserve((size_t)n * 28);
+  for (int i = 0; i < n; i++) { put_g(s, rows[(size_t)i * 8], 10, 3); s += "   "; put_g(s, rows[(size_t)i * 8 + 1], 10, 3); s += "   "; s += ((int)rows[(size_t)i * 8 + 2] == 1 ? "1\n" : "2\n"); }
   return s;
 }
 std::string smc_fmt_quarks(const double* rows, int n) {                // Nucleus::dumpQuarks, Nucleus.cpp:780-797: x y at precision 3, the box at the default 6
-  std::string s; char b[128];
+  std::string s; s.reserve((size_t)n * 64);
   for (int i = 0; i < n; i++) {
     const double* r = rows + (size_t)i * 6;
-    put(s, "%10.3g", r[0]); put(s, "%10.3g", r[1]);
-    int k = std::snprintf(b, sizeof b, " %g %g %g %g\n", r[2], r[3], r[4], r[5]); s.append(b, k);
+    put_g(s, r[0], 10, 3); put_g(s, r[1], 10, 3);
+    for (int k = 2; k < 6; k++) { s += ' '; put_g(s, r[k], 0, 6); }
+    s += "\n";
   }
   return s;
 }
 std::string smc_fmt_spectators(const double* rows, int n) {            // scientific, setprecision(4), setw(10) on x only
-  std::string s; char b[96];
-  for (int i = 0; i < n; i++) { int k = std::snprintf(b, sizeof b, "%10.4e  %.4e  %.4e\n", rows[(size_t)i * 3], rows[(size_t)i * 3 + 1], rows[(size_t)i * 3 + 2]); s.append(b, k); }
+  std::string s; s.reserve((size_t)n * 36);
+  auto sci = [&](double v, int width) { char b[40]; const auto r = std::to_chars(b, b + sizeof b, v, std::chars_format::scientific, 4); const int k = (int)(r.ptr - b); if (k < width) s.append((size_t)(width - k), ' '); s.append(b, (size_t)k); };
+  for (int i = 0; i < n; i++) { sci(rows[(size_t)i * 3], 10); s += "  "; sci(rows[(size_t)i * 3 + 1], 0); s += "  "; sci(rows[(size_t)i * 3 + 2], 0); s += "\n"; }
   return s;
 }
 
@@ -456,8 +460,18 @@ static int ebe_common(MakeDensity* self, smc_ctx* ctx, ParameterReader* paraRdr,
   rapMin = rapMin + (-rapMin - rapMin) / ny * (ny - 1);
   auto P = [&](const char* fmt, long ev) { char b[160]; std::snprintf(b, sizeof b, fmt, ev); return data_dir + "/" + b; };
   // one page-locked block per (batch, grid kind), filled by ONE strided device->host copy and shared by the writer jobs
-  struct PinBuf { double* p; explicit PinBuf(size_t n) : p((double*)smc_pinned_alloc(n * sizeof(double))) {} ~PinBuf() { smc_pinned_free(p); } };
+  // (page-locking 140 MB takes tens of milliseconds: the blocks go back to a free list when the last writer job lets go)
+  struct PinBuf { double* p; size_t n; explicit PinBuf(size_t n_) : p((double*)smc_pinned_alloc(n_ * sizeof(double))), n(n_) {} ~PinBuf() { smc_pinned_free(p); } };
   typedef std::shared_ptr<PinBuf> Buf;
+  struct PinPool { std::mutex m; std::vector<PinBuf*> free_list; ~PinPool() { for (PinBuf* b : free_list) delete b; } };
+  auto pins = std::make_shared<PinPool>();
+  auto pin_get = [pins](size_t n) -> Buf {
+    PinBuf* b = nullptr;
+    { std::lock_guard<std::mutex> l(pins->m);
+      for (size_t i = 0; i < pins->free_list.size(); i++) if (pins->free_list[i]->n >= n) { b = pins->free_list[i]; pins->free_list.erase(pins->free_list.begin() + (long)i); break; } }
+    if (!b) b = new PinBuf(n);
+    return Buf(b, [pins](PinBuf* q) { std::lock_guard<std::mutex> l(pins->m); pins->free_list.push_back(q); });
+  };
   // stem2 (optional): a second file set with the same numbers (sd and ed are identical, quirk Q2): formatted once, written twice
   auto grid_job = [&](Buf keep, const double* g, const std::string& stem, double npart, const std::string& stem2 = std::string()) {
     auto both = [=](const char* ext, const std::string& text) { write_file(stem + ext, text, false); if (!stem2.empty()) write_file(stem2 + ext, text, false); };
@@ -466,7 +480,7 @@ static int ebe_common(MakeDensity* self, smc_ctx* ctx, ParameterReader* paraRdr,
     if (use_block) pool.submit([=] { (void)keep; std::string s; MakeDensity::formatDensityBlock(g, Maxx, Maxy, s); both("_block.dat", s); });
   };
   auto fetch_all = [&](int n, int which, double scale) -> Buf {
-    Buf b = std::make_shared<PinBuf>((size_t)n * G);
+    Buf b = pin_get((size_t)n * G);
     if (!b->p) { err = "smc_pinned_alloc failed"; return Buf(); }
     if (smc_get_grids(ctx, 0, n, which, b->p) != SMC_OK) { err = smc_last_error(ctx); return Buf(); }
     if (scale != 1.0) for (size_t q = 0; q < (size_t)n * G; q++) b->p[q] *= scale;
@@ -475,17 +489,25 @@ static int ebe_common(MakeDensity* self, smc_ctx* ctx, ParameterReader* paraRdr,
   const double ff = self->params.finalfactor;
   batch = std::max(1, std::min(batch, smc_max_batch(ctx)));               // the getters address one device batch
   auto ck = [&](int rc) { if (rc != SMC_OK && err.empty()) err = smc_last_error(ctx); return rc != SMC_OK; };
+  std::vector<double> last_part, last_nu[2]; bool have_last = false;      // the event wounded.data / nucl1.data / nucl2.data end up holding
+  const bool timing = std::getenv("SMC_TIMING") != nullptr;
+  double t_run = 0, t_fetch = 0, t_lists = 0; auto now = [] { return std::chrono::steady_clock::now(); };
+  auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
   for (int done = 0; done < count; done += batch) {
     const int n = std::min(batch, count - done);
+    const auto t0 = now();
     if (smc_run_events(ctx, first + done, n, flags, out_all.data()) != SMC_OK) { err = smc_last_error(ctx); return 1; }
+    const auto t1 = now(); t_run += secs(t0, t1);
     Buf b_rho, b_rb, b_ta, b_tb, b_sum, b_sa, b_sb;
     if ((use_sd || use_ed) && !(b_rho = fetch_all(n, SMC_GRID_RHO, ff))) return 1;
     if (o_rb && !(b_rb = fetch_all(n, SMC_GRID_RHO_BINARY, 1.0))) return 1;
     if (o_ta || o_rhob) {
       if (!(b_ta = fetch_all(n, SMC_GRID_TA1, 1.0)) || !(b_tb = fetch_all(n, SMC_GRID_TA2, 1.0))) return 1;
-      if (o_rhob) { b_sum = std::make_shared<PinBuf>((size_t)n * G); if (!b_sum->p) { err = "smc_pinned_alloc failed"; return 1; } for (size_t q = 0; q < (size_t)n * G; q++) b_sum->p[q] = b_ta->p[q] + b_tb->p[q]; }
+      if (o_rhob) { b_sum = pin_get((size_t)n * G); if (!b_sum->p) { err = "smc_pinned_alloc failed"; return 1; } for (size_t q = 0; q < (size_t)n * G; q++) b_sum->p[q] = b_ta->p[q] + b_tb->p[q]; }
     }
     if (o_sp && (!(b_sa = fetch_all(n, SMC_GRID_SPEC_A, 1.0)) || !(b_sb = fetch_all(n, SMC_GRID_SPEC_B, 1.0)))) return 1;
+    const auto t2 = now(); t_fetch += secs(t1, t2);
+    std::string app_binary, app_quarks;      // binary.dat / quarks.data grow by one block per event: appended once per batch
     for (int e = 0; e < n; e++) {
       const long event = (long)(first + done + e) + 1;                   // the reference counts events from 1
       const smc_event_out* out = out_all.data() + (size_t)e * ny - e;     // out[e] = slice 0 of event e
@@ -496,22 +518,24 @@ static int ebe_common(MakeDensity* self, smc_ctx* ctx, ParameterReader* paraRdr,
       std::vector<double> part((size_t)std::max(np, 1) * 8), coll((size_t)std::max(nc, 1) * 6);
       if (ck(smc_get_participants(ctx, e, part.data(), &np)) || ck(smc_get_collisions(ctx, e, coll.data(), &nc))) return 1;
       if (jet) {
-        write_file(P("ParticipantTable_event_%ld.dat", event), smc_fmt_participants(part.data(), np), true);
         if (ck(smc_get_spectators(ctx, e, nullptr, &ns))) return 1;
         std::vector<double> spec((size_t)std::max(ns, 1) * 3); if (ck(smc_get_spectators(ctx, e, spec.data(), &ns))) return 1;
-        write_file(P("Spectators_event_%ld.dat", event), smc_fmt_spectators(spec.data(), ns), false);
-        write_file(P("BinaryCollisionTable_event_%ld.dat", event), smc_fmt_xy(coll.data(), nc, 6), true);
-      } else write_file(data_dir + "/binary.dat", smc_fmt_xy(coll.data(), nc, 6), true);
-      // dumpBinaryTable side files (MCnucl.cpp:1193-1209)
-      write_file(data_dir + "/wounded.data", smc_fmt_participants(part.data(), np), false);
+        const std::string f1 = P("ParticipantTable_event_%ld.dat", event), f2 = P("Spectators_event_%ld.dat", event), f3 = P("BinaryCollisionTable_event_%ld.dat", event);
+        pool.submit([=] { write_file(f1, smc_fmt_participants(part.data(), np), true); write_file(f2, smc_fmt_spectators(spec.data(), ns), false);
+                          write_file(f3, smc_fmt_xy(coll.data(), nc, 6), true); });
+      } else app_binary += smc_fmt_xy(coll.data(), nc, 6);
+      // dumpBinaryTable side files (MCnucl.cpp:1193-1209).  wounded.data, nucl1.data and nucl2.data are rewritten by every
+      // event: what remains is the last event's, which is the only one written here
+      last_part.assign(part.begin(), part.begin() + (size_t)np * 8);
       { int nq = 0; if (ck(smc_get_quarks(ctx, e, nullptr, &nq))) return 1;
         std::vector<double> qk((size_t)std::max(nq, 1) * 6); if (ck(smc_get_quarks(ctx, e, qk.data(), &nq))) return 1;
-        write_file(data_dir + "/quarks.data", smc_fmt_quarks(qk.data(), nq), true); }
+        app_quarks += smc_fmt_quarks(qk.data(), nq); }
       for (int s = 0; s < 2; s++) {
         int na = 0; if (ck(smc_get_nucleons(ctx, e, s, nullptr, &na))) return 1;
-        std::vector<double> nu((size_t)std::max(na, 1) * 8); if (ck(smc_get_nucleons(ctx, e, s, nu.data(), &na))) return 1;
-        write_file(data_dir + (s == 0 ? "/nucl1.data" : "/nucl2.data"), smc_fmt_xy(nu.data(), na, 8), false);
+        last_nu[s].resize((size_t)std::max(na, 1) * 8); if (ck(smc_get_nucleons(ctx, e, s, last_nu[s].data(), &na))) return 1;
+        last_nu[s].resize((size_t)na * 8);
       }
+      have_last = true;
       if (jet) for (int f = 0; f < 2; f++) {                              // per-event eccentricity files (:327-345)
         if ((f == 0 && !use_sd) || (f == 1 && !use_ed)) continue;
         char nm[160];
@@ -534,6 +558,15 @@ static int ebe_common(MakeDensity* self, smc_ctx* ctx, ParameterReader* paraRdr,
       if (o_rhob) grid_job(b_sum, b_sum->p + (size_t)e * G, P("rhob_event_%ld", event), npart);
       if (o_sp) { grid_job(b_sa, b_sa->p + (size_t)e * G, P("spectator_density_A_event_%ld", event), npart); grid_job(b_sb, b_sb->p + (size_t)e * G, P("spectator_density_B_event_%ld", event), npart); }
     }
+    if (!app_binary.empty()) write_file(data_dir + "/binary.dat", app_binary, true);
+    if (!app_quarks.empty()) write_file(data_dir + "/quarks.data", app_quarks, true);
+    t_lists += secs(t2, now());
+  }
+  if (timing) std::cerr << "# operation 1/2 main thread: smc_run_events " << t_run << " s, lattices device->host " << t_fetch
+                        << " s, lists + job hand-over (blocks when the writers lag) " << t_lists << " s" << std::endl;
+  if (have_last) {
+    write_file(data_dir + "/wounded.data", smc_fmt_participants(last_part.data(), (int)(last_part.size() / 8)), false);
+    for (int s = 0; s < 2; s++) write_file(data_dir + (s == 0 ? "/nucl1.data" : "/nucl2.data"), smc_fmt_xy(last_nu[s].data(), (int)(last_nu[s].size() / 8), 8), false);
   }
   pool.wait();
   return 0;
