@@ -285,7 +285,8 @@ def main():
     try:      # DRAM bytes per event of each kernel from the committed `ncu --set full` capture of this command
         if kln:
             raise KeyError("the committed capture is of the MC-Glauber workload")
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json")))
+        tp = [os.path.join(ROOT, "profiles", f) for f in ("r02_dram_traffic.json", "r01_dram_traffic.json")]
+        tj = json.load(open([f for f in tp if os.path.exists(f)][0]))
         traffic = tj[dom + "_kernel"]["dram_bytes_per_event"] * a.batch      # per launch (one launch = one batch)
     except Exception:
         pass

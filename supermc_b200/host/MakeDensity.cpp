@@ -154,6 +154,7 @@ MakeDensity::MakeDensity(ParameterReader* p, int device, smc_shard sh, const std
     const double ptflag = p->getVal("PT_Flag");
     params.pt_order = ptflag < 0 ? ival(p, "PT_order") : 1;
     params.max_batch = (int)p->getVal("gpu_batch", 0);
+    params.ncoll_cap = (int)p->getVal("ncoll_cap", 0);                  // extension: collision-list capacity per event (0: min(A*B, 6144))
     binRapidity = ival(p, "ny");
     rapMin = -p->getVal("ymax"); rapMax = -rapMin;                       // MakeDensity.cpp:54-58
     params.ny = binRapidity; params.ymax = p->getVal("ymax");
