@@ -43,6 +43,24 @@ WORKLOAD_KLN = dict(WORKLOAD, which_mc_model=1, sub_model=7, cc_fluctuation_mode
 WORKLOAD_KLN_NAME = "MC-KLN Pb+Pb 2.76 TeV min-bias eccentricity scan (operation 9), 261x261 grid, orders 1-9, 211x211 dN/dy table built on the device"
 
 
+# the other scan configurations of BASELINE.json / SURVEY.md 8(d) input 5 (parity-test cases; `--workload <name>` prints a full
+# line for each, reference binary beside it): overrides of WORKLOAD and of REF_ARGS
+def _ref_args(**kv):
+    out = [x for x in REF_ARGS if x.split("=")[0] not in kv]
+    return out + ["%s=%s" % (k, v) for k, v in kv.items()]
+OTHER_WORKLOADS = {
+    "ppb": ("MC-Glauber p+Pb 5.02 TeV min-bias eccentricity scan (operation 9), 261x261 grid, orders 1-9",
+            dict(aproj=1, atarg=208, ecm=5020.0), _ref_args(Aproj=1, Atarg=208, ecm=5020)),
+    "auau": ("MC-Glauber Au+Au 200 GeV min-bias eccentricity scan (operation 9), 261x261 grid, orders 1-9",
+             dict(aproj=197, atarg=197, ecm=200.0, alpha=0.14, cc_fluctuation_gamma_theta=0.61),
+             _ref_args(Aproj=197, Atarg=197, ecm=200, alpha=0.14, cc_fluctuation_Gamma_theta=0.61)),
+    "sqrt": ("Pb+Pb 2.76 TeV sqrt(TA TB) scaling (which_mc_model=7) eccentricity scan (operation 9), 261x261 grid, orders 1-9",
+             dict(which_mc_model=7), _ref_args(which_mc_model=7)),
+    "nbd": ("MC-Glauber Pb+Pb 2.76 TeV with NBD multiplicity fluctuations (cc_fluctuation_model=1, k=0.75), eccentricity scan (operation 9), 261x261 grid",
+            dict(cc_fluctuation_model=1, cc_fluctuation_k=0.75), _ref_args(cc_fluctuation_model=1, cc_fluctuation_k=0.75)),
+}
+
+
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
@@ -89,17 +107,17 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def algorithmic_flops(ev, width, dx, kln=False):
+def algorithmic_flops(ev, width, dx, kln=False, A=208, B=208):
     """F_dep = 2[Np n4^2 (rho_WN) + Nc n5^2 (rho_BC)] (operation 9 with MC-Glauber needs no
     TA1/TA2, so that term is not claimed), F_mom = 200 per non-zero cell.  MC-KLN: F_dep = 2 Np n5^2 (TA1 + TA2,
     participants only -- quirk Q6); the 6-point table lookup (~30 FLOP per cell) is counted with the moments."""
     import numpy as np
     n5, n4 = 2 * 5 * width / dx, 8 * width / dx
     npart = (ev["npart1"] + ev["npart2"]).astype(np.float64); nc = ev["ncoll"].astype(np.float64)
-    f_dep = 2.0 * (npart * n5 * n5) if kln else 2.0 * (npart * n4 * n4 + nc * n5 * n5)
+    f_dep = 2.0 * (npart * n5 * n5) if kln is True else 2.0 * (npart * n4 * n4) if kln == "sqrt" else 2.0 * (npart * n4 * n4 + nc * n5 * n5)
     f_mom = 200.0 * ev["nonzero_cells"].astype(np.float64)
-    # collisions 6AB FLOP per try, hard-core scan 3A^2 per nucleus per try (A = B = 208)
-    f_smp = ev["tries"].astype(np.float64) * (6.0 * 208 * 208 + 2 * 3.0 * 208 * 208)
+    # collisions 6AB FLOP per try, hard-core scan 3A^2 per nucleus per try
+    f_smp = ev["tries"].astype(np.float64) * (6.0 * A * B + 3.0 * A * A + 3.0 * B * B)
     return float(f_dep.sum()), float(f_mom.sum()), float(f_smp.sum())
 
 
@@ -119,7 +137,7 @@ def ref_paths():
     return exe, run
 
 
-def run_reference_once(nproc, nev_each, seed0):
+def run_reference_once(nproc, nev_each, seed0, args=None):
     """`nproc` concurrent copies of the reference binary (its own 8-process mode,
     CollectDataAccordingToSettings.py:110-115), separate working directories; returns wall seconds."""
     exe, run = ref_paths()
@@ -131,7 +149,7 @@ def run_reference_once(nproc, nev_each, seed0):
             os.symlink(os.path.join(run, f), os.path.join(d, f))
         dirs.append(d)
     t0 = time.perf_counter()
-    procs = [subprocess.Popen([exe] + REF_ARGS + ["nev=%d" % nev_each, "randomSeed=%d" % (seed0 + i)], cwd=d,
+    procs = [subprocess.Popen([exe] + (args or REF_ARGS) + ["nev=%d" % nev_each, "randomSeed=%d" % (seed0 + i)], cwd=d,
                               stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for i, d in enumerate(dirs)]
     for p in procs:
         p.wait()
@@ -147,14 +165,14 @@ def run_reference_once(nproc, nev_each, seed0):
     return dt, n_ok
 
 
-def cpu_baseline(cores, nev_each):
+def cpu_baseline(cores, nev_each, args=None):
     """bounded sample of the same workload on the host cores; start-up (EOS + QuarkPos load) subtracted
     with a 1-event run as BASELINE.md section 3 prescribes."""
     exe, _ = ref_paths()
     if not os.path.exists(exe):
         return None
-    t1, _ = run_reference_once(cores, 1, 77)
-    t, n = run_reference_once(cores, nev_each, 177)
+    t1, _ = run_reference_once(cores, 1, 77, args)
+    t, n = run_reference_once(cores, nev_each, 177, args)
     loop = max(t - t1, 1e-3) if n > cores else t
     return dict(value=(n - cores) / loop if n > cores else n / t, unit="events/s", cores=cores, kind="reference",
                 sample="%d concurrent process(es) x %d accepted events of the bench workload (sd+ed as in BASELINE.md), "
@@ -173,7 +191,7 @@ def main():
     ap.add_argument("--batch", type=int, default=2048, help="events resident per launch wave")
     ap.add_argument("--cpu-sample-events", type=int, default=150)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="glauber", choices=["glauber", "kln", "ebe", "scan-exe", "avg"],
+    ap.add_argument("--workload", default="glauber", choices=["glauber", "kln", "ebe", "scan-exe", "avg"] + sorted(OTHER_WORKLOADS),
                     help="glauber = BASELINE.json configs[1] (the headline line); kln = the same scan with the MC-KLN density; "
                          "ebe = BASELINE.json configs[0] through the drop-in executable, text output included; "
                          "scan-exe = configs[1] through the drop-in executable (superMC_b200.e operation=9, tables written); "
@@ -215,6 +233,10 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     kln = a.workload == "kln"
     wl, wl_name = (WORKLOAD_KLN, WORKLOAD_KLN_NAME) if kln else (WORKLOAD, WORKLOAD_NAME)
+    ref_args = None
+    if a.workload in OTHER_WORKLOADS:
+        wl_name, over, ref_args = OTHER_WORKLOADS[a.workload]
+        wl = dict(WORKLOAD, **over)
     ctx = smc.Context(smc.capi.default_params(max_batch=a.batch, randomseed=20261017, **wl), device=local)
     table_s = None
     if kln:      # one-off start-up (MCnucl::makeTable, 12.5 min on one reference core), outside the timed region
@@ -250,7 +272,7 @@ def main():
     barrier()
     wall = time.perf_counter() - t0
     for cols in kept:
-        fd, fm, fs = algorithmic_flops(cols, ctx.k.width, WORKLOAD["dx"], kln); f_dep += fd; f_mom += fm; f_smp += fs
+        fd, fm, fs = algorithmic_flops(cols, ctx.k.width, WORKLOAD["dx"], True if kln else ("sqrt" if wl["which_mc_model"] == 7 else False), wl["aproj"], wl["atarg"]); f_dep += fd; f_mom += fm; f_smp += fs
     launches = ctx.launches - l0
     ck = clocks.stop()
     # per-kernel durations: the same steps once more with CUDA events around every launch; this pass runs the
@@ -321,8 +343,8 @@ def main():
             # be sampled within the bench budget: the per-event loop is timed with the oracle port on the same table
             cb = port_baseline(min(a.cpu_sample_events, 60), kln_table=kln_table, kln_dt=ctx.k.kln_dt)
         else:
-            cb = cpu_baseline(1, a.cpu_sample_events)
-            if cb is None:
+            cb = cpu_baseline(1, a.cpu_sample_events, ref_args)
+            if cb is None and ref_args is None:
                 # the unmodified reference binary is not on this box: time the oracle port instead
                 cb = port_baseline(a.cpu_sample_events)
         line["cpu_baseline"] = cb

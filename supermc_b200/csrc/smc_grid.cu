@@ -133,7 +133,7 @@ struct KindList { int n; int kind[8]; };
 #endif
 #define DEP_XP 4
 #ifndef DEP_YP
-#define DEP_YP 16
+#define DEP_YP 64      // columns of yg one build item covers (16 / 32 / 64 / 128 measured: 745 / 748 / 756 / 704 k events/s with DEP_XG 16 / 16 / 16 / 32)
 #endif
 #ifndef DEP_MINCTA
 #define DEP_MINCTA 3
@@ -145,7 +145,10 @@ struct KindList { int n; int kind[8]; };
 #ifndef SMC_DEP_PERSIST_DEFAULT
 #define SMC_DEP_PERSIST_DEFAULT 1     // 1: persistent CTAs over bbox_kernel's tile list; k > 1: k x as many CTAs as fit
 #endif
-#define DEP_NXG (DEP_BAND / 16)
+#ifndef DEP_XG
+#define DEP_XG 16       // rows of xg one build item covers (one exp pair + a DEP_XG-step recurrence)
+#endif
+#define DEP_NXG (DEP_BAND / DEP_XG)
 #define DEP_NXI (DEP_BAND / DEP_XP)
 #define DEP_NYI (DEP_COLS / DEP_YP)
 
@@ -338,12 +341,12 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_MINCTA) deposit_kernel(DevCfg
   auto build_item = [&](int chunk, int id) {
     DepTab& T = tab[chunk & 1];
     const int nch = min(DEP_CH, nact - chunk * DEP_CH);
-    if (id < DEP_CH * DEP_NXG) {                                            // ---- rows: xg, 16 rows per item ----
+    if (id < DEP_CH * DEP_NXG) {                                            // ---- rows: xg, DEP_XG rows per item ----
       const int t = id % DEP_CH, part = id / DEP_CH;
       if (t >= nch) return;
       const SrcRec s = srcs[(chunk & 1) * DEP_CH + t];
-      const int rb = part * 16, i0 = r0 + rb;
-      const int ka = max(s.iL - i0, 0), kb = min(s.iR - i0, 16);
+      const int rb = part * DEP_XG, i0 = r0 + rb;
+      const int ka = max(s.iL - i0, 0), kb = min(s.iR - i0, DEP_XG);
       if (ka >= kb) return;
       double g = s.W, q = 1.0, rec = 1.0;
       if (s.flat != 1) {

@@ -53,28 +53,25 @@ inline double sigma_gg_newton(double siginNN, double width) {
   return sg;
 }
 
-// E1-type integral of exp(-t)/t over [a, b] by the reference's own doubling Simpson rule (src/arsenal.cpp:531-571,
-// called with epsilon 1e-10 and the default depth 50): the width of shape 3 inherits its rounding
-inline double simpson_exp_over_t(double a, double b, double epsilon) {
-  auto f = [](double t) { return 1. / t * std::exp(-t); };
-  double f_1 = f(a) + f(b), f_2 = 0., f_4 = 0.;
-  double sum_previous = 0., sum_current = 0.;
-  long count = 1;
-  const double length = (b - a);
-  double step = length / count;
-  int depth = 1;
-  f_4 = f(a + 0.5 * step);
-  sum_current = (length / 6) * (f_1 + f_2 * 2. + f_4 * 4.);
-  do {
-    sum_previous = sum_current;
-    f_2 += f_4;
-    count *= 2; step /= 2.0; f_4 = 0.;
-    for (long i = 0; i < count; i++) f_4 += f(a + step * (i + 0.5));
-    sum_current = (length / 6 / count) * (f_1 + f_2 * 2. + f_4 * 4.);
-    if (depth > 50) break;
-    depth++;
-  } while (std::fabs(sum_current - sum_previous) > epsilon);
-  return sum_current;
+// Integral of exp(-t)/t over [lo, hi] by nested Simpson refinement: level L uses 2^L panels whose midpoints are the only new
+// nodes, so every integrand value is computed once.  The width of shape_of_nucleons 3 inherits the rounding of the
+// reference's integrator (src/arsenal.cpp:531-571, called with tolerance 1e-10): the node formula lo + h (k + 1/2), the order
+// of the three partial sums and the stopping rule (refined - previous <= tol, at most 51 refinements) are the same, which is
+// what makes the constants bit-equal (tests/test_oracle_golden.py, pbpb5020_lambda_width).
+inline double simpson_exp_over_t(double lo, double hi, double tol) {
+  const auto integrand = [](double t) { return 1. / t * std::exp(-t); };
+  const double span = hi - lo, ends = integrand(lo) + integrand(hi);
+  double interior = 0.0;      // integrand summed over the interior panel boundaries of the current level
+  double h = span;            // panel width of the current level
+  double estimate = 0.0;
+  for (int level = 0;; level++) {
+    const long panels = 1L << level;
+    double mid = 0.0;
+    for (long k = 0; k < panels; k++) mid += integrand(lo + h * (k + 0.5));
+    const double refined = (span / 6 / panels) * (ends + interior * 2. + mid * 4.);
+    if (level > 0 && (!(std::fabs(refined - estimate) > tol) || level > 50)) return refined;
+    estimate = refined; interior += mid; h /= 2.0;
+  }
 }
 
 // GaussianNucleonsCal constructor (src/GaussianNucleonsCal.cpp:24-55); false for an unknown shape
