@@ -508,46 +508,68 @@ static int ebe_common(MakeDensity* self, smc_ctx* ctx, ParameterReader* paraRdr,
     }
     if (o_sp && (!(b_sa = fetch_all(n, SMC_GRID_SPEC_A, 1.0)) || !(b_sb = fetch_all(n, SMC_GRID_SPEC_B, 1.0)))) return 1;
     const auto t2 = now(); t_fetch += secs(t1, t2);
-    std::string app_binary, app_quarks;      // binary.dat / quarks.data grow by one block per event: appended once per batch
+    // The per-event lists (participants, collisions, quarks, nucleons -> text) are independent of each other: a few threads
+    // walk the batch (the getters only read the host mirror of the batch's records), the main thread then appends the
+    // blocks of binary.dat / quarks.data in event order, once per batch.
+    std::vector<std::string> bin_s(n), quark_s(n);
+    int e_last = -1; for (int e = 0; e < n; e++) if (out_all[(size_t)e * ny].status == SMC_OK) e_last = e;
+    { int np0 = 0; if (n > 0 && e_last >= 0 && ck(smc_get_participants(ctx, e_last, nullptr, &np0))) return 1; }      // fills the mirror before the threads start
+    const unsigned nlt = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    std::vector<int> lerr(nlt, 0);
+    std::vector<std::thread> lth;
+    for (unsigned q = 0; q < nlt; q++) lth.emplace_back([&, q] {
+      auto bad = [&](int rc) { if (rc != SMC_OK) lerr[q] = 1; return rc != SMC_OK; };
+      for (int e = (int)q; e < n; e += (int)nlt) {
+        const long event = (long)(first + done + e) + 1;                   // the reference counts events from 1
+        const smc_event_out* out = out_all.data() + (size_t)e * ny - e;     // out[e] = slice 0 of event e
+        if (out[e].status != SMC_OK) continue;
+        int np = 0, nc = 0, ns = 0;
+        if (bad(smc_get_participants(ctx, e, nullptr, &np)) || bad(smc_get_collisions(ctx, e, nullptr, &nc))) return;
+        std::vector<double> part((size_t)std::max(np, 1) * 8), coll((size_t)std::max(nc, 1) * 6);
+        if (bad(smc_get_participants(ctx, e, part.data(), &np)) || bad(smc_get_collisions(ctx, e, coll.data(), &nc))) return;
+        if (jet) {
+          if (bad(smc_get_spectators(ctx, e, nullptr, &ns))) return;
+          std::vector<double> spec((size_t)std::max(ns, 1) * 3); if (bad(smc_get_spectators(ctx, e, spec.data(), &ns))) return;
+          write_file(P("ParticipantTable_event_%ld.dat", event), smc_fmt_participants(part.data(), np), true);
+          write_file(P("Spectators_event_%ld.dat", event), smc_fmt_spectators(spec.data(), ns), false);
+          write_file(P("BinaryCollisionTable_event_%ld.dat", event), smc_fmt_xy(coll.data(), nc, 6), true);
+        } else bin_s[e] = smc_fmt_xy(coll.data(), nc, 6);
+        { int nq = 0; if (bad(smc_get_quarks(ctx, e, nullptr, &nq))) return;
+          std::vector<double> qk((size_t)std::max(nq, 1) * 6); if (bad(smc_get_quarks(ctx, e, qk.data(), &nq))) return;
+          quark_s[e] = smc_fmt_quarks(qk.data(), nq); }
+        // dumpBinaryTable side files (MCnucl.cpp:1193-1209).  wounded.data, nucl1.data and nucl2.data are rewritten by every
+        // event: what remains is the last event's, the only one kept here (written after the loop)
+        if (e == e_last) {
+          last_part.assign(part.begin(), part.begin() + (size_t)np * 8);
+          for (int sd = 0; sd < 2; sd++) {
+            int na = 0; if (bad(smc_get_nucleons(ctx, e, sd, nullptr, &na))) return;
+            last_nu[sd].resize((size_t)std::max(na, 1) * 8); if (bad(smc_get_nucleons(ctx, e, sd, last_nu[sd].data(), &na))) return;
+            last_nu[sd].resize((size_t)na * 8);
+          }
+          have_last = true;
+        }
+        if (jet) for (int f = 0; f < 2; f++) {                              // per-event eccentricity files (:327-345)
+          if ((f == 0 && !use_sd) || (f == 1 && !use_ed)) continue;
+          char nm[160];
+          for (int o = std::max(from_order, 1); o <= std::min(to_order, 9); o++) {
+            std::snprintf(nm, sizeof nm, "%s_ecc_eccp_%d_event_%ld.dat", f == 0 ? "sn" : "en", o, event);
+            std::string rows; for (int iy = 0; iy < ny; iy++) rows += MakeDensity::formatEccRow(out[e + iy], o, deformed);
+            write_file(data_dir + "/" + nm, rows, true);
+          }
+          std::snprintf(nm, sizeof nm, "%s_ecc_eccp_%d_event_%ld.dat", f == 0 ? "sn" : "en", 10, event);
+          { std::string rows; for (int iy = 0; iy < ny; iy++) rows += MakeDensity::formatEccRowAll(out[e + iy], deformed); write_file(data_dir + "/" + nm, rows, true); }
+        }
+      }
+    });
+    for (auto& t : lth) t.join();
+    for (int v : lerr) if (v) { if (err.empty()) err = smc_last_error(ctx); return 1; }
+    std::string app_binary, app_quarks;
+    for (int e = 0; e < n; e++) { app_binary += bin_s[e]; app_quarks += quark_s[e]; }
     for (int e = 0; e < n; e++) {
-      const long event = (long)(first + done + e) + 1;                   // the reference counts events from 1
-      const smc_event_out* out = out_all.data() + (size_t)e * ny - e;     // out[e] = slice 0 of event e
+      const long event = (long)(first + done + e) + 1;
+      const smc_event_out* out = out_all.data() + (size_t)e * ny - e;
       if (out[e].status != SMC_OK) { std::cerr << "event " << event << ": status " << out[e].status << std::endl; continue; }
       const double npart = out[e].npart1 + out[e].npart2;
-      int np = 0, nc = 0, ns = 0;
-      if (ck(smc_get_participants(ctx, e, nullptr, &np)) || ck(smc_get_collisions(ctx, e, nullptr, &nc))) return 1;
-      std::vector<double> part((size_t)std::max(np, 1) * 8), coll((size_t)std::max(nc, 1) * 6);
-      if (ck(smc_get_participants(ctx, e, part.data(), &np)) || ck(smc_get_collisions(ctx, e, coll.data(), &nc))) return 1;
-      if (jet) {
-        if (ck(smc_get_spectators(ctx, e, nullptr, &ns))) return 1;
-        std::vector<double> spec((size_t)std::max(ns, 1) * 3); if (ck(smc_get_spectators(ctx, e, spec.data(), &ns))) return 1;
-        const std::string f1 = P("ParticipantTable_event_%ld.dat", event), f2 = P("Spectators_event_%ld.dat", event), f3 = P("BinaryCollisionTable_event_%ld.dat", event);
-        pool.submit([=] { write_file(f1, smc_fmt_participants(part.data(), np), true); write_file(f2, smc_fmt_spectators(spec.data(), ns), false);
-                          write_file(f3, smc_fmt_xy(coll.data(), nc, 6), true); });
-      } else app_binary += smc_fmt_xy(coll.data(), nc, 6);
-      // dumpBinaryTable side files (MCnucl.cpp:1193-1209).  wounded.data, nucl1.data and nucl2.data are rewritten by every
-      // event: what remains is the last event's, which is the only one written here
-      last_part.assign(part.begin(), part.begin() + (size_t)np * 8);
-      { int nq = 0; if (ck(smc_get_quarks(ctx, e, nullptr, &nq))) return 1;
-        std::vector<double> qk((size_t)std::max(nq, 1) * 6); if (ck(smc_get_quarks(ctx, e, qk.data(), &nq))) return 1;
-        app_quarks += smc_fmt_quarks(qk.data(), nq); }
-      for (int s = 0; s < 2; s++) {
-        int na = 0; if (ck(smc_get_nucleons(ctx, e, s, nullptr, &na))) return 1;
-        last_nu[s].resize((size_t)std::max(na, 1) * 8); if (ck(smc_get_nucleons(ctx, e, s, last_nu[s].data(), &na))) return 1;
-        last_nu[s].resize((size_t)na * 8);
-      }
-      have_last = true;
-      if (jet) for (int f = 0; f < 2; f++) {                              // per-event eccentricity files (:327-345)
-        if ((f == 0 && !use_sd) || (f == 1 && !use_ed)) continue;
-        char nm[160];
-        for (int o = std::max(from_order, 1); o <= std::min(to_order, 9); o++) {
-          std::snprintf(nm, sizeof nm, "%s_ecc_eccp_%d_event_%ld.dat", f == 0 ? "sn" : "en", o, event);
-          std::string rows; for (int iy = 0; iy < ny; iy++) rows += MakeDensity::formatEccRow(out[e + iy], o, deformed);
-          write_file(data_dir + "/" + nm, rows, true);
-        }
-        std::snprintf(nm, sizeof nm, "%s_ecc_eccp_%d_event_%ld.dat", f == 0 ? "sn" : "en", 10, event);
-        { std::string rows; for (int iy = 0; iy < ny; iy++) rows += MakeDensity::formatEccRowAll(out[e + iy], deformed); write_file(data_dir + "/" + nm, rows, true); }
-      }
       if (use_sd || use_ed) {
         const double* g = b_rho->p + (size_t)e * G;
         if (use_sd && use_ed) grid_job(b_rho, g, P("sd_event_%ld", event), npart, P("ed_event_%ld", event));   // identical numbers (quirk Q2)
