@@ -892,15 +892,19 @@ __global__ void __launch_bounds__(MOM_THREADS, MOM_MINCTA) moments_kernel(DevCfg
       const double d2 = d * r2, d2m = d2 * w;
       rn[0] += d;
       nrm += d2m;
-      double an = 1.0, bn = 0.0, p = d, q = d * w;
+      // A_n + i B_n = rho w e^{i n phi} by the three-term recurrence c_n = 2 cos(phi) c_(n-1) - c_(n-2) (linear, so the cell's
+      // masked density rides along): nine FP64 operations per order -- 2 recurrence, r^n, <r^n>, 2 for eps_n, 3 for eps'_n
+      const double dw = d * w, tux = 2.0 * ux;
+      double An = dw, Bn = 0.0, Ap = dw * ux, Bp = -dw * uy, rpow = 1.0;      // (Ap, Bp): order n - 2; n = 1 starts from -phi
 #pragma unroll
       for (int n = 1; n < 10; n++) {
-        const double a2 = an * ux - bn * uy; bn = an * uy + bn * ux; an = a2;
-        p *= r; q *= r;
-        rn[n] += p;
-        mr[n] += d2m * an; mi[n] += d2m * bn;
-        const double pm = (n == 1) ? d2m * r : q;
-        pr[n] += pm * an; pi[n] += pm * bn; npw[n] += pm;
+        const double A2 = fma(tux, An, -Ap), B2 = fma(tux, Bn, -Bp);
+        Ap = An; Bp = Bn; An = A2; Bn = B2;
+        rpow *= r;
+        rn[n] = fma(d, rpow, rn[n]);
+        mr[n] = fma(r2, An, mr[n]); mi[n] = fma(r2, Bn, mi[n]);
+        const double wt = (n == 1) ? r2 * rpow : rpow;                        // eps'_1 is weighted with r^3
+        pr[n] = fma(wt, An, pr[n]); pi[n] = fma(wt, Bn, pi[n]); npw[n] = fma(dw, wt, npw[n]);
       }
       }
     }
