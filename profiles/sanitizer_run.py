@@ -28,7 +28,7 @@ elif which == "pos":          # the from-positions entry (golden positions and w
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
     from helpers import Golden, event_in_from
     g = Golden("pbpb2760_glb")
-    ctx = smc.Context(g.smc_params(smc.capi, max_batch=16))
+    ctx = smc.Context(g.smc_params(smc.capi, max_batch=64))
     evs = [event_in_from(t) for t in g.tries()]          # golden positions and weights; the pair uniforms come from Philox
     out = ctx.run_from_positions(evs, smc.RUN_MOMENTS | smc.RUN_THICKNESS | smc.RUN_RHO_BINARY | smc.RUN_SPECTATORS)
     print("pos", out["ncoll"][:6], ctx.collisions(3).shape, ctx.participants(3).shape, ctx.spectators(3).shape)
