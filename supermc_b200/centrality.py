@@ -149,6 +149,53 @@ def assignment_args(params):
     return ["%s=%s" % (k, ("%.17g" % v) if isinstance(v, float) else v) for k, v in params.items()]
 
 
+def minbias_rows(ev):
+    """smc_event_out rows -> the (nev, 5) array of collision_data: b, Npart, Ncoll, dS/dy, dE/dy (== dS/dy, quirk Q2)"""
+    out = np.zeros((len(ev), 5))
+    out[:, 0] = ev["b"]; out[:, 1] = ev["npart1"] + ev["npart2"]; out[:, 2] = ev["ncoll"]; out[:, 3] = ev["total"]; out[:, 4] = ev["total"]
+    return out
+
+
+def minbias_table(a):
+    """One minimum-bias run of `nev` accepted events, sharded over the ranks of torchrun by global event id (so the event
+    set does not depend on the GPU count), rows gathered on rank 0, sorted by the device radix sort, table written in the
+    format of scripts/centrality_cut_tables/*.dat.  scripts/centrality_cut_h5.py + collect_into_hdf5.py without the files."""
+    import supermc_b200 as smc
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    p = {k.lower(): v for k, v in model_parameters(a.model, a.ecm, a.collsys).items()}
+    p.update(finalfactor=1.0, randomseed=a.seed, maxx=13.0, maxy=13.0)
+    for kv in a.extra:
+        k, v = kv.split("=", 1); k = k.lower()
+        p[k] = float(v) if ("." in v or "e" in v.lower()) else int(v)
+    if p.get("which_mc_model") == 5:
+        p.setdefault("cc_fluctuation_gamma_theta", 0.75 if a.ecm > 1000 else 0.61)
+    ctx = smc.Context(smc.capi.default_params(**p), device=local)
+    if p["which_mc_model"] == 1:
+        ctx.build_kln_table()
+    if world > 1:
+        ctx.comm_init(rank, world, os.environ.get("MASTER_ADDR", "127.0.0.1"), int(os.environ.get("SMC_COMM_PORT", int(os.environ.get("MASTER_PORT", "29500")) + 1)))
+    lo, hi = a.nev * rank // world, a.nev * (rank + 1) // world
+    ev = ctx.run_events(lo, hi - lo)
+    ev = ev[ev["status"] == 0]
+    rows = minbias_rows(ev)
+    if world > 1:
+        flat, _ = ctx.comm_gather(rows, world)
+        rows = flat.reshape(-1, 5)
+    rc = 0
+    if rank == 0:
+        coll = rows.astype(np.float32)           # collect_into_hdf5.py stores float32; the shipped tables inherit that rounding
+        alpha = float(p.get("alpha", 0.118))
+        text = centrality_table_text(coll, device_order(ctx, coll, a.cut, alpha), a.cut, alpha)
+        name = table_file_name(a.cut, p["which_mc_model"], p["aproj"], p["atarg"], p["ecm"], p["cc_fluctuation_model"])
+        os.makedirs(a.out, exist_ok=True)
+        open(os.path.join(a.out, name), "w").write(text)
+        print(os.path.join(a.out, name), "%d events" % len(coll))
+    if world > 1:
+        ctx.comm_barrier()
+    ctx.close()
+    return rc
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser(prog="python -m supermc_b200.centrality")
     sub = ap.add_subparsers(dest="cmd", required=True)
@@ -162,7 +209,16 @@ def main(argv=None):
     r.add_argument("--operation", type=int, default=3); r.add_argument("--nev", type=int, default=1000)
     r.add_argument("--gpus", type=int, default=1); r.add_argument("--dry-run", action="store_true")
     r.add_argument("extra", nargs="*", help="further name=value parameters")
+    m = sub.add_parser("minbias", help="minimum-bias scan in memory -> centrality cut table (no text tables in between).  Under torchrun "
+                                       "every rank takes its range of global event ids, rank 0 gathers the per-event rows "
+                                       "(smc_comm_gather_doubles) and sorts them on its GPU")
+    m.add_argument("--model", default="MCGlb", choices=["MCGlb", "MCKLN", "Trento"]); m.add_argument("--ecm", type=float, default=2760)
+    m.add_argument("--collsys", nargs=2, default=["Pb", "Pb"]); m.add_argument("--nev", type=int, default=100000)
+    m.add_argument("--cut", default="total_entropy"); m.add_argument("--seed", type=int, default=1); m.add_argument("--out", default=".")
+    m.add_argument("extra", nargs="*", help="further name=value parameters (names of smc_params, e.g. maxx=13)")
     a = ap.parse_args(argv)
+    if a.cmd == "minbias":
+        return minbias_table(a)
     if a.cmd == "table":
         import supermc_b200 as smc
         rows = np.loadtxt(os.path.join(a.data_dir, "sn_ecc_eccp_10.dat"))

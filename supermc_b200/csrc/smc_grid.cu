@@ -735,6 +735,11 @@ cudaError_t launch_fluctuate(const DevCfg& c, const Store& st, int nev, cudaStre
 #ifndef MOM_MINCTA
 #define MOM_MINCTA 3
 #endif
+#ifndef MOM_UNROLL
+#define MOM_UNROLL 1    // cells of a lane's column step in flight at once
+#endif
+#define SMC_PRAGMA_(x) _Pragma(#x)
+#define SMC_UNROLL(n) SMC_PRAGMA_(unroll n)
 __device__ __forceinline__ double block_sum(double v, double* red, int tid) {
   v = warp_sum(v);
   __syncthreads();
@@ -877,7 +882,7 @@ __global__ void __launch_bounds__(MOM_THREADS, MOM_MINCTA) moments_kernel(DevCfg
     const uint32_t* mrow = mask + i * MW;
     const double* src = stage + (size_t)(t & 1) * MOM_LD * MOM_THREADS + tid;
     {
-#pragma unroll 1
+      SMC_UNROLL(MOM_UNROLL)
       for (int u = 0; u < MOM_LD; u++) {
       const int j = jb + 32 * u;
       const double d = src[u * MOM_THREADS] * c.finalFactor;

@@ -79,3 +79,31 @@ def test_two_ranks_on_one_gpu(tmp_path):
     for f in files:
         x, y = np.loadtxt(a / f), np.loadtxt(b / f)
         assert np.allclose(x, y, rtol=1e-10, atol=1e-14), f
+
+
+def _minbias(tmp, world, port, nev=3000):
+    d = tmp / ("m%d" % world); os.makedirs(d)
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK="0", MASTER_ADDR="127.0.0.1", SMC_COMM_PORT=str(port), PYTHONPATH=ROOT)
+        procs.append(subprocess.Popen([sys.executable, "-m", "supermc_b200.centrality", "minbias", "--nev", str(nev), "--seed", "5", "--out", str(d)],
+                                      cwd=d, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    f = [x for x in os.listdir(d) if x.startswith("iebe_centralityCut_")]
+    assert len(f) == 1
+    return d / f[0]
+
+
+def test_minbias_centrality_table_in_memory(tmp_path):
+    """python -m supermc_b200.centrality minbias: per-event rows gathered on rank 0 (smc_comm_gather_doubles) and sorted on
+    its GPU.  Two ranks give the one-rank table byte for byte; the table agrees with the one built from the executable's
+    text tables of the same run (those pass through 8 printed digits)."""
+    one = _minbias(tmp_path, 1, 29731); two = _minbias(tmp_path, 2, 29732)
+    assert one.read_bytes() == two.read_bytes()
+    t = np.loadtxt(one)
+    assert t.shape == (110, 6) and np.all(np.diff(t[1:, 1]) <= 0) and t[-1, 0] == 100.0
+    d, _ = _exe_run(tmp_path / "txt", 1, ["operation=9", "nev=3000", "use_ed=1"], 29733)
+    subprocess.check_call([sys.executable, "-m", "supermc_b200.centrality", "table", str(d)], env=dict(os.environ, PYTHONPATH=ROOT), stdout=subprocess.DEVNULL)
+    ref = np.loadtxt(d / "iebe_centralityCut_total_entropy_data.dat")
+    assert np.allclose(t, ref, rtol=2e-6, atol=1e-6)
