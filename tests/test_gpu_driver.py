@@ -149,3 +149,21 @@ def test_centrality_tools_end_to_end(tmp_path):
                           cwd=d, env=env, stdout=subprocess.DEVNULL)
     g = np.loadtxt(d / "data" / "sdAvg_order_2_block.dat")
     assert g.shape == (261, 261) and g.sum() * 0.01 > tab[19, 1] * 0.9          # every averaged event passed the 0-10 % dS/dy cut
+
+
+def test_mcnucl_adapter_drives_a_reference_style_loop(tmp_path):
+    """host/MCnuclB200.h (the binding INTEGRATION.md describes) under a MakeDensity-style loop: the reference's own grid loops
+    over getRho reproduce the columns the engine computed on the device, and the events are those of the C ABI"""
+    import supermc_b200 as smc
+    d = _rundir(tmp_path)
+    out = subprocess.run([os.path.join(ROOT, "supermc_b200", "adapter_demo.e"), "100"] + ARGS, cwd=d, stdout=subprocess.PIPE, check=True, text=True).stdout
+    t = np.array([[float(x) for x in ln.split()] for ln in out.splitlines() if ln and ln[0].isdigit()])
+    assert t.shape == (100, 10)
+    ctx = smc.Context(smc.capi.default_params(which_mc_model=5, sub_model=1, ecm=2760.0, alpha=0.118, maxx=13.0, maxy=13.0,
+                                              finalfactor=1.0, randomseed=5, cc_fluctuation_model=6))
+    ev = ctx.run_events(0, 100)
+    assert np.array_equal(t[:, 1], ev["npart1"]) and np.array_equal(t[:, 2], ev["npart2"]) and np.array_equal(t[:, 3], ev["ncoll"])
+    assert np.allclose(t[:, 9], ev["b"], rtol=1e-14)
+    assert np.allclose(t[:, 4], t[:, 5], rtol=1e-12) and np.allclose(t[:, 5], ev["total"], rtol=1e-12)      # host loop over getRho == device sum
+    assert np.allclose(t[:, 6], t[:, 7], rtol=1e-10)                                                         # <r^2> about the centre of mass
+    assert (t[:, 8] > 0).all()                                                                               # TA1 lattice present
