@@ -955,7 +955,8 @@ __global__ void __launch_bounds__(MOM_THREADS, MOM_MINCTA) moments_kernel(DevCfg
 }
 
 cudaError_t launch_moments(const DevCfg& c, const Store& st, int nev, cudaStream_t s) {
-  const size_t smem = ((MOM_THREADS / 32 + 1) * 64 + 2 * MOM_LD * MOM_THREADS) * sizeof(double) + (size_t)c.Maxx * ((c.Maxy + 31) / 32) * sizeof(uint32_t);
+  static const size_t pad = getenv("SMC_MOM_PAD") ? (size_t)atoi(getenv("SMC_MOM_PAD")) : 0;      // tuning aid: caps the CTAs per SM so that other kernels' CTAs co-reside
+  const size_t smem = ((MOM_THREADS / 32 + 1) * 64 + 2 * MOM_LD * MOM_THREADS) * sizeof(double) + (size_t)c.Maxx * ((c.Maxy + 31) / 32) * sizeof(uint32_t) + pad;
   cudaFuncSetAttribute(moments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   moments_kernel<<<nev, MOM_THREADS, smem, s>>>(c, st, nev);
   return cudaGetLastError();
