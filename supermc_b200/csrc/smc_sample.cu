@@ -129,8 +129,47 @@ __device__ __forceinline__ void sort_by_xl(const DevCfg& c, const Store& st, con
   int rk[MK]; double key[MK];
 #pragma unroll
   for (int m = 0; m < MK; m++) { const int k = lane + 32 * m; rk[m] = 0; key[m] = (k < A) ? S_(sm, s, NXL, k) : 0.0; }
-  // rank = #{j : key_j < key_k or (key_j == key_k and j < k)}; for keys of another 32-block the index comparison is
-  // known at compile time, which leaves one compare per pair
+  // rank = #{j : key_j < key_k or (key_j == key_k and j < k)}
+  if (MK > 1 && MK <= 8) {
+    // 32 buckets over [min, max] of the keys (the bucket index is a monotone function of the key): a key's rank is the
+    // number of keys in lower buckets plus its rank among the keys of its own bucket -- about A/32 compares per key
+    // instead of A.  Scratch: this warp's Woods-Saxon queue (idle now): 33 counters + A 16-bit indices.
+    int* cnt = reinterpret_cast<int*>(sm.wsq + (size_t)s * 128);
+    unsigned short* idx = reinterpret_cast<unsigned short*>(cnt + 34);
+    double kmin = 1e300, kmax = -1e300;
+#pragma unroll
+    for (int m = 0; m < MK; m++) if (lane + 32 * m < A) { kmin = fmin(kmin, key[m]); kmax = fmax(kmax, key[m]); }
+    for (int o = 16; o > 0; o >>= 1) { kmin = fmin(kmin, __shfl_xor_sync(0xffffffffu, kmin, o)); kmax = fmax(kmax, __shfl_xor_sync(0xffffffffu, kmax, o)); }
+    const double scale = (kmax > kmin) ? 32.0 / (kmax - kmin) : 0.0;
+    cnt[lane] = 0;
+    __syncwarp();
+    int bk[MK], pos[MK];
+#pragma unroll
+    for (int m = 0; m < MK; m++) {
+      bk[m] = min(31, (int)((key[m] - kmin) * scale)); pos[m] = 0;
+      if (lane + 32 * m < A) pos[m] = atomicAdd(&cnt[bk[m]], 1);
+    }
+    __syncwarp();
+    const int mine = cnt[lane]; int incl = mine;
+    for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += n; }
+    __syncwarp();
+    cnt[lane] = incl - mine; if (lane == 31) cnt[32] = incl;          // exclusive offsets, cnt[32] = A
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < MK; m++) if (lane + 32 * m < A) idx[cnt[bk[m]] + pos[m]] = (unsigned short)(lane + 32 * m);
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < MK; m++) {
+      const int k = lane + 32 * m;
+      if (k < A) {
+        const int t0 = cnt[bk[m]], t1 = cnt[bk[m] + 1];
+        int r = t0;
+        for (int t = t0; t < t1; t++) { const int j = idx[t]; const double o = S_(sm, s, NXL, j); r += (o < key[m]) || (o == key[m] && j < k); }
+        rk[m] = r;
+      }
+    }
+  } else {
+  // all pairs; for keys of another 32-block the index comparison is known at compile time, which leaves one compare per pair
 #pragma unroll
   for (int jb = 0; jb < MK; jb++) {
     const int jend = min(32, A - 32 * jb);
@@ -144,6 +183,7 @@ __device__ __forceinline__ void sort_by_xl(const DevCfg& c, const Store& st, con
         else rk[m] += (o < key[m]) || (o == key[m] && jj < lane);
       }
     }
+  }
   }
   __syncwarp();
 #pragma unroll 1
@@ -242,6 +282,7 @@ __device__ void sample_nucleus(const DevCfg& c, const Store& st, const SampleSme
     const smc_stream s_an = smc_make_stream(c.seed_lo, c.seed_hi, ev, tr, SMC_K_ANGLE, s);
     const double rad = c.rad[s], dr = c.dr[s], rmaxCut = c.rmaxCut[s], rwMax = c.rwMax[s];
     const double rmin = 0.9 * 0.9;
+    const float rmaxCut_f = (float)rmaxCut, rad_f = (float)rad, inv_dr_f = (float)(1.0 / dr);
     // The Woods-Saxon rejection draws form ONE flat stream per nucleus (draw n -> Philox (WS, n)): whether draw n is
     // accepted depends on nothing else, so 32 draws are tested at once and the accepted ones, in stream order, are
     // exactly the radii a sequential do/while loop hands to candidates 0, 1, 2, ...  (queue in shared memory)
@@ -263,8 +304,14 @@ __device__ void sample_nucleus(const DevCfg& c, const Store& st, const SampleSme
           ok = !(u2 * rwMax1 > 1.0 / (1.0 + exp((r - rad1) / dr)));
         } else {                                                // Nucleus.cpp:610-613
           double u1, u2; smc_uniform2(s_ws, n, 0, &u1, &u2);
-          r = rmaxCut * cbrt(u1);
-          ok = !(u2 * rwMax > 1.0 / (1.0 + exp((r - rad) / dr)));
+          // the accept test in single precision (error of the right-hand side < 2e-5 relative); a draw within 2e-4 of the
+          // boundary is settled by the reference's double expression, so every decision is the reference's.  The queue
+          // keeps u1: the radius rmaxCut * cbrt(u1) is taken in double precision for the accepted draws only (below)
+          const float rf = rmaxCut_f * cbrtf((float)u1);
+          const float ff = __fdividef(1.0f, 1.0f + __expf((rf - rad_f) * inv_dr_f)), lf = (float)(u2 * rwMax);
+          ok = !(lf > ff);
+          if (fabsf(lf - ff) <= 2e-4f * ff) ok = !(u2 * rwMax > 1.0 / (1.0 + exp((rmaxCut * cbrt(u1) - rad) / dr)));
+          r = u1;
         }
         const unsigned m = __ballot_sync(0xffffffffu, ok);
         if (ok) { const int pos = nq + __popc(m & below); qr[pos] = r; qc[pos] = cx; }
@@ -272,7 +319,7 @@ __device__ void sample_nucleus(const DevCfg& c, const Store& st, const SampleSme
         __syncwarp();
       }
       const uint32_t cand = cand_base + lane;
-      const double r = qr[lane], cxq = qc[lane];
+      const double r = deformed ? qr[lane] : rmaxCut * cbrt(qr[lane]), cxq = qc[lane];
       { double t0 = 0, t1 = 0; const bool mv = lane + 32 < nq;
         if (mv) { t0 = qr[lane + 32]; t1 = qc[lane + 32]; }
         __syncwarp();
@@ -636,7 +683,13 @@ __global__ void __launch_bounds__(64, 6) sample_collide_kernel(DevCfg c, Store s
     }
   }
   __syncthreads();
-  for (int k = tid; k < 2 * Amax * NROW; k += 64) { const int sd = k / (Amax * NROW), i = (k / NROW) % Amax, f = k % NROW; gn[k] = S_(sm, sd, f, i); }
+  // rows [side][i][NROW] in global memory <- structure of arrays in shared memory: one 64-byte row per thread step
+  for (int sd = 0; sd < 2; sd++)
+    for (int i = tid; i < Amax; i += 64) {
+      double2* row = reinterpret_cast<double2*>(gn + ((size_t)sd * Amax + i) * NROW);
+#pragma unroll
+      for (int f = 0; f < NROW; f += 2) row[f >> 1] = make_double2(S_(sm, sd, f, i), S_(sm, sd, f + 1, i));
+    }
 }
 
 size_t sample_smem_bytes(int Amax) {
