@@ -71,6 +71,8 @@ class ClockSampler:
         self.index, self.proc, self.lines = index, None, []
 
     def start(self):
+        if os.environ.get("SMC_BENCH_NO_CLOCKS"):      # diagnostic: is nvidia-smi's start-up visible in the timed region?
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -513,8 +515,11 @@ def avg_main(a, rank, world, local):
     clocks = ClockSampler(local); clocks.start()
     l0 = ctx.launches
     t0 = time.perf_counter()
+    step_ms = []
     for _ in range(a.steps):
+        ts = time.perf_counter()
         out, g = step()
+        step_ms.append(round(1e3 * (time.perf_counter() - ts), 2))
     if world > 1:
         ctx.comm_barrier()
     wall = time.perf_counter() - t0
@@ -542,7 +547,7 @@ def avg_main(a, rank, world, local):
     achieved = total * bytes_per_event / wall / 1e9
     line = {"metric": "events/sec", "value": total / wall, "unit": "events/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": 1e3 * wall / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": AVG_NAME, "events_per_step_per_gpu": n, "batch": min(a.batch, 1024), "kln_table_build_s": table_s,
+            "config": {"workload": AVG_NAME, "events_per_step_per_gpu": n, "batch": min(a.batch, 1024), "kln_table_build_s": table_s, "step_ms": step_ms,
                        "collective": "one all-reduce of %d doubles per step (%s)" % (2 * 4 * 7 * G, backend),
                        "allreduce_ms": (sum(ar_ms) / len(ar_ms)) if ar_ms else None,
                        "l2": "each density evaluation of a batch writes %d MB of lattices (> 126 MB L2)" % int(6 * 8 * G * min(a.batch, 1024) / 1e6)},

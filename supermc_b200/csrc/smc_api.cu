@@ -53,7 +53,7 @@ extern "C" int smc_create(const smc_params* p, int device, smc_ctx** out) {
   ctx->p = *p; ctx->device = device; ctx->launches = 0; ctx->last_ms = 0; ctx->last_n = 0; ctx->last_flags = 0;
   ctx->d_grids = nullptr; ctx->grids_bytes = 0; ctx->d_srcrec = nullptr; ctx->srcrec_bytes = 0; ctx->d_cmpart = nullptr; ctx->d_pair_u = nullptr; ctx->pair_u_bytes = 0; ctx->d_coll_w = nullptr; ctx->coll_w_bytes = 0;
   ctx->d_rcbk = nullptr; ctx->rcbk_q = ctx->rcbk_y = ctx->rcbk_k = 0;
-  ctx->d_quark = nullptr; ctx->d_cfgtab[0] = ctx->d_cfgtab[1] = nullptr; ctx->d_kln = nullptr; ctx->d_avg = nullptr; ctx->avg_doubles = 0; ctx->avg_count = 0;
+  ctx->d_quark = nullptr; ctx->d_cfgtab[0] = ctx->d_cfgtab[1] = nullptr; ctx->d_kln = nullptr; ctx->d_avg = nullptr; ctx->d_avg_part = nullptr; ctx->avg_part_bytes = 0; ctx->avg_doubles = 0; ctx->avg_count = 0;
   ctx->stream = nullptr; ctx->ev0 = ctx->ev1 = nullptr; ctx->profile = 0; ctx->cur_slot = 0; ctx->comm = nullptr; ctx->epoch = 1; ctx->lists.epoch = 0; ctx->lists.n = 0; ctx->ny = p->ny; ctx->slice = 0; std::memset(&ctx->sortbuf, 0, sizeof ctx->sortbuf);
   std::memset(ctx->slots, 0, sizeof ctx->slots);
   for (int i = 0; i < 8; i++) { ctx->stage_ms[i] = 0; ctx->pev[i] = nullptr; }
@@ -181,6 +181,7 @@ extern "C" void smc_destroy(smc_ctx* ctx) {
   if (ctx->d_kln) cudaFree(ctx->d_kln);
   if (ctx->d_rcbk) cudaFree(ctx->d_rcbk);
   if (ctx->d_avg) cudaFree(ctx->d_avg);
+  if (ctx->d_avg_part) cudaFree(ctx->d_avg_part);
   cudaFree(ctx->sortbuf.k1); cudaFree(ctx->sortbuf.k2); cudaFree(ctx->sortbuf.v1); cudaFree(ctx->sortbuf.v2); cudaFree(ctx->sortbuf.tmp);
   bool any_slot = false;
   for (int q = 0; q < SMC_MAX_SLOTS; q++) any_slot |= ctx->slots[q].ready;

@@ -108,40 +108,65 @@ __global__ void transform_kernel(DevCfg c, Store st, int rotate) {
   }
 }
 
-struct AccList { int n; int dst[8]; int srcA[8]; int srcB[8]; int whole[8]; double scale[8]; };
-// acc[dst] += sum over the batch of grid[srcA] (* grid[srcB]) * scale, event order fixed => deterministic.  The deposits only
-// write each event's bounding rectangle (no zero fill in this mode), so a cell takes the events whose rectangle holds it;
-// the rectangles of the batch sit in shared memory.  Spectator lattices are written whole.
-#define ACC_EV 2048
-__global__ void __launch_bounds__(256) accumulate_kernel(DevCfg c, Store st, AccList al, double* acc, int nev) {
-  __shared__ short rect[ACC_EV][4];
+// Accumulation of one density evaluation of a batch into the running sums (MakeDensity.cpp:1299-1330, 1341-1386).
+// One thread owns one lattice cell and a slice of the batch's events; it reads rho, TA1, TA2, rho_binary (and the spectator
+// lattices of the rotated pass) of every event of the slice whose bounding rectangle holds the cell -- the deposits of this mode
+// only write rectangles, spectator lattices are written whole -- and keeps all seven sums in registers: every lattice is read once
+// (TA1 and TA2 feed three sums), ACC_UNROLL events are in flight per thread, the rectangle test is done once per event.  The
+// slices leave partial sums that acc_finish_kernel adds in slice order: the result does not depend on the launch geometry.
+struct AccList { int with_spec; int dst0; double sd_scale; };      // dst0: accumulator slot of quantity 0 (the seven are consecutive)
+#define ACC_SLICE 128      // events per slice (<= 8 slices per batch of 1024)
+#define ACC_UNROLL 2
+__global__ void __launch_bounds__(256, 3) accumulate_kernel(DevCfg c, Store st, AccList al, double* part, int nev) {
+  __shared__ short4 rect[ACC_SLICE];
   const size_t G = (size_t)c.Maxx * c.Maxy;
-  const int q = blockIdx.y;
+  const int e0 = blockIdx.y * ACC_SLICE, ne = min(ACC_SLICE, nev - e0);
   const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int i = (int)(k / c.Maxy), j = (int)(k % c.Maxy);
-  const int sa = st.kind_slot[al.srcA[q]], sb = al.srcB[q] >= 0 ? st.kind_slot[al.srcB[q]] : -1;
-  double s = 0.0;
-  for (int e0 = 0; e0 < nev; e0 += ACC_EV) {
-    const int ne = min(ACC_EV, nev - e0);
-    __syncthreads();
-    for (int e = threadIdx.x; e < ne; e += blockDim.x) {
+  for (int e = threadIdx.x; e < ACC_SLICE; e += blockDim.x) {
+    short4 r = make_short4(0, 0, 0, -1);                          // .w < 0: the event does not count (not accepted, or beyond the batch)
+    if (e < ne) {
       const int* hi = st.hdr_i + (size_t)(e0 + e) * HDR_I;
-      const bool ok = hi[H_STATUS] == 0;
-      if (al.whole[q]) { rect[e][0] = 0; rect[e][1] = ok ? (short)c.Maxx : 0; rect[e][2] = 0; rect[e][3] = (short)c.Maxy; }
-      else { rect[e][0] = (short)hi[H_RLO]; rect[e][1] = ok ? (short)hi[H_RHI] : 0; rect[e][2] = (short)hi[H_CLO]; rect[e][3] = (short)hi[H_CHI]; }
+      if (hi[H_STATUS] == 0) r = make_short4((short)hi[H_RLO], (short)hi[H_RHI], (short)hi[H_CLO], (short)hi[H_CHI]);
     }
-    __syncthreads();
-    if (k < G) {
-      for (int e = 0; e < ne; e++) {
-        if (i < rect[e][0] || i >= rect[e][1] || j < rect[e][2] || j >= rect[e][3]) continue;
-        const double* base = st.grids + (size_t)(e0 + e) * st.nkinds * G;
-        double v = base[(size_t)sa * G + k];
-        if (sb >= 0) v *= base[(size_t)sb * G + k];
-        s += v * al.scale[q];
-      }
+    rect[e] = r;
+  }
+  __syncthreads();
+  if (k >= G) return;
+  const size_t g_rho = (size_t)st.kind_slot[GK_RHO] * G + k, g_ta1 = (size_t)st.kind_slot[GK_TA1] * G + k, g_ta2 = (size_t)st.kind_slot[GK_TA2] * G + k;
+  const size_t g_bin = (size_t)st.kind_slot[GK_RHO_BINARY] * G + k, g_sa = (size_t)st.kind_slot[GK_SPEC_A] * G + k, g_sb = (size_t)st.kind_slot[GK_SPEC_B] * G + k;
+  const bool spec = al.with_spec != 0;
+  double s_sd = 0, s_tatb = 0, s_bin = 0, s_ta = 0, s_tb = 0, s_sa = 0, s_sb = 0;
+  for (int eb = 0; eb < ne; eb += ACC_UNROLL) {
+    double v_rho[ACC_UNROLL], v_ta1[ACC_UNROLL], v_ta2[ACC_UNROLL], v_bin[ACC_UNROLL], v_sa[ACC_UNROLL], v_sb[ACC_UNROLL];
+#pragma unroll
+    for (int u = 0; u < ACC_UNROLL; u++) {
+      const short4 r = rect[min(eb + u, ACC_SLICE - 1)];
+      const bool live = (eb + u < ne) && r.w >= 0, in = live && i >= r.x && i < r.y && j >= r.z && j < r.w;
+      const double* base = st.grids + (size_t)(e0 + eb + u) * st.nkinds * G;
+      v_rho[u] = in ? base[g_rho] : 0.0; v_ta1[u] = in ? base[g_ta1] : 0.0; v_ta2[u] = in ? base[g_ta2] : 0.0; v_bin[u] = in ? base[g_bin] : 0.0;
+      v_sa[u] = (spec && live) ? base[g_sa] : 0.0; v_sb[u] = (spec && live) ? base[g_sb] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < ACC_UNROLL; u++) {                        // event order
+      s_sd += v_rho[u] * al.sd_scale; s_tatb += v_ta1[u] * v_ta2[u]; s_bin += v_bin[u]; s_ta += v_ta1[u]; s_tb += v_ta2[u];
+      s_sa += v_sa[u]; s_sb += v_sb[u];
     }
   }
-  if (k < G) acc[(size_t)al.dst[q] * G + k] += s;
+  double* o = part + (size_t)blockIdx.y * SMC_AVG_QUANTITIES * G + k;
+  o[(size_t)SMC_AVG_SD * G] = s_sd; o[(size_t)SMC_AVG_TATB * G] = s_tatb; o[(size_t)SMC_AVG_RHO_BINARY * G] = s_bin;
+  o[(size_t)SMC_AVG_TA * G] = s_ta; o[(size_t)SMC_AVG_TB * G] = s_tb;
+  if (spec) { o[(size_t)SMC_AVG_SPEC_A * G] = s_sa; o[(size_t)SMC_AVG_SPEC_B * G] = s_sb; }
+}
+// acc[dst[q]] += sum over the slices, in slice order
+__global__ void __launch_bounds__(256) acc_finish_kernel(DevCfg c, AccList al, const double* part, double* acc, int nslices) {
+  const size_t G = (size_t)c.Maxx * c.Maxy;
+  const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int q = blockIdx.y;
+  if (k >= G || (!al.with_spec && (q == SMC_AVG_SPEC_A || q == SMC_AVG_SPEC_B))) return;
+  double s = 0.0;
+  for (int sl = 0; sl < nslices; sl++) s += part[((size_t)sl * SMC_AVG_QUANTITIES + q) * G + k];
+  acc[(size_t)(al.dst0 + q) * G + k] += s;
 }
 }  // namespace smc
 
@@ -153,9 +178,10 @@ extern "C" int smc_avg_begin(smc_ctx* ctx, int from_order, int to_order, int wit
   CK(cudaSetDevice(ctx->device));
   ctx->avg_from = from_order; ctx->avg_to = to_order; ctx->avg_rp = with_rp ? 1 : 0; ctx->avg_ed = branches; ctx->avg_count = 0;
   const int norders = to_order - from_order + 1;
-  ctx->avg_doubles = (int64_t)norders * 4 * SMC_AVG_QUANTITIES * (int64_t)ctx->G;
-  if (ctx->d_avg) { cudaFree(ctx->d_avg); ctx->d_avg = nullptr; }
-  CK(cudaMalloc(&ctx->d_avg, (size_t)ctx->avg_doubles * sizeof(double)));
+  const int64_t want = (int64_t)norders * 4 * SMC_AVG_QUANTITIES * (int64_t)ctx->G;
+  if (ctx->d_avg && want != ctx->avg_doubles) { cudaFree(ctx->d_avg); ctx->d_avg = nullptr; }      // a run of the same shape reuses the block
+  ctx->avg_doubles = want;
+  if (!ctx->d_avg) CK(cudaMalloc(&ctx->d_avg, (size_t)ctx->avg_doubles * sizeof(double)));
   CK(cudaMemset(ctx->d_avg, 0, (size_t)ctx->avg_doubles * sizeof(double)));
   { const int rc = smc_ensure_extra(ctx); if (rc) return rc; }
   return SMC_OK;
@@ -189,16 +215,19 @@ static int avg_sequence(smc_ctx* ctx, int m) {
   auto cm = [&](int order, double scale) -> int { smc::cm_angle_kernel<<<m, AVG_THREADS, 0, ctx->stream>>>(c, st, order, scale); ctx->launches++; CK(cudaGetLastError()); return SMC_OK; };
   auto tf = [&](int rot) -> int { smc::transform_kernel<<<m, 128, 0, ctx->stream>>>(c, st, rot); ctx->launches++; CK(cudaGetLastError()); return SMC_OK; };
   auto acc = [&](int io, int variant, int branch) -> int {
-    smc::AccList al; int n = 0;
-    auto add = [&](int quantity, int a, int b, double scale) { al.dst[n] = avg_slot(io, variant, branch, quantity); al.srcA[n] = a; al.srcB[n] = b; al.scale[n] = scale;
-                                                               al.whole[n] = (a == smc::GK_SPEC_A || a == smc::GK_SPEC_B); n++; };
-    add(SMC_AVG_SD, smc::GK_RHO, -1, c.finalFactor);                                  // setSd/setEd: rho * finalFactor
-    add(SMC_AVG_TATB, smc::GK_TA1, smc::GK_TA2, 1.0); add(SMC_AVG_RHO_BINARY, smc::GK_RHO_BINARY, -1, 1.0);
-    add(SMC_AVG_TA, smc::GK_TA1, -1, 1.0); add(SMC_AVG_TB, smc::GK_TA2, -1, 1.0);
-    if (variant == 0) { add(SMC_AVG_SPEC_A, smc::GK_SPEC_A, -1, 1.0); add(SMC_AVG_SPEC_B, smc::GK_SPEC_B, -1, 1.0); }
-    al.n = n;
-    dim3 g((unsigned)((ctx->G + 255) / 256), n);
-    smc::accumulate_kernel<<<g, 256, 0, ctx->stream>>>(c, st, al, ctx->d_avg, m); ctx->launches++; CK(cudaGetLastError());
+    smc::AccList al;
+    al.dst0 = avg_slot(io, variant, branch, 0);
+    al.with_spec = (variant == 0); al.sd_scale = c.finalFactor;                        // setSd/setEd: rho * finalFactor
+    const int nslices = (m + ACC_SLICE - 1) / ACC_SLICE;
+    const size_t need = (size_t)nslices * SMC_AVG_QUANTITIES * ctx->G * sizeof(double);
+    if (need > ctx->avg_part_bytes) {
+      CK(cudaStreamSynchronize(ctx->stream));
+      if (ctx->d_avg_part) { cudaFree(ctx->d_avg_part); ctx->d_avg_part = nullptr; ctx->avg_part_bytes = 0; }
+      CK(cudaMalloc(&ctx->d_avg_part, need)); ctx->avg_part_bytes = need;
+    }
+    dim3 g((unsigned)((ctx->G + 255) / 256), nslices), g2((unsigned)((ctx->G + 255) / 256), SMC_AVG_QUANTITIES);
+    smc::accumulate_kernel<<<g, 256, 0, ctx->stream>>>(c, st, al, ctx->d_avg_part, m);
+    smc::acc_finish_kernel<<<g2, 256, 0, ctx->stream>>>(c, al, ctx->d_avg_part, ctx->d_avg, nslices); ctx->launches += 2; CK(cudaGetLastError());
     return SMC_OK;
   };
   ctx->epoch++;                          // positions and boxes are about to move: host mirrors of the lists are stale

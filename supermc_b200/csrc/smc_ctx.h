@@ -53,6 +53,7 @@ struct smc_ctx {
   // averaged profiles (operation 3)
   int profile; double stage_ms[8]; cudaEvent_t pev[8];
   smc_slot slots[SMC_MAX_SLOTS]; int cur_slot;
+  double* d_avg_part; size_t avg_part_bytes;      // per-slice partial sums of one accumulation (smc_avg.cu)
   double* d_avg; int64_t avg_doubles; int64_t avg_count; int avg_from, avg_to, avg_rp, avg_ed;
   void* comm;                                      // multi-GPU state (smc_comm.cu)
   uint64_t epoch; smc_list_cache lists;            // epoch: bumped whenever the device records change
