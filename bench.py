@@ -93,6 +93,12 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        if not self.lines:      # a timed region shorter than nvidia-smi's first sample: one query right after it
+            try:
+                self.lines = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                            capture_output=True, text=True, timeout=10).stdout.strip().splitlines()
+            except Exception:
+                pass
         sm, mx, reasons = [], [], set()
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]

@@ -20,6 +20,8 @@ for p in $parts; do
     scanexe) timeout 400 python bench.py --workload scan-exe --steps 2 --warmup 1 > ${O}_bench_scanexe.json 2> ${O}_bench_scanexe.err ;;
     ebe)   timeout 400 python bench.py --workload ebe --steps 2 --warmup 1 > ${O}_bench_ebe.json 2> ${O}_bench_ebe.err ;;
     avg)   timeout 600 python bench.py --workload avg --steps 2 --warmup 1 > ${O}_bench_avg.json 2> ${O}_bench_avg.err ;;
+    others) for w in ppb auau sqrt nbd; do timeout 300 python bench.py --workload $w --cpu-sample-events 100 > ${O}_bench_$w.json 2> ${O}_bench_$w.err; done ;;
+    sanit) for w in glb kln nbd sqrt; do timeout 600 compute-sanitizer --tool memcheck python profiles/sanitizer_run.py $w 2>&1 | tail -1 > ${O}_mem_$w.txt; timeout 700 compute-sanitizer --tool racecheck python profiles/sanitizer_run.py $w 2>&1 | tail -1 > ${O}_race_$w.txt; done ;;
     sass)  cuobjdump -sass supermc_b200/libsupermc_b200.so > ${O}_sass.txt 2>&1 ;;
   esac
 done

@@ -37,24 +37,30 @@ __global__ void __launch_bounds__(AVG_THREADS) cm_angle_kernel(DevCfg c, Store s
   const size_t G = (size_t)c.Maxx * c.Maxy;
   const double* rho = st.grids + ((size_t)e * st.nkinds + st.kind_slot[GK_RHO]) * G;
   // rho vanishes outside the event's bounding rectangle (bbox_kernel) and that part of the lattice is not even written
-  const int ilo = hi[H_RLO], jlo = hi[H_CLO], wj = max(hi[H_CHI] - jlo, 0), ncell = max(hi[H_RHI] - ilo, 0) * wj;
+  // warps walk the rows of the rectangle, lanes its columns (no index divisions; the row coordinate is hoisted)
+  const int ilo = hi[H_RLO], ihi = hi[H_RHI], jlo = hi[H_CLO], jhi = hi[H_CHI];
+  const int lane = tid & 31, warp = tid >> 5;
   double w = 0, sx = 0, sy = 0;
-  for (int q = tid; q < ncell; q += AVG_THREADS) {
-    const int i = ilo + q / wj, j = jlo + q % wj;
-    const double wei = rho[(size_t)i * c.Maxy + j] * scale * c.dx * c.dy;
-    w += wei; sx += xg_of(c, i) * wei; sy += yg_of(c, j) * wei;
+  for (int i = ilo + warp; i < ihi; i += AVG_THREADS / 32) {
+    const double* row = rho + (size_t)i * c.Maxy; const double xi = xg_of(c, i);
+    for (int j = jlo + lane; j < jhi; j += 32) {
+      const double wei = row[j] * scale * c.dx * c.dy;
+      w += wei; sx += xi * wei; sy += yg_of(c, j) * wei;
+    }
   }
   const double weight = bsum(w, red, tid);
   const double xc = bsum(sx, red, tid) / weight, yc = bsum(sy, red, tid) / weight;
   double nr = 0, ni = 0;
-  for (int q = tid; q < ncell; q += AVG_THREADS) {
-    const int i = ilo + q / wj, j = jlo + q % wj;
-    const double d = rho[(size_t)i * c.Maxy + j] * scale;
-    if (d == 0.0) continue;
-    const double x = xg_of(c, i) - xc, y = yg_of(c, j) - yc;
-    double a = 1.0, b = 0.0;                 // (x + i y)^n = r^n e^{i n theta}
-    for (int k2 = 0; k2 < order; k2++) { const double a2 = a * x - b * y; b = a * y + b * x; a = a2; }
-    nr += a * d; ni += b * d;
+  for (int i = ilo + warp; i < ihi; i += AVG_THREADS / 32) {
+    const double* row = rho + (size_t)i * c.Maxy; const double x = xg_of(c, i) - xc;
+    for (int j = jlo + lane; j < jhi; j += 32) {
+      const double d = row[j] * scale;
+      if (d == 0.0) continue;
+      const double y = yg_of(c, j) - yc;
+      double a = 1.0, b = 0.0;                 // (x + i y)^n = r^n e^{i n theta}
+      for (int k2 = 0; k2 < order; k2++) { const double a2 = a * x - b * y; b = a * y + b * x; a = a2; }
+      nr += a * d; ni += b * d;
+    }
   }
   const double Nr = bsum(nr, red, tid), Ni = bsum(ni, red, tid);
   if (tid == 0) { double* o = st.cm + (size_t)e * 4; o[0] = xc; o[1] = yc; o[2] = -atan2(-Ni, -Nr) / order; o[3] = weight; }

@@ -164,6 +164,7 @@ __device__ __forceinline__ void sort_by_xl(const DevCfg& c, const Store& st, con
       if (k < A) {
         const int t0 = cnt[bk[m]], t1 = cnt[bk[m] + 1];
         int r = t0;
+#pragma unroll 1
         for (int t = t0; t < t1; t++) { const int j = idx[t]; const double o = S_(sm, s, NXL, j); r += (o < key[m]) || (o == key[m] && j < k); }
         rk[m] = r;
       }
@@ -202,6 +203,7 @@ __device__ __forceinline__ void sort_by_xl(const DevCfg& c, const Store& st, con
       const int k = lane + 32 * m;
       if (k < A) {
         const double* a = st.nuc_extra_tmp + (((size_t)e * 2 + s) * c.Amax + k) * NEXTRA; double* b2 = st.nuc_extra + (((size_t)e * 2 + s) * c.Amax + rk[m]) * NEXTRA;
+#pragma unroll 1
         for (int f = 0; f < NEXTRA; f++) b2[f] = a[f];
       }
     }
@@ -501,6 +503,7 @@ __global__ void __launch_bounds__(64, 6) sample_collide_kernel(DevCfg c, Store s
     };
     int start_carry = 0;                                        // start(i) is non-decreasing in i (x-sorted sweep)
     double tXRmax = -1e300;                                     // no target box reaches beyond it: rows further right test nothing
+#pragma unroll 1
     for (int j = lane; j < B; j += 32) tXRmax = fmax(tXRmax, S_(sm, 1, NXR, j));
     for (int o = 16; o > 0; o >>= 1) tXRmax = fmax(tXRmax, __shfl_xor_sync(0xffffffffu, tXRmax, o));
     for (int i = warp; i < A; i += 2) {
@@ -684,7 +687,9 @@ __global__ void __launch_bounds__(64, 6) sample_collide_kernel(DevCfg c, Store s
   }
   __syncthreads();
   // rows [side][i][NROW] in global memory <- structure of arrays in shared memory: one 64-byte row per thread step
+#pragma unroll 1
   for (int sd = 0; sd < 2; sd++)
+#pragma unroll 1
     for (int i = tid; i < Amax; i += 64) {
       double2* row = reinterpret_cast<double2*>(gn + ((size_t)sd * Amax + i) * NROW);
 #pragma unroll
