@@ -637,13 +637,13 @@ __global__ void __launch_bounds__(64, 6) sample_collide_kernel(DevCfg c, Store s
   // collision list in (i,j) order (createBinaryCollisions, MCnucl.cpp:326-352): the sparse pass only records the pair
   int* cij = st.coll_ij + (size_t)e * c.ncoll_cap;
   if (accepted) {
-    for (int i = warp; i < A; i += 2) {
+    for (int i = tid; i < A; i += 64) {            // one projectile row per lane: its hit words in order, bit by bit
       int off = sm.rowoff[i];
       if (sm.rowoff[i + 1] == off) continue;
+#pragma unroll 1
       for (int wj = 0; wj < HW; wj++) {
-        const unsigned hm = sm.hit[(size_t)i * HW + wj];
-        if ((hm >> lane) & 1u) { const int k = off + __popc(hm & ((1u << lane) - 1u)); if (k < c.ncoll_cap) cij[k] = (i << 16) | (wj * 32 + lane); }
-        off += __popc(hm);
+        unsigned hm = sm.hit[(size_t)i * HW + wj];
+        while (hm) { const int b = __ffs(hm) - 1; hm &= hm - 1; if (off < c.ncoll_cap) cij[off] = (i << 16) | (wj * 32 + b); off++; }
       }
     }
   }
