@@ -516,9 +516,9 @@ def avg_main(a, rank, world, local):
     for _ in range(a.warmup):
         step()
     del ar_ms[:]
-    if world > 1:
-        ctx.comm_barrier()
     clocks = ClockSampler(local); clocks.start()
+    if world > 1:      # after the sampler's start-up: a rank that enters the timed region early would time the others' skew
+        ctx.comm_barrier()
     l0 = ctx.launches
     t0 = time.perf_counter()
     step_ms = []
