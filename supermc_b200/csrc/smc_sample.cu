@@ -480,6 +480,31 @@ __global__ void __launch_bounds__(64, 6) sample_collide_kernel(DevCfg c, Store s
     __syncthreads();
     for (int k = tid; k < Amax; k += 64) { sm.ncB[k] = 0; sm.firstB[k] = 0x7fffffff; }
     for (int k = tid; k < Amax * HW; k += 64) sm.hit[k] = 0;
+    // Window [start, end) of target nucleons the sweep tests for every projectile row (MCnucl.cpp:253-270), one row per lane:
+    //   start = first j with tXR_j >= pXL_i.  The reference carries its starting index from row to row, but rows are sorted by
+    //           xL: whatever an earlier row skipped has tXR_j < pXL of that row <= pXL_i, so the carry does not change the result.
+    //   end:    pair j is tested iff pXR_i >= tXL of the box looked at before it (the box at `start` for j = start and start + 1);
+    //           targets are sorted by xL, so with U = #{j : tXL_j <= pXR_i} that is "start < U and j <= U".
+    // Both come from binary searches on tXL (start: from the first box whose xL could reach pXL_i given the widest box, then the
+    // exact predicate).  Packed into rowoff[] (free until the row counts are taken).
+    {
+      double wmax = 0.0;
+#pragma unroll 1
+      for (int j = lane; j < B; j += 32) wmax = fmax(wmax, S_(sm, 1, NXR, j) - S_(sm, 1, NXL, j));
+      for (int o = 16; o > 0; o >>= 1) wmax = fmax(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+#pragma unroll 1
+      for (int i = tid; i < A; i += 64) {
+        const double pXL = S_(sm, 0, NXL, i), pXR = S_(sm, 0, NXR, i);
+        const double key = pXL - wmax * (1.0 + 1e-12) - 1e-12;       // boxes that start left of it end left of pXL
+        int lo = 0, hi2 = B;
+        while (lo < hi2) { const int mid = (lo + hi2) >> 1; if (S_(sm, 1, NXL, mid) < key) lo = mid + 1; else hi2 = mid; }
+        while (lo < B && !(S_(sm, 1, NXR, lo) >= pXL)) lo++;           // skip loop of the sweep, MCnucl.cpp:255-261
+        int ul = 0, uh = B;
+        while (ul < uh) { const int mid = (ul + uh) >> 1; if (S_(sm, 1, NXL, mid) <= pXR) ul = mid + 1; else uh = mid; }
+        const int end = (lo < ul) ? min(ul + 1, B) : lo;
+        sm.rowoff[i] = lo | (end << 16);
+      }
+    }
     __syncthreads();
     // ---- collisions: rows of the projectile, 32 target nucleons per step ----
     const smc_stream s_p = smc_make_stream(c.seed_lo, c.seed_hi, ev, tr, SMC_K_PAIR, 0);
@@ -501,29 +526,15 @@ __global__ void __launch_bounds__(64, 6) sample_collide_kernel(DevCfg c, Store s
       }
       __syncwarp();
     };
-    int start_carry = 0;                                        // start(i) is non-decreasing in i (x-sorted sweep)
-    double tXRmax = -1e300;                                     // no target box reaches beyond it: rows further right test nothing
-#pragma unroll 1
-    for (int j = lane; j < B; j += 32) tXRmax = fmax(tXRmax, S_(sm, 1, NXR, j));
-    for (int o = 16; o > 0; o >>= 1) tXRmax = fmax(tXRmax, __shfl_xor_sync(0xffffffffu, tXRmax, o));
     for (int i = warp; i < A; i += 2) {
-      const double px = S_(sm, 0, NX, i), py = S_(sm, 0, NY, i);
-      const double pXL = S_(sm, 0, NXL, i), pXR = S_(sm, 0, NXR, i), pYL = S_(sm, 0, NYL, i), pYR = S_(sm, 0, NYR, i);
-      if (pXL > tXRmax) break;                                  // rows are sorted by xL: the skip loop of the sweep finds no start
-      int start = -1;
-      const int jbeg = start_carry & ~31;
-      for (int j0 = jbeg; j0 < B; j0 += 32) {
-        const int j = j0 + lane; const bool in = j < B;
-        const int jj = in ? j : 0;
-        if (start < 0) {                                        // skip loop of the sweep, MCnucl.cpp:255-261
-          unsigned m = __ballot_sync(0xffffffffu, in && j >= start_carry && (S_(sm, 1, NXR, jj) >= pXL));
-          if (m) { start = j0 + __ffs(m) - 1; start_carry = start; }
-        }
-        if (start >= 0) {
-          // the sweep tests pair j iff j >= start and projXR >= XL of the *previous* box looked at (MCnucl.cpp:266-270)
-          bool tst = in && j >= start;
-          if (tst) { int jp = j - 1 > start ? j - 1 : start; tst = pXR >= S_(sm, 1, NXL, jp); }
-          const unsigned alive = __ballot_sync(0xffffffffu, tst);
+      const int win = sm.rowoff[i], start = win & 0xffff, end = win >> 16;
+      if (start >= B) break;                                    // rows are sorted by xL: no later row finds a start either
+      if (start >= end) continue;
+      const double px = S_(sm, 0, NX, i), py = S_(sm, 0, NY, i), pYL = S_(sm, 0, NYL, i), pYR = S_(sm, 0, NYR, i);
+      for (int j0 = start; j0 < end; j0 += 32) {
+        {
+          const int j = j0 + lane; const bool tst = j < end;
+          const int jj = tst ? j : 0;
           bool maybe = false; double u = 0.0;
           if (tst && pYL <= S_(sm, 1, NYR, jj) && pYR >= S_(sm, 1, NYL, jj)) {
             const double ddx = S_(sm, 1, NX, jj) - px, ddy = S_(sm, 1, NY, jj) - py;
@@ -565,7 +576,6 @@ __global__ void __launch_bounds__(64, 6) sample_collide_kernel(DevCfg c, Store s
               nq -= 32; __syncwarp();
             }
           }
-          if (!alive && j0 + 32 > start) break;                // x-sorted: nothing further can be tested
         }
       }
     }
