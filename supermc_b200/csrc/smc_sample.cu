@@ -131,29 +131,29 @@ __device__ __forceinline__ void sort_by_xl(const DevCfg& c, const Store& st, con
   for (int m = 0; m < MK; m++) { const int k = lane + 32 * m; rk[m] = 0; key[m] = (k < A) ? S_(sm, s, NXL, k) : 0.0; }
   // rank = #{j : key_j < key_k or (key_j == key_k and j < k)}
   if (MK > 1 && MK <= 8) {
-    // 32 buckets over [min, max] of the keys (the bucket index is a monotone function of the key): a key's rank is the
-    // number of keys in lower buckets plus its rank among the keys of its own bucket -- about A/32 compares per key
-    // instead of A.  Scratch: this warp's Woods-Saxon queue (idle now): 33 counters + A 16-bit indices.
+    // 64 buckets over [min, max] of the keys (the bucket index is a monotone function of the key): a key's rank is the
+    // number of keys in lower buckets plus its rank among the keys of its own bucket -- about A/64 compares per key
+    // instead of A.  Scratch: this warp's Woods-Saxon queue (idle now): 65 counters + A 16-bit indices.
     int* cnt = reinterpret_cast<int*>(sm.wsq + (size_t)s * 128);
-    unsigned short* idx = reinterpret_cast<unsigned short*>(cnt + 34);
+    unsigned short* idx = reinterpret_cast<unsigned short*>(cnt + 68);
     double kmin = 1e300, kmax = -1e300;
 #pragma unroll
     for (int m = 0; m < MK; m++) if (lane + 32 * m < A) { kmin = fmin(kmin, key[m]); kmax = fmax(kmax, key[m]); }
     for (int o = 16; o > 0; o >>= 1) { kmin = fmin(kmin, __shfl_xor_sync(0xffffffffu, kmin, o)); kmax = fmax(kmax, __shfl_xor_sync(0xffffffffu, kmax, o)); }
-    const double scale = (kmax > kmin) ? 32.0 / (kmax - kmin) : 0.0;
-    cnt[lane] = 0;
+    const double scale = (kmax > kmin) ? 64.0 / (kmax - kmin) : 0.0;
+    cnt[lane] = 0; cnt[lane + 32] = 0;
     __syncwarp();
     int bk[MK], pos[MK];
 #pragma unroll
     for (int m = 0; m < MK; m++) {
-      bk[m] = min(31, (int)((key[m] - kmin) * scale)); pos[m] = 0;
+      bk[m] = min(63, (int)((key[m] - kmin) * scale)); pos[m] = 0;
       if (lane + 32 * m < A) pos[m] = atomicAdd(&cnt[bk[m]], 1);
     }
     __syncwarp();
-    const int mine = cnt[lane]; int incl = mine;
+    const int c0 = cnt[2 * lane], c1 = cnt[2 * lane + 1]; int incl = c0 + c1;      // lane owns buckets 2 lane, 2 lane + 1
     for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += n; }
     __syncwarp();
-    cnt[lane] = incl - mine; if (lane == 31) cnt[32] = incl;          // exclusive offsets, cnt[32] = A
+    cnt[2 * lane] = incl - c0 - c1; cnt[2 * lane + 1] = incl - c1; if (lane == 31) cnt[64] = incl;          // exclusive offsets, cnt[64] = A
     __syncwarp();
 #pragma unroll
     for (int m = 0; m < MK; m++) if (lane + 32 * m < A) idx[cnt[bk[m]] + pos[m]] = (unsigned short)(lane + 32 * m);
@@ -164,7 +164,7 @@ __device__ __forceinline__ void sort_by_xl(const DevCfg& c, const Store& st, con
       if (k < A) {
         const int t0 = cnt[bk[m]], t1 = cnt[bk[m] + 1];
         int r = t0;
-#pragma unroll 1
+#pragma unroll 2
         for (int t = t0; t < t1; t++) { const int j = idx[t]; const double o = S_(sm, s, NXL, j); r += (o < key[m]) || (o == key[m] && j < k); }
         rk[m] = r;
       }
