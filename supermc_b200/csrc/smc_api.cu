@@ -755,9 +755,11 @@ extern "C" int smc_get_grid(smc_ctx* ctx, int slot, int which, double* host) {
     int hi[smc::HDR_I];
     CK(cudaMemcpy(hi, ctx->st.hdr_i + (size_t)slot * smc::HDR_I, sizeof hi, cudaMemcpyDeviceToHost));
     const int My = ctx->cfg.Maxy;
+    const bool spec = which == SMC_GRID_SPEC_A || which == SMC_GRID_SPEC_B;      // the spectator deposits have a rectangle of their own
+    const int rl = hi[spec ? smc::H_SRLO : smc::H_RLO], rh = hi[spec ? smc::H_SRHI : smc::H_RHI], cl = hi[spec ? smc::H_SCLO : smc::H_CLO], ch = hi[spec ? smc::H_SCHI : smc::H_CHI];
     for (int i = 0; i < ctx->cfg.Maxx; i++)
       for (int j = 0; j < My; j++)
-        if (i < hi[smc::H_RLO] || i >= hi[smc::H_RHI] || j < hi[smc::H_CLO] || j >= hi[smc::H_CHI]) host[(size_t)i * My + j] = 0.0;
+        if (i < rl || i >= rh || j < cl || j >= ch) host[(size_t)i * My + j] = 0.0;
   }
   return SMC_OK;
 }

@@ -97,7 +97,8 @@ struct Store {
   int nbd_pass;       // how often this batch has been (re)deposited: part of the NBD uniforms' address (operation 3)
   int e0;             // first event of the launch (the grid stages run in L2-sized sub-batches)
 };
-enum { H_NP1 = 0, H_NP2, H_NCOLL, H_TRIES, H_NSPEC1, H_NSPEC2, H_STATUS, H_RLO, H_RHI, H_CLO, H_CHI, H_GIVENW, HDR_I = 16 };
+// H_RLO..H_CHI: bounding rectangle (cells) of the participant / collision deposits; H_SRLO..H_SCHI: that of the spectator deposits
+enum { H_NP1 = 0, H_NP2, H_NCOLL, H_TRIES, H_NSPEC1, H_NSPEC2, H_STATUS, H_RLO, H_RHI, H_CLO, H_CHI, H_GIVENW, H_SRLO, H_SRHI, H_SCLO, H_SCHI, HDR_I = 16 };
 enum { HD_B = 0, HDR_D = 4 };
 enum { MOM_OUT = 64 };   // 0..44 mom[9][5], 45 rn0, 46 total, 47 xc, 48 yc, 49 dsdy
 

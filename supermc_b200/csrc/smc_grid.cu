@@ -174,60 +174,64 @@ __device__ __forceinline__ DepWork dep_work(const Store& st) {
 }
 __device__ __forceinline__ int dep_tile_class(int band, int nb, int sgroup) { return min(abs(2 * band - (nb - 1)) + 3 * sgroup, DEP_NCLS - 1); }
 
-// bounding rectangle (cells) of every source window of the participant/collision deposits of one event
+// bounding rectangles (cells) of the source windows of one event: one for the participant / collision deposits, one for the
+// spectator deposits (they cover different parts of the lattice); nothing outside them is ever written or read
 __global__ void bbox_kernel(DevCfg c, Store st, KindList kl, int nev, int list_tiles) {
-  __shared__ int red[4][4];
-  __shared__ int s_cnt[10], s_nb;
+  __shared__ int red[4][8];
+  __shared__ int s_cnt[10], s_nb[2];
   const int e = blockIdx.x + st.e0, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (st.redo && !st.redo[e]) return;
   int* hi = st.hdr_i + (size_t)e * HDR_I;
-  int ilo = c.Maxx, ihi = 0, jlo = c.Maxy, jhi = 0;
+  int lo[4] = {c.Maxx, c.Maxy, c.Maxx, c.Maxy}, hh[4] = {0, 0, 0, 0};      // (rows, columns) of the two rectangles
   const int status = hi[H_STATUS];
   if (status == 0 || status == 4) {
     for (int q = 0; q < kl.n; q++) {
       const int kind = kl.kind[q];
-      const bool whole = (kind == GK_SPEC_A || kind == GK_SPEC_B);      // spectator grids span the whole lattice
+      const int w = (kind == GK_SPEC_A || kind == GK_SPEC_B) ? 2 : 0;
       const int ns = src_count(c, hi, kind);
       SrcRec* recs = st.src_rec + ((size_t)e * kl.n + q) * st.src_stride;
       for (int k = tid; k < ns; k += blockDim.x) {
         Src s; load_src(c, st, e, hi, kind, k, s);
         SrcRec r; r.x = s.x; r.y = s.y; r.W = s.W; r.thr = s.thr; r.iL = (short)s.iL; r.iR = (short)s.iR; r.jL = (short)s.jL; r.jR = (short)s.jR; r.flat = s.flat; r.pad = 0;
         recs[k] = r;
-        if (!whole && s.iL < s.iR && s.jL < s.jR) { ilo = min(ilo, s.iL); ihi = max(ihi, s.iR); jlo = min(jlo, s.jL); jhi = max(jhi, s.jR); }
+        if (s.iL < s.iR && s.jL < s.jR) { lo[w] = min(lo[w], s.iL); hh[w] = max(hh[w], s.iR); lo[w + 1] = min(lo[w + 1], s.jL); hh[w + 1] = max(hh[w + 1], s.jR); }
       }
     }
   }
-  for (int o = 16; o > 0; o >>= 1) {
-    ilo = min(ilo, __shfl_xor_sync(0xffffffffu, ilo, o)); ihi = max(ihi, __shfl_xor_sync(0xffffffffu, ihi, o));
-    jlo = min(jlo, __shfl_xor_sync(0xffffffffu, jlo, o)); jhi = max(jhi, __shfl_xor_sync(0xffffffffu, jhi, o));
+#pragma unroll
+  for (int q = 0; q < 4; q++)
+    for (int o = 16; o > 0; o >>= 1) { lo[q] = min(lo[q], __shfl_xor_sync(0xffffffffu, lo[q], o)); hh[q] = max(hh[q], __shfl_xor_sync(0xffffffffu, hh[q], o)); }
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) { red[warp][q] = lo[q]; red[warp][4 + q] = hh[q]; }
   }
-  if (lane == 0) { red[warp][0] = ilo; red[warp][1] = ihi; red[warp][2] = jlo; red[warp][3] = jhi; }
   __syncthreads();
   if (tid == 0) {
-    for (int w = 1; w < (int)(blockDim.x >> 5); w++) { ilo = min(ilo, red[w][0]); ihi = max(ihi, red[w][1]); jlo = min(jlo, red[w][2]); jhi = max(jhi, red[w][3]); }
-    if (ihi <= ilo || jhi <= jlo) { ilo = ihi = jlo = jhi = 0; }
-    hi[H_RLO] = ilo; hi[H_RHI] = ihi; hi[H_CLO] = jlo; hi[H_CHI] = jhi;
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++)
+      for (int q = 0; q < 4; q++) { lo[q] = min(lo[q], red[w][q]); hh[q] = max(hh[q], red[w][4 + q]); }
+    for (int w = 0; w < 4; w += 2) if (hh[w] <= lo[w] || hh[w + 1] <= lo[w + 1]) { lo[w] = hh[w] = lo[w + 1] = hh[w + 1] = 0; }
+    hi[H_RLO] = lo[0]; hi[H_RHI] = hh[0]; hi[H_CLO] = lo[1]; hi[H_CHI] = hh[1];
+    hi[H_SRLO] = lo[2]; hi[H_SRHI] = hh[2]; hi[H_SCLO] = lo[3]; hi[H_SCHI] = hh[3];
     if (list_tiles) {
-      const int nb = (ihi - ilo + DEP_BAND - 1) / DEP_BAND, ng = (jhi - jlo + DEP_COLS - 1) / DEP_COLS;
-      const int nbF = (c.Maxx + DEP_BAND - 1) / DEP_BAND, ngF = (c.Maxy + DEP_COLS - 1) / DEP_COLS;
       int tot = 0;
+      for (int w = 0; w < 2; w++) s_nb[w] = (hh[2 * w] - lo[2 * w] + DEP_BAND - 1) / DEP_BAND;
       for (int q = 0; q < kl.n; q++) {
-        const bool whole = (kl.kind[q] == GK_SPEC_A || kl.kind[q] == GK_SPEC_B);
+        const int w = (kl.kind[q] == GK_SPEC_A || kl.kind[q] == GK_SPEC_B) ? 1 : 0;
         s_cnt[q] = tot;
-        if (status == 0 || status == 4) tot += whole ? nbF * ngF : nb * ng;
+        if (status == 0 || status == 4) tot += s_nb[w] * ((hh[2 * w + 1] - lo[2 * w + 1] + DEP_COLS - 1) / DEP_COLS);
       }
-      s_cnt[kl.n] = tot; s_nb = nb;
+      s_cnt[kl.n] = tot;
     }
   }
   if (!list_tiles) return;
   __syncthreads();
-  const int tot = s_cnt[kl.n], nbF = (c.Maxx + DEP_BAND - 1) / DEP_BAND;
+  const int tot = s_cnt[kl.n];
   const DepWork wk = dep_work(st);
   for (int k = tid; k < tot; k += blockDim.x) {
     int q = 0;
     while (k >= s_cnt[q + 1]) q++;
-    const bool whole = (kl.kind[q] == GK_SPEC_A || kl.kind[q] == GK_SPEC_B);
-    const int t = k - s_cnt[q], nb = whole ? nbF : s_nb, band = t % nb, sgroup = t / nb;
+    const int w = (kl.kind[q] == GK_SPEC_A || kl.kind[q] == GK_SPEC_B) ? 1 : 0;
+    const int t = k - s_cnt[q], nb = s_nb[w], band = t % nb, sgroup = t / nb;
     const int cls = dep_tile_class(band, nb, sgroup);
     const int pos = atomicAdd(wk.ctr + 1 + cls, 1);
     wk.items[(size_t)cls * wk.cap + pos] = make_int2(e, (q << 16) | (sgroup << 8) | band);
@@ -289,10 +293,10 @@ __global__ void __launch_bounds__(DEP_THREADS, DEP_MINCTA) deposit_kernel(DevCfg
   const int kind = kl.kind[kq], tile_slot = sgroup * nbands + band;
   const int* hi = st.hdr_i + (size_t)e * HDR_I;
   // bands and column groups are laid out from the corner of the event's own bounding rectangle (bbox_kernel),
-  // so a CTA is either inside the populated region or exits at once; spectator grids span the whole lattice
-  const bool whole = (kind == GK_SPEC_A || kind == GK_SPEC_B);
-  const int r_org = whole ? 0 : hi[H_RLO], r_end = whole ? c.Maxx : hi[H_RHI];
-  const int c_org = whole ? 0 : hi[H_CLO], c_end = whole ? c.Maxy : hi[H_CHI];
+  // so a CTA is either inside the populated region or exits at once; spectator grids have a rectangle of their own
+  const bool spec = (kind == GK_SPEC_A || kind == GK_SPEC_B);
+  const int r_org = hi[spec ? H_SRLO : H_RLO], r_end = hi[spec ? H_SRHI : H_RHI];
+  const int c_org = hi[spec ? H_SCLO : H_CLO], c_end = hi[spec ? H_SCHI : H_CHI];
   const int r0 = r_org + band * DEP_BAND, c0 = c_org + sgroup * DEP_COLS;
   if (!PERSIST && (r0 >= r_end || c0 >= c_end)) return;
   const int wr = warp / DEP_NSTR, ws = warp % DEP_NSTR, lr = lane >> 3, lc = lane & 7;
