@@ -483,7 +483,7 @@ AVG_NAME = ("MC-KLN Au+Au 200 GeV averaged smooth profiles (operation 3), 261x26
             "all seven averaged quantities, one centrality window (20-30 %)")
 AVG_REF_ARGS = ["which_mc_model=1", "sub_model=7", "lambda=0.218", "Aproj=197", "Atarg=197", "ecm=200", "cc_fluctuation_model=0", "maxx=13", "maxy=13",
                 "dx=0.1", "dy=0.1", "finalFactor=1", "operation=3", "Npmin=127", "Npmax=234", "bmin=5.7851427", "bmax=8.6297897", "average_from_order=2",
-                "average_to_order=3", "use_sd=1", "use_ed=1", "use_block=1", "use_4col=0", "tmax=24", "tmax_subdivision=3"]
+                "average_to_order=3", "use_sd=1", "use_ed=1", "use_block=1", "use_4col=0"]
 
 
 def avg_main(a, rank, world, local):
@@ -570,25 +570,41 @@ def avg_main(a, rank, world, local):
     return 0
 
 
-def avg_cpu_baseline(nev=12):
-    """the unmodified reference on the same window, one process; the table build (its start-up) is subtracted with a
-    1-event run (tmax=24: a 70x70 table, enough for this centrality window, keeps the start-up at ~25 s)"""
+def avg_cpu_baseline(nev=40):
+    """the unmodified reference on the same window, one process.  Its start-up is the dN/dy table build (tmax=24: a 70x70 table,
+    enough for this centrality window: ~35 s of BASES Monte Carlo whose duration varies by seconds from run to run), so the
+    event loop is timed from the moment the program writes data/dNdyTable.dat (the last thing MCnucl::makeTable does,
+    src/MCnucl.cpp:959) to its exit, and the fixed cost of writing the 48 averaged files at the end is removed by the
+    difference of two runs (4 and 4 + nev events)."""
     exe, run = ref_paths()
     if not os.path.exists(exe):
         return {"value": None, "unit": "events/s", "cores": 1, "kind": "reference", "sample": "oracle/_ref/superMC_ref.e not built on this box"}
+
+    nfiles = [0]
 
     def once(n):
         d = tempfile.mkdtemp(prefix="smcavg_"); os.makedirs(os.path.join(d, "data"))
         for f in ("parameters.dat", "EOS", "tables"):
             os.symlink(os.path.join(run, f), os.path.join(d, f))
-        t0 = time.perf_counter()
-        subprocess.call([exe] + AVG_REF_ARGS + ["nev=%d" % n, "randomSeed=3"], cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-        dt = time.perf_counter() - t0
+        t0 = time.time()
+        # tmax=40 covers this window's thickness (the reference exits with "increase the dimension of dndyTable" below ~28);
+        # one subdivision instead of three keeps the table build short and does not change the work per event
+        rc = subprocess.call([exe] + AVG_REF_ARGS + ["tmax=40", "tmax_subdivision=1", "nev=%d" % n, "randomSeed=3"], cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        nfiles[0] = len([f for f in os.listdir(os.path.join(d, "data")) if "Avg" in f or "order" in f])
+        t_end = time.time()
+        try:
+            t_tab = os.path.getmtime(os.path.join(d, "data", "dNdyTable.dat"))
+        except OSError:
+            t_tab = t0
         subprocess.call(["rm", "-rf", d])
-        return dt
-    t1 = once(1); t = once(nev + 1)
-    return {"value": nev / max(t - t1, 1e-3), "unit": "events/s", "cores": 1, "kind": "reference",
-            "sample": "%d accepted events of the same window (operation 3, all outputs), oracle/_ref/superMC_ref.e, 1-event run (incl. the dN/dy table build, %.1f s) subtracted" % (nev, t1),
+        return t_end - t_tab, t_tab - t0
+    (l1, tab1), (l2, tab2) = once(4), once(4 + nev)
+    if nfiles[0] == 0 or l2 <= l1:      # the reference wrote no averaged profile: do not report a rate
+        return {"value": None, "unit": "events/s", "cores": 1, "kind": "reference", "sample": "the reference run of this window failed (event loops %.2f / %.2f s, %d output files)" % (l1, l2, nfiles[0])}
+    return {"value": nev / max(l2 - l1, 1e-3), "unit": "events/s", "cores": 1, "kind": "reference",
+            "sample": "%d accepted events of the same window (operation 3, all outputs; tmax=40, one table subdivision), oracle/_ref/superMC_ref.e: event loops of a %d- and a 4-event run "
+                      "(%.2f s and %.2f s, timed from the write of data/dNdyTable.dat to exit) subtracted; the dN/dy table builds took %.1f and %.1f s"
+                      % (nev, 4 + nev, l2, l1, tab2, tab1),
             **host_info()}
 
 
