@@ -651,7 +651,9 @@ __device__ double nbd_pmf(double p, double r, double k_in) {
 }
 // pmf(k+1) = pmf(k) p (k + r) / (k + 1): one multiply chain serves all thirteen envelope edges and both passes over the
 // support, so a cell costs one pow (or three lgamma when the support starts far from 0) instead of ~20 pmf evaluations
-__device__ long nbd_quantile(double p, double r, double u) {
+// (the uniform is a callable: most cells of an event's rim return 0 before they would use it, and a Philox call costs ~100 instructions)
+template <class U>
+__device__ long nbd_quantile(double p, double r, U uniform) {
   const double ZERO = 1e-15;
   if (p < ZERO || p + ZERO > 1.0) return 0;
   const double mode = (r <= 1) ? 1e-30 : p * (r - 1) / (1 - p), sd = sqrt(p * r) / (1 - p);
@@ -676,8 +678,9 @@ __device__ long nbd_quantile(double p, double r, double u) {
       hgt[m] = pl > pc ? pl : pc; pl = pc;
     }
   }
-  double tot = 0;
+  double tot = 0, u = 0;
   for (int pass = 0; pass < 2; pass++) {
+    if (pass == 1) u = uniform();
     double acc = 0, pk = pka; const double target = u * tot;
     for (long k = ka; k <= kb; k++) {
       double w = 0;
@@ -712,13 +715,14 @@ __global__ void fluctuate_kernel(DevCfg c, Store st, int nev) {
     const int ir = idx / wj, i = ilo + ir, j = jlo + (idx - ir * wj);
     const size_t q = (size_t)i * c.Maxy + j;
     const double nb = rho[q] * cell;
+    auto draw = [&]() { return smc_uniform_cell(c.seed_lo, c.seed_hi, ev, (uint32_t)st.nbd_pass, (uint32_t)q); };
     double n;
     if (c.cc_fluct == 1) {
-      n = (nb == 0.0) ? 0.0 : (double)nbd_quantile(nb / (nb + c.cc_k), c.cc_k, smc_uniform_cell(c.seed_lo, c.seed_hi, ev, (uint32_t)st.nbd_pass, (uint32_t)q));
+      n = (nb == 0.0) ? 0.0 : (double)nbd_quantile(nb / (nb + c.cc_k), c.cc_k, draw);
     } else {
       const double k = kpp * fmin(ta[q], tb[q]) * c.siginNN / 10;
       if (nb < 1e-10) n = nb;
-      else n = (double)nbd_quantile(nb / (nb + k), k, smc_uniform_cell(c.seed_lo, c.seed_hi, ev, (uint32_t)st.nbd_pass, (uint32_t)q));
+      else n = (double)nbd_quantile(nb / (nb + k), k, draw);
     }
     rho[q] = n / cell;
   }
